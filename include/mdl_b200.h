@@ -1,0 +1,131 @@
+/* mdl_b200.h -- C ABI of libmdl_b200.so, the sm_100a message-passing engine.
+ *
+ * The reference (Fung-Lab/MatDeepLearn) has no FFI: its hot path is reached by
+ * Python attribute access into torch_geometric / torch_scatter.  Each entry
+ * point below names the reference call site (file:line under /root/reference)
+ * whose device work it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked "host"; the caller owns
+ *     all memory (outputs and workspace included); the library allocates nothing
+ *   - all floating point is fp32, all indices the library consumes are int32
+ *     except the reference-layout inputs of mdl_csr_from_coo (int64)
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it
+ *     and is CUDA-graph capturable (no syncs, no allocations inside)
+ *   - return 0 on success; non-zero = error, text via mdl_last_error()
+ *     (thread-local).  Nothing throws or exits across this boundary.
+ *   - entry points are re-entrant (forward runs on the Python main thread,
+ *     backward on autograd's worker thread)
+ *
+ * Engine edge order.  mdl_csr_from_coo sorts the E directed edges
+ * (row=source j -> col=destination i, PyG flow source_to_target) stably by
+ * destination.  "slot" s in [0,E) is a position in that order; edge-level
+ * operands handed to the conv kernels (edge_attr, filters ...) are in slot
+ * order (use mdl_gather_rows with dst_eid to permute reference-order tensors).
+ */
+#ifndef MDL_B200_H
+#define MDL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MDL_API __attribute__((visibility("default")))
+#else
+#define MDL_API
+#endif
+
+#define MDL_OK 0
+#define MDL_ERR_ARG 1      /* bad shape / null pointer / unsupported size */
+#define MDL_ERR_CUDA 2     /* a CUDA runtime call or launch failed */
+#define MDL_ERR_WORKSPACE 3
+
+#define MDL_REDUCE_SUM 0
+#define MDL_REDUCE_MEAN 1
+#define MDL_REDUCE_MAX 2
+
+MDL_API int mdl_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated) */
+MDL_API int mdl_last_error(char* buf, size_t n);
+/* number of kernels this library has launched since load (all threads);
+ * bench.py reports it as gpu_launches */
+MDL_API int64_t mdl_launch_count(void);
+
+/* ---- graph layout: replaces PyG MessagePassing.__collect__'s per-layer
+ * index_select/scatter bookkeeping (triggered at reference
+ * matdeeplearn/models/cgcnn.py:142, schnet.py:140, mpnn.py:154) with a
+ * once-per-batch sort.  Inputs are the reference's tensors as collated at
+ * training/training.py:300-307: edge_index int64 [2,E], batch int64 [N]. ---- */
+MDL_API size_t mdl_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+MDL_API int mdl_csr_from_coo(const int64_t* edge_index, const int64_t* batch,
+                     int64_t num_nodes, int64_t num_edges, int64_t num_graphs,
+                     int32_t* dst_ptr,   /* [N+1] slots of destination n: [dst_ptr[n],dst_ptr[n+1]) */
+                     int32_t* dst_src,   /* [E] source node of slot s */
+                     int32_t* dst_dst,   /* [E] destination node of slot s */
+                     int32_t* dst_eid,   /* [E] reference edge id of slot s */
+                     int32_t* src_ptr,   /* [N+1] by-source segments over positions p */
+                     int32_t* src_slot,  /* [E] slot s of by-source position p */
+                     float* inv_deg_dst, /* [N] 1/max(1,in-degree)  */
+                     float* inv_deg_src, /* [N] 1/max(1,out-degree) */
+                     int32_t* graph_ptr, /* [B+1] node range of graph b */
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[r,:] = src[idx[r],:]   (rows of `width` floats) */
+MDL_API int mdl_gather_rows(const float* src, const int32_t* idx, float* out,
+                    int64_t rows, int64_t width, void* stream);
+/* out[idx[r],:] = src[r,:]   (inverse permutation of mdl_gather_rows) */
+MDL_API int mdl_scatter_rows(const float* src, const int32_t* idx, float* out,
+                     int64_t rows, int64_t width, void* stream);
+
+/* ---- GaussianSmearing, reference matdeeplearn/process/process.py:580-590:
+ * out[e,k] = exp(coeff * (d[e] - offset[k])^2); offset = the module's
+ * registered linspace buffer (process.py:583), coeff per process.py:585 ---- */
+MDL_API int mdl_gaussian_smear(const float* d, const float* offset, float* out, int64_t num_edges,
+                       int32_t G, float coeff, void* stream);
+
+/* ---- segmented reduce over contiguous segments: replaces torch_scatter
+ * scatter(..., reduce=) / torch_geometric global_{mean,add,max}_pool
+ * (reference cgcnn.py:154,169; megnet.py:86,130-132,346-348).
+ * out[s,:] = reduce_{r in [ptr[s],ptr[s+1])} src[perm ? perm[r] : r, :]
+ * empty segments give 0.  argmax (may be NULL unless MAX+backward) receives
+ * the winning row.  bwd: grad_src[row,:] (+)= weight * grad_out[s,:]. ---- */
+MDL_API int mdl_segment_reduce_fwd(const float* src, const int32_t* ptr, const int32_t* perm,
+                           float* out, int32_t* argmax, int64_t num_segments,
+                           int64_t width, int32_t reduce, void* stream);
+MDL_API int mdl_segment_reduce_bwd(const float* grad_out, const int32_t* ptr, const int32_t* perm,
+                           const int32_t* argmax, float* grad_src, int64_t num_segments,
+                           int64_t num_rows, int64_t width, int32_t reduce, void* stream);
+
+/* ---- CGConv, PyG CGConv(channels=C, dim=G, aggr, batch_norm=False) as
+ * constructed at reference matdeeplearn/models/cgcnn.py:80-82 and called at
+ * cgcnn.py:136-145.  The caller splits lin_f/lin_s column-wise into
+ * [W_i | W_j | W_e] and supplies the node-level projections
+ *   PQ[n, 0:2C]  = x[n] W_i^T + b   (f rows then s rows)   "P", used at destination
+ *   PQ[n, 2C:4C] = x[n] W_j^T       (f rows then s rows)   "Q", used at source
+ * and We = [W_e of lin_f ; W_e of lin_s]  [2C, G].
+ * fwd: out[i] = aggr_{s: dst=i} sigmoid(a_f) * softplus(a_s) + x[i],
+ *      a = P[i] + Q[src(s)] + We . ea[s]
+ * bwd: given grad_out [N,C] returns dPQ [N,4C] (dP = sum over in-edges of da,
+ *      dQ = sum over out-edges of da), dWe [2C,G]; the caller finishes with
+ *      dense node-level GEMMs (dx = grad_out + dPQ . Wn, dWn = dPQ^T x). ---- */
+MDL_API size_t mdl_cgconv_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G);
+MDL_API int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, const float* We,
+                   const int32_t* dst_ptr, const int32_t* dst_src, const int32_t* dst_dst,
+                   const float* inv_deg_dst, float* out,
+                   int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
+                   int32_t reduce, void* stream);
+MDL_API int mdl_cgconv_bwd(const float* grad_out, const float* PQ, const float* ea, const float* We,
+                   const int32_t* dst_ptr, const int32_t* dst_src, const int32_t* dst_dst,
+                   const int32_t* src_ptr, const int32_t* src_slot,
+                   const float* inv_deg_dst, float* dPQ, float* dWe,
+                   int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
+                   int32_t reduce, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDL_B200_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of libmdl_b200.so (the C ABI declared in include/mdl_b200.h).
+
+There is no CPU fallback: importing an operator without the built library, or
+calling one on a non-CUDA tensor, raises.  Build with
+`python -c "import __graft_entry__ as g; g.build()"` or `make -C matdeeplearn_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmdl_b200.so")
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f32 = C.c_float
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/mdl_b200.h
+SIGNATURES = {
+    "mdl_version": (C.c_int, []),
+    "mdl_last_error": (C.c_int, [C.c_char_p, _sz]),
+    "mdl_launch_count": (_i64, []),
+    "mdl_csr_workspace_bytes": (_sz, [_i64, _i64]),
+    "mdl_csr_from_coo": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mdl_gather_rows": (C.c_int, [_p, _p, _p, _i64, _i64, _p]),
+    "mdl_scatter_rows": (C.c_int, [_p, _p, _p, _i64, _i64, _p]),
+    "mdl_gaussian_smear": (C.c_int, [_p, _p, _p, _i64, _i32, _f32, _p]),
+    "mdl_segment_reduce_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),
+    "mdl_segment_reduce_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
+    "mdl_cgconv_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "mdl_cgconv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
+    "mdl_cgconv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
+}
+
+REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2}
+
+_lib = None
+
+
+def load():
+    """Return the loaded library, binding prototypes on first use."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built "
+            "(run __graft_entry__.build()).  matdeeplearn_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    load().mdl_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses host tensors."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("matdeeplearn_b200 operators need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("matdeeplearn_b200 operators need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().mdl_launch_count())

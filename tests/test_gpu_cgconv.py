@@ -1,0 +1,169 @@
+"""GPU parity: engine layout, segmented reduce and the fused CGConv kernels vs
+the CPU oracle (fp64 ground truth), through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_close, random_graph, contiguous_batch_vector
+
+pytestmark = pytest.mark.gpu
+
+# fp32 kernels vs fp64 oracle.  Forward values: rtol 1e-5 (+ 2e-6 of the tensor's
+# scale as absolute floor); gradients (long fp32 sums over E): rtol 1e-4.
+FWD = dict(rtol=1e-5, atol_rel=2e-6)
+BWD = dict(rtol=1e-4, atol_rel=2e-5)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _csr_reference(ei, n):
+    row, col = ei[0].numpy(), ei[1].numpy()
+    eid = np.argsort(col, kind="stable")
+    dst_dst, dst_src = col[eid], row[eid]
+    pos = np.argsort(dst_src, kind="stable")
+    dst_ptr = np.concatenate([[0], np.cumsum(np.bincount(col, minlength=n))])
+    src_ptr = np.concatenate([[0], np.cumsum(np.bincount(row, minlength=n))])
+    return eid, dst_src, dst_dst, pos, dst_ptr, src_ptr
+
+
+@pytest.mark.parametrize("n,e,hub,iso", [(40, 300, None, 0), (500, 6000, (7, 300), 5), (3, 2, None, 1)])
+def test_csr_matches_stable_sort(dev, n, e, hub, iso):
+    from matdeeplearn_b200.csr import GraphCSR
+    ei = random_graph(n, e, 1, hub, iso)
+    batch = contiguous_batch_vector(n, min(4, n), 2)
+    csr = GraphCSR.from_coo(ei.to(dev), batch.to(dev), num_graphs=min(4, n))
+    eid, dst_src, dst_dst, pos, dst_ptr, src_ptr = _csr_reference(ei, n)
+    assert np.array_equal(csr.dst_eid.cpu().numpy(), eid)
+    assert np.array_equal(csr.dst_src.cpu().numpy(), dst_src)
+    assert np.array_equal(csr.dst_dst.cpu().numpy(), dst_dst)
+    assert np.array_equal(csr.src_slot.cpu().numpy(), pos)
+    assert np.array_equal(csr.dst_ptr.cpu().numpy(), dst_ptr)
+    assert np.array_equal(csr.src_ptr.cpu().numpy(), src_ptr)
+    gp = np.concatenate([[0], np.cumsum(np.bincount(batch.numpy(), minlength=min(4, n)))])
+    assert np.array_equal(csr.graph_ptr.cpu().numpy(), gp)
+    indeg = np.maximum(1, np.diff(dst_ptr))
+    assert np.allclose(csr.inv_deg_dst.cpu().numpy(), 1.0 / indeg)
+
+
+def test_csr_empty_edges(dev):
+    from matdeeplearn_b200.csr import GraphCSR
+    ei = torch.zeros(2, 0, dtype=torch.int64, device=dev)
+    csr = GraphCSR.from_coo(ei, num_nodes=5)
+    assert csr.dst_ptr.cpu().tolist() == [0] * 6 and csr.src_ptr.cpu().tolist() == [0] * 6
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean", "max"])
+@pytest.mark.parametrize("width", [1, 64, 100, 300])
+def test_scatter_matches_oracle(dev, reduce, width):
+    import matdeeplearn_b200.nn as mnn
+    from oracle import pyg_ops as O
+    torch.manual_seed(0)
+    n, s = 777, 40
+    index = contiguous_batch_vector(n, s - 3, 3)  # 3 trailing empty segments
+    src = torch.randn(n, width, dtype=torch.float64)
+    ref_in = src.clone().requires_grad_(True)
+    ref = O.scatter(ref_in, index, 0, s, reduce)
+    got_in = src.float().to(dev).requires_grad_(True)
+    got = mnn.scatter(got_in, index.to(dev), 0, s, reduce)
+    assert_close(got, ref, **FWD, what=f"scatter {reduce}")
+    w = torch.randn_like(ref)
+    ref.backward(w)
+    got.backward(w.float().to(dev))
+    assert_close(got_in.grad, ref_in.grad, **FWD, what=f"scatter {reduce} grad")
+
+
+def test_scatter_unsorted_index(dev):
+    import matdeeplearn_b200.nn as mnn
+    from oracle import pyg_ops as O
+    torch.manual_seed(1)
+    index = torch.randint(0, 50, (1000,))
+    src = torch.randn(1000, 32, dtype=torch.float64)
+    for red in ("sum", "mean", "max"):
+        ref = O.scatter(src, index, 0, None, red)
+        got = mnn.scatter(src.float().to(dev), index.to(dev), 0, None, red)
+        assert_close(got, ref, **FWD, what=red)
+
+
+def _cgconv_case(dev, n, e, C, G, aggr, hub=None, iso=0, seed=0):
+    import matdeeplearn_b200.nn as mnn
+    from oracle import pyg_ops as O
+    torch.manual_seed(seed)
+    ei = random_graph(n, e, seed, hub, iso)
+    E = ei.shape[1]
+    x = torch.randn(n, C, dtype=torch.float64)
+    ea = torch.rand(E, G, dtype=torch.float64)
+    ref_conv = O.CGConv(C, G, aggr=aggr).double()
+    conv = mnn.CGConv(C, G, aggr=aggr)
+    conv.load_state_dict({k: v.float() for k, v in ref_conv.state_dict().items()})
+    conv = conv.to(dev)
+    xr = x.clone().requires_grad_(True)
+    ref = ref_conv(xr, ei, ea)
+    xg = x.float().to(dev).requires_grad_(True)
+    got = conv(xg, ei.to(dev), ea.float().to(dev))
+    assert_close(got, ref, **FWD, what=f"cgconv fwd C={C} G={G} {aggr}")
+    w = torch.randn_like(ref)
+    ref.backward(w)
+    got.backward(w.float().to(dev))
+    assert_close(xg.grad, xr.grad, **BWD, what="dx")
+    for name, pr in ref_conv.named_parameters():
+        pg = dict(conv.named_parameters())[name]
+        assert_close(pg.grad, pr.grad, **BWD, what=f"d{name}")
+    return got
+
+
+@pytest.mark.parametrize("C,G", [(64, 50), (100, 50), (128, 100), (64, 200), (8, 3), (128, 200)])
+def test_cgconv_shapes(dev, C, G):
+    _cgconv_case(dev, n=300, e=3000, C=C, G=G, aggr="mean")
+
+
+def test_cgconv_add_aggr(dev):
+    _cgconv_case(dev, n=200, e=1500, C=64, G=50, aggr="add")
+
+
+def test_cgconv_hub_and_isolated(dev):
+    # in-degree 400 (> several rounds of 128 slots) and 7 nodes with no edges at all
+    _cgconv_case(dev, n=600, e=4000, C=64, G=50, aggr="mean", hub=(11, 400), iso=7)
+
+
+def test_cgconv_tiny(dev):
+    _cgconv_case(dev, n=2, e=1, C=64, G=50, aggr="mean")
+
+
+def test_cgconv_deterministic(dev):
+    a = _cgconv_case(dev, n=400, e=5000, C=64, G=50, aggr="mean", seed=5)
+    b = _cgconv_case(dev, n=400, e=5000, C=64, G=50, aggr="mean", seed=5)
+    assert torch.equal(a, b), "CSR reduction must be bitwise reproducible"
+
+
+def test_cgconv_rejects_cpu_tensors():
+    import matdeeplearn_b200.nn as mnn
+    conv = mnn.CGConv(8, 4, aggr="mean")
+    with pytest.raises(RuntimeError):
+        conv(torch.randn(3, 8), torch.zeros(2, 1, dtype=torch.long), torch.randn(1, 4))
+
+
+def test_cgcnn_model_matches_oracle(dev):
+    from matdeeplearn_b200 import models as M, process as pr
+    from oracle import models as OM
+    ds = pr.synthetic_dataset("bulk", 24, seed=7)
+    batch = ds.batch()
+    torch.manual_seed(0)
+    cfg = dict(dim1=64, dim2=64, pre_fc_count=1, gc_count=4, post_fc_count=2)
+    ref_model = OM.CGCNN(ds, **cfg).double()
+    model = M.CGCNN(ds, **cfg)
+    model.load_state_dict({k: v.float() if v.is_floating_point() else v
+                           for k, v in ref_model.state_dict().items()})
+    model = model.to(dev)
+    ref = ref_model(batch.double())
+    got = model(batch.to(dev))
+    assert_close(got, ref, rtol=1e-4, atol_rel=1e-5, what="CGCNN forward")
+    ref_loss = torch.nn.functional.l1_loss(ref, batch.y.double())
+    got_loss = torch.nn.functional.l1_loss(got, batch.y.to(dev))
+    ref_loss.backward()
+    got_loss.backward()
+    for name, pr_ in ref_model.named_parameters():
+        pg = dict(model.named_parameters())[name]
+        assert_close(pg.grad, pr_.grad, rtol=1e-3, atol_rel=1e-4, what=f"grad {name}")
