@@ -26,6 +26,7 @@ namespace mdl {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus static __shared__
 
 enum CgMode { CG_FWD = 0, CG_BWD_DST = 1, CG_BWD_SRC = 2 };
 
@@ -308,7 +309,7 @@ static size_t cg_smem_bytes(int mode, int CC, int G, int cap) {
 
 // largest channel chunk / slot capacity that fits the 227 KB opt-in limit
 static bool cg_plan(int mode, int C, int G, CgPlan* plan) {
-  const size_t limit = 227 * 1024;
+  const size_t limit = kMaxDynSmem;
   for (int CC = C; CC >= 4; CC = ((CC / 2) + 3) & ~3) {
     const int W2 = 2 * CC, GS = (G + 7) & ~7;
     const int n_dw = (W2 / 4) * (GS / 8);
@@ -333,7 +334,7 @@ static int cg_launch(const CgParams& p, size_t smem, int grid, cudaStream_t st) 
   static std::atomic<int> configured{0};  // opt in to >48 KB dynamic smem once per instantiation
   if (!configured.load(std::memory_order_acquire)) {
     MDL_CUDA(cudaFuncSetAttribute(k_cgconv<MODE, NITEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
+                                  kMaxDynSmem));
     configured.store(1, std::memory_order_release);
   }
   k_cgconv<MODE, NITEM><<<grid, kThreads, smem, st>>>(p);

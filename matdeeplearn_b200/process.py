@@ -74,7 +74,7 @@ def gaussian_expand(d_hat, resolution=DEFAULT_EDGE_LENGTH, start=0.0, stop=1.0, 
     mu = torch.linspace(start, stop, resolution, dtype=d_hat.dtype)
     coeff = -0.5 / ((stop - start) * width) ** 2
     diff = d_hat[:, None] - mu[None, :]
-    return torch.exp(coeff * diff * diff)
+    return torch.exp(coeff * (diff * diff))
 
 
 def pairwise_distances(pos, cell_lengths=None):

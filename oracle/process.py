@@ -62,7 +62,7 @@ def gaussian_smearing(dist, start=0.0, stop=1.0, resolution=50, width=0.2):
     offset = torch.linspace(start, stop, resolution, dtype=dist.dtype)
     coeff = -0.5 / ((stop - start) * width) ** 2
     d = dist.unsqueeze(-1) - offset.view(1, -1)
-    return torch.exp(coeff * d * d)
+    return torch.exp(coeff * (d * d))
 
 
 def normalize_edges(weights):
