@@ -125,6 +125,13 @@ MDL_API int mdl_cgconv_bwd(const float* grad_out, const float* PQ, const float* 
                    int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
                    int32_t reduce, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- tensor-core self-test: D[128,N] = A[128,K] . B[N,K]^T through the same
+ * tcgen05/TMEM conventions (umma.cuh) the fused kernels use.  split=0: plain
+ * TF32 (operands truncated by the hardware); split=1: 3xTF32 (fp32-faithful).
+ * No reference counterpart: test infrastructure for the kernels above. ---- */
+MDL_API int mdl_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                              int32_t split, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

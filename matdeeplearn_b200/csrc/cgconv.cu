@@ -20,33 +20,12 @@
 // Backward recomputes the gates (saves nothing per edge), produces
 //   dP[i] = sum_{s: dst=i} da[s]   (BWD_DST pass, also accumulates dWe = da^T ea in
 //   dQ[j] = sum_{s: src=j} da[s]    registers across all tiles of the CTA)
-#include "common.cuh"
+#include "cgconv.cuh"
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace mdl {
-
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus static __shared__
-
-enum CgMode { CG_FWD = 0, CG_BWD_DST = 1, CG_BWD_SRC = 2 };
-
-struct CgParams {
-  const float* x;         // FWD  [N,C]
-  const float* gout;      // BWD  [N,C]
-  const float* PQ;        // [N,4C]
-  const float* ea;        // [E,G] slot order
-  const float* WeT;       // [G,2C] (k-major: f channels then s channels)
-  const int32_t* seg_ptr; // dst_ptr (FWD, BWD_DST) or src_ptr (BWD_SRC)  [N+1]
-  const int32_t* dst_src; // [E] slot -> source node
-  const int32_t* dst_dst; // [E] slot -> destination node
-  const int32_t* src_slot;// [E] by-source position -> slot (BWD_SRC)
-  const float* inv_deg;   // [N] destination 1/deg (mean) or nullptr (sum)
-  float* out;             // FWD: out [N,C]; BWD: dPQ [N,4C]
-  float* dW_part;         // BWD_DST: [gridDim.x][G][2*CC] partials
-  int N, E, C, G;
-  int c_off, CC;          // channel chunk handled by this launch
-  int cap, te, n_tiles;
-};
 
 template <int MODE, int NITEM>
 __global__ void __launch_bounds__(kThreads, 1) k_cgconv(const CgParams p) {
@@ -353,6 +332,13 @@ static int cg_check(int64_t N, int64_t E, int C, int G, int reduce) {
   return MDL_OK;
 }
 
+// MDL_CGCONV_IMPL=simt forces the SIMT kernels (cross-checks, fallback timing)
+static bool use_tc(int mode, int C, int G) {
+  const char* env = getenv("MDL_CGCONV_IMPL");
+  if (env && strcmp(env, "simt") == 0) return false;
+  return cgtc_supported(mode, C, G);
+}
+
 }  // namespace mdl
 
 using namespace mdl;
@@ -378,6 +364,7 @@ extern "C" int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, 
   p.x = x; p.PQ = PQ; p.ea = ea; p.WeT = WeT; p.seg_ptr = dst_ptr; p.dst_src = dst_src;
   p.dst_dst = dst_dst; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg_dst : nullptr;
   p.out = out; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
+  if (use_tc(CG_FWD, C, G)) return cgtc_launch(CG_FWD, p, as_stream(stream), nullptr);
   p.cap = plan.cap; p.te = plan.te;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(E, plan.te));
   for (int c_off = 0; c_off < C; c_off += plan.CC) {
@@ -412,7 +399,14 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
   p.out = dPQ; p.dW_part = (float*)workspace; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
 
   // pass A: destination order -> dP and dWe
-  {
+  if (use_tc(CG_BWD_DST, C, G)) {
+    p.seg_ptr = dst_ptr;
+    int grid = 0;
+    if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid)) return rc;
+    const int tot = G * 2 * C;
+    k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, grid, G, C, 0, C, dWeT);
+    MDL_LAUNCHED();
+  } else {
     CgPlan plan;
     MDL_REQUIRE(cg_plan(CG_BWD_DST, C, G, &plan), "cgconv_bwd: C=%d G=%d does not fit", C, G);
     p.seg_ptr = dst_ptr; p.cap = plan.cap; p.te = plan.te;
@@ -432,7 +426,10 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
     }
   }
   // pass B: source order -> dQ
-  {
+  if (use_tc(CG_BWD_SRC, C, G)) {
+    p.seg_ptr = src_ptr;
+    if (int rc = cgtc_launch(CG_BWD_SRC, p, st, nullptr)) return rc;
+  } else {
     CgPlan plan;
     MDL_REQUIRE(cg_plan(CG_BWD_SRC, C, G, &plan), "cgconv_bwd: C=%d G=%d does not fit", C, G);
     p.seg_ptr = src_ptr; p.cap = plan.cap; p.te = plan.te;

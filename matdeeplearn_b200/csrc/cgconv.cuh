@@ -1,0 +1,38 @@
+// cgconv.cuh -- declarations shared by the SIMT (cgconv.cu) and tensor-core
+// (cgconv_tc.cu) implementations of the fused CGConv edge kernels.
+#pragma once
+#include "common.cuh"
+
+namespace mdl {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus static __shared__
+
+enum CgMode { CG_FWD = 0, CG_BWD_DST = 1, CG_BWD_SRC = 2 };
+
+struct CgParams {
+  const float* x;         // FWD  [N,C]
+  const float* gout;      // BWD  [N,C]
+  const float* PQ;        // [N,4C]
+  const float* ea;        // [E,G] slot order
+  const float* WeT;       // [G,2C] (k-major: f channels then s channels)
+  const int32_t* seg_ptr; // dst_ptr (FWD, BWD_DST) or src_ptr (BWD_SRC)  [N+1]
+  const int32_t* dst_src; // [E] slot -> source node
+  const int32_t* dst_dst; // [E] slot -> destination node
+  const int32_t* src_slot;// [E] by-source position -> slot (BWD_SRC)
+  const float* inv_deg;   // [N] destination 1/deg (mean) or nullptr (sum)
+  float* out;             // FWD: out [N,C]; BWD: dPQ [N,4C]
+  float* dW_part;         // BWD_DST: [gridDim.x][G][2*CC] partials
+  int N, E, C, G;
+  int c_off, CC;          // channel chunk handled by this launch
+  int cap, te, n_tiles;
+};
+
+
+// tensor-core path (cgconv_tc.cu).  Returns false if (C, G, mode) does not fit its
+// shared-memory / TMEM plan, in which case the caller uses the SIMT kernel.
+bool cgtc_supported(int mode, int C, int G);
+int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out);
+
+}  // namespace mdl

@@ -1,0 +1,137 @@
+// umma.cuh -- thin inline-PTX layer over the sm_100a tensor-core path used by the
+// fused edge kernels: tcgen05.mma (kind::tf32, cta_group::1, operands in shared
+// memory, fp32 accumulators in TMEM), mbarrier completion, tcgen05.ld epilogue.
+//
+// Operand layout ("canonical K-major, no swizzle"): a [rows x K] fp32 tile is
+// stored as 16-byte chunks of 4 consecutive k; 8 rows x 16 B form one contiguous
+// 128-byte core matrix; core matrices of successive 8-row groups are SBO = 128 B
+// apart, successive k-chunks LBO = rows*16 B apart:
+//     byte(r, k) = (k/4) * rows*16 + (r/8)*128 + (r%8)*16 + (k%4)*4
+// One tcgen05.mma consumes K = 8 tf32 = two k-chunks.
+//
+// fp32-faithful products ("3xTF32"): x = hi + lo with hi = rna_tf32(x); the
+// tensor core computes A_hi*B_hi + A_hi*B_lo + A_lo*B_hi into the same fp32
+// accumulator (the dropped lo*lo term is < 2^-22 relative).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdl {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- operand tile addressing -------------------------------------------------
+__host__ __device__ __forceinline__ int tile_offset_bytes(int r, int k, int rows) {
+  return (k >> 2) * rows * 16 + (r >> 3) * 128 + (r & 7) * 16 + (k & 3) * 4;
+}
+
+// shared-memory matrix descriptor (K-major, SWIZZLE_NONE), sm_100 "version 1"
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, dense
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- tf32 split -----------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- mbarrier -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Bounded wait: a descriptor/protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
+// ---- TMEM -----------------------------------------------------------------------
+// whole warp; ncols power of two >= 32; result lands in *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---- MMA issue (ONE thread) -------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread -> one arrival on `bar` when they retire
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- epilogue: 16 consecutive fp32 columns of this thread's TMEM lane ---------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// TMEM address of (lane quadrant of this warp, column)
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int warp_in_group, int col) {
+  return base + ((uint32_t)(32 * (warp_in_group & 3)) << 16) + (uint32_t)col;
+}
+
+}  // namespace umma
+}  // namespace mdl

@@ -1,0 +1,111 @@
+// umma_selftest.cu -- D[128,N] = A[128,K] . B[N,K]^T on the tcgen05 tensor core,
+// single CTA.  Exists so tests/test_gpu_umma.py can pin the descriptor / layout /
+// TMEM-readback conventions of umma.cuh against a CPU matmul independently of the
+// fused edge kernels that build on them.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mdl {
+
+__global__ void __launch_bounds__(128, 1)
+k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                int N, int K, int split, int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int a_bytes = 128 * K * 4, b_bytes = N * K * 4;
+  uint8_t* sAhi = sm;
+  uint8_t* sAlo = sAhi + a_bytes;
+  uint8_t* sBhi = sAlo + a_bytes;
+  uint8_t* sBlo = sBhi + b_bytes;
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < 128 * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    const float x = A[i];
+    const float hi = split ? umma::tf32_hi(x) : x;
+    const int off = umma::tile_offset_bytes(r, k, 128);
+    *reinterpret_cast<float*>(sAhi + off) = hi;
+    *reinterpret_cast<float*>(sAlo + off) = x - hi;
+  }
+  for (int i = tid; i < N * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    const float x = B[i];
+    const float hi = split ? umma::tf32_hi(x) : x;
+    const int off = umma::tile_offset_bytes(r, k, N);
+    *reinterpret_cast<float*>(sBhi + off) = hi;
+    *reinterpret_cast<float*>(sBlo + off) = x - hi;
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_tf32(128, N);
+    const uint32_t step_a = 2 * 128 * 16, step_b = 2 * N * 16;  // two k-chunks per MMA
+    uint32_t acc = 0;
+    for (int pass = 0; pass < (split ? 3 : 1); ++pass) {
+      const uint8_t* a = (pass == 2) ? sAlo : sAhi;
+      const uint8_t* b = (pass == 1) ? sBlo : sBhi;
+      for (int kk = 0; kk < K / 8; ++kk) {
+        const uint64_t ad = umma::make_desc(umma::smem_u32(a) + kk * step_a, lbo_a, sbo_a);
+        const uint64_t bd = umma::make_desc(umma::smem_u32(b) + kk * step_b, lbo_b, sbo_b);
+        umma::mma_tf32(tmem, ad, bd, idesc, acc);
+        acc = 1;
+      }
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  const int row = tid;  // TMEM lane == D row for M=128, cta_group::1
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(umma::tmem_addr(tmem, warp, c0), v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) D[(size_t)row * N + c0 + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace mdl
+
+using namespace mdl;
+
+static int selftest_launch(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                           int32_t split, int lbo_a, int sbo_a, int lbo_b, int sbo_b, void* stream) {
+  MDL_REQUIRE(A && B && D, "selftest_umma: null pointer");
+  MDL_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "selftest_umma: N must be a multiple of 16 in [16,256]");
+  MDL_REQUIRE(K >= 8 && K % 8 == 0, "selftest_umma: K must be a multiple of 8");
+  size_t smem = (size_t)2 * (128 + N) * K * 4;
+  MDL_REQUIRE(smem <= 200 * 1024, "selftest_umma: tile too large");
+  MDL_CUDA(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_umma_selftest<<<1, 128, smem, as_stream(stream)>>>(A, B, D, N, K, split, lbo_a, sbo_a, lbo_b, sbo_b);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+extern "C" int mdl_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                                 int32_t split, void* stream) {
+  return selftest_launch(A, B, D, N, K, split, 128 * 16, 128, N * 16, 128, stream);
+}
+
+// descriptor-field probe (development aid; same staging layout, caller-chosen LBO/SBO)
+extern "C" __attribute__((visibility("default"))) int mdl_selftest_umma_ex(
+    const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, int32_t lbo_a,
+    int32_t sbo_a, int32_t lbo_b, int32_t sbo_b, void* stream) {
+  return selftest_launch(A, B, D, N, K, split, lbo_a, sbo_a, lbo_b, sbo_b, stream);
+}
