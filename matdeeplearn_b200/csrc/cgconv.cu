@@ -69,12 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv(const CgParams p) {
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    if (tid == 0) {
-      const int lo_key = tile * p.te;
-      sh_bounds[0] = lower_bound_i32(p.seg_ptr, p.N, lo_key);
-      // the last tile also owns trailing empty segments (seg_ptr[n] == E)
-      sh_bounds[1] = (tile == p.n_tiles - 1) ? p.N : lower_bound_i32(p.seg_ptr, p.N, lo_key + p.te);
-    }
+    tile_bounds<MODE>(p, tile, p.te, tid, sh_bounds);  // the last tile also owns trailing empty segments
     __syncthreads();
     const int n_lo = sh_bounds[0], n_hi = sh_bounds[1];
     if (n_hi <= n_lo) { __syncthreads(); continue; }
@@ -159,10 +154,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv(const CgParams p) {
                            acc[i][6] + ps.z + qs.z, acc[i][7] + ps.w + qs.w};
             if (MODE == CG_FWD) {
               float4 m;
-              m.x = sigmoidf_(af[0]) * softplusf_(as[0]);
-              m.y = sigmoidf_(af[1]) * softplusf_(as[1]);
-              m.z = sigmoidf_(af[2]) * softplusf_(as[2]);
-              m.w = sigmoidf_(af[3]) * softplusf_(as[3]);
+              m.x = sigmoid_fast_(af[0]) * softplusf_(as[0]);
+              m.y = sigmoid_fast_(af[1]) * softplusf_(as[1]);
+              m.z = sigmoid_fast_(af[2]) * softplusf_(as[2]);
+              m.w = sigmoid_fast_(af[3]) * softplusf_(as[3]);
               *reinterpret_cast<float4*>(sV + e * VW + 4 * cg) = m;
             } else {
               const int d = sDst[e];
@@ -172,10 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv(const CgParams p) {
               float dfv[4], dsv[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float sg = sigmoidf_(af[j]);
+                const float sg = sigmoid_fast_(af[j]);
                 const float sp = softplusf_(as[j]);
                 dfv[j] = gg[j] * sp * sg * (1.0f - sg);
-                dsv[j] = gg[j] * sg * sigmoidf_(as[j]);
+                dsv[j] = gg[j] * sg * sigmoid_fast_(as[j]);
               }
               *reinterpret_cast<float4*>(sV + e * VW + 4 * cg) = make_float4(dfv[0], dfv[1], dfv[2], dfv[3]);
               *reinterpret_cast<float4*>(sV + e * VW + CC + 4 * cg) = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);

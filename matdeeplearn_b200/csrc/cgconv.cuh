@@ -29,6 +29,29 @@ struct CgParams {
   int cap, te, n_tiles;
 };
 
+// First segment whose start offset seg_ptr[n] is >= position s (what a lower_bound over
+// seg_ptr returns), found through the position -> segment maps the CSR already holds:
+// 2-3 dependent loads instead of a ~20-step binary search per tile.
+template <int MODE>
+__device__ __forceinline__ int first_segment_at_or_after(const CgParams& p, int s) {
+  if (s >= p.E) return (p.E == 0 && s == 0) ? 0 : p.N;
+  const int slot = (MODE == CG_BWD_SRC) ? __ldg(p.src_slot + s) : s;
+  const int seg = (MODE == CG_BWD_SRC) ? __ldg(p.dst_src + slot) : __ldg(p.dst_dst + slot);
+  int n = (__ldg(p.seg_ptr + seg) == s) ? seg : seg + 1;
+  while (n > 0 && __ldg(p.seg_ptr + n - 1) >= s) --n;  // empty segments that start exactly at s
+  return n;
+}
+
+// tile t owns segments [bounds0, bounds1): computed by two threads in parallel
+template <int MODE>
+__device__ __forceinline__ void tile_bounds(const CgParams& p, int tile, int te, int tid, int* sh_bounds) {
+  if (tid == 0) sh_bounds[0] = first_segment_at_or_after<MODE>(p, tile * te);
+  if (tid == 32)
+    sh_bounds[1] = (tile == p.n_tiles - 1) ? p.N : first_segment_at_or_after<MODE>(p, (tile + 1) * te);
+}
+
+// 1/(1+exp(-x)) with an approximate (<= 1 ulp) reciprocal instead of an IEEE division
+__device__ __forceinline__ float sigmoid_fast_(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 
 // tensor-core path (cgconv_tc.cu).  Returns false if (C, G, mode) does not fit its
 // shared-memory / TMEM plan, in which case the caller uses the SIMT kernel.
