@@ -37,23 +37,24 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   if (((GS >> 2) & 1) == 0) GS += 4;  // odd number of 16-byte chunks per row: conflict-free float4 column reads
   const int VW = (mode == CG_FWD ? C : 2 * C) + 4;
   uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)kTcRows * KP * 4;
-  uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 3 * kTcRows * 4;
+  uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 4 * kTcRows * 4;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
   pl->tmem_cols = 32;
   while (pl->tmem_cols < NP) pl->tmem_cols <<= 1;
-  const int n_dw = (2 * C / 4) * ((GS + 7) / 8);
+  const int n_dw = (2 * C / 4) * (KP / 8);
   pl->nitem = (n_dw + kThreads - 1) / kThreads;
   if (mode == CG_BWD_DST && pl->nitem > 2) return false;
   pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
-  // value tile: own region if it fits, else aliased over the A tiles (dead once the MMAs retired)
-  // and, outside BWD_DST (whose dWe pass still reads the row-major ea copy), over the ea copy too.
+  // value tile: own region if it fits, else aliased over the A tiles, which are dead between the
+  // retirement of a round's MMAs and the next round's operand split.  Not for BWD_DST (its dWe
+  // pass reads the A tiles next to the value tile), and never over the ea landing zone (the next
+  // round's rows are already arriving there while this round's values are being written).
   uint32_t end = pl->offEA + ea;
   if (end + v + idx <= (uint32_t)kMaxDynSmem) {
     pl->offV = end; pl->offIdx = end + v; pl->total = end + v + idx;
     return true;
   }
-  const uint32_t alias_room = 2 * a + (mode == CG_BWD_DST ? 0 : ea);
-  if (v <= alias_room && end + idx <= (uint32_t)kMaxDynSmem) {
+  if (mode != CG_BWD_DST && v <= 2 * a && end + idx <= (uint32_t)kMaxDynSmem) {
     pl->offV = pl->offAhi; pl->offIdx = end; pl->total = end + idx;
     return true;
   }
@@ -68,12 +69,41 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- gate math on the MUFU pipe (ex2 / lg2 / rcp approximations, abs. error ~2e-7) ----
+__device__ __forceinline__ float ex2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float sigmoid_mufu(float x) { return rcp_(1.0f + ex2_(-kLog2e * x)); }
+// softplus(x) = max(x,0) + log1p(exp(-|x|))   (== F.softplus incl. its x>20 branch to fp32 rounding)
+__device__ __forceinline__ float softplus_mufu(float x) {
+  return fmaf(kLn2, lg2_(1.0f + ex2_(-kLog2e * fabsf(x))), fmaxf(x, 0.0f));
+}
+
+struct TileInfo { int n_lo, n_hi, e_lo, e_hi; };
+
+// Persistent CTA, software-pipelined over "rounds" of <=128 slots:
+//   while round r's MMAs run and its epilogue executes, round r+1's indices and ea rows are
+//   already in flight (cp.async) and the node projections for round r are being gathered.
 template <int MODE, int NITEM>
 __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, const TcPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ int sh_bounds[2];
+  __shared__ TileInfo sh_tile[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C, G = p.G, W2 = 2 * C;
   const int NP = pl.NP, KP = pl.KP, GS = pl.GS, VW = pl.VW;
@@ -82,28 +112,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
   uint8_t* sBlo = smem + pl.offBlo;
   uint8_t* sAhi = smem + pl.offAhi;
   uint8_t* sAlo = smem + pl.offAlo;
-  float* sEA = reinterpret_cast<float*>(smem + pl.offEA);  // [128][GS] row-major, pads zero
+  float* sEA = reinterpret_cast<float*>(smem + pl.offEA);  // [128][GS] row-major landing zone
   float* sV = reinterpret_cast<float*>(smem + pl.offV);    // [128][VW]
-  int* sSrc = reinterpret_cast<int*>(smem + pl.offIdx);
-  int* sDst = sSrc + kTcRows;
-  int* sSlot = sDst + kTcRows;
+  int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);    // [2 buffers][src|dst][128]
 
-  // ---- one-time setup: TMEM, barrier, resident weight tiles (hi/lo split)
+  // tiles of this CTA: blockIdx.x, +gridDim.x, ...
+  const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto compute_info = [&](int k) {  // one thread
+    TileInfo t;
+    if (k < my_tiles) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      t.n_lo = first_segment_at_or_after<MODE>(p, tile * kTcTE);
+      t.n_hi = (tile == p.n_tiles - 1) ? p.N : first_segment_at_or_after<MODE>(p, (tile + 1) * kTcTE);
+      if (t.n_hi < t.n_lo) t.n_hi = t.n_lo;
+      t.e_lo = __ldg(p.seg_ptr + t.n_lo);
+      t.e_hi = __ldg(p.seg_ptr + t.n_hi);
+    } else {
+      t.n_lo = t.n_hi = t.e_lo = t.e_hi = 0;
+    }
+    sh_tile[k % 3] = t;
+  };
+
+  // ---- one-time setup
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
-  if (tid == 0) {
+  if (tid == 32) {
     umma::mbar_init(&bar, 1);
     umma::fence_mbar_init();
   }
+  if (tid == 64) compute_info(0);
+  if (tid == 96) compute_info(1);
   for (int i = tid; i < NP * KP; i += kThreads) {
-    const int n = i % NP, k = i / NP;  // consecutive threads -> consecutive columns of WeT (coalesced)
+    const int n = i % NP, k = i / NP;
     const float w = (k < G && n < W2) ? __ldg(p.WeT + (size_t)k * W2 + n) : 0.0f;
     const float hi = umma::tf32_hi(w);
     const int off = umma::tile_offset_bytes(n, k, NP);
     *reinterpret_cast<float*>(sBhi + off) = hi;
     *reinterpret_cast<float*>(sBlo + off) = w - hi;
   }
-  for (int i = tid; i < kTcRows * GS; i += kThreads) sEA[i] = 0.0f;
-
   float dw[NITEM][4][8];
   if (MODE == CG_BWD_DST) {
 #pragma unroll
@@ -121,33 +166,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
   const uint32_t idesc = umma::make_idesc_tf32(kTcRows, NP);
   uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    tile_bounds<MODE>(p, tile, kTcTE, tid, sh_bounds);
-    __syncthreads();
-    const int n_lo = sh_bounds[0], n_hi = sh_bounds[1];
-    if (n_hi <= n_lo) { __syncthreads(); continue; }
-    const int e_lo = __ldg(p.seg_ptr + n_lo), e_hi = __ldg(p.seg_ptr + n_hi);
-    const int rounds = max(1, (e_hi - e_lo + kTcRows - 1) / kTcRows);
-
-    for (int rd = 0; rd < rounds; ++rd) {
-      const int r_lo = e_lo + rd * kTcRows;
-      const int r_hi = min(e_hi, r_lo + kTcRows);
-      const int cnt = r_hi - r_lo;
-
-      // ---- stage 1: indices, then raw ea rows (coalesced async copies, row-major)
-      if (tid < kTcRows) {
-        int slot = 0, s = 0, d = 0;
-        if (tid < cnt) {
-          slot = (MODE == CG_BWD_SRC) ? __ldg(p.src_slot + r_lo + tid) : (r_lo + tid);
-          s = __ldg(p.dst_src + slot);
-          d = __ldg(p.dst_dst + slot);
-        }
-        sSlot[tid] = slot; sSrc[tid] = s; sDst[tid] = d;
+  // prefetch of one round: warp w owns rows [16w, 16w+16): indices -> smem, ea rows -> cp.async
+  auto prefetch = [&](int r_lo, int cnt, int buf) {
+    int* bSrc = sIdx + buf * 2 * kTcRows;
+    int* bDst = bSrc + kTcRows;
+    const int row0 = warp * 16;
+    int slot = 0;
+    if (lane < 16) {
+      const int e = row0 + lane;
+      int s = 0, d = 0;
+      if (e < cnt) {
+        slot = (MODE == CG_BWD_SRC) ? __ldg(p.src_slot + r_lo + e) : (r_lo + e);
+        s = __ldg(p.dst_src + slot);
+        d = __ldg(p.dst_dst + slot);
       }
-      if (MODE == CG_BWD_SRC) __syncthreads();
-      for (int e = warp; e < cnt; e += kWarps) {
-        const int slot = (MODE == CG_BWD_SRC) ? sSlot[e] : (r_lo + e);
-        const float* row = p.ea + (size_t)slot * G;
+      bSrc[e] = s;
+      bDst[e] = d;
+    }
+    for (int i = 0; i < 16; ++i) {
+      const int e = row0 + i;
+      const int sl = __shfl_sync(0xffffffffu, slot, i);
+      if (e < cnt) {
+        const float* row = p.ea + (size_t)sl * G;
         float* dst = sEA + e * GS;
         if ((G & 1) == 0) {
           for (int k2 = lane; k2 < (G >> 1); k2 += 32) cp_async8(dst + 2 * k2, row + 2 * k2);
@@ -155,183 +195,234 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
           for (int k = lane; k < G; k += 32) cp_async4(dst + k, row + k);
         }
       }
-      cp_async_wait_all();
-      __syncthreads();
+    }
+  };
 
-      // ---- stage 2: split hi/lo into the canonical MMA operand layout
-      {
-        const int e = tid & (kTcRows - 1);
-        const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-        for (int j = (tid >> 7); j < (KP >> 2); j += 2) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < cnt && 4 * j < GS) {
-            v = *reinterpret_cast<const float4*>(sEA + e * GS + 4 * j);
-            // columns >= G are padding: force exact zeros (the value tile may alias this buffer)
-            if (4 * j + 0 >= G) v.x = 0.f;
-            if (4 * j + 1 >= G) v.y = 0.f;
-            if (4 * j + 2 >= G) v.z = 0.f;
-            if (4 * j + 3 >= G) v.w = 0.f;
-          }
-          float4 hi;
-          hi.x = umma::tf32_hi(v.x); hi.y = umma::tf32_hi(v.y);
-          hi.z = umma::tf32_hi(v.z); hi.w = umma::tf32_hi(v.w);
-          const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-          const uint32_t off = (uint32_t)j * (kTcRows * 16) + row_off;
-          *reinterpret_cast<float4*>(sAhi + off) = hi;
-          *reinterpret_cast<float4*>(sAlo + off) = lo;
-        }
-      }
-      umma::fence_proxy_async_smem();
-      umma::fence_before_sync();
-      __syncthreads();
+  int k = 0, rd = 0, buf = 0;
+  if (my_tiles > 0) {
+    const TileInfo t0 = sh_tile[0];
+    prefetch(t0.e_lo, min(t0.e_hi - t0.e_lo, kTcRows), 0);
+  }
 
-      // ---- contraction on the tensor core
-      if (tid == 0) {
-        umma::fence_after_sync();
-        const uint32_t step_a = 2 * kTcRows * 16, step_b = 2 * (uint32_t)NP * 16;
-        const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
-        const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = (pass == 2) ? a_lo : a_hi;
-          const uint32_t b = (pass == 1) ? b_lo : b_hi;
-          for (int kk = 0; kk < (KP >> 3); ++kk) {
-            const uint64_t ad = umma::make_desc(a + kk * step_a, kTcRows * 16, 128);
-            const uint64_t bd = umma::make_desc(b + kk * step_b, (uint32_t)NP * 16, 128);
-            umma::mma_tf32(tmem, ad, bd, idesc, acc);
-            acc = 1;
-          }
+  while (k < my_tiles) {
+    const TileInfo T = sh_tile[k % 3];
+    const int rounds = max(1, (T.e_hi - T.e_lo + kTcRows - 1) / kTcRows);
+    const int r_lo = T.e_lo + rd * kTcRows;
+    const int r_hi = min(T.e_hi, r_lo + kTcRows);
+    const int cnt = r_hi - r_lo;
+    const int n_lo = T.n_lo, n_hi = T.n_hi;
+    // next work item
+    const bool same_tile = (rd + 1 < rounds);
+    const int nk = same_tile ? k : k + 1, nrd = same_tile ? rd + 1 : 0;
+    const int* bSrc = sIdx + buf * 2 * kTcRows;
+    const int* bDst = bSrc + kTcRows;
+
+    cp_async_wait_all();
+    __syncthreads();  // [S1] rows + indices of this round visible; sV / A tiles free
+
+    // ---- split hi/lo into the canonical MMA operand layout
+    {
+      const int e = tid & (kTcRows - 1);
+      const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
+      for (int j = (tid >> 7); j < (KP >> 2); j += 2) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < cnt && 4 * j < GS) {
+          v = *reinterpret_cast<const float4*>(sEA + e * GS + 4 * j);
+          if (4 * j + 0 >= G) v.x = 0.f;  // padding columns: exact zeros
+          if (4 * j + 1 >= G) v.y = 0.f;
+          if (4 * j + 2 >= G) v.z = 0.f;
+          if (4 * j + 3 >= G) v.w = 0.f;
         }
-        umma::mma_commit(&bar);
+        float4 hi;
+        hi.x = umma::tf32_hi(v.x); hi.y = umma::tf32_hi(v.y);
+        hi.z = umma::tf32_hi(v.z); hi.w = umma::tf32_hi(v.w);
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        const uint32_t off = (uint32_t)j * (kTcRows * 16) + row_off;
+        *reinterpret_cast<float4*>(sAhi + off) = hi;
+        *reinterpret_cast<float4*>(sAlo + off) = lo;
       }
-      umma::mbar_wait(&bar, phase);
-      phase ^= 1;
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();  // [S2] operands staged; sEA free for the next round's rows
+
+    // ---- contraction on the tensor core (asynchronous)
+    if (tid == 0 && cnt > 0) {
       umma::fence_after_sync();
-
-      // ---- epilogue: thread = slot (TMEM lane), warps split the channel range
-      {
-        const int q = warp & 3, half = warp >> 2;
-        const int e = 32 * q + lane;
-        const int chh = ((C / 2 + 15) / 16) * 16;
-        const int c_begin = half * chh;
-        const int c_end = min(C, c_begin + chh);
-        const bool live = e < cnt;
-        const int d_node = sDst[e];
-        const float* Pd = p.PQ + (size_t)d_node * (4 * C);
-        const float* Qs = p.PQ + (size_t)sSrc[e] * (4 * C) + 2 * C;
-        float gsc = 1.0f;
-        const float* grow = nullptr;
-        if (MODE != CG_FWD) {
-          grow = p.gout + (size_t)d_node * C;
-          if (p.inv_deg && live) gsc = __ldg(p.inv_deg + d_node);
+      const uint32_t step_a = 2 * kTcRows * 16, step_b = 2 * (uint32_t)NP * 16;
+      const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
+      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+      uint32_t acc = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 2) ? a_lo : a_hi;
+        const uint32_t b = (pass == 1) ? b_lo : b_hi;
+        for (int kk = 0; kk < (KP >> 3); ++kk) {
+          const uint64_t ad = umma::make_desc(a + kk * step_a, kTcRows * 16, 128);
+          const uint64_t bd = umma::make_desc(b + kk * step_b, (uint32_t)NP * 16, 128);
+          umma::mma_tf32(tmem, ad, bd, idesc, acc);
+          acc = 1;
         }
-        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-          float f[16], s[16];
-          umma::tmem_ld16(umma::tmem_addr(tmem, q, c0), f);
-          umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c0), s);
-          umma::tmem_ld_wait();
-          if (live) {
+      }
+      umma::mma_commit(&bar);
+    }
+
+    // ---- overlap window: look two tiles ahead, put the next round's loads in flight
+    if (rd == 0 && tid == 64) compute_info(k + 2);
+    if (nk < my_tiles) {
+      const TileInfo Tn = sh_tile[nk % 3];
+      const int nr_lo = Tn.e_lo + nrd * kTcRows;
+      prefetch(nr_lo, min(Tn.e_hi - nr_lo, kTcRows), buf ^ 1);
+    }
+
+    // ---- epilogue: thread = slot (TMEM lane), warps split the channel range
+    if (cnt > 0) {
+      const int q = warp & 3, half = warp >> 2;
+      const int e = 32 * q + lane;
+      const int chh = ((C / 2 + 15) / 16) * 16;
+      const int c_begin = half * chh;
+      const int c_end = min(C, c_begin + chh);
+      const bool live = e < cnt;
+      const int d_node = bDst[e];
+      const float* Pd = p.PQ + (size_t)d_node * (4 * C);
+      const float* Qs = p.PQ + (size_t)bSrc[e] * (4 * C) + 2 * C;
+      const float* grow = (MODE != CG_FWD) ? p.gout + (size_t)d_node * C : nullptr;
+      float gsc = 1.0f;
+      if (MODE != CG_FWD && p.inv_deg && live) gsc = __ldg(p.inv_deg + d_node);
+      bool waited = false;
+      for (int cb = c_begin; cb < c_end; cb += 32) {
+        // gather the node projections for 32 channels BEFORE touching the accumulator
+        float bf[32], bs[32], gg[(MODE != CG_FWD) ? 32 : 1];
 #pragma unroll
-            for (int j4 = 0; j4 < 16; j4 += 4) {
-              const int c = c0 + j4;
-              if (c < c_end) {
-                const float4 pf = __ldg(reinterpret_cast<const float4*>(Pd + c));
-                const float4 ps = __ldg(reinterpret_cast<const float4*>(Pd + C + c));
-                const float4 qf = __ldg(reinterpret_cast<const float4*>(Qs + c));
-                const float4 qs = __ldg(reinterpret_cast<const float4*>(Qs + C + c));
-                const float af[4] = {f[j4] + pf.x + qf.x, f[j4 + 1] + pf.y + qf.y,
-                                     f[j4 + 2] + pf.z + qf.z, f[j4 + 3] + pf.w + qf.w};
-                const float as[4] = {s[j4] + ps.x + qs.x, s[j4 + 1] + ps.y + qs.y,
-                                     s[j4 + 2] + ps.z + qs.z, s[j4 + 3] + ps.w + qs.w};
-                if (MODE == CG_FWD) {
-                  float4 m;
-                  m.x = sigmoid_fast_(af[0]) * softplusf_(as[0]);
-                  m.y = sigmoid_fast_(af[1]) * softplusf_(as[1]);
-                  m.z = sigmoid_fast_(af[2]) * softplusf_(as[2]);
-                  m.w = sigmoid_fast_(af[3]) * softplusf_(as[3]);
-                  *reinterpret_cast<float4*>(sV + e * VW + c) = m;
-                } else {
-                  const float4 g = __ldg(reinterpret_cast<const float4*>(grow + c));
-                  const float gg[4] = {g.x * gsc, g.y * gsc, g.z * gsc, g.w * gsc};
-                  float dfv[4], dsv[4];
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int c = cb + j4;
+          float4 pf = make_float4(0.f, 0.f, 0.f, 0.f), ps = pf, qf = pf, qs = pf, g4 = pf;
+          if (live && c < c_end) {
+            pf = __ldg(reinterpret_cast<const float4*>(Pd + c));
+            ps = __ldg(reinterpret_cast<const float4*>(Pd + C + c));
+            qf = __ldg(reinterpret_cast<const float4*>(Qs + c));
+            qs = __ldg(reinterpret_cast<const float4*>(Qs + C + c));
+            if (MODE != CG_FWD) g4 = __ldg(reinterpret_cast<const float4*>(grow + c));
+          }
+          bf[j4] = pf.x + qf.x; bf[j4 + 1] = pf.y + qf.y; bf[j4 + 2] = pf.z + qf.z; bf[j4 + 3] = pf.w + qf.w;
+          bs[j4] = ps.x + qs.x; bs[j4 + 1] = ps.y + qs.y; bs[j4 + 2] = ps.z + qs.z; bs[j4 + 3] = ps.w + qs.w;
+          if (MODE != CG_FWD) {
+            gg[j4] = g4.x * gsc; gg[j4 + 1] = g4.y * gsc; gg[j4 + 2] = g4.z * gsc; gg[j4 + 3] = g4.w * gsc;
+          }
+        }
+        if (!waited) {
+          umma::mbar_wait(&bar, phase);
+          umma::fence_after_sync();
+          waited = true;
+        }
+#pragma unroll
+        for (int sub = 0; sub < 32; sub += 16) {
+          const int c0 = cb + sub;
+          if (c0 < c_end) {  // warp-uniform
+            float f[16], s[16];
+            umma::tmem_ld16(umma::tmem_addr(tmem, q, c0), f);
+            umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c0), s);
+            umma::tmem_ld_wait();
+            if (live) {
+#pragma unroll
+              for (int j4 = 0; j4 < 16; j4 += 4) {
+                const int c = c0 + j4;
+                if (c < c_end) {
+                  float r0[4], r1[4];
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    const float sg = sigmoid_fast_(af[j]);
-                    const float sp = softplusf_(as[j]);
-                    dfv[j] = gg[j] * sp * sg * (1.0f - sg);
-                    dsv[j] = gg[j] * sg * sigmoid_fast_(as[j]);
+                    const float af = f[j4 + j] + bf[sub + j4 + j];
+                    const float as = s[j4 + j] + bs[sub + j4 + j];
+                    const float sg = sigmoid_mufu(af);
+                    const float sp = softplus_mufu(as);
+                    if (MODE == CG_FWD) {
+                      r0[j] = sg * sp;
+                    } else {
+                      const float g = gg[sub + j4 + j];
+                      r0[j] = g * sp * sg * (1.0f - sg);
+                      r1[j] = g * sg * sigmoid_mufu(as);
+                    }
                   }
-                  *reinterpret_cast<float4*>(sV + e * VW + c) = make_float4(dfv[0], dfv[1], dfv[2], dfv[3]);
-                  *reinterpret_cast<float4*>(sV + e * VW + C + c) = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
+                  *reinterpret_cast<float4*>(sV + e * VW + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+                  if (MODE != CG_FWD)
+                    *reinterpret_cast<float4*>(sV + e * VW + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
                 }
               }
             }
           }
         }
       }
-      umma::fence_before_sync();  // accumulator reads done before the next round's MMAs overwrite it
-      __syncthreads();
+      if (!waited) {  // warps with an empty channel range still have to consume the phase
+        umma::mbar_wait(&bar, phase);
+        umma::fence_after_sync();
+      }
+      phase ^= 1;
+    }
+    umma::fence_before_sync();  // accumulator reads done before the next round's MMAs overwrite it
+    __syncthreads();            // [S3] value tile complete
 
-      // ---- segmented sum over the owned segments that have slots in this round
-      for (int n = n_lo + warp; n < n_hi; n += kWarps) {
-        const int a = __ldg(p.seg_ptr + n), b = __ldg(p.seg_ptr + n + 1);
-        const int lo = max(a, r_lo), hi = min(b, r_hi);
-        const bool empty_seg = (a == b);
-        if (empty_seg ? (rd != 0) : (lo >= hi)) continue;
-        const bool first = empty_seg || (a >= r_lo);
-        const bool last = empty_seg || (b <= r_hi);
-        if (MODE == CG_FWD) {
-          float* o = p.out + (size_t)n * C;
-          const float* xr = p.x + (size_t)n * C;
-          const float sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
-          for (int c = lane; c < C; c += 32) {
-            float acc = first ? 0.0f : o[c];
-            for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
-            o[c] = last ? fmaf(acc, sc, __ldg(xr + c)) : acc;
-          }
-        } else {
-          float* o = p.out + (size_t)n * (4 * C) + (MODE == CG_BWD_SRC ? 2 * C : 0);
-          for (int c = lane; c < W2; c += 32) {
-            float acc = first ? 0.0f : o[c];
-            for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
-            o[c] = acc;
+    // ---- segmented sum over the owned segments that have slots in this round
+    for (int n = n_lo + warp; n < n_hi; n += kWarps) {
+      const int a = __ldg(p.seg_ptr + n), b = __ldg(p.seg_ptr + n + 1);
+      const int lo = max(a, r_lo), hi = min(b, r_hi);
+      const bool empty_seg = (a == b);
+      if (empty_seg ? (rd != 0) : (lo >= hi)) continue;
+      const bool first = empty_seg || (a >= r_lo);
+      const bool last = empty_seg || (b <= r_hi);
+      if (MODE == CG_FWD) {
+        float* o = p.out + (size_t)n * C;
+        const float* xr = p.x + (size_t)n * C;
+        const float sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
+        for (int c = lane; c < C; c += 32) {
+          float acc = first ? 0.0f : o[c];
+          for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
+          o[c] = last ? fmaf(acc, sc, __ldg(xr + c)) : acc;
+        }
+      } else {
+        float* o = p.out + (size_t)n * (4 * C) + (MODE == CG_BWD_SRC ? 2 * C : 0);
+        for (int c = lane; c < W2; c += 32) {
+          float acc = first ? 0.0f : o[c];
+          for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
+          o[c] = acc;
+        }
+      }
+    }
+
+    // ---- dWe += da^T . ea   (ea re-assembled exactly as hi + lo from the operand tiles)
+    if (MODE == CG_BWD_DST) {
+      const int n_c4 = W2 >> 2;
+      const int n_dw = n_c4 * (KP >> 3);
+#pragma unroll
+      for (int j = 0; j < NITEM; ++j) {
+        const int it = tid + j * kThreads;
+        if (it < n_dw) {
+          const int c4 = it % n_c4, k8 = it / n_c4;
+          const uint8_t* h0 = sAhi + (uint32_t)(2 * k8) * (kTcRows * 16);
+          const uint8_t* l0 = sAlo + (uint32_t)(2 * k8) * (kTcRows * 16);
+          for (int e = 0; e < cnt; ++e) {
+            const uint32_t ro = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
+            const float4 da = *reinterpret_cast<const float4*>(sV + e * VW + 4 * c4);
+            const float4 ah = *reinterpret_cast<const float4*>(h0 + ro);
+            const float4 al = *reinterpret_cast<const float4*>(l0 + ro);
+            const float4 bh = *reinterpret_cast<const float4*>(h0 + kTcRows * 16 + ro);
+            const float4 bl = *reinterpret_cast<const float4*>(l0 + kTcRows * 16 + ro);
+            const float dv[4] = {da.x, da.y, da.z, da.w};
+            const float ev[8] = {ah.x + al.x, ah.y + al.y, ah.z + al.z, ah.w + al.w,
+                                 bh.x + bl.x, bh.y + bl.y, bh.z + bl.z, bh.w + bl.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 8; ++b) dw[j][a][b] = fmaf(dv[a], ev[b], dw[j][a][b]);
           }
         }
       }
-
-      // ---- dWe += da^T . ea (register tiles 4 channels x 8 k per work item)
-      if (MODE == CG_BWD_DST) {
-        const int n_c4 = W2 >> 2;
-        const int n_dw = n_c4 * ((GS + 7) >> 3);
-#pragma unroll
-        for (int j = 0; j < NITEM; ++j) {
-          const int it = tid + j * kThreads;
-          if (it < n_dw) {
-            const int c4 = it % n_c4, k8 = it / n_c4;
-            const bool second = (8 * k8 + 4) < GS;
-            for (int e = 0; e < cnt; ++e) {
-              const float4 da = *reinterpret_cast<const float4*>(sV + e * VW + 4 * c4);
-              const float4 e0 = *reinterpret_cast<const float4*>(sEA + e * GS + 8 * k8);
-              const float4 e1 = second ? *reinterpret_cast<const float4*>(sEA + e * GS + 8 * k8 + 4)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float dv[4] = {da.x, da.y, da.z, da.w};
-              const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-              for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) dw[j][a][b] = fmaf(dv[a], ev[b], dw[j][a][b]);
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }  // rounds
-  }    // tiles
+    }
+    k = nk; rd = nrd; buf ^= 1;
+  }  // work items
 
   if (MODE == CG_BWD_DST) {
     const int n_c4 = W2 >> 2;
-    const int n_dw = n_c4 * ((GS + 7) >> 3);
+    const int n_dw = n_c4 * (KP >> 3);
     float* part = p.dW_part + (size_t)blockIdx.x * G * W2;
 #pragma unroll
     for (int j = 0; j < NITEM; ++j) {
@@ -340,14 +431,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
         const int c4 = it % n_c4, k8 = it / n_c4;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          const int k = 8 * k8 + b;
-          if (k < G)
-            *reinterpret_cast<float4*>(part + (size_t)k * W2 + 4 * c4) =
+          const int kcol = 8 * k8 + b;
+          if (kcol < G)
+            *reinterpret_cast<float4*>(part + (size_t)kcol * W2 + 4 * c4) =
                 make_float4(dw[j][0][b], dw[j][1][b], dw[j][2][b], dw[j][3][b]);
         }
       }
     }
   }
+  cp_async_wait_all();
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)pl.tmem_cols);
