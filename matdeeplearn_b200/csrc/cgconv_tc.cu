@@ -29,13 +29,13 @@ struct TcPlan {
 };
 
 static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
-  if (C < 8 || C % 4 != 0) return false;
+  if (C != 32 && C != 64) return false;  // epilogue lane mapping: 16 or 32 channels per warp half
   const int NP = (2 * C + 15) & ~15;
   if (NP > 256) return false;
   const int KP = (G + 7) & ~7;
   int GS = (G + 3) & ~3;
   if (((GS >> 2) & 1) == 0) GS += 4;  // odd number of 16-byte chunks per row: conflict-free float4 column reads
-  const int VW = (mode == CG_FWD ? C : 2 * C) + 4;
+  const int VW = 2 * C + 4;  // [f | s] per slot (+4 floats: conflict-free float4 row access)
   uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)kTcRows * KP * 4;
   uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 4 * kTcRows * 4;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
@@ -45,17 +45,11 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   pl->nitem = (n_dw + kThreads - 1) / kThreads;
   if (mode == CG_BWD_DST && pl->nitem > 2) return false;
   pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
-  // value tile: own region if it fits, else aliased over the A tiles, which are dead between the
-  // retirement of a round's MMAs and the next round's operand split.  Not for BWD_DST (its dWe
-  // pass reads the A tiles next to the value tile), and never over the ea landing zone (the next
-  // round's rows are already arriving there while this round's values are being written).
+  // The value tile has its own region: it is filled (gathered node projections) while the MMAs of
+  // the same round are still reading the operand tiles, so it cannot alias them.
   uint32_t end = pl->offEA + ea;
   if (end + v + idx <= (uint32_t)kMaxDynSmem) {
     pl->offV = end; pl->offIdx = end + v; pl->total = end + v + idx;
-    return true;
-  }
-  if (mode != CG_BWD_DST && v <= 2 * a && end + idx <= (uint32_t)kMaxDynSmem) {
-    pl->offV = pl->offAhi; pl->offIdx = end; pl->total = end + idx;
     return true;
   }
   return false;
@@ -275,88 +269,85 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
       prefetch(nr_lo, min(Tn.e_hi - nr_lo, kTcRows), buf ^ 1);
     }
 
-    // ---- epilogue: thread = slot (TMEM lane), warps split the channel range
+    // ---- gather P[dst] + Q[src] for this round, coalesced, into the value tile.
+    // Warp (q, half) owns slots 32q..32q+31 and channels [half*chh, half*chh+chh) for BOTH the
+    // gather and the epilogue below, so only a __syncwarp separates the two.
+    // One LDG.128 per lane: lanes [0,chh/2) = 16-byte chunks of P (f half | s half), lanes
+    // [chh/2, chh) = the same chunks of Q; with chh = 32 a warp instruction covers one slot
+    // (4 full 128-byte lines), with chh = 16 two slots.
+    const int q = warp & 3, half = warp >> 2;
+    const int chh = (C >= 64) ? 32 : 16;
+    const int c_begin = half * chh;
+    const bool has_ch = c_begin < C;
+    if (cnt > 0 && has_ch) {
+      const int rows_per_inst = 32 / chh;            // 1 or 2
+      const int sub = lane / chh;                    // slot within the instruction
+      const int l = lane % chh;                      // lane within the slot's group
+      const int is_q = l / (chh / 2);                // 0: P (destination side), 1: Q (source side)
+      const int l2 = l % (chh / 2);
+      const int is_s = l2 / (chh / 4);               // 0: f channels, 1: s channels
+      const int c = c_begin + 4 * (l2 % (chh / 4));  // first of this lane's 4 channels
+      const int col = is_q * 2 * C + is_s * C + c;   // column inside a PQ row
+#pragma unroll 8
+      for (int i = 0; i < 32; i += rows_per_inst) {
+        const int e = 32 * q + i + sub;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < cnt) {
+          const int node = is_q ? bSrc[e] : bDst[e];
+          v = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)node * (4 * C) + col));
+        }
+        // P + Q: partner lane holds the other operand of the same (slot, channel chunk)
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, chh / 2);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, chh / 2);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, chh / 2);
+        v.w += __shfl_xor_sync(0xffffffffu, v.w, chh / 2);
+        if (!is_q && e < cnt) *reinterpret_cast<float4*>(sV + e * VW + is_s * C + c) = v;
+      }
+      __syncwarp();
+    }
+
+    // ---- epilogue: thread = slot (TMEM lane); a = accumulator + gathered projections
     if (cnt > 0) {
-      const int q = warp & 3, half = warp >> 2;
       const int e = 32 * q + lane;
-      const int chh = ((C / 2 + 15) / 16) * 16;
-      const int c_begin = half * chh;
-      const int c_end = min(C, c_begin + chh);
       const bool live = e < cnt;
-      const int d_node = bDst[e];
-      const float* Pd = p.PQ + (size_t)d_node * (4 * C);
-      const float* Qs = p.PQ + (size_t)bSrc[e] * (4 * C) + 2 * C;
-      const float* grow = (MODE != CG_FWD) ? p.gout + (size_t)d_node * C : nullptr;
-      float gsc = 1.0f;
-      if (MODE != CG_FWD && p.inv_deg && live) gsc = __ldg(p.inv_deg + d_node);
-      bool waited = false;
-      for (int cb = c_begin; cb < c_end; cb += 32) {
-        // gather the node projections for 32 channels BEFORE touching the accumulator
-        float bf[32], bs[32], gg[(MODE != CG_FWD) ? 32 : 1];
+      umma::mbar_wait(&bar, phase);
+      umma::fence_after_sync();
+      phase ^= 1;
+      if (has_ch) {
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const int c = cb + j4;
-          float4 pf = make_float4(0.f, 0.f, 0.f, 0.f), ps = pf, qf = pf, qs = pf, g4 = pf;
-          if (live && c < c_end) {
-            pf = __ldg(reinterpret_cast<const float4*>(Pd + c));
-            ps = __ldg(reinterpret_cast<const float4*>(Pd + C + c));
-            qf = __ldg(reinterpret_cast<const float4*>(Qs + c));
-            qs = __ldg(reinterpret_cast<const float4*>(Qs + C + c));
-            if (MODE != CG_FWD) g4 = __ldg(reinterpret_cast<const float4*>(grow + c));
-          }
-          bf[j4] = pf.x + qf.x; bf[j4 + 1] = pf.y + qf.y; bf[j4 + 2] = pf.z + qf.z; bf[j4 + 3] = pf.w + qf.w;
-          bs[j4] = ps.x + qs.x; bs[j4 + 1] = ps.y + qs.y; bs[j4 + 2] = ps.z + qs.z; bs[j4 + 3] = ps.w + qs.w;
-          if (MODE != CG_FWD) {
-            gg[j4] = g4.x * gsc; gg[j4 + 1] = g4.y * gsc; gg[j4 + 2] = g4.z * gsc; gg[j4 + 3] = g4.w * gsc;
-          }
-        }
-        if (!waited) {
-          umma::mbar_wait(&bar, phase);
-          umma::fence_after_sync();
-          waited = true;
-        }
+        for (int c0 = c_begin; c0 < c_begin + chh; c0 += 16) {
+          float f[16], sacc[16];
+          umma::tmem_ld16(umma::tmem_addr(tmem, q, c0), f);
+          umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c0), sacc);
+          umma::tmem_ld_wait();
+          if (live) {
+            float* rowv = sV + e * VW;
 #pragma unroll
-        for (int sub = 0; sub < 32; sub += 16) {
-          const int c0 = cb + sub;
-          if (c0 < c_end) {  // warp-uniform
-            float f[16], s[16];
-            umma::tmem_ld16(umma::tmem_addr(tmem, q, c0), f);
-            umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c0), s);
-            umma::tmem_ld_wait();
-            if (live) {
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const int c = c0 + j4;
+              const float4 bf = *reinterpret_cast<const float4*>(rowv + c);
+              const float4 bs = *reinterpret_cast<const float4*>(rowv + C + c);
+              const float af[4] = {f[j4] + bf.x, f[j4 + 1] + bf.y, f[j4 + 2] + bf.z, f[j4 + 3] + bf.w};
+              const float as[4] = {sacc[j4] + bs.x, sacc[j4 + 1] + bs.y, sacc[j4 + 2] + bs.z, sacc[j4 + 3] + bs.w};
+              float r0[4], r1[4];
 #pragma unroll
-              for (int j4 = 0; j4 < 16; j4 += 4) {
-                const int c = c0 + j4;
-                if (c < c_end) {
-                  float r0[4], r1[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float af = f[j4 + j] + bf[sub + j4 + j];
-                    const float as = s[j4 + j] + bs[sub + j4 + j];
-                    const float sg = sigmoid_mufu(af);
-                    const float sp = softplus_mufu(as);
-                    if (MODE == CG_FWD) {
-                      r0[j] = sg * sp;
-                    } else {
-                      const float g = gg[sub + j4 + j];
-                      r0[j] = g * sp * sg * (1.0f - sg);
-                      r1[j] = g * sg * sigmoid_mufu(as);
-                    }
-                  }
-                  *reinterpret_cast<float4*>(sV + e * VW + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
-                  if (MODE != CG_FWD)
-                    *reinterpret_cast<float4*>(sV + e * VW + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+              for (int j = 0; j < 4; ++j) {
+                const float sg = sigmoid_mufu(af[j]);
+                const float sp = softplus_mufu(as[j]);
+                if (MODE == CG_FWD) {
+                  r0[j] = sg * sp;
+                } else {  // d(message)/d(a_f), d(message)/d(a_s); the grad_out factor is applied in the reduce stage
+                  r0[j] = sp * sg * (1.0f - sg);
+                  r1[j] = sg * sigmoid_mufu(as[j]);
                 }
               }
+              *reinterpret_cast<float4*>(rowv + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+              if (MODE != CG_FWD)
+                *reinterpret_cast<float4*>(rowv + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
             }
           }
         }
       }
-      if (!waited) {  // warps with an empty channel range still have to consume the phase
-        umma::mbar_wait(&bar, phase);
-        umma::fence_after_sync();
-      }
-      phase ^= 1;
     }
     umma::fence_before_sync();  // accumulator reads done before the next round's MMAs overwrite it
     __syncthreads();            // [S3] value tile complete
@@ -378,15 +369,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
           for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
           o[c] = last ? fmaf(acc, sc, __ldg(xr + c)) : acc;
         }
-      } else {
-        float* o = p.out + (size_t)n * (4 * C) + (MODE == CG_BWD_SRC ? 2 * C : 0);
+      } else if (MODE == CG_BWD_DST) {
+        // segment = destination: one grad_out row scales every slot of the segment.  The scaled
+        // per-slot values are written back: the dWe pass below needs da = g * bracket per slot.
+        float* o = p.out + (size_t)n * (4 * C);
+        const float sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
         for (int c = lane; c < W2; c += 32) {
+          const float g = __ldg(p.gout + (size_t)n * C + (c < C ? c : c - C)) * sc;
           float acc = first ? 0.0f : o[c];
-          for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
+          for (int s = lo; s < hi; ++s) {
+            const float v = sV[(s - r_lo) * VW + c] * g;
+            sV[(s - r_lo) * VW + c] = v;
+            acc += v;
+          }
+          o[c] = acc;
+        }
+      } else {
+        // segment = source: every slot has its own destination, hence its own grad_out row
+        float* o = p.out + (size_t)n * (4 * C) + 2 * C;
+        for (int c = lane; c < W2; c += 32) {
+          const int cc = (c < C ? c : c - C);
+          float acc = first ? 0.0f : o[c];
+#pragma unroll 4
+          for (int s = lo; s < hi; ++s) {
+            const int d = bDst[s - r_lo];
+            const float g = __ldg(p.gout + (size_t)d * C + cc) * (p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f);
+            acc = fmaf(sV[(s - r_lo) * VW + c], g, acc);
+          }
           o[c] = acc;
         }
       }
     }
+    if (MODE == CG_BWD_DST) __syncthreads();  // scaled value tile visible to the dWe pass
 
     // ---- dWe += da^T . ea   (ea re-assembled exactly as hi + lo from the operand tiles)
     if (MODE == CG_BWD_DST) {
