@@ -341,7 +341,7 @@ using namespace mdl;
 extern "C" size_t mdl_cgconv_workspace_bytes(int64_t N, int64_t E, int32_t C, int32_t G) {
   (void)N; (void)E;
   // per-CTA dWe partials for the BWD_DST pass
-  return (size_t)kNumSMs * (size_t)G * 2 * (size_t)C * 4 + 256;
+  return (size_t)2 * kNumSMs * (size_t)G * 2 * (size_t)C * 4 + 256;  // TC path: two partials per CTA
 }
 
 extern "C" int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, const float* WeT,
@@ -399,7 +399,7 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
     int grid = 0;
     if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid)) return rc;
     const int tot = G * 2 * C;
-    k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, grid, G, C, 0, C, dWeT);
+    k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, 2 * grid, G, C, 0, C, dWeT);
     MDL_LAUNCHED();
   } else {
     CgPlan plan;

@@ -20,6 +20,8 @@
 
 namespace mdl {
 
+constexpr int kTcThreads = 512;  // 16 warps: 4 per scheduler, the epilogue/gather math is latency-bound otherwise
+constexpr int kTcWarps = kTcThreads / 32;
 constexpr int kTcRows = 128;  // slots per round = MMA M
 constexpr int kTcTE = 112;    // ownership granularity (leaves head-room for straddling segments)
 
@@ -29,7 +31,7 @@ struct TcPlan {
 };
 
 static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
-  if (C != 32 && C != 64) return false;  // epilogue lane mapping: 16 or 32 channels per warp half
+  if (C != 64) return false;  // epilogue mapping: 4 lane quadrants x 4 channel quarters of 16
   const int NP = (2 * C + 15) & ~15;
   if (NP > 256) return false;
   const int KP = (G + 7) & ~7;
@@ -42,8 +44,8 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   pl->tmem_cols = 32;
   while (pl->tmem_cols < NP) pl->tmem_cols <<= 1;
   const int n_dw = (2 * C / 4) * (KP / 8);
-  pl->nitem = (n_dw + kThreads - 1) / kThreads;
-  if (mode == CG_BWD_DST && pl->nitem > 2) return false;
+  pl->nitem = (n_dw + kTcThreads / 2 - 1) / (kTcThreads / 2);  // two thread groups split the slots
+  if (mode == CG_BWD_DST && pl->nitem > 1) return false;
   pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
   // The value tile has its own region: it is filled (gathered node projections) while the MMAs of
   // the same round are still reading the operand tiles, so it cannot alias them.
@@ -93,7 +95,7 @@ struct TileInfo { int n_lo, n_hi, e_lo, e_hi; };
 //   while round r's MMAs run and its epilogue executes, round r+1's indices and ea rows are
 //   already in flight (cp.async) and the node projections for round r are being gathered.
 template <int MODE, int NITEM>
-__global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, const TcPlan pl) {
+__global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, const TcPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
   }
   if (tid == 64) compute_info(0);
   if (tid == 96) compute_info(1);
-  for (int i = tid; i < NP * KP; i += kThreads) {
+  for (int i = tid; i < NP * KP; i += kTcThreads) {
     const int n = i % NP, k = i / NP;
     const float w = (k < G && n < W2) ? __ldg(p.WeT + (size_t)k * W2 + n) : 0.0f;
     const float hi = umma::tf32_hi(w);
@@ -160,13 +162,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
   const uint32_t idesc = umma::make_idesc_tf32(kTcRows, NP);
   uint32_t phase = 0;
 
-  // prefetch of one round: warp w owns rows [16w, 16w+16): indices -> smem, ea rows -> cp.async
+  // prefetch of one round: warp w owns rows [8w, 8w+8): indices -> smem, ea rows -> cp.async
   auto prefetch = [&](int r_lo, int cnt, int buf) {
     int* bSrc = sIdx + buf * 2 * kTcRows;
     int* bDst = bSrc + kTcRows;
-    const int row0 = warp * 16;
+    const int row0 = warp * (kTcRows / kTcWarps);
     int slot = 0;
-    if (lane < 16) {
+    if (lane < kTcRows / kTcWarps) {
       const int e = row0 + lane;
       int s = 0, d = 0;
       if (e < cnt) {
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
       bSrc[e] = s;
       bDst[e] = d;
     }
-    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+    for (int i = 0; i < kTcRows / kTcWarps; ++i) {
       const int e = row0 + i;
       const int sl = __shfl_sync(0xffffffffu, slot, i);
       if (e < cnt) {
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
     {
       const int e = tid & (kTcRows - 1);
       const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-      for (int j = (tid >> 7); j < (KP >> 2); j += 2) {
+      for (int j = (tid >> 7); j < (KP >> 2); j += kTcThreads / kTcRows) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < cnt && 4 * j < GS) {
           v = *reinterpret_cast<const float4*>(sEA + e * GS + 4 * j);
@@ -275,12 +278,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
     // One LDG.128 per lane: lanes [0,chh/2) = 16-byte chunks of P (f half | s half), lanes
     // [chh/2, chh) = the same chunks of Q; with chh = 32 a warp instruction covers one slot
     // (4 full 128-byte lines), with chh = 16 two slots.
-    const int q = warp & 3, half = warp >> 2;
-    const int chh = (C >= 64) ? 32 : 16;
-    const int c_begin = half * chh;
+    const int q = warp & 3, part = warp >> 2;        // lane quadrant, channel quarter
+    constexpr int chh = 16;                         // channels per warp
+    const int c_begin = part * chh;
     const bool has_ch = c_begin < C;
     if (cnt > 0 && has_ch) {
-      const int rows_per_inst = 32 / chh;            // 1 or 2
+      constexpr int rows_per_inst = 32 / chh;         // 2
       const int sub = lane / chh;                    // slot within the instruction
       const int l = lane % chh;                      // lane within the slot's group
       const int is_q = l / (chh / 2);                // 0: P (destination side), 1: Q (source side)
@@ -288,20 +291,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
       const int is_s = l2 / (chh / 4);               // 0: f channels, 1: s channels
       const int c = c_begin + 4 * (l2 % (chh / 4));  // first of this lane's 4 channels
       const int col = is_q * 2 * C + is_s * C + c;   // column inside a PQ row
-#pragma unroll 8
-      for (int i = 0; i < 32; i += rows_per_inst) {
+      float4 v[32 / rows_per_inst];
+#pragma unroll
+      for (int i = 0; i < 32; i += rows_per_inst) {  // all loads first: one latency exposure
         const int e = 32 * q + i + sub;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i / rows_per_inst] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < cnt) {
           const int node = is_q ? bSrc[e] : bDst[e];
-          v = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)node * (4 * C) + col));
+          v[i / rows_per_inst] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)node * (4 * C) + col));
         }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += rows_per_inst) {
+        const int e = 32 * q + i + sub;
+        float4 t = v[i / rows_per_inst];
         // P + Q: partner lane holds the other operand of the same (slot, channel chunk)
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, chh / 2);
-        v.y += __shfl_xor_sync(0xffffffffu, v.y, chh / 2);
-        v.z += __shfl_xor_sync(0xffffffffu, v.z, chh / 2);
-        v.w += __shfl_xor_sync(0xffffffffu, v.w, chh / 2);
-        if (!is_q && e < cnt) *reinterpret_cast<float4*>(sV + e * VW + is_s * C + c) = v;
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, chh / 2);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, chh / 2);
+        t.z += __shfl_xor_sync(0xffffffffu, t.z, chh / 2);
+        t.w += __shfl_xor_sync(0xffffffffu, t.w, chh / 2);
+        if (!is_q && e < cnt) *reinterpret_cast<float4*>(sV + e * VW + is_s * C + c) = t;
       }
       __syncwarp();
     }
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
       phase ^= 1;
       if (has_ch) {
 #pragma unroll
-        for (int c0 = c_begin; c0 < c_begin + chh; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_begin + chh; c0 += 16) {  // one pass: chh == 16
           float f[16], sacc[16];
           umma::tmem_ld16(umma::tmem_addr(tmem, q, c0), f);
           umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c0), sacc);
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
     __syncthreads();            // [S3] value tile complete
 
     // ---- segmented sum over the owned segments that have slots in this round
-    for (int n = n_lo + warp; n < n_hi; n += kWarps) {
+    for (int n = n_lo + warp; n < n_hi; n += kTcWarps) {
       const int a = __ldg(p.seg_ptr + n), b = __ldg(p.seg_ptr + n + 1);
       const int lo = max(a, r_lo), hi = min(b, r_hi);
       const bool empty_seg = (a == b);
@@ -365,9 +374,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
         const float* xr = p.x + (size_t)n * C;
         const float sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
         for (int c = lane; c < C; c += 32) {
+          const float xv = last ? __ldg(xr + c) : 0.0f;  // issued before the sum: latency overlaps it
           float acc = first ? 0.0f : o[c];
           for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
-          o[c] = last ? fmaf(acc, sc, __ldg(xr + c)) : acc;
+          o[c] = last ? fmaf(acc, sc, xv) : acc;
         }
       } else if (MODE == CG_BWD_DST) {
         // segment = destination: one grad_out row scales every slot of the segment.  The scaled
@@ -402,32 +412,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
     }
     if (MODE == CG_BWD_DST) __syncthreads();  // scaled value tile visible to the dWe pass
 
-    // ---- dWe += da^T . ea   (ea re-assembled exactly as hi + lo from the operand tiles)
+    // ---- dWe += da^T . ea   (ea re-assembled exactly as hi + lo from the operand tiles).
+    // Two thread groups take alternate slots; each keeps its own register tile and partial.
     if (MODE == CG_BWD_DST) {
       const int n_c4 = W2 >> 2;
       const int n_dw = n_c4 * (KP >> 3);
+      const int grp = tid / (kTcThreads / 2), it = tid % (kTcThreads / 2);
+      if (it < n_dw) {
+        const int c4 = it % n_c4, k8 = it / n_c4;
+        const uint8_t* h0 = sAhi + (uint32_t)(2 * k8) * (kTcRows * 16);
+        const uint8_t* l0 = sAlo + (uint32_t)(2 * k8) * (kTcRows * 16);
+#pragma unroll 2
+        for (int e = grp; e < cnt; e += 2) {
+          const uint32_t ro = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
+          const float4 da = *reinterpret_cast<const float4*>(sV + e * VW + 4 * c4);
+          const float4 ah = *reinterpret_cast<const float4*>(h0 + ro);
+          const float4 al = *reinterpret_cast<const float4*>(l0 + ro);
+          const float4 bh = *reinterpret_cast<const float4*>(h0 + kTcRows * 16 + ro);
+          const float4 bl = *reinterpret_cast<const float4*>(l0 + kTcRows * 16 + ro);
+          const float dv[4] = {da.x, da.y, da.z, da.w};
+          const float ev[8] = {ah.x + al.x, ah.y + al.y, ah.z + al.z, ah.w + al.w,
+                               bh.x + bl.x, bh.y + bl.y, bh.z + bl.z, bh.w + bl.w};
 #pragma unroll
-      for (int j = 0; j < NITEM; ++j) {
-        const int it = tid + j * kThreads;
-        if (it < n_dw) {
-          const int c4 = it % n_c4, k8 = it / n_c4;
-          const uint8_t* h0 = sAhi + (uint32_t)(2 * k8) * (kTcRows * 16);
-          const uint8_t* l0 = sAlo + (uint32_t)(2 * k8) * (kTcRows * 16);
-          for (int e = 0; e < cnt; ++e) {
-            const uint32_t ro = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-            const float4 da = *reinterpret_cast<const float4*>(sV + e * VW + 4 * c4);
-            const float4 ah = *reinterpret_cast<const float4*>(h0 + ro);
-            const float4 al = *reinterpret_cast<const float4*>(l0 + ro);
-            const float4 bh = *reinterpret_cast<const float4*>(h0 + kTcRows * 16 + ro);
-            const float4 bl = *reinterpret_cast<const float4*>(l0 + kTcRows * 16 + ro);
-            const float dv[4] = {da.x, da.y, da.z, da.w};
-            const float ev[8] = {ah.x + al.x, ah.y + al.y, ah.z + al.z, ah.w + al.w,
-                                 bh.x + bl.x, bh.y + bl.y, bh.z + bl.z, bh.w + bl.w};
+          for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int b = 0; b < 8; ++b) dw[j][a][b] = fmaf(dv[a], ev[b], dw[j][a][b]);
-          }
+            for (int b = 0; b < 8; ++b) dw[0][a][b] = fmaf(dv[a], ev[b], dw[0][a][b]);
         }
       }
     }
@@ -437,19 +446,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv_tc(const CgParams p, con
   if (MODE == CG_BWD_DST) {
     const int n_c4 = W2 >> 2;
     const int n_dw = n_c4 * (KP >> 3);
-    float* part = p.dW_part + (size_t)blockIdx.x * G * W2;
+    const int grp = tid / (kTcThreads / 2), it = tid % (kTcThreads / 2);
+    float* part = p.dW_part + ((size_t)blockIdx.x * 2 + grp) * G * W2;
+    if (it < n_dw) {
+      const int c4 = it % n_c4, k8 = it / n_c4;
 #pragma unroll
-    for (int j = 0; j < NITEM; ++j) {
-      const int it = tid + j * kThreads;
-      if (it < n_dw) {
-        const int c4 = it % n_c4, k8 = it / n_c4;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int kcol = 8 * k8 + b;
-          if (kcol < G)
-            *reinterpret_cast<float4*>(part + (size_t)kcol * W2 + 4 * c4) =
-                make_float4(dw[j][0][b], dw[j][1][b], dw[j][2][b], dw[j][3][b]);
-        }
+      for (int b = 0; b < 8; ++b) {
+        const int kcol = 8 * k8 + b;
+        if (kcol < G)
+          *reinterpret_cast<float4*>(part + (size_t)kcol * W2 + 4 * c4) =
+              make_float4(dw[0][0][b], dw[0][1][b], dw[0][2][b], dw[0][3][b]);
       }
     }
   }
@@ -467,7 +473,7 @@ static int tc_launch_t(const CgParams& p, const TcPlan& pl, int grid, cudaStream
                                   kMaxDynSmem));
     configured.store(1, std::memory_order_release);
   }
-  k_cgconv_tc<MODE, NITEM><<<grid, kThreads, pl.total, st>>>(p, pl);
+  k_cgconv_tc<MODE, NITEM><<<grid, kTcThreads, pl.total, st>>>(p, pl);
   MDL_LAUNCHED();
   return MDL_OK;
 }
@@ -487,9 +493,7 @@ int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out) {
   switch (mode) {
     case CG_FWD: return tc_launch_t<CG_FWD, 1>(p, pl, grid, st);
     case CG_BWD_SRC: return tc_launch_t<CG_BWD_SRC, 1>(p, pl, grid, st);
-    case CG_BWD_DST:
-      return pl.nitem <= 1 ? tc_launch_t<CG_BWD_DST, 1>(p, pl, grid, st)
-                           : tc_launch_t<CG_BWD_DST, 2>(p, pl, grid, st);
+    case CG_BWD_DST: return tc_launch_t<CG_BWD_DST, 1>(p, pl, grid, st);
   }
   MDL_REQUIRE(false, "cgconv_tc: bad mode");
 }
