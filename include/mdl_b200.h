@@ -125,6 +125,10 @@ MDL_API int mdl_cgconv_bwd(const float* grad_out, const float* PQ, const float* 
                    int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
                    int32_t reduce, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- development aid: 16 x uint64 device counters that receive per-phase cycle sums
+ * (thread 0 of every CTA) from the tensor-core CGConv kernels; NULL disables. ---- */
+MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr);
+
 /* ---- tensor-core self-test: D[128,N] = A[128,K] . B[N,K]^T through the same
  * tcgen05/TMEM conventions (umma.cuh) the fused kernels use.  split=0: plain
  * TF32 (operands truncated by the hardware); split=1: 3xTF32 (fp32-faithful).

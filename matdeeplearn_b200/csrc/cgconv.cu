@@ -399,7 +399,7 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
     int grid = 0;
     if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid)) return rc;
     const int tot = G * 2 * C;
-    k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, 2 * grid, G, C, 0, C, dWeT);
+    k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, grid, G, C, 0, C, dWeT);
     MDL_LAUNCHED();
   } else {
     CgPlan plan;
@@ -436,5 +436,12 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
       if (int rc = cg_launch<CG_BWD_SRC, 1>(p, smem, grid, st)) return rc;
     }
   }
+  return MDL_OK;
+}
+
+// development aid: 16 x uint64 device counters receiving per-phase cycle sums of the
+// tensor-core kernels (NULL disables).  Not part of the reference-facing surface.
+extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
+  cgtc_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   return MDL_OK;
 }

@@ -57,5 +57,6 @@ __device__ __forceinline__ float sigmoid_fast_(float x) { return __fdividef(1.0f
 // shared-memory / TMEM plan, in which case the caller uses the SIMT kernel.
 bool cgtc_supported(int mode, int C, int G);
 int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out);
+void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
 
 }  // namespace mdl

@@ -25,7 +25,12 @@ constexpr int kTcWarps = kTcThreads / 32;
 constexpr int kTcRows = 128;  // slots per round = MMA M
 constexpr int kTcTE = 112;    // ownership granularity (leaves head-room for straddling segments)
 
+// optional per-phase cycle accounting (development aid): 16 counters, thread 0 of each CTA adds
+// the cycles it spent between consecutive phase marks.  Enabled by mdl_debug_set_phase_buffer.
+static unsigned long long* g_phase_buf = nullptr;
+
 struct TcPlan {
+  unsigned long long* prof;
   int NP, KP, GS, VW, tmem_cols, nitem;
   uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, total;
 };
@@ -40,12 +45,14 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   const int VW = 2 * C + 4;  // [f | s] per slot (+4 floats: conflict-free float4 row access)
   uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)kTcRows * KP * 4;
   uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 4 * kTcRows * 4;
+  pl->prof = g_phase_buf;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
   pl->tmem_cols = 32;
   while (pl->tmem_cols < NP) pl->tmem_cols <<= 1;
   const int n_dw = (2 * C / 4) * (KP / 8);
-  pl->nitem = (n_dw + kTcThreads / 2 - 1) / (kTcThreads / 2);  // two thread groups split the slots
-  if (mode == CG_BWD_DST && pl->nitem > 1) return false;
+  pl->nitem = 1;
+  (void)n_dw;
+  if (mode == CG_BWD_DST && KP / 8 > 8) return false;  // dWe warp tiling: 2 x 4 k-tiles of 8
   pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
   // The value tile has its own region: it is filled (gathered node projections) while the MMAs of
   // the same round are still reading the operand tiles, so it cannot alias them.
@@ -90,6 +97,15 @@ __device__ __forceinline__ float softplus_mufu(float x) {
 }
 
 struct TileInfo { int n_lo, n_hi, e_lo, e_hi; };
+
+// D[16x8] += A[16x8] * B[8x8]  (tf32 inputs, fp32 accumulate; legacy warp-level tensor path)
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+        "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
 
 // Persistent CTA, software-pipelined over "rounds" of <=128 slots:
 //   while round r's MMAs run and its epilogue executes, round r+1's indices and ea rows are
@@ -145,15 +161,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     *reinterpret_cast<float*>(sBhi + off) = hi;
     *reinterpret_cast<float*>(sBlo + off) = w - hi;
   }
-  float dw[NITEM][4][8];
-  if (MODE == CG_BWD_DST) {
-#pragma unroll
-    for (int j = 0; j < NITEM; ++j)
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) dw[j][a][b] = 0.0f;
-  }
   umma::fence_proxy_async_smem();
   umma::fence_before_sync();
   __syncthreads();
@@ -162,44 +169,77 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   const uint32_t idesc = umma::make_idesc_tf32(kTcRows, NP);
   uint32_t phase = 0;
 
-  // prefetch of one round: warp w owns rows [8w, 8w+8): indices -> smem, ea rows -> cp.async
-  auto prefetch = [&](int r_lo, int cnt, int buf) {
-    int* bSrc = sIdx + buf * 2 * kTcRows;
-    int* bDst = bSrc + kTcRows;
-    const int row0 = warp * (kTcRows / kTcWarps);
-    int slot = 0;
-    if (lane < kTcRows / kTcWarps) {
+  // ---- per-round loads are split into an "issue" half (registers) and a "land" half so that
+  // every global load of the overlap window is in flight before the first one is consumed.
+  constexpr int kRowsPerWarp = kTcRows / kTcWarps;  // 8
+  const int row0 = warp * kRowsPerWarp;
+  struct NextIdx { int slot, s, d; };
+  auto issue_idx = [&](int r_lo, int cnt) {  // lanes < 8: indices of this warp's rows of a round
+    NextIdx ni{0, 0, 0};
+    if (lane < kRowsPerWarp) {
       const int e = row0 + lane;
-      int s = 0, d = 0;
       if (e < cnt) {
-        slot = (MODE == CG_BWD_SRC) ? __ldg(p.src_slot + r_lo + e) : (r_lo + e);
-        s = __ldg(p.dst_src + slot);
-        d = __ldg(p.dst_dst + slot);
+        ni.slot = (MODE == CG_BWD_SRC) ? __ldg(p.src_slot + r_lo + e) : (r_lo + e);
+        ni.s = __ldg(p.dst_src + ni.slot);
+        ni.d = __ldg(p.dst_dst + ni.slot);
       }
-      bSrc[e] = s;
-      bDst[e] = d;
+    }
+    return ni;
+  };
+  auto land_idx_and_rows = [&](const NextIdx& ni, int cnt, int buf) {
+    int* bS = sIdx + buf * 2 * kTcRows;
+    int* bD = bS + kTcRows;
+    if (lane < kRowsPerWarp) {
+      bS[row0 + lane] = ni.s;
+      bD[row0 + lane] = ni.d;
     }
 #pragma unroll
-    for (int i = 0; i < kTcRows / kTcWarps; ++i) {
+    for (int i = 0; i < kRowsPerWarp; ++i) {
       const int e = row0 + i;
-      const int sl = __shfl_sync(0xffffffffu, slot, i);
+      const int sl = __shfl_sync(0xffffffffu, ni.slot, i);
       if (e < cnt) {
         const float* row = p.ea + (size_t)sl * G;
         float* dst = sEA + e * GS;
         if ((G & 1) == 0) {
           for (int k2 = lane; k2 < (G >> 1); k2 += 32) cp_async8(dst + 2 * k2, row + 2 * k2);
         } else {
-          for (int k = lane; k < G; k += 32) cp_async4(dst + k, row + k);
+          for (int kx = lane; kx < G; kx += 32) cp_async4(dst + kx, row + kx);
         }
       }
     }
   };
 
+  long long t_prev = clock64();
+  auto mark = [&](int slot) {
+    if (pl.prof && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
+      t_prev = now;
+    }
+  };
+
+  // dWe accumulators of the mma.sync path (BWD_DST): warp tile = 16 channels x (4 | 3) k-tiles of 8
+  float dacc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dacc[a][b] = 0.0f;
+  const int dw_mt = warp & 7;                 // channel tile (16 rows of dWe^T)
+  const int dw_nt0 = (warp >> 3) * 4;         // first k-tile of this warp
+  const int n_ktiles = KP >> 3;
+  const int dw_nts = min(4, max(0, n_ktiles - dw_nt0));
+
   int k = 0, rd = 0, buf = 0;
   if (my_tiles > 0) {
     const TileInfo t0 = sh_tile[0];
-    prefetch(t0.e_lo, min(t0.e_hi - t0.e_lo, kTcRows), 0);
+    const int c0 = min(t0.e_hi - t0.e_lo, kTcRows);
+    const NextIdx ni = issue_idx(t0.e_lo, c0);
+    land_idx_and_rows(ni, c0, 0);
   }
+
+  const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
+  constexpr int chh = 16;
+  const int c_begin = part * chh;
 
   while (k < my_tiles) {
     const TileInfo T = sh_tile[k % 3];
@@ -208,14 +248,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     const int r_hi = min(T.e_hi, r_lo + kTcRows);
     const int cnt = r_hi - r_lo;
     const int n_lo = T.n_lo, n_hi = T.n_hi;
-    // next work item
     const bool same_tile = (rd + 1 < rounds);
     const int nk = same_tile ? k : k + 1, nrd = same_tile ? rd + 1 : 0;
     const int* bSrc = sIdx + buf * 2 * kTcRows;
     const int* bDst = bSrc + kTcRows;
 
+    mark(0);
     cp_async_wait_all();
-    __syncthreads();  // [S1] rows + indices of this round visible; sV / A tiles free
+    __syncthreads();  // [S1] rows + indices of this round visible; value / operand tiles free
+    mark(1);
 
     // ---- split hi/lo into the canonical MMA operand layout
     {
@@ -241,10 +282,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     }
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
-    __syncthreads();  // [S2] operands staged; sEA free for the next round's rows
+    __syncthreads();  // [S2] operands staged; the ea landing zone is free for the next round
+    mark(2);
 
-    // ---- contraction on the tensor core (asynchronous)
-    if (tid == 0 && cnt > 0) {
+    // ---- contraction on the tensor core (asynchronous; the issuing lane belongs to the LAST warp,
+    // whose other duties in this window are the lightest)
+    if (tid == kTcThreads - 32 && cnt > 0) {
       umma::fence_after_sync();
       const uint32_t step_a = 2 * kTcRows * 16, step_b = 2 * (uint32_t)NP * 16;
       const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
@@ -263,57 +306,87 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       }
       umma::mma_commit(&bar);
     }
+    mark(3);
 
-    // ---- overlap window: look two tiles ahead, put the next round's loads in flight
-    if (rd == 0 && tid == 64) compute_info(k + 2);
+    // ---- overlap window, part 1: ISSUE every global load (nothing below waits on memory yet)
+    // (b) what the reduce stage will need for this warp's first segment
+    const int n0 = n_lo + warp;
+    int seg_a = 0, seg_b = 0;
+    float seg_sc = 1.0f, seg_x0 = 0.0f, seg_x1 = 0.0f;
+    if (n0 < n_hi) {
+      seg_a = __ldg(p.seg_ptr + n0);
+      seg_b = __ldg(p.seg_ptr + n0 + 1);
+      if (MODE == CG_FWD) {
+        if (p.inv_deg) seg_sc = __ldg(p.inv_deg + n0);
+        seg_x0 = __ldg(p.x + (size_t)n0 * C + lane);
+        seg_x1 = __ldg(p.x + (size_t)n0 * C + 32 + lane);
+      }
+    }
+    // (c) backward: grad_out rows (x 1/deg) of this warp's 8 slots, lanes = channels
+    float g0[(MODE != CG_FWD) ? kRowsPerWarp : 1], g1[(MODE != CG_FWD) ? kRowsPerWarp : 1];
+    if (MODE != CG_FWD) {
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int e = row0 + i;
+        g0[i] = g1[i] = 0.0f;
+        if (e < cnt) {
+          const int d = bDst[e];
+          const float sc = p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f;
+          g0[i] = __ldg(p.gout + (size_t)d * C + lane) * sc;
+          g1[i] = __ldg(p.gout + (size_t)d * C + 32 + lane) * sc;
+        }
+      }
+    }
+    // (d) node projections P[dst] / Q[src] of this warp's 32 slots x 16 channels, coalesced:
+    // lanes [0,8) = 16-byte chunks of P (f | s), lanes [8,16) = the same chunks of Q, two slots
+    // per instruction.
+    constexpr int rows_per_inst = 32 / chh;         // 2
+    const int g_sub = lane / chh, g_l = lane % chh;
+    const int g_isq = g_l / (chh / 2), g_l2 = g_l % (chh / 2);
+    const int g_iss = g_l2 / (chh / 4);
+    const int g_c = c_begin + 4 * (g_l2 % (chh / 4));
+    const int g_col = g_isq * 2 * C + g_iss * C + g_c;
+    float4 v[32 / rows_per_inst];
+    if (cnt > 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += rows_per_inst) {
+        const int e = 32 * q + i + g_sub;
+        v[i / rows_per_inst] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < cnt) {
+          const int node = g_isq ? bSrc[e] : bDst[e];
+          v[i / rows_per_inst] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)node * (4 * C) + g_col));
+        }
+      }
+    }
+    // (a) indices of the next round -- last: in BWD_SRC they are a dependent chain, which now
+    // overlaps with everything issued above
+    int ncnt = 0;
+    NextIdx ni{0, 0, 0};
     if (nk < my_tiles) {
       const TileInfo Tn = sh_tile[nk % 3];
       const int nr_lo = Tn.e_lo + nrd * kTcRows;
-      prefetch(nr_lo, min(Tn.e_hi - nr_lo, kTcRows), buf ^ 1);
+      ncnt = min(Tn.e_hi - nr_lo, kTcRows);
+      ni = issue_idx(nr_lo, ncnt);
     }
+    if (rd == 0 && tid == 64) compute_info(k + 2);  // two tiles ahead (own dependent loads)
+    mark(4);
 
-    // ---- gather P[dst] + Q[src] for this round, coalesced, into the value tile.
-    // Warp (q, half) owns slots 32q..32q+31 and channels [half*chh, half*chh+chh) for BOTH the
-    // gather and the epilogue below, so only a __syncwarp separates the two.
-    // One LDG.128 per lane: lanes [0,chh/2) = 16-byte chunks of P (f half | s half), lanes
-    // [chh/2, chh) = the same chunks of Q; with chh = 32 a warp instruction covers one slot
-    // (4 full 128-byte lines), with chh = 16 two slots.
-    const int q = warp & 3, part = warp >> 2;        // lane quadrant, channel quarter
-    constexpr int chh = 16;                         // channels per warp
-    const int c_begin = part * chh;
-    const bool has_ch = c_begin < C;
-    if (cnt > 0 && has_ch) {
-      constexpr int rows_per_inst = 32 / chh;         // 2
-      const int sub = lane / chh;                    // slot within the instruction
-      const int l = lane % chh;                      // lane within the slot's group
-      const int is_q = l / (chh / 2);                // 0: P (destination side), 1: Q (source side)
-      const int l2 = l % (chh / 2);
-      const int is_s = l2 / (chh / 4);               // 0: f channels, 1: s channels
-      const int c = c_begin + 4 * (l2 % (chh / 4));  // first of this lane's 4 channels
-      const int col = is_q * 2 * C + is_s * C + c;   // column inside a PQ row
-      float4 v[32 / rows_per_inst];
-#pragma unroll
-      for (int i = 0; i < 32; i += rows_per_inst) {  // all loads first: one latency exposure
-        const int e = 32 * q + i + sub;
-        v[i / rows_per_inst] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < cnt) {
-          const int node = is_q ? bSrc[e] : bDst[e];
-          v[i / rows_per_inst] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)node * (4 * C) + col));
-        }
-      }
+    // ---- overlap window, part 2: LAND.  Next round's indices + ea rows, then this round's P+Q.
+    if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
+    if (cnt > 0) {
 #pragma unroll
       for (int i = 0; i < 32; i += rows_per_inst) {
-        const int e = 32 * q + i + sub;
+        const int e = 32 * q + i + g_sub;
         float4 t = v[i / rows_per_inst];
-        // P + Q: partner lane holds the other operand of the same (slot, channel chunk)
         t.x += __shfl_xor_sync(0xffffffffu, t.x, chh / 2);
         t.y += __shfl_xor_sync(0xffffffffu, t.y, chh / 2);
         t.z += __shfl_xor_sync(0xffffffffu, t.z, chh / 2);
         t.w += __shfl_xor_sync(0xffffffffu, t.w, chh / 2);
-        if (!is_q && e < cnt) *reinterpret_cast<float4*>(sV + e * VW + is_s * C + c) = t;
+        if (!g_isq && e < cnt) *reinterpret_cast<float4*>(sV + e * VW + g_iss * C + g_c) = t;
       }
       __syncwarp();
     }
+    mark(5);
 
     // ---- epilogue: thread = slot (TMEM lane); a = accumulator + gathered projections
     if (cnt > 0) {
@@ -322,48 +395,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       umma::mbar_wait(&bar, phase);
       umma::fence_after_sync();
       phase ^= 1;
-      if (has_ch) {
+      mark(6);
+      float f[16], sacc[16];
+      umma::tmem_ld16(umma::tmem_addr(tmem, q, c_begin), f);
+      umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c_begin), sacc);
+      umma::tmem_ld_wait();
+      if (live) {
+        float* rowv = sV + e * VW;
 #pragma unroll
-        for (int c0 = c_begin; c0 < c_begin + chh; c0 += 16) {  // one pass: chh == 16
-          float f[16], sacc[16];
-          umma::tmem_ld16(umma::tmem_addr(tmem, q, c0), f);
-          umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c0), sacc);
-          umma::tmem_ld_wait();
-          if (live) {
-            float* rowv = sV + e * VW;
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int c = c_begin + j4;
+          const float4 bf = *reinterpret_cast<const float4*>(rowv + c);
+          const float4 bs = *reinterpret_cast<const float4*>(rowv + C + c);
+          const float af[4] = {f[j4] + bf.x, f[j4 + 1] + bf.y, f[j4 + 2] + bf.z, f[j4 + 3] + bf.w};
+          const float as[4] = {sacc[j4] + bs.x, sacc[j4 + 1] + bs.y, sacc[j4 + 2] + bs.z, sacc[j4 + 3] + bs.w};
+          float r0[4], r1[4];
 #pragma unroll
-            for (int j4 = 0; j4 < 16; j4 += 4) {
-              const int c = c0 + j4;
-              const float4 bf = *reinterpret_cast<const float4*>(rowv + c);
-              const float4 bs = *reinterpret_cast<const float4*>(rowv + C + c);
-              const float af[4] = {f[j4] + bf.x, f[j4 + 1] + bf.y, f[j4 + 2] + bf.z, f[j4 + 3] + bf.w};
-              const float as[4] = {sacc[j4] + bs.x, sacc[j4 + 1] + bs.y, sacc[j4 + 2] + bs.z, sacc[j4 + 3] + bs.w};
-              float r0[4], r1[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float sg = sigmoid_mufu(af[j]);
-                const float sp = softplus_mufu(as[j]);
-                if (MODE == CG_FWD) {
-                  r0[j] = sg * sp;
-                } else {  // d(message)/d(a_f), d(message)/d(a_s); the grad_out factor is applied in the reduce stage
-                  r0[j] = sp * sg * (1.0f - sg);
-                  r1[j] = sg * sigmoid_mufu(as[j]);
-                }
-              }
-              *reinterpret_cast<float4*>(rowv + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
-              if (MODE != CG_FWD)
-                *reinterpret_cast<float4*>(rowv + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+          for (int j = 0; j < 4; ++j) {
+            const float sg = sigmoid_mufu(af[j]);
+            const float sp = softplus_mufu(as[j]);
+            if (MODE == CG_FWD) {
+              r0[j] = sg * sp;
+            } else {  // d m / d a_f and d m / d a_s; the grad_out factor follows in the scale pass
+              r0[j] = sp * sg * (1.0f - sg);
+              r1[j] = sg * sigmoid_mufu(as[j]);
             }
           }
+          *reinterpret_cast<float4*>(rowv + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+          if (MODE != CG_FWD)
+            *reinterpret_cast<float4*>(rowv + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
         }
       }
     }
+    mark(7);
     umma::fence_before_sync();  // accumulator reads done before the next round's MMAs overwrite it
     __syncthreads();            // [S3] value tile complete
+    mark(8);
+
+    // ---- backward: da = grad_out[dst] / deg[dst] * bracket, applied row-wise (lanes = channels)
+    if (MODE != CG_FWD) {
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int e = row0 + i;
+        if (e < cnt) {
+          float* rowv = sV + e * VW;
+          rowv[lane] *= g0[i];
+          rowv[32 + lane] *= g1[i];
+          rowv[C + lane] *= g0[i];
+          rowv[C + 32 + lane] *= g1[i];
+        }
+      }
+      __syncthreads();  // [S3b]
+    }
 
     // ---- segmented sum over the owned segments that have slots in this round
-    for (int n = n_lo + warp; n < n_hi; n += kTcWarps) {
-      const int a = __ldg(p.seg_ptr + n), b = __ldg(p.seg_ptr + n + 1);
+    for (int n = n0; n < n_hi; n += kTcWarps) {
+      int a, b;
+      if (n == n0) { a = seg_a; b = seg_b; }
+      else { a = __ldg(p.seg_ptr + n); b = __ldg(p.seg_ptr + n + 1); }
       const int lo = max(a, r_lo), hi = min(b, r_hi);
       const bool empty_seg = (a == b);
       if (empty_seg ? (rd != 0) : (lo >= hi)) continue;
@@ -371,91 +460,94 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       const bool last = empty_seg || (b <= r_hi);
       if (MODE == CG_FWD) {
         float* o = p.out + (size_t)n * C;
-        const float* xr = p.x + (size_t)n * C;
-        const float sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
-        for (int c = lane; c < C; c += 32) {
-          const float xv = last ? __ldg(xr + c) : 0.0f;  // issued before the sum: latency overlaps it
-          float acc = first ? 0.0f : o[c];
-          for (int s = lo; s < hi; ++s) acc += sV[(s - r_lo) * VW + c];
-          o[c] = last ? fmaf(acc, sc, xv) : acc;
+        float sc = seg_sc, x0 = seg_x0, x1 = seg_x1;
+        if (n != n0) {
+          sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
+          x0 = __ldg(p.x + (size_t)n * C + lane);
+          x1 = __ldg(p.x + (size_t)n * C + 32 + lane);
         }
-      } else if (MODE == CG_BWD_DST) {
-        // segment = destination: one grad_out row scales every slot of the segment.  The scaled
-        // per-slot values are written back: the dWe pass below needs da = g * bracket per slot.
-        float* o = p.out + (size_t)n * (4 * C);
-        const float sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
-        for (int c = lane; c < W2; c += 32) {
-          const float g = __ldg(p.gout + (size_t)n * C + (c < C ? c : c - C)) * sc;
-          float acc = first ? 0.0f : o[c];
-          for (int s = lo; s < hi; ++s) {
-            const float v = sV[(s - r_lo) * VW + c] * g;
-            sV[(s - r_lo) * VW + c] = v;
-            acc += v;
-          }
-          o[c] = acc;
+        float acc0 = first ? 0.0f : o[lane], acc1 = first ? 0.0f : o[32 + lane];
+        for (int s = lo; s < hi; ++s) {
+          acc0 += sV[(s - r_lo) * VW + lane];
+          acc1 += sV[(s - r_lo) * VW + 32 + lane];
         }
+        o[lane] = last ? fmaf(acc0, sc, x0) : acc0;
+        o[32 + lane] = last ? fmaf(acc1, sc, x1) : acc1;
       } else {
-        // segment = source: every slot has its own destination, hence its own grad_out row
-        float* o = p.out + (size_t)n * (4 * C) + 2 * C;
-        for (int c = lane; c < W2; c += 32) {
-          const int cc = (c < C ? c : c - C);
-          float acc = first ? 0.0f : o[c];
-#pragma unroll 4
-          for (int s = lo; s < hi; ++s) {
-            const int d = bDst[s - r_lo];
-            const float g = __ldg(p.gout + (size_t)d * C + cc) * (p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f);
-            acc = fmaf(sV[(s - r_lo) * VW + c], g, acc);
-          }
-          o[c] = acc;
+        float* o = p.out + (size_t)n * (4 * C) + (MODE == CG_BWD_SRC ? 2 * C : 0);
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = first ? 0.0f : o[32 * u + lane];
+        for (int s = lo; s < hi; ++s) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += sV[(s - r_lo) * VW + 32 * u + lane];
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[32 * u + lane] = acc[u];
       }
     }
-    if (MODE == CG_BWD_DST) __syncthreads();  // scaled value tile visible to the dWe pass
+    mark(9);
 
-    // ---- dWe += da^T . ea   (ea re-assembled exactly as hi + lo from the operand tiles).
-    // Two thread groups take alternate slots; each keeps its own register tile and partial.
-    if (MODE == CG_BWD_DST) {
-      const int n_c4 = W2 >> 2;
-      const int n_dw = n_c4 * (KP >> 3);
-      const int grp = tid / (kTcThreads / 2), it = tid % (kTcThreads / 2);
-      if (it < n_dw) {
-        const int c4 = it % n_c4, k8 = it / n_c4;
-        const uint8_t* h0 = sAhi + (uint32_t)(2 * k8) * (kTcRows * 16);
-        const uint8_t* l0 = sAlo + (uint32_t)(2 * k8) * (kTcRows * 16);
-#pragma unroll 2
-        for (int e = grp; e < cnt; e += 2) {
-          const uint32_t ro = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-          const float4 da = *reinterpret_cast<const float4*>(sV + e * VW + 4 * c4);
-          const float4 ah = *reinterpret_cast<const float4*>(h0 + ro);
-          const float4 al = *reinterpret_cast<const float4*>(l0 + ro);
-          const float4 bh = *reinterpret_cast<const float4*>(h0 + kTcRows * 16 + ro);
-          const float4 bl = *reinterpret_cast<const float4*>(l0 + kTcRows * 16 + ro);
-          const float dv[4] = {da.x, da.y, da.z, da.w};
-          const float ev[8] = {ah.x + al.x, ah.y + al.y, ah.z + al.z, ah.w + al.w,
-                               bh.x + bl.x, bh.y + bl.y, bh.z + bl.z, bh.w + bl.w};
+    // ---- dWe^T[ch, k] += sum_slots da[slot, ch] * ea[slot, k] on the legacy tensor-core path
+    // (mma.sync m16n8k8 tf32, 3xTF32).  A = da^T from the value tile (split in registers),
+    // B = ea straight from the already split operand tiles: element (slot e, column g) sits at
+    // (g/4)*2048 + (e/8)*128 + (e%8)*16 + (g%4)*4 in both sAhi and sAlo.
+    if (MODE == CG_BWD_DST && cnt > 0 && dw_nts > 0) {
+      const int gid = lane >> 2, tig = lane & 3;
+      const int ch0 = dw_mt * 16 + gid;
+      for (int e0 = 0; e0 < cnt; e0 += 8) {
+        // A fragment: rows = channels (ch0, ch0+8), cols = slots (e0+tig, e0+tig+4)
+        float ah[4], al[4];
+        {
+          const int ea_ = e0 + tig, eb_ = e0 + tig + 4;
+          float av[4];
+          av[0] = (ea_ < cnt) ? sV[ea_ * VW + ch0] : 0.0f;
+          av[1] = (ea_ < cnt) ? sV[ea_ * VW + ch0 + 8] : 0.0f;
+          av[2] = (eb_ < cnt) ? sV[eb_ * VW + ch0] : 0.0f;
+          av[3] = (eb_ < cnt) ? sV[eb_ * VW + ch0 + 8] : 0.0f;
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+          for (int u = 0; u < 4; ++u) { ah[u] = umma::tf32_hi(av[u]); al[u] = av[u] - ah[u]; }
+        }
+        const uint32_t rb0 = (uint32_t)((e0 + tig) >> 3) * 128 + (uint32_t)((e0 + tig) & 7) * 16;
+        const uint32_t rb1 = (uint32_t)((e0 + tig + 4) >> 3) * 128 + (uint32_t)((e0 + tig + 4) & 7) * 16;
 #pragma unroll
-            for (int b = 0; b < 8; ++b) dw[0][a][b] = fmaf(dv[a], ev[b], dw[0][a][b]);
+        for (int t = 0; t < 4; ++t) {
+          if (t < dw_nts) {
+            const int g = (dw_nt0 + t) * 8 + gid;  // B fragment column
+            const uint32_t cb = (uint32_t)(g >> 2) * (kTcRows * 16) + (uint32_t)(g & 3) * 4;
+            const float bh0 = *reinterpret_cast<const float*>(sAhi + cb + rb0);
+            const float bh1 = *reinterpret_cast<const float*>(sAhi + cb + rb1);
+            const float bl0 = *reinterpret_cast<const float*>(sAlo + cb + rb0);
+            const float bl1 = *reinterpret_cast<const float*>(sAlo + cb + rb1);
+            mma_tf32_16x8x8(dacc[t], ah, bh0, bh1);
+            mma_tf32_16x8x8(dacc[t], ah, bl0, bl1);
+            mma_tf32_16x8x8(dacc[t], al, bh0, bh1);
+          }
         }
       }
     }
+    mark(10);
+    if (pl.prof && tid == 0) atomicAdd(pl.prof + 15, 1ull);
     k = nk; rd = nrd; buf ^= 1;
   }  // work items
 
-  if (MODE == CG_BWD_DST) {
-    const int n_c4 = W2 >> 2;
-    const int n_dw = n_c4 * (KP >> 3);
-    const int grp = tid / (kTcThreads / 2), it = tid % (kTcThreads / 2);
-    float* part = p.dW_part + ((size_t)blockIdx.x * 2 + grp) * G * W2;
-    if (it < n_dw) {
-      const int c4 = it % n_c4, k8 = it / n_c4;
+  if (MODE == CG_BWD_DST && dw_nts > 0) {
+    // C fragment: rows (channels) gid, gid+8; cols (k) 2*tig, 2*tig+1
+    const int gid = lane >> 2, tig = lane & 3;
+    float* part = p.dW_part + (size_t)blockIdx.x * G * W2;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int kcol = 8 * k8 + b;
-        if (kcol < G)
-          *reinterpret_cast<float4*>(part + (size_t)kcol * W2 + 4 * c4) =
-              make_float4(dw[0][0][b], dw[0][1][b], dw[0][2][b], dw[0][3][b]);
+    for (int t = 0; t < 4; ++t) {
+      if (t < dw_nts) {
+        const int kc = (dw_nt0 + t) * 8 + 2 * tig;
+        const int ch = dw_mt * 16 + gid;
+        if (kc < G) {
+          part[(size_t)kc * W2 + ch] = dacc[t][0];
+          part[(size_t)kc * W2 + ch + 8] = dacc[t][2];
+        }
+        if (kc + 1 < G) {
+          part[(size_t)(kc + 1) * W2 + ch] = dacc[t][1];
+          part[(size_t)(kc + 1) * W2 + ch + 8] = dacc[t][3];
+        }
       }
     }
   }
@@ -477,6 +569,8 @@ static int tc_launch_t(const CgParams& p, const TcPlan& pl, int grid, cudaStream
   MDL_LAUNCHED();
   return MDL_OK;
 }
+
+void cgtc_set_phase_buffer(unsigned long long* dev_ptr) { g_phase_buf = dev_ptr; }
 
 bool cgtc_supported(int mode, int C, int G) {
   TcPlan pl;

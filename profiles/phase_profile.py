@@ -1,0 +1,64 @@
+"""Per-phase cycle breakdown of the tensor-core CGConv kernels (thread 0 of every
+CTA; phases are separated by CTA barriers so this is the CTA's timeline).
+Usage on the GPU box:  python profiles/phase_profile.py [graphs]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from matdeeplearn_b200 import _lib, process as pr  # noqa: E402
+from matdeeplearn_b200.csr import GraphCSR, gather_rows  # noqa: E402
+
+NAMES = ["loop/setup", "S1 wait rows", "split hi/lo + S2", "MMA issue", "prefetch issue", "gather P/Q",
+         "wait MMA", "gate math", "S3", "reduce", "dWe", "", "", "", "", "rounds"]
+lib = _lib.load()
+dev = torch.device("cuda:0")
+graphs = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+base = min(graphs, 1024)
+reps = max(1, graphs // base)
+ds = pr.synthetic_dataset("bulk", base, seed=7)
+b = ds.batch().to(dev)
+n0 = b.x.shape[0]
+ei = torch.cat([b.edge_index + i * n0 for i in range(reps)], 1).contiguous()
+ea = b.edge_attr.repeat(reps, 1).contiguous()
+N, E, C, G = n0 * reps, ei.shape[1], 64, ea.shape[1]
+csr = GraphCSR.from_coo(ei, num_nodes=N)
+ea_s = gather_rows(ea, csr.dst_eid)
+x = torch.randn(N, C, device=dev)
+PQ = torch.randn(N, 4 * C, device=dev) * 0.5
+WeT = torch.randn(G, 2 * C, device=dev) * 0.1
+gout = torch.randn(N, C, device=dev)
+out = torch.empty(N, C, device=dev)
+dPQ = torch.empty(N, 4 * C, device=dev)
+dWeT = torch.empty(G, 2 * C, device=dev)
+wsb = lib.mdl_cgconv_workspace_bytes(N, E, C, G)
+ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+prof = torch.zeros(16, dtype=torch.int64, device=dev)
+P, st = _lib.ptr, _lib.stream()
+
+
+def fwd():
+    _lib.check(lib.mdl_cgconv_fwd(P(x), P(PQ), P(ea_s), P(WeT), P(csr.dst_ptr), P(csr.dst_src), P(csr.dst_dst),
+                                  P(csr.inv_deg_dst), P(out), N, E, C, G, 1, st), "fwd")
+
+
+def bwd():
+    _lib.check(lib.mdl_cgconv_bwd(P(gout), P(PQ), P(ea_s), P(WeT), P(csr.dst_ptr), P(csr.dst_src), P(csr.dst_dst),
+                                  P(csr.src_ptr), P(csr.src_slot), P(csr.inv_deg_dst), P(dPQ), P(dWeT), N, E, C, G,
+                                  1, P(ws), wsb, st), "bwd")
+
+
+for name, fn in (("fwd", fwd), ("bwd (dst pass + src pass)", bwd)):
+    fn(); torch.cuda.synchronize()
+    lib.mdl_debug_set_phase_buffer(P(prof))
+    prof.zero_()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); fn(); c.record(); torch.cuda.synchronize()
+    lib.mdl_debug_set_phase_buffer(None)
+    v = prof.cpu().tolist()
+    rounds = max(v[15], 1)
+    print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, "
+          f"{sum(v[:11]) / rounds:.0f} cycles/round")
+    for i in range(11):
+        print(f"   {NAMES[i]:18s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / max(sum(v[:11]), 1):5.1f}%")
