@@ -52,7 +52,7 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   const int n_dw = (2 * C / 4) * (KP / 8);
   pl->nitem = 1;
   (void)n_dw;
-  if (mode == CG_BWD_DST && KP / 8 > 8) return false;  // dWe warp tiling: 2 x 4 k-tiles of 8
+  if (mode == CG_BWD_DST && KP > 64) return false;  // dWe warp tiling: 4 column groups of 16
   pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
   // The value tile has its own region: it is filled (gathered node projections) while the MMAs of
   // the same round are still reading the operand tiles, so it cannot alias them.
@@ -218,16 +218,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     }
   };
 
-  // dWe accumulators of the mma.sync path (BWD_DST): warp tile = 16 channels x (4 | 3) k-tiles of 8
+  // dWe accumulators of the mma.sync path (BWD_DST): 2 x 2 tiles of 16 channels x 8 k-columns
   float dacc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) dacc[a][b] = 0.0f;
-  const int dw_mt = warp & 7;                 // channel tile (16 rows of dWe^T)
-  const int dw_nt0 = (warp >> 3) * 4;         // first k-tile of this warp
-  const int n_ktiles = KP >> 3;
-  const int dw_nts = min(4, max(0, n_ktiles - dw_nt0));
 
   int k = 0, rd = 0, buf = 0;
   if (my_tiles > 0) {
@@ -337,24 +333,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         }
       }
     }
-    // (d) node projections P[dst] / Q[src] of this warp's 32 slots x 16 channels, coalesced:
-    // lanes [0,8) = 16-byte chunks of P (f | s), lanes [8,16) = the same chunks of Q, two slots
-    // per instruction.
-    constexpr int rows_per_inst = 32 / chh;         // 2
-    const int g_sub = lane / chh, g_l = lane % chh;
-    const int g_isq = g_l / (chh / 2), g_l2 = g_l % (chh / 2);
-    const int g_iss = g_l2 / (chh / 4);
-    const int g_c = c_begin + 4 * (g_l2 % (chh / 4));
-    const int g_col = g_isq * 2 * C + g_iss * C + g_c;
-    float4 v[32 / rows_per_inst];
+    // (d) node projections of this warp's 8 slots: one LDG.128 per lane reads a whole 512-byte
+    // P row ([f | s], 4 full lines) resp. Q row -- lane l owns floats [4l, 4l+4) of the row.
+    float4 vp[kRowsPerWarp], vq[kRowsPerWarp];
     if (cnt > 0) {
 #pragma unroll
-      for (int i = 0; i < 32; i += rows_per_inst) {
-        const int e = 32 * q + i + g_sub;
-        v[i / rows_per_inst] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int e = row0 + i;
+        vp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vq[i] = vp[i];
         if (e < cnt) {
-          const int node = g_isq ? bSrc[e] : bDst[e];
-          v[i / rows_per_inst] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)node * (4 * C) + g_col));
+          vp[i] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)bDst[e] * (4 * C)) + lane);
+          vq[i] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)bSrc[e] * (4 * C) + 2 * C) + lane);
         }
       }
     }
@@ -375,17 +365,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
     if (cnt > 0) {
 #pragma unroll
-      for (int i = 0; i < 32; i += rows_per_inst) {
-        const int e = 32 * q + i + g_sub;
-        float4 t = v[i / rows_per_inst];
-        t.x += __shfl_xor_sync(0xffffffffu, t.x, chh / 2);
-        t.y += __shfl_xor_sync(0xffffffffu, t.y, chh / 2);
-        t.z += __shfl_xor_sync(0xffffffffu, t.z, chh / 2);
-        t.w += __shfl_xor_sync(0xffffffffu, t.w, chh / 2);
-        if (!g_isq && e < cnt) *reinterpret_cast<float4*>(sV + e * VW + g_iss * C + g_c) = t;
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int e = row0 + i;
+        if (e < cnt)
+          *(reinterpret_cast<float4*>(sV + e * VW) + lane) =
+              make_float4(vp[i].x + vq[i].x, vp[i].y + vq[i].y, vp[i].z + vq[i].z, vp[i].w + vq[i].w);
       }
-      __syncwarp();
     }
+    __syncthreads();  // [S2c] gathered projections visible to the epilogue threads of every warp
     mark(5);
 
     // ---- epilogue: thread = slot (TMEM lane); a = accumulator + gathered projections
@@ -488,40 +475,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     }
     mark(9);
 
-    // ---- dWe^T[ch, k] += sum_slots da[slot, ch] * ea[slot, k] on the legacy tensor-core path
-    // (mma.sync m16n8k8 tf32, 3xTF32).  A = da^T from the value tile (split in registers),
-    // B = ea straight from the already split operand tiles: element (slot e, column g) sits at
-    // (g/4)*2048 + (e/8)*128 + (e%8)*16 + (g%4)*4 in both sAhi and sAlo.
-    if (MODE == CG_BWD_DST && cnt > 0 && dw_nts > 0) {
+    // ---- dWe^T[ch, k] += sum_slots da[slot, ch] * ea[slot, k] on the warp-level tensor path
+    // (mma.sync m16n8k8 tf32, 3xTF32).  Warp (mgrp, ngrp) owns 32 channels x 16 k-columns = 2x2
+    // MMA tiles whose rows/columns are PERMUTED so that every fragment is a vector load:
+    //   channel(tile mi, fragment row gid | gid+8) = mgrp*32 + 4*gid + 2*mi + {0 | 1}
+    //   column (tile ni, fragment col gid)        = ngrp*16 + 2*gid + ni
+    // A = da^T from the value tile (float4 per slot, split hi/lo in registers); B = ea straight
+    // from the already split operand tiles (float2 per slot, element (slot e, column g) sits at
+    // (g/4)*2048 + (e/8)*128 + (e%8)*16 + (g%4)*4 in sAhi / sAlo).
+    if (MODE == CG_BWD_DST && cnt > 0) {
       const int gid = lane >> 2, tig = lane & 3;
-      const int ch0 = dw_mt * 16 + gid;
+      const int mgrp = warp & 3, ngrp = warp >> 2;
+      const int chunk = ngrp * 4 + (gid >> 1);           // 16-byte chunk of the operand tiles
+      const bool col_ok = chunk < (KP >> 2);
+      const uint32_t cb = (uint32_t)chunk * (kTcRows * 16) + (uint32_t)(gid & 1) * 8;
       for (int e0 = 0; e0 < cnt; e0 += 8) {
-        // A fragment: rows = channels (ch0, ch0+8), cols = slots (e0+tig, e0+tig+4)
-        float ah[4], al[4];
-        {
-          const int ea_ = e0 + tig, eb_ = e0 + tig + 4;
-          float av[4];
-          av[0] = (ea_ < cnt) ? sV[ea_ * VW + ch0] : 0.0f;
-          av[1] = (ea_ < cnt) ? sV[ea_ * VW + ch0 + 8] : 0.0f;
-          av[2] = (eb_ < cnt) ? sV[eb_ * VW + ch0] : 0.0f;
-          av[3] = (eb_ < cnt) ? sV[eb_ * VW + ch0 + 8] : 0.0f;
+        const int ea_ = e0 + tig, eb_ = e0 + tig + 4;
+        float4 a_lo_row = make_float4(0.f, 0.f, 0.f, 0.f), a_hi_row = a_lo_row;
+        if (ea_ < cnt) a_lo_row = *reinterpret_cast<const float4*>(sV + ea_ * VW + mgrp * 32 + 4 * gid);
+        if (eb_ < cnt) a_hi_row = *reinterpret_cast<const float4*>(sV + eb_ * VW + mgrp * 32 + 4 * gid);
+        float2 bh0 = make_float2(0.f, 0.f), bh1 = bh0, bl0 = bh0, bl1 = bh0;
+        if (col_ok) {
+          const uint32_t rb0 = (uint32_t)(ea_ >> 3) * 128 + (uint32_t)(ea_ & 7) * 16;
+          const uint32_t rb1 = (uint32_t)(eb_ >> 3) * 128 + (uint32_t)(eb_ & 7) * 16;
+          bh0 = *reinterpret_cast<const float2*>(sAhi + cb + rb0);  // rows >= cnt are zero in the tiles
+          bh1 = *reinterpret_cast<const float2*>(sAhi + cb + rb1);
+          bl0 = *reinterpret_cast<const float2*>(sAlo + cb + rb0);
+          bl1 = *reinterpret_cast<const float2*>(sAlo + cb + rb1);
+        }
+        const float ar0[4] = {a_lo_row.x, a_lo_row.y, a_lo_row.z, a_lo_row.w};  // slot e0+tig
+        const float ar1[4] = {a_hi_row.x, a_hi_row.y, a_hi_row.z, a_hi_row.w};  // slot e0+tig+4
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          // fragment order: (row gid, k tig), (row gid+8, k tig), (row gid, k tig+4), (row gid+8, k tig+4)
+          const float av[4] = {ar0[2 * mi], ar0[2 * mi + 1], ar1[2 * mi], ar1[2 * mi + 1]};
+          float ah[4], al[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) { ah[u] = umma::tf32_hi(av[u]); al[u] = av[u] - ah[u]; }
-        }
-        const uint32_t rb0 = (uint32_t)((e0 + tig) >> 3) * 128 + (uint32_t)((e0 + tig) & 7) * 16;
-        const uint32_t rb1 = (uint32_t)((e0 + tig + 4) >> 3) * 128 + (uint32_t)((e0 + tig + 4) & 7) * 16;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (t < dw_nts) {
-            const int g = (dw_nt0 + t) * 8 + gid;  // B fragment column
-            const uint32_t cb = (uint32_t)(g >> 2) * (kTcRows * 16) + (uint32_t)(g & 3) * 4;
-            const float bh0 = *reinterpret_cast<const float*>(sAhi + cb + rb0);
-            const float bh1 = *reinterpret_cast<const float*>(sAhi + cb + rb1);
-            const float bl0 = *reinterpret_cast<const float*>(sAlo + cb + rb0);
-            const float bl1 = *reinterpret_cast<const float*>(sAlo + cb + rb1);
-            mma_tf32_16x8x8(dacc[t], ah, bh0, bh1);
-            mma_tf32_16x8x8(dacc[t], ah, bl0, bl1);
-            mma_tf32_16x8x8(dacc[t], al, bh0, bh1);
+          for (int ni = 0; ni < 2; ++ni) {
+            const float h0 = ni ? bh0.y : bh0.x, h1 = ni ? bh1.y : bh1.x;
+            const float l0 = ni ? bl0.y : bl0.x, l1 = ni ? bl1.y : bl1.x;
+            mma_tf32_16x8x8(dacc[2 * mi + ni], ah, h0, h1);
+            mma_tf32_16x8x8(dacc[2 * mi + ni], ah, l0, l1);
+            mma_tf32_16x8x8(dacc[2 * mi + ni], al, h0, h1);
           }
         }
       }
@@ -531,25 +528,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     k = nk; rd = nrd; buf ^= 1;
   }  // work items
 
-  if (MODE == CG_BWD_DST && dw_nts > 0) {
-    // C fragment: rows (channels) gid, gid+8; cols (k) 2*tig, 2*tig+1
+  if (MODE == CG_BWD_DST) {
+    // C fragment of tile (mi, ni): rows gid | gid+8 -> channels 2*mi | 2*mi+1 of this lane's quad,
+    // cols 2*tig | 2*tig+1 -> fragment columns, i.e. k = ngrp*16 + 2*(2*tig | 2*tig+1) + ni
     const int gid = lane >> 2, tig = lane & 3;
+    const int mgrp = warp & 3, ngrp = warp >> 2;
     float* part = p.dW_part + (size_t)blockIdx.x * G * W2;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (t < dw_nts) {
-        const int kc = (dw_nt0 + t) * 8 + 2 * tig;
-        const int ch = dw_mt * 16 + gid;
-        if (kc < G) {
-          part[(size_t)kc * W2 + ch] = dacc[t][0];
-          part[(size_t)kc * W2 + ch + 8] = dacc[t][2];
-        }
-        if (kc + 1 < G) {
-          part[(size_t)(kc + 1) * W2 + ch] = dacc[t][1];
-          part[(size_t)(kc + 1) * W2 + ch + 8] = dacc[t][3];
-        }
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int ch = mgrp * 32 + 4 * gid + 2 * mi;
+        const int k0 = ngrp * 16 + 2 * (2 * tig) + ni, k1 = ngrp * 16 + 2 * (2 * tig + 1) + ni;
+        const float* d = dacc[2 * mi + ni];
+        if (k0 < G) { part[(size_t)k0 * W2 + ch] = d[0]; part[(size_t)k0 * W2 + ch + 1] = d[2]; }
+        if (k1 < G) { part[(size_t)k1 * W2 + ch] = d[1]; part[(size_t)k1 * W2 + ch + 1] = d[3]; }
       }
-    }
   }
   cp_async_wait_all();
   umma::fence_before_sync();
