@@ -125,6 +125,41 @@ MDL_API int mdl_cgconv_bwd(const float* grad_out, const float* PQ, const float* 
                    int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
                    int32_t reduce, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- CFConv aggregate, PyG CFConv inside InteractionBlock as built at reference
+ * matdeeplearn/models/schnet.py:81 and called schnet.py:134-143:
+ *   out[i,:] = sum_{p in [ptr[i],ptr[i+1])} h[nbr[p],:] * w[eid[p],:]
+ * forward: ptr=dst_ptr, nbr=dst_src, eid=dst_eid, w = filter [E,F] in REFERENCE edge order;
+ * backward (dh): ptr=src_ptr, nbr = destination of each by-source position, eid = its edge id,
+ * h := grad_out.  eid/nbr may be NULL (identity). ---- */
+MDL_API int mdl_spmm_edge(const float* h, const float* w, const int32_t* ptr, const int32_t* nbr,
+                          const int32_t* eid, float* out, int64_t num_segments, int64_t width,
+                          void* stream);
+/* out[eid[p],:] = a[ia[p],:] * b[ib[p],:]  -- CFConv filter gradient dW = grad_out[dst] * h[src] */
+MDL_API int mdl_edge_mul(const float* a, const float* b, const int32_t* ia, const int32_t* ib,
+                         const int32_t* eid, float* out, int64_t num_edges, int64_t width, void* stream);
+
+/* ---- Megnet_EdgeModel's first Linear on cat[x[row], x[col], e, u[batch[row]]] (reference
+ * matdeeplearn/models/megnet.py:41-47) with the weight split column-wise:
+ *   out[e,:] = act(base[e,:] + A[ia[e],:] + B[ib[e],:] + U[ig[ia[e]],:] + bias)
+ * base = e W_e^T (edge-level GEMM by the caller), A = x W_src^T, B = x W_dst^T, U = u W_u^T;
+ * ia/ib = edge_index rows (int64, reference layout), ig = batch (int64). ---- */
+MDL_API int mdl_edge_gather_add(const float* base, const float* A, const float* B, const float* U,
+                                const int64_t* ia, const int64_t* ib, const int64_t* ig,
+                                const float* bias, float* out, int64_t num_edges, int64_t width,
+                                int32_t relu, void* stream);
+
+/* ---- NNConv message, PyG NNConv as built at reference matdeeplearn/models/mpnn.py:83-88,
+ * re-associated so that the [E, C*C] per-edge weight tensor is never formed:
+ *   XT[j,k,:] = x[j] . T[k]   (T = second edge-network Linear reshaped [K, C, O]; caller's GEMM)
+ *   m[e,:]    = sum_k hid[e,k] * XT[src(e),k,:] + XB[src(e),:]   (XB = x . reshape(bias2))
+ * by-source CSR: src_ptr [N+1], src_eid [E] = reference edge id of each position. ---- */
+MDL_API int mdl_nnconv_msg_fwd(const float* hid, const float* XT, const float* XB, const int32_t* src_ptr,
+                               const int32_t* src_eid, float* m, int64_t num_nodes, int32_t K, int32_t O,
+                               void* stream);
+MDL_API int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* dm, const int32_t* src_ptr,
+                               const int32_t* src_eid, float* dhid, float* dXT, float* dXB,
+                               int64_t num_nodes, int32_t K, int32_t O, void* stream);
+
 /* ---- development aid: 16 x uint64 device counters that receive per-phase cycle sums
  * (thread 0 of every CTA) from the tensor-core CGConv kernels; NULL disables. ---- */
 MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr);

@@ -35,6 +35,11 @@ SIGNATURES = {
     "mdl_cgconv_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mdl_cgconv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "mdl_cgconv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
+    "mdl_spmm_edge": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "mdl_edge_mul": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "mdl_edge_gather_add": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),
+    "mdl_nnconv_msg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
+    "mdl_nnconv_msg_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
 }

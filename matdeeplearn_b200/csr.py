@@ -15,7 +15,7 @@ from . import _lib
 
 class GraphCSR:
     __slots__ = ("N", "E", "B", "dst_ptr", "dst_src", "dst_dst", "dst_eid", "src_ptr",
-                 "src_slot", "inv_deg_dst", "inv_deg_src", "graph_ptr", "src_eid", "__weakref__")
+                 "src_slot", "inv_deg_dst", "inv_deg_src", "graph_ptr", "src_eid", "src_nbr", "__weakref__")
 
     @classmethod
     def from_coo(cls, edge_index, batch=None, num_nodes=None, num_graphs=None):
@@ -59,6 +59,7 @@ class GraphCSR:
             _lib.ptr(ws), ws_bytes, _lib.stream())
         _lib.check(rc, "mdl_csr_from_coo")
         self.src_eid = None
+        self.src_nbr = None
         if batch is not None:
             # let pools / scatter(x, batch) find the graph segments without a sort
             try:
@@ -85,6 +86,12 @@ class GraphCSR:
         except Exception:
             pass
         return out
+
+    def source_order_nbr(self):
+        """destination node of each by-source position (dst_dst[src_slot])."""
+        if self.src_nbr is None:
+            self.src_nbr = self.dst_dst[self.src_slot.long()].contiguous()
+        return self.src_nbr
 
     def source_order_eid(self):
         """reference edge id of each by-source position (dst_eid[src_slot])."""

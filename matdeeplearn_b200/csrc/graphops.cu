@@ -1,0 +1,269 @@
+// graphops.cu -- CSR graph primitives behind the SchNet / MPNN / MEGNet operator surface
+// (include/mdl_b200.h).  All are deterministic (segment-ordered sums, no atomics) and keep the
+// reference's edge order at the interface: `eid` arrays translate a CSR position to the
+// reference edge id, so edge-level tensors never need to be permuted in HBM.
+//
+//   spmm_edge      out[i]      = sum_{p in seg(i)} h[nbr(p)] (*) w[eid(p)]      CFConv aggregate
+//                                                                               (schnet.py:140 -> PyG CFConv)
+//   edge_mul       out[eid(p)] = a[ia(p)] (*) b[ib(p)]                           its filter gradient
+//   edge_gather_add out[e]     = act(base[e] + A[ia[e]] + B[ib[e]] + U[ig[e]] + bias)
+//                                                                               Megnet_EdgeModel's first
+//                                                                               Linear on cat[...] (megnet.py:41-47)
+//   nnconv_msg     m[eid(p)]   = sum_k hid[eid(p),k] * XT[j,k,:] + XB[j,:]       NNConv message, re-associated
+//                                                                               (mpnn.py:83-88 -> PyG NNConv)
+#include "common.cuh"
+
+namespace mdl {
+
+// ---- out[i,:] = sum_{p in [ptr[i],ptr[i+1])} h[nbr[p],:] * w[eid[p],:]   (warp per segment)
+__global__ void __launch_bounds__(256)
+k_spmm_edge(const float* __restrict__ h, const float* __restrict__ w, const int32_t* __restrict__ ptr,
+            const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid, float* __restrict__ out,
+            int64_t S, int width) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = width >> 2;  // float4 per row
+  for (int64_t s = warp; s < S; s += nwarps) {
+    const int lo = __ldg(ptr + s), hi = __ldg(ptr + s + 1);
+    for (int v0 = 0; v0 < nv; v0 += 32) {
+      const int v = v0 + lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < nv) {
+#pragma unroll 4
+        for (int p = lo; p < hi; ++p) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(h + (size_t)(nbr ? __ldg(nbr + p) : p) * width) + v);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(w + (size_t)(eid ? __ldg(eid + p) : p) * width) + v);
+          acc.x = fmaf(a.x, b.x, acc.x); acc.y = fmaf(a.y, b.y, acc.y);
+          acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);
+        }
+        *(reinterpret_cast<float4*>(out + (size_t)s * width) + v) = acc;
+      }
+    }
+  }
+}
+
+// ---- out[eid[p],:] = a[ia[p],:] * b[ib[p],:]   (warp per position)
+__global__ void __launch_bounds__(256)
+k_edge_mul(const float* __restrict__ a, const float* __restrict__ b, const int32_t* __restrict__ ia,
+           const int32_t* __restrict__ ib, const int32_t* __restrict__ eid, float* __restrict__ out,
+           int64_t E, int width) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = width >> 2;
+  for (int64_t p = warp; p < E; p += nwarps) {
+    const float4* ra = reinterpret_cast<const float4*>(a + (size_t)__ldg(ia + p) * width);
+    const float4* rb = reinterpret_cast<const float4*>(b + (size_t)__ldg(ib + p) * width);
+    float4* ro = reinterpret_cast<float4*>(out + (size_t)(eid ? __ldg(eid + p) : p) * width);
+    for (int v = lane; v < nv; v += 32) {
+      const float4 x = __ldg(ra + v), y = __ldg(rb + v);
+      ro[v] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+    }
+  }
+}
+
+// ---- out[e,:] = act(base[e,:] + A[ia[e],:] + B[ib[e],:] + U[ig[e],:] + bias)   (warp per edge)
+__global__ void __launch_bounds__(256)
+k_edge_gather_add(const float* __restrict__ base, const float* __restrict__ A, const float* __restrict__ B,
+                  const float* __restrict__ U, const int64_t* __restrict__ ia, const int64_t* __restrict__ ib,
+                  const int64_t* __restrict__ ig, const float* __restrict__ bias, float* __restrict__ out,
+                  int64_t E, int width, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = width >> 2;
+  for (int64_t e = warp; e < E; e += nwarps) {
+    const int64_t ja = ia[e], jb = ib[e];
+    const int64_t jg = U ? (ig ? ig[ja] : 0) : 0;  // graph of the edge = graph of its source node
+    for (int v = lane; v < nv; v += 32) {
+      float4 s = __ldg(reinterpret_cast<const float4*>(base + (size_t)e * width) + v);
+      const float4 x = __ldg(reinterpret_cast<const float4*>(A + (size_t)ja * width) + v);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(B + (size_t)jb * width) + v);
+      s.x += x.x + y.x; s.y += x.y + y.y; s.z += x.z + y.z; s.w += x.w + y.w;
+      if (U) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(U + (size_t)jg * width) + v);
+        s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w;
+      }
+      if (bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + v);
+        s.x += bb.x; s.y += bb.y; s.z += bb.z; s.w += bb.w;
+      }
+      if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+      *(reinterpret_cast<float4*>(out + (size_t)e * width) + v) = s;
+    }
+  }
+}
+
+// ---- NNConv message, by-source order.  One CTA per source node j: XT[j] ([K,O], the node's
+// features already contracted with the edge-network's output weights) is staged in smem once
+// and reused by every out-edge of j.
+//   fwd: m[eid(p), o] = sum_k hid[eid(p), k] * XT[j, k, o] + XB[j, o]
+//   bwd: dhid[eid(p), k] = sum_o XT[j, k, o] * dm[eid(p), o]
+//        dXT[j, k, o]    = sum_p hid[eid(p), k] * dm[eid(p), o]
+//        dXB[j, o]       = sum_p dm[eid(p), o]
+constexpr int kNnChunk = 16;   // edges staged per pass in the backward kernel
+constexpr int kNnMaxAcc = 40;  // dXT entries per thread (K*O <= 40*256)
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+k_nnconv_msg(const float* __restrict__ hid, const float* __restrict__ XT, const float* __restrict__ XB,
+             const float* __restrict__ dm, const int32_t* __restrict__ ptr, const int32_t* __restrict__ eid,
+             float* __restrict__ m, float* __restrict__ dhid, float* __restrict__ dXT,
+             float* __restrict__ dXB, int64_t N, int K, int O) {
+  extern __shared__ __align__(16) float sm[];
+  const int OS = O + 1;                     // padded row: conflict-free both along k and along o
+  float* sXT = sm;                          // [K][OS]
+  float* sH = sm + K * OS;                  // [kNnChunk][K]   hidden rows of the staged edges
+  float* sD = sH + kNnChunk * K;            // [kNnChunk][O]   dm rows (bwd)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KO = K * O;
+  for (int64_t j = blockIdx.x; j < N; j += gridDim.x) {
+    const int lo = __ldg(ptr + j), hi = __ldg(ptr + j + 1);
+    __syncthreads();
+    for (int i = tid; i < KO; i += blockDim.x) {
+      const int k = i / O, o = i - k * O;
+      sXT[k * OS + o] = __ldg(XT + (size_t)j * KO + i);
+    }
+    float acc[kNnMaxAcc];
+    if (BWD) {
+#pragma unroll
+      for (int r = 0; r < kNnMaxAcc; ++r) acc[r] = 0.0f;
+    }
+    float accb = 0.0f;  // dXB entry of thread tid (tid < O)
+    for (int c0 = lo; c0 < hi; c0 += kNnChunk) {
+      const int nc = min(kNnChunk, hi - c0);
+      __syncthreads();
+      for (int i = tid; i < nc * K; i += blockDim.x) {
+        const int r = i / K, k = i - r * K;
+        sH[r * K + k] = __ldg(hid + (size_t)__ldg(eid + c0 + r) * K + k);
+      }
+      if (BWD) {
+        for (int i = tid; i < nc * O; i += blockDim.x) {
+          const int r = i / O, o = i - r * O;
+          sD[r * O + o] = __ldg(dm + (size_t)__ldg(eid + c0 + r) * O + o);
+        }
+      }
+      __syncthreads();
+      if (!BWD) {
+        for (int r = warp; r < nc; r += 8) {
+          const size_t e = (size_t)__ldg(eid + c0 + r);
+          for (int o = lane; o < O; o += 32) {
+            float a = __ldg(XB + (size_t)j * O + o);
+            for (int k = 0; k < K; ++k) a = fmaf(sH[r * K + k], sXT[k * OS + o], a);
+            m[e * O + o] = a;
+          }
+        }
+      } else {
+        for (int r = warp; r < nc; r += 8) {  // dhid: lanes over k
+          const size_t e = (size_t)__ldg(eid + c0 + r);
+          for (int k = lane; k < K; k += 32) {
+            float a = 0.0f;
+            for (int o = 0; o < O; ++o) a = fmaf(sXT[k * OS + o], sD[r * O + o], a);
+            dhid[e * K + k] = a;
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < kNnMaxAcc; ++rr) {  // dXT entries owned by this thread
+          const int i = tid + rr * 256;
+          if (i < KO) {
+            const int k = i / O, o = i - k * O;
+            float a = acc[rr];
+            for (int r = 0; r < nc; ++r) a = fmaf(sH[r * K + k], sD[r * O + o], a);
+            acc[rr] = a;
+          }
+        }
+        if (tid < O)
+          for (int r = 0; r < nc; ++r) accb += sD[r * O + tid];
+      }
+    }
+    if (BWD) {
+#pragma unroll
+      for (int rr = 0; rr < kNnMaxAcc; ++rr) {
+        const int i = tid + rr * 256;
+        if (i < KO) dXT[(size_t)j * KO + i] = acc[rr];
+      }
+      for (int o = tid; o < O; o += blockDim.x) {
+        // O > 256 never happens for the supported sizes; accb covers tid < O <= 256
+        dXB[(size_t)j * O + o] = accb;
+      }
+    }
+  }
+}
+
+static int warp_grid(int64_t items) {
+  int64_t blocks = ceil_div<int64_t>(items, 8);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  return (int)(blocks > 0 ? blocks : 1);
+}
+
+}  // namespace mdl
+
+using namespace mdl;
+
+extern "C" int mdl_spmm_edge(const float* h, const float* w, const int32_t* ptr, const int32_t* nbr,
+                             const int32_t* eid, float* out, int64_t S, int64_t width, void* stream) {
+  MDL_REQUIRE(S >= 0 && width > 0 && width % 4 == 0, "spmm_edge: width must be a multiple of 4");
+  if (S == 0) return MDL_OK;
+  MDL_REQUIRE(h && w && ptr && out, "spmm_edge: null pointer");
+  k_spmm_edge<<<warp_grid(S), 256, 0, as_stream(stream)>>>(h, w, ptr, nbr, eid, out, S, (int)width);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+extern "C" int mdl_edge_mul(const float* a, const float* b, const int32_t* ia, const int32_t* ib,
+                            const int32_t* eid, float* out, int64_t E, int64_t width, void* stream) {
+  MDL_REQUIRE(E >= 0 && width > 0 && width % 4 == 0, "edge_mul: width must be a multiple of 4");
+  if (E == 0) return MDL_OK;
+  MDL_REQUIRE(a && b && ia && ib && out, "edge_mul: null pointer");
+  k_edge_mul<<<warp_grid(E), 256, 0, as_stream(stream)>>>(a, b, ia, ib, eid, out, E, (int)width);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+extern "C" int mdl_edge_gather_add(const float* base, const float* A, const float* B, const float* U,
+                                   const int64_t* ia, const int64_t* ib, const int64_t* ig,
+                                   const float* bias, float* out, int64_t E, int64_t width,
+                                   int32_t relu, void* stream) {
+  MDL_REQUIRE(E >= 0 && width > 0 && width % 4 == 0, "edge_gather_add: width must be a multiple of 4");
+  if (E == 0) return MDL_OK;
+  MDL_REQUIRE(base && A && B && ia && ib && out, "edge_gather_add: null pointer");
+  k_edge_gather_add<<<warp_grid(E), 256, 0, as_stream(stream)>>>(base, A, B, U, ia, ib, ig, bias, out, E,
+                                                                   (int)width, relu);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+static int nnconv_launch(bool bwd, const float* hid, const float* XT, const float* XB, const float* dm,
+                         const int32_t* ptr, const int32_t* eid, float* m, float* dhid, float* dXT,
+                         float* dXB, int64_t N, int32_t K, int32_t O, void* stream) {
+  MDL_REQUIRE(N >= 0 && K > 0 && O > 0, "nnconv_msg: bad shape");
+  if (N == 0) return MDL_OK;
+  size_t smem = ((size_t)K * (O + 1) + (size_t)kNnChunk * (K + O)) * 4;
+  MDL_REQUIRE(smem <= 200 * 1024 && (int64_t)K * O <= (int64_t)kNnMaxAcc * 256 && O <= 256,
+              "nnconv_msg: hidden %d x out %d outside the supported range", K, O);
+  int grid = (int)std::min<int64_t>(N, (int64_t)kNumSMs * 4);
+  if (bwd) {
+    MDL_CUDA(cudaFuncSetAttribute(k_nnconv_msg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nnconv_msg<true><<<grid, 256, smem, as_stream(stream)>>>(hid, XT, XB, dm, ptr, eid, m, dhid, dXT, dXB, N, K, O);
+  } else {
+    MDL_CUDA(cudaFuncSetAttribute(k_nnconv_msg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nnconv_msg<false><<<grid, 256, smem, as_stream(stream)>>>(hid, XT, XB, dm, ptr, eid, m, dhid, dXT, dXB, N, K, O);
+  }
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+extern "C" int mdl_nnconv_msg_fwd(const float* hid, const float* XT, const float* XB, const int32_t* src_ptr,
+                                  const int32_t* src_eid, float* m, int64_t N, int32_t K, int32_t O,
+                                  void* stream) {
+  MDL_REQUIRE(hid && XT && XB && src_ptr && src_eid && m, "nnconv_msg_fwd: null pointer");
+  return nnconv_launch(false, hid, XT, XB, nullptr, src_ptr, src_eid, m, nullptr, nullptr, nullptr, N, K, O, stream);
+}
+
+extern "C" int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* dm, const int32_t* src_ptr,
+                                  const int32_t* src_eid, float* dhid, float* dXT, float* dXB, int64_t N,
+                                  int32_t K, int32_t O, void* stream) {
+  MDL_REQUIRE(hid && XT && dm && src_ptr && src_eid && dhid && dXT && dXB, "nnconv_msg_bwd: null pointer");
+  return nnconv_launch(true, hid, XT, nullptr, dm, src_ptr, src_eid, nullptr, dhid, dXT, dXB, N, K, O, stream);
+}

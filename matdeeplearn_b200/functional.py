@@ -131,3 +131,124 @@ class CGConvFn(torch.autograd.Function):
 
 def cgconv(x, w_f, b_f, w_s, b_s, ea_slots, csr, reduce="mean"):
     return CGConvFn.apply(x, w_f, b_f, w_s, b_s, ea_slots, csr, reduce)
+
+
+# ----------------------------------------------------------------------------
+# CFConv aggregate:  out[i] = sum_{e: dst(e)=i} h[src(e)] * W[e]
+# ----------------------------------------------------------------------------
+class CFConvAggFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, W, csr: GraphCSR):
+        lib = _lib.load()
+        h, W = h.contiguous(), W.contiguous()
+        N, F_ = h.shape
+        out = torch.empty_like(h)
+        rc = lib.mdl_spmm_edge(_lib.ptr(h), _lib.ptr(W), _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src),
+                               _lib.ptr(csr.dst_eid), _lib.ptr(out), N, F_, _lib.stream())
+        _lib.check(rc, "mdl_spmm_edge")
+        ctx.save_for_backward(h, W)
+        ctx.csr = csr
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        h, W = ctx.saved_tensors
+        csr = ctx.csr
+        g = g.contiguous()
+        N, F_ = h.shape
+        dh = dW = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty_like(h)
+            rc = lib.mdl_spmm_edge(_lib.ptr(g), _lib.ptr(W), _lib.ptr(csr.src_ptr),
+                                   _lib.ptr(csr.source_order_nbr()), _lib.ptr(csr.source_order_eid()),
+                                   _lib.ptr(dh), N, F_, _lib.stream())
+            _lib.check(rc, "mdl_spmm_edge(bwd)")
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            rc = lib.mdl_edge_mul(_lib.ptr(g), _lib.ptr(h), _lib.ptr(csr.dst_dst), _lib.ptr(csr.dst_src),
+                                  _lib.ptr(csr.dst_eid), _lib.ptr(dW), csr.E, F_, _lib.stream())
+            _lib.check(rc, "mdl_edge_mul")
+        return dh, dW, None
+
+
+def cfconv_aggregate(h, W, csr):
+    return CFConvAggFn.apply(h, W, csr)
+
+
+# ----------------------------------------------------------------------------
+# NNConv message:  m[e] = sum_k hid[e,k] * XT[src(e),k,:] + XB[src(e),:]
+# ----------------------------------------------------------------------------
+class NNConvMsgFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hid, XT, XB, csr: GraphCSR):
+        lib = _lib.load()
+        hid, XT, XB = hid.contiguous(), XT.contiguous(), XB.contiguous()
+        E, K = hid.shape
+        N, O = XB.shape
+        assert XT.shape == (N, K * O)
+        m = torch.empty((E, O), dtype=hid.dtype, device=hid.device)
+        rc = lib.mdl_nnconv_msg_fwd(_lib.ptr(hid), _lib.ptr(XT), _lib.ptr(XB), _lib.ptr(csr.src_ptr),
+                                    _lib.ptr(csr.source_order_eid()), _lib.ptr(m), N, K, O, _lib.stream())
+        _lib.check(rc, "mdl_nnconv_msg_fwd")
+        ctx.save_for_backward(hid, XT)
+        ctx.csr, ctx.dims = csr, (N, K, O)
+        return m
+
+    @staticmethod
+    def backward(ctx, dm):
+        lib = _lib.load()
+        hid, XT = ctx.saved_tensors
+        csr = ctx.csr
+        N, K, O = ctx.dims
+        dm = dm.contiguous()
+        dhid = torch.empty_like(hid)
+        dXT = torch.empty_like(XT)
+        dXB = torch.empty((N, O), dtype=hid.dtype, device=hid.device)
+        rc = lib.mdl_nnconv_msg_bwd(_lib.ptr(hid), _lib.ptr(XT), _lib.ptr(dm), _lib.ptr(csr.src_ptr),
+                                    _lib.ptr(csr.source_order_eid()), _lib.ptr(dhid), _lib.ptr(dXT),
+                                    _lib.ptr(dXB), N, K, O, _lib.stream())
+        _lib.check(rc, "mdl_nnconv_msg_bwd")
+        return dhid, dXT, dXB, None
+
+
+def nnconv_message(hid, XT, XB, csr):
+    return NNConvMsgFn.apply(hid, XT, XB, csr)
+
+
+# ----------------------------------------------------------------------------
+# MEGNet edge update, first Linear on cat[x[row], x[col], e, u[batch[row]]] with split weights
+# ----------------------------------------------------------------------------
+class EdgeGatherAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base, A, B, U, bias, edge_index, batch, csr: GraphCSR, relu):
+        lib = _lib.load()
+        base, A, B = base.contiguous(), A.contiguous(), B.contiguous()
+        U = U.contiguous() if U is not None else None
+        E, D = base.shape
+        out = torch.empty_like(base)
+        row, col = edge_index[0].contiguous(), edge_index[1].contiguous()
+        rc = lib.mdl_edge_gather_add(_lib.ptr(base), _lib.ptr(A), _lib.ptr(B), _lib.ptr(U), _lib.ptr(row),
+                                     _lib.ptr(col), _lib.ptr(batch), _lib.ptr(bias), _lib.ptr(out), E, D,
+                                     1 if relu else 0, _lib.stream())
+        _lib.check(rc, "mdl_edge_gather_add")
+        ctx.save_for_backward(out if relu else None)
+        ctx.csr, ctx.relu = csr, relu
+        ctx.has = (U is not None, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        csr = ctx.csr
+        dpre = (g * (out > 0)) if ctx.relu else g
+        dpre = dpre.contiguous()
+        dA = segment_reduce(dpre, csr.src_ptr, csr.source_order_eid(), "sum")   # edges leaving each node
+        dB = segment_reduce(dpre, csr.dst_ptr, csr.dst_eid, "sum")              # edges entering each node
+        dU = segment_reduce(dA, csr.graph_ptr, None, "sum") if ctx.has[0] else None
+        dbias = dpre.sum(0) if ctx.has[1] else None
+        return dpre, dA, dB, dU, dbias, None, None, None, None
+
+
+def edge_gather_add(base, A, B, U, bias, edge_index, batch, csr, relu):
+    return EdgeGatherAddFn.apply(base, A, B, U, bias, edge_index, batch, csr, relu)

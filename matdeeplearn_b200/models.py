@@ -99,3 +99,206 @@ class CGCNN(_ConvStackModel):
                 h = self.bn_list[i](h)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return self._readout(h, data)
+
+
+class SchNet(_ConvStackModel):
+    """reference matdeeplearn/models/schnet.py:16-172"""
+
+    def __init__(self, data, dim1=64, dim2=64, dim3=64, cutoff=8, pre_fc_count=1, gc_count=3,
+                 post_fc_count=1, pool="global_mean_pool", pool_order="early", batch_norm="True",
+                 batch_track_stats="True", act="relu", dropout_rate=0.0, **kwargs):
+        super().__init__(data, dim1, dim2, pre_fc_count, gc_count, post_fc_count, pool,
+                         pool_order, batch_norm, batch_track_stats, act, dropout_rate)
+        for _ in range(gc_count):
+            self.conv_list.append(mnn.InteractionBlock(self.gc_dim, data.num_edge_features, dim3, cutoff))
+            self._add_bn()
+
+    def forward(self, data):
+        csr = _prepare(data)
+        h = self._embed(data)
+        for i, conv in enumerate(self.conv_list):
+            h = h + conv(h, data.edge_index, data.edge_weight, data.edge_attr, csr=csr)  # residual outside the block
+            if self.batch_norm == "True":
+                h = self.bn_list[i](h)
+            h = F.dropout(h, p=self.dropout_rate, training=self.training)
+        return self._readout(h, data)
+
+
+class MPNN(_ConvStackModel):
+    """reference matdeeplearn/models/mpnn.py:17-188"""
+
+    def __init__(self, data, dim1=64, dim2=64, dim3=64, pre_fc_count=1, gc_count=3, post_fc_count=1,
+                 pool="global_mean_pool", pool_order="early", batch_norm="True",
+                 batch_track_stats="True", act="relu", dropout_rate=0.0, **kwargs):
+        super().__init__(data, dim1, dim2, pre_fc_count, gc_count, post_fc_count, pool,
+                         pool_order, batch_norm, batch_track_stats, act, dropout_rate)
+        g = self.gc_dim
+        self.gru_list = tnn.ModuleList()
+        for _ in range(gc_count):
+            edge_net = tnn.Sequential(tnn.Linear(data.num_edge_features, dim3), tnn.ReLU(),
+                                      tnn.Linear(dim3, g * g))
+            self.conv_list.append(mnn.NNConv(g, g, edge_net, aggr="mean"))
+            self.gru_list.append(tnn.GRU(g, g))
+            self._add_bn()
+
+    def forward(self, data):
+        csr = _prepare(data)
+        out = self._embed(data)
+        hidden = out.unsqueeze(0)          # GRU state threads through all layers (mpnn.py:141-144)
+        for i, conv in enumerate(self.conv_list):
+            m = conv(out, data.edge_index, data.edge_attr, csr=csr)
+            if self.batch_norm == "True":
+                m = self.bn_list[i](m)
+            m = self._activation(m)
+            m = F.dropout(m, p=self.dropout_rate, training=self.training)
+            out, hidden = self.gru_list[i](m.unsqueeze(0), hidden)
+            out = out.squeeze(0)
+        return self._readout(out, data)
+
+
+# ---------------------------------------------------------------------------- MEGNet
+class _MegnetStack(tnn.Module):
+    """(Linear -> act -> BatchNorm -> dropout) x (fc_layers + 1), reference megnet.py:28-56."""
+
+    def __init__(self, first_in, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers, name):
+        super().__init__()
+        self.act, self.batch_norm, self.dropout_rate = act, batch_norm, dropout_rate
+        # reference quirk: MEGNet passes a bool here and compares it with the string "False"
+        track = not (batch_track_stats == "False")
+        self._name = name
+        setattr(self, name, tnn.ModuleList(
+            tnn.Linear(first_in if i == 0 else dim, dim) for i in range(fc_layers + 1)))
+        self.bn_list = tnn.ModuleList(
+            tnn.BatchNorm1d(dim, track_running_stats=track) for _ in range(fc_layers + 1)
+        ) if batch_norm == "True" else tnn.ModuleList()
+
+    def _run(self, h, first_done=False):
+        layers = getattr(self, self._name)
+        for i, lin in enumerate(layers):
+            if not (i == 0 and first_done):
+                h = getattr(F, self.act)(lin(h))
+            if self.batch_norm == "True":
+                h = self.bn_list[i](h)
+            h = F.dropout(h, p=self.dropout_rate, training=self.training)
+        return h
+
+
+class Megnet_EdgeModel(_MegnetStack):
+    def __init__(self, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers=2):
+        super().__init__(dim * 4, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers, "edge_mlp")
+        self.dim = dim
+
+    def forward(self, src, dest, edge_attr, u, batch):      # PyG MetaLayer call convention
+        return self._run(torch.cat([src, dest, edge_attr, u[batch]], dim=1))
+
+    def forward_fused(self, x, edge_index, edge_attr, u, batch):
+        """Linear(cat[x[row], x[col], e, u[batch[row]]]) = x W_s^T [row] + x W_d^T [col] + e W_e^T
+        + u W_u^T [batch[row]] + b : three node/graph-level GEMMs, one edge-level GEMM, one fused
+        gather-add(-ReLU) kernel; the [E, 4D] concatenation never exists."""
+        D = self.dim
+        lin = self.edge_mlp[0]
+        W = lin.weight
+        A = x @ W[:, :D].t()
+        B = x @ W[:, D:2 * D].t()
+        base = edge_attr @ W[:, 2 * D:3 * D].t()
+        U = u @ W[:, 3 * D:].t()
+        csr = csr_for(edge_index, batch, num_nodes=x.shape[0], num_graphs=u.shape[0])
+        relu = self.act == "relu"
+        h = MF_edge_gather_add(base, A, B, U, lin.bias, edge_index, batch, csr, relu)
+        if not relu:
+            h = getattr(F, self.act)(h)
+        return self._run(h, first_done=True)
+
+
+class Megnet_NodeModel(_MegnetStack):
+    def __init__(self, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers=2):
+        super().__init__(dim * 3, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers, "node_mlp")
+
+    def forward(self, x, edge_index, edge_attr, u, batch):
+        v_e = mnn.scatter_mean(edge_attr, edge_index[0, :], dim=0)     # by SOURCE node (megnet.py:86)
+        return self._run(torch.cat([x, v_e, u[batch]], dim=1))
+
+
+class Megnet_GlobalModel(_MegnetStack):
+    def __init__(self, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers=2):
+        super().__init__(dim * 3, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers, "global_mlp")
+
+    def forward(self, x, edge_index, edge_attr, u, batch):
+        u_e = mnn.scatter_mean(edge_attr, edge_index[0, :], dim=0)
+        u_e = mnn.scatter_mean(u_e, batch, dim=0)
+        u_v = mnn.scatter_mean(x, batch, dim=0)
+        return self._run(torch.cat([u_e, u_v, u], dim=1))
+
+
+def MF_edge_gather_add(*args):
+    from . import functional as MF
+    return MF.edge_gather_add(*args)
+
+
+class MEGNet(tnn.Module):
+    """reference matdeeplearn/models/megnet.py:150-371"""
+
+    def __init__(self, data, dim1=64, dim2=64, dim3=64, pre_fc_count=1, gc_count=3, gc_fc_count=2,
+                 post_fc_count=1, pool="global_mean_pool", pool_order="early", batch_norm="True",
+                 batch_track_stats="True", act="relu", dropout_rate=0.0, **kwargs):
+        super().__init__()
+        if gc_count <= 0:
+            raise AssertionError("Need at least 1 GC layer")
+        if pool == "set2set":
+            raise NotImplementedError("Set2Set readout is outside the engine's scope (SURVEY.md 8f)")
+        track = not (batch_track_stats == "False")
+        self.batch_norm, self.pool, self.act = batch_norm, pool, act
+        self.pool_order, self.dropout_rate = pool_order, dropout_rate
+        self.pool_reduce = {"global_mean_pool": "mean", "global_max_pool": "max",
+                            "global_sum_pool": "sum"}.get(pool)   # reference leaves add_pool undefined
+        gc_dim = dim1 if pre_fc_count > 0 else data.num_features
+        self.pre_lin_list = tnn.ModuleList(
+            tnn.Linear(data.num_features if i == 0 else dim1, dim1) for i in range(pre_fc_count))
+
+        def embed(n_in):
+            return tnn.Sequential(tnn.Linear(n_in, dim3), tnn.ReLU(), tnn.Linear(dim3, dim3), tnn.ReLU())
+
+        self.e_embed_list, self.x_embed_list = tnn.ModuleList(), tnn.ModuleList()
+        self.u_embed_list, self.conv_list = tnn.ModuleList(), tnn.ModuleList()
+        self.bn_list = tnn.ModuleList()
+        for i in range(gc_count):
+            self.e_embed_list.append(embed(data.num_edge_features if i == 0 else dim3))
+            self.x_embed_list.append(embed(gc_dim if i == 0 else dim3))
+            self.u_embed_list.append(embed(data[0].u.shape[1] if i == 0 else dim3))
+            args = (dim3, act, batch_norm, track, dropout_rate, gc_fc_count)
+            self.conv_list.append(mnn.MetaLayer(Megnet_EdgeModel(*args), Megnet_NodeModel(*args),
+                                                Megnet_GlobalModel(*args)))
+        post_in = dim3 * 3 if pool_order == "early" else dim3
+        self.post_lin_list = tnn.ModuleList(
+            tnn.Linear(post_in if i == 0 else dim2, dim2) for i in range(post_fc_count))
+        self.lin_out = tnn.Linear(dim2 if post_fc_count > 0 else post_in, _target_dim(data))
+
+    def forward(self, data):
+        _prepare(data)
+        act = getattr(F, self.act)
+        h = data.x
+        for lin in self.pre_lin_list:
+            h = act(lin(h))
+        x, e, u = h, data.edge_attr, data.u
+        for i, block in enumerate(self.conv_list):
+            e_t, x_t, u_t = self.e_embed_list[i](e), self.x_embed_list[i](x), self.u_embed_list[i](u)
+            x_o, e_o, u_o = block(x_t, data.edge_index, e_t, u_t, data.batch)
+            if i == 0:   # first block: residual onto the embedded inputs (megnet.py:313-315)
+                x, e, u = x_o + x_t, e_o + e_t, u_o + u_t
+            else:        # later blocks: onto the running state (megnet.py:334-336)
+                x, e, u = x_o + x, e_o + e, u_o + u
+        if self.pool_order == "early":
+            x_pool = mnn.scatter(x, data.batch, dim=0, reduce=self.pool_reduce)
+            e_pool = mnn.scatter(e, data.edge_index[0, :], dim=0, reduce=self.pool_reduce)
+            e_pool = mnn.scatter(e_pool, data.batch, dim=0, reduce=self.pool_reduce)
+            out = torch.cat([x_pool, e_pool, u], dim=1)
+            for lin in self.post_lin_list:
+                out = act(lin(out))
+            out = self.lin_out(out)
+        else:
+            out = x
+            for lin in self.post_lin_list:
+                out = act(lin(out))
+            out = self.lin_out(out)
+            out = getattr(mnn, self.pool)(out, data.batch)
+        return out.view(-1) if out.shape[1] == 1 else out

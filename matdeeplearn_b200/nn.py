@@ -129,3 +129,150 @@ class CGConv(nn.Module):
         ea = csr.to_slots(edge_attr)
         return MF.cgconv(x, self.lin_f.weight, self.lin_f.bias, self.lin_s.weight, self.lin_s.bias,
                          ea, csr, _AGGR[self.aggr])
+
+
+# ----------------------------------------------------------------------------
+# SchNet interaction (torch_geometric.nn.models.schnet.InteractionBlock / CFConv)
+# ----------------------------------------------------------------------------
+class ShiftedSoftplus(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.shift = math.log(2.0)
+
+    def forward(self, x):
+        return F.softplus(x) - self.shift
+
+
+class CFConv(nn.Module):
+    """PyG CFConv: lin2( sum_j lin1(x)_j * (nn(e_ij) * C(d_ij)) ), C = cosine cutoff.
+    The filter MLP runs as dense edge-level GEMMs; gather * filter -> destination sum is the
+    fused CSR kernel (no [E,F] message tensor, no atomics)."""
+
+    def __init__(self, in_channels, out_channels, num_filters, mlp, cutoff):
+        super().__init__()
+        self.lin1 = nn.Linear(in_channels, num_filters, bias=False)
+        self.lin2 = nn.Linear(num_filters, out_channels)
+        self.nn = mlp
+        self.cutoff = cutoff
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.lin1.weight)
+        nn.init.xavier_uniform_(self.lin2.weight)
+        self.lin2.bias.data.fill_(0)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr, csr: GraphCSR | None = None):
+        _require_cuda(x, "CFConv")
+        if csr is None:
+            csr = csr_for(edge_index, num_nodes=x.shape[0])
+        C = 0.5 * (torch.cos(edge_weight * math.pi / self.cutoff) + 1.0)
+        W = self.nn(edge_attr) * C.view(-1, 1)          # [E, F], reference edge order
+        h = self.lin1(x)
+        agg = MF.cfconv_aggregate(h, W, csr)
+        return self.lin2(agg)
+
+
+class InteractionBlock(nn.Module):
+    """Same constructor / parameters as PyG's (reference schnet.py:81)."""
+
+    def __init__(self, hidden_channels, num_gaussians, num_filters, cutoff):
+        super().__init__()
+        self.mlp = nn.Sequential(
+            nn.Linear(num_gaussians, num_filters),
+            ShiftedSoftplus(),
+            nn.Linear(num_filters, num_filters),
+        )
+        self.conv = CFConv(hidden_channels, hidden_channels, num_filters, self.mlp, cutoff)
+        self.act = ShiftedSoftplus()
+        self.lin = nn.Linear(hidden_channels, hidden_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.mlp[0].weight)
+        self.mlp[0].bias.data.fill_(0)
+        nn.init.xavier_uniform_(self.mlp[2].weight)
+        self.mlp[2].bias.data.fill_(0)
+        self.conv.reset_parameters()
+        nn.init.xavier_uniform_(self.lin.weight)
+        self.lin.bias.data.fill_(0)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr, csr: GraphCSR | None = None):
+        x = self.conv(x, edge_index, edge_weight, edge_attr, csr=csr)
+        return self.lin(self.act(x))
+
+
+# ----------------------------------------------------------------------------
+# NNConv (edge-conditioned convolution), reference mpnn.py:83-88
+# ----------------------------------------------------------------------------
+class NNConv(nn.Module):
+    """x_i' = x_i W_root + b + aggr_j x_j . reshape(nn(e_ij), [C_in, C_out]).
+
+    When `nn` ends in a Linear (the reference's Sequential(Linear, ReLU, Linear)), the per-edge
+    [C_in, C_out] weight is never formed: with hid = nn[:-1](e) and T = last weight reshaped
+    [K, C_in, C_out],  x_j . Theta_e = sum_k hid_e[k] * (x_j . T[k]) + x_j . B2, and the per-node
+    products x_j . T[k] are one dense GEMM shared by all out-edges of j."""
+
+    def __init__(self, in_channels, out_channels, nn_module, aggr="add", root_weight=True, bias=True):
+        super().__init__()
+        if aggr not in _AGGR:
+            raise NotImplementedError(aggr)
+        self.in_channels, self.out_channels, self.aggr = in_channels, out_channels, aggr
+        self.nn = nn_module
+        self.lin = nn.Linear(in_channels, out_channels, bias=False) if root_weight else None
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        if self.lin is not None:
+            bound = 1.0 / math.sqrt(in_channels)
+            nn.init.uniform_(self.lin.weight, -bound, bound)
+
+    def forward(self, x, edge_index, edge_attr, csr: GraphCSR | None = None):
+        _require_cuda(x, "NNConv")
+        if csr is None:
+            csr = csr_for(edge_index, num_nodes=x.shape[0])
+        Ci, Co = self.in_channels, self.out_channels
+        last = self.nn[-1] if isinstance(self.nn, nn.Sequential) and isinstance(self.nn[-1], nn.Linear) else None
+        if last is None:
+            raise NotImplementedError("NNConv: edge network must end in a Linear (as the reference's does)")
+        hid = edge_attr
+        for layer in list(self.nn)[:-1]:
+            hid = layer(hid)                                   # [E, K] dense edge-level GEMM + act
+        K = hid.shape[1]
+        # last.weight [Ci*Co, K]: Theta_e[i,o] = sum_k W[i*Co+o, k] hid[k] + b[i*Co+o]
+        Tm = last.weight.view(Ci, Co, K).permute(0, 2, 1).reshape(Ci, K * Co)   # x . Tm -> [N, K*Co]
+        XT = x @ Tm
+        XB = x @ last.bias.view(Ci, Co) if last.bias is not None else x.new_zeros(x.shape[0], Co)
+        m = MF.nnconv_message(hid, XT, XB, csr)                # [E, Co], reference edge order
+        out = MF.segment_reduce(m, csr.dst_ptr, csr.dst_eid, _AGGR[self.aggr])
+        if self.lin is not None:
+            out = out + self.lin(x)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
+# ----------------------------------------------------------------------------
+# MetaLayer (reference megnet.py:235-239)
+# ----------------------------------------------------------------------------
+class MetaLayer(nn.Module):
+    """PyG MetaLayer.  Edge models that define `forward_fused(x, edge_index, edge_attr, u, batch)`
+    (the engine's Megnet_EdgeModel does) are called that way, so x[row] / x[col] / u[batch[row]]
+    and their concatenation are never materialised; any other edge model gets PyG's call."""
+
+    def __init__(self, edge_model=None, node_model=None, global_model=None):
+        super().__init__()
+        self.edge_model = edge_model
+        self.node_model = node_model
+        self.global_model = global_model
+
+    def forward(self, x, edge_index, edge_attr=None, u=None, batch=None):
+        row, col = edge_index[0], edge_index[1]
+        if self.edge_model is not None:
+            if hasattr(self.edge_model, "forward_fused"):
+                edge_attr = self.edge_model.forward_fused(x, edge_index, edge_attr, u, batch)
+            else:
+                edge_attr = self.edge_model(x[row], x[col], edge_attr, u,
+                                            batch if batch is None else batch[row])
+        if self.node_model is not None:
+            x = self.node_model(x, edge_index, edge_attr, u, batch)
+        if self.global_model is not None:
+            u = self.global_model(x, edge_index, edge_attr, u, batch)
+        return x, edge_attr, u

@@ -1,0 +1,147 @@
+"""GPU parity of the four model families against the fixtures produced by the
+reference's own model files (tests/golden/make_golden.py; fp64, PyG ops bound to
+the oracle), and of the individual SchNet / NNConv / MEGNet operators against the
+fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.make_golden import MODEL_CFGS
+from tests.test_oracle_golden import _DS, load_batch, load_model_fixture
+from tests.util import assert_close, random_graph, contiguous_batch_vector
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _log(tag, got, ref):
+    import os
+    err = (got.detach().double().cpu() - ref.detach().double().cpu()).abs().max().item()
+    scale = ref.detach().abs().max().item()
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_errors.txt", "a") as f:
+        f.write(f"{tag}: max|err|={err:.3e} scale={scale:.3e} rel={err / max(scale, 1e-30):.3e}\n")
+
+
+@pytest.mark.parametrize("tag", list(MODEL_CFGS))
+def test_model_matches_reference_glue_fixture(tag):
+    from matdeeplearn_b200 import models as M
+    b = load_batch()
+    z, sd, grads = load_model_fixture(tag)
+    model = getattr(M, tag.split("_")[0])(_DS(b), **MODEL_CFGS[tag])
+    model.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
+    model = model.to(DEV).train()
+    gb = b.to(DEV)
+    out = model(gb)
+    ref = torch.from_numpy(z["out_train"])
+    _log(f"model {tag} out_train", out, ref)
+    assert_close(out, ref, rtol=1e-4, atol_rel=2e-5, what=f"{tag} forward (train)")
+    loss = torch.nn.functional.l1_loss(out, gb.y)
+    assert abs(loss.item() - float(z["loss"])) < 2e-5 * max(1.0, abs(float(z["loss"])))
+    loss.backward()
+    for name, p in model.named_parameters():
+        r = grads[name]
+        if r.numel() == 0:
+            continue
+        _log(f"model {tag} grad {name}", p.grad, r)
+        assert_close(p.grad, r, rtol=1e-3, atol_rel=5e-4, what=f"{tag} grad {name}")
+    model.eval()
+    with torch.no_grad():
+        ev = model(gb)
+    assert_close(ev, torch.from_numpy(z["out_eval"]), rtol=1e-4, atol_rel=5e-5, what=f"{tag} forward (eval)")
+
+
+def _graph(n, e, seed):
+    ei = random_graph(n, e, seed)
+    return ei, ei.shape[1]
+
+
+def test_interaction_block_matches_oracle():
+    import matdeeplearn_b200.nn as mnn
+    from oracle import pyg_ops as O
+    torch.manual_seed(0)
+    n, C, G, Fi = 300, 128, 50, 128
+    ei, E = _graph(n, 3000, 3)
+    x = torch.randn(n, C, dtype=torch.float64)
+    ea = torch.rand(E, G, dtype=torch.float64)
+    ew = torch.rand(E, dtype=torch.float64) * 8.0
+    ref_m = O.InteractionBlock(C, G, Fi, 8.0).double()
+    m = mnn.InteractionBlock(C, G, Fi, 8.0)
+    m.load_state_dict({k: v.float() for k, v in ref_m.state_dict().items()})
+    m = m.to(DEV)
+    xr = x.clone().requires_grad_(True)
+    ref = ref_m(xr, ei, ew, ea)
+    xg = x.float().to(DEV).requires_grad_(True)
+    got = m(xg, ei.to(DEV), ew.float().to(DEV), ea.float().to(DEV))
+    _log("InteractionBlock fwd", got, ref)
+    assert_close(got, ref, rtol=1e-5, atol_rel=5e-6, what="InteractionBlock fwd")
+    w = torch.randn_like(ref)
+    ref.backward(w)
+    got.backward(w.float().to(DEV))
+    assert_close(xg.grad, xr.grad, rtol=1e-4, atol_rel=2e-5, what="InteractionBlock dx")
+    for name, pr in ref_m.named_parameters():
+        pg = dict(m.named_parameters())[name]
+        _log(f"InteractionBlock d{name}", pg.grad, pr.grad)
+        assert_close(pg.grad, pr.grad, rtol=1e-4, atol_rel=2e-5, what=f"InteractionBlock d{name}")
+
+
+@pytest.mark.parametrize("C,K,G", [(64, 64, 50), (16, 20, 37), (100, 100, 50)])
+def test_nnconv_matches_oracle(C, K, G):
+    import matdeeplearn_b200.nn as mnn
+    from oracle import pyg_ops as O
+    torch.manual_seed(1)
+    n = 200
+    ei, E = _graph(n, 1500, 4)
+    x = torch.randn(n, C, dtype=torch.float64)
+    ea = torch.rand(E, G, dtype=torch.float64)
+
+    def net():
+        return torch.nn.Sequential(torch.nn.Linear(G, K), torch.nn.ReLU(), torch.nn.Linear(K, C * C))
+
+    ref_m = O.NNConv(C, C, net(), aggr="mean").double()
+    m = mnn.NNConv(C, C, net(), aggr="mean")
+    m.load_state_dict({k: v.float() for k, v in ref_m.state_dict().items()})
+    m = m.to(DEV)
+    xr = x.clone().requires_grad_(True)
+    ref = ref_m(xr, ei, ea)
+    xg = x.float().to(DEV).requires_grad_(True)
+    got = m(xg, ei.to(DEV), ea.float().to(DEV))
+    _log(f"NNConv fwd C={C}", got, ref)
+    assert_close(got, ref, rtol=1e-5, atol_rel=5e-6, what="NNConv fwd")
+    w = torch.randn_like(ref)
+    ref.backward(w)
+    got.backward(w.float().to(DEV))
+    assert_close(xg.grad, xr.grad, rtol=1e-4, atol_rel=2e-5, what="NNConv dx")
+    for name, pr in ref_m.named_parameters():
+        pg = dict(m.named_parameters())[name]
+        _log(f"NNConv d{name} C={C}", pg.grad, pr.grad)
+        assert_close(pg.grad, pr.grad, rtol=1e-4, atol_rel=2e-5, what=f"NNConv d{name}")
+
+
+def test_metalayer_fused_edge_model_equals_pyg_call_convention():
+    """forward_fused (split weights + gather-add kernel) == the PyG-style call on gathered,
+    concatenated inputs, for values and gradients."""
+    from matdeeplearn_b200 import models as M
+    torch.manual_seed(2)
+    n, D, B = 120, 32, 5
+    ei, E = _graph(n, 900, 5)
+    batch = contiguous_batch_vector(n, B, 6)
+    x = torch.randn(n, D)
+    e = torch.randn(E, D)
+    u = torch.randn(B, D)
+    model = M.Megnet_EdgeModel(D, "relu", "True", True, 0.0, 2).to(DEV).train()
+    xs = [t.to(DEV).requires_grad_(True) for t in (x, e, u)]
+    eid, bd = ei.to(DEV), batch.to(DEV)
+    out_f = model.forward_fused(xs[0], eid, xs[1], xs[2], bd)
+    g = torch.randn_like(out_f)
+    out_f.backward(g)
+    grads_f = [t.grad.clone() for t in xs] + [p.grad.clone() for p in model.parameters()]
+    for t in xs:
+        t.grad = None
+    model.zero_grad()
+    out_p = model(xs[0][eid[0]], xs[0][eid[1]], xs[1], xs[2], bd[eid[0]])
+    out_p.backward(g)
+    grads_p = [t.grad for t in xs] + [p.grad for p in model.parameters()]
+    assert_close(out_f, out_p, rtol=1e-5, atol_rel=2e-6, what="fused edge model fwd")
+    for a, b in zip(grads_f, grads_p):
+        assert_close(a, b, rtol=1e-4, atol_rel=2e-5, what="fused edge model grads")
