@@ -151,7 +151,10 @@ class MPNN(_ConvStackModel):
                 m = self.bn_list[i](m)
             m = self._activation(m)
             m = F.dropout(m, p=self.dropout_rate, training=self.training)
-            out, hidden = self.gru_list[i](m.unsqueeze(0), hidden)
+            # fp32 contract: keep cuDNN's RNN path off TF32 (the reference itself runs with cuDNN
+            # disabled under DDP, training/training.py:236)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                out, hidden = self.gru_list[i](m.unsqueeze(0), hidden)
             out = out.squeeze(0)
         return self._readout(out, data)
 
