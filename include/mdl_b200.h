@@ -109,7 +109,8 @@ MDL_API int mdl_segment_reduce_bwd(const float* grad_out, const int32_t* ptr, co
  * and We = [W_e of lin_f ; W_e of lin_s]  [2C, G].
  * fwd: out[i] = aggr_{s: dst=i} sigmoid(a_f) * softplus(a_s) + x[i],
  *      a = P[i] + Q[src(s)] + We . ea[s]
- * bwd: given grad_out [N,C] returns dPQ [N,4C] (dP = sum over in-edges of da,
+ * bwd: given grad_out [N,C] (for MEAN: already multiplied row-wise by inv_deg_dst -- a node-level
+ *      elementwise op the caller fuses with its other node work) returns dPQ [N,4C] (dP = sum over in-edges of da,
  *      dQ = sum over out-edges of da), dWe [2C,G]; the caller finishes with
  *      dense node-level GEMMs (dx = grad_out + dPQ . Wn, dWn = dPQ^T x). ---- */
 MDL_API size_t mdl_cgconv_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G);

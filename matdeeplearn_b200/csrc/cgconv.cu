@@ -162,8 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cgconv(const CgParams p) {
             } else {
               const int d = sDst[e];
               float4 g = __ldg(reinterpret_cast<const float4*>(p.gout + (size_t)d * C + c0));
-              const float sc = p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f;
-              float gg[4] = {g.x * sc, g.y * sc, g.z * sc, g.w * sc};
+              float gg[4] = {g.x, g.y, g.z, g.w};  // grad_out arrives pre-divided by the degree (mean)
               float dfv[4], dsv[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {

@@ -318,7 +318,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         seg_x1 = __ldg(p.x + (size_t)n0 * C + 32 + lane);
       }
     }
-    // (c) backward: grad_out rows (x 1/deg) of this warp's 8 slots, lanes = channels
+    // (c) backward: grad_out rows of this warp's 8 slots, lanes = channels.  For mean aggregation
+    // the rows arrive pre-divided by the destination degree (p.gout = grad_out * inv_deg, a node-level
+    // elementwise op done by the host wrapper), so nothing here depends on a second load.
     float g0[(MODE != CG_FWD) ? kRowsPerWarp : 1], g1[(MODE != CG_FWD) ? kRowsPerWarp : 1];
     if (MODE != CG_FWD) {
 #pragma unroll
@@ -327,9 +329,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         g0[i] = g1[i] = 0.0f;
         if (e < cnt) {
           const int d = bDst[e];
-          const float sc = p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f;
-          g0[i] = __ldg(p.gout + (size_t)d * C + lane) * sc;
-          g1[i] = __ldg(p.gout + (size_t)d * C + 32 + lane) * sc;
+          g0[i] = __ldg(p.gout + (size_t)d * C + lane);
+          g1[i] = __ldg(p.gout + (size_t)d * C + 32 + lane);
         }
       }
     }
@@ -505,22 +506,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         }
         const float ar0[4] = {a_lo_row.x, a_lo_row.y, a_lo_row.z, a_lo_row.w};  // slot e0+tig
         const float ar1[4] = {a_hi_row.x, a_hi_row.y, a_hi_row.z, a_hi_row.w};  // slot e0+tig+4
+        float ah[2][4], al[2][4];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           // fragment order: (row gid, k tig), (row gid+8, k tig), (row gid, k tig+4), (row gid+8, k tig+4)
           const float av[4] = {ar0[2 * mi], ar0[2 * mi + 1], ar1[2 * mi], ar1[2 * mi + 1]};
-          float ah[4], al[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { ah[u] = umma::tf32_hi(av[u]); al[u] = av[u] - ah[u]; }
-#pragma unroll
-          for (int ni = 0; ni < 2; ++ni) {
-            const float h0 = ni ? bh0.y : bh0.x, h1 = ni ? bh1.y : bh1.x;
-            const float l0 = ni ? bl0.y : bl0.x, l1 = ni ? bl1.y : bl1.x;
-            mma_tf32_16x8x8(dacc[2 * mi + ni], ah, h0, h1);
-            mma_tf32_16x8x8(dacc[2 * mi + ni], ah, l0, l1);
-            mma_tf32_16x8x8(dacc[2 * mi + ni], al, h0, h1);
-          }
+          for (int u = 0; u < 4; ++u) { ah[mi][u] = umma::tf32_hi(av[u]); al[mi][u] = av[u] - ah[mi][u]; }
         }
+        // pass-major order: four independent accumulators back to back (no dependent MMA chain)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+              const float b0 = (pass == 1) ? (ni ? bl0.y : bl0.x) : (ni ? bh0.y : bh0.x);
+              const float b1 = (pass == 1) ? (ni ? bl1.y : bl1.x) : (ni ? bh1.y : bh1.x);
+              mma_tf32_16x8x8(dacc[2 * mi + ni], (pass == 2) ? al[mi] : ah[mi], b0, b1);
+            }
       }
     }
     mark(10);

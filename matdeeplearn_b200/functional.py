@@ -108,11 +108,14 @@ class CGConvFn(torch.autograd.Function):
         N, C = x.shape
         G = ea_slots.shape[1]
         g = g.contiguous()
+        # mean aggregation: d(mean)/d(message) = 1/deg(dst); applied once per node here instead of
+        # once per edge inside the kernel
+        gk = g * csr.inv_deg_dst.unsqueeze(1) if ctx.reduce == "mean" else g
         dPQ = torch.empty_like(PQ)
         dWeT = torch.empty_like(WeT)
         ws_bytes = lib.mdl_cgconv_workspace_bytes(N, csr.E, C, G)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        rc = lib.mdl_cgconv_bwd(_lib.ptr(g), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
+        rc = lib.mdl_cgconv_bwd(_lib.ptr(gk), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
                                 _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src), _lib.ptr(csr.dst_dst),
                                 _lib.ptr(csr.src_ptr), _lib.ptr(csr.src_slot),
                                 _lib.ptr(csr.inv_deg_dst), _lib.ptr(dPQ), _lib.ptr(dWeT), N, csr.E,
