@@ -110,7 +110,7 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[
 // Persistent CTA, software-pipelined over "rounds" of <=128 slots:
 //   while round r's MMAs run and its epilogue executes, round r+1's indices and ea rows are
 //   already in flight (cp.async) and the node projections for round r are being gathered.
-template <int MODE, int NITEM>
+template <int MODE, int PROFILE>
 __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, const TcPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -193,25 +193,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       bS[row0 + lane] = ni.s;
       bD[row0 + lane] = ni.d;
     }
-#pragma unroll
-    for (int i = 0; i < kRowsPerWarp; ++i) {
-      const int e = row0 + i;
-      const int sl = __shfl_sync(0xffffffffu, ni.slot, i);
-      if (e < cnt) {
-        const float* row = p.ea + (size_t)sl * G;
-        float* dst = sEA + e * GS;
-        if ((G & 1) == 0) {
-          for (int k2 = lane; k2 < (G >> 1); k2 += 32) cp_async8(dst + 2 * k2, row + 2 * k2);
-        } else {
-          for (int kx = lane; kx < G; kx += 32) cp_async4(dst + kx, row + kx);
-        }
+    // the warp's 8 rows as one flat list of 8-byte (even G) or 4-byte chunks: every lane issues
+    // ceil(8*chunks/32) cp.async instead of one mostly idle 32-lane pass per row
+    const int wcnt = min(kRowsPerWarp, cnt - row0);  // rows of this warp that exist (may be <= 0)
+    if ((G & 1) == 0) {
+      const int cpr = G >> 1;
+      for (int base = 0; base < kRowsPerWarp * cpr; base += 32) {  // warp-uniform trip count (shfl inside)
+        const int i = base + lane;
+        const bool ok = i < kRowsPerWarp * cpr;
+        const int r = ok ? i / cpr : 0, c = i - r * cpr;
+        const int sl = __shfl_sync(0xffffffffu, ni.slot, r);
+        if (ok && r < wcnt) cp_async8(sEA + (row0 + r) * GS + 2 * c, p.ea + (size_t)sl * G + 2 * c);
+      }
+    } else {
+      for (int base = 0; base < kRowsPerWarp * G; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < kRowsPerWarp * G;
+        const int r = ok ? i / G : 0, c = i - r * G;
+        const int sl = __shfl_sync(0xffffffffu, ni.slot, r);
+        if (ok && r < wcnt) cp_async4(sEA + (row0 + r) * GS + c, p.ea + (size_t)sl * G + c);
       }
     }
   };
 
-  long long t_prev = clock64();
+  long long t_prev = PROFILE ? clock64() : 0;
   auto mark = [&](int slot) {
-    if (pl.prof && tid == 0) {
+    if (PROFILE && pl.prof && tid == 0) {
       const long long now = clock64();
       atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
       t_prev = now;
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       }
     }
     mark(10);
-    if (pl.prof && tid == 0) atomicAdd(pl.prof + 15, 1ull);
+    if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 15, 1ull);
     k = nk; rd = nrd; buf ^= 1;
   }  // work items
 
@@ -555,15 +562,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)pl.tmem_cols);
 }
 
-template <int MODE, int NITEM>
+template <int MODE, int PROFILE>
 static int tc_launch_t(const CgParams& p, const TcPlan& pl, int grid, cudaStream_t st) {
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_tc<MODE, NITEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_tc<MODE, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMaxDynSmem));
     configured.store(1, std::memory_order_release);
   }
-  k_cgconv_tc<MODE, NITEM><<<grid, kTcThreads, pl.total, st>>>(p, pl);
+  k_cgconv_tc<MODE, PROFILE><<<grid, kTcThreads, pl.total, st>>>(p, pl);
   MDL_LAUNCHED();
   return MDL_OK;
 }
@@ -582,10 +589,13 @@ int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out) {
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTcTE));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
   if (grid_out) *grid_out = grid;
+  const bool prof = pl.prof != nullptr;  // instrumented instantiation only while a phase buffer is set
   switch (mode) {
-    case CG_FWD: return tc_launch_t<CG_FWD, 1>(p, pl, grid, st);
-    case CG_BWD_SRC: return tc_launch_t<CG_BWD_SRC, 1>(p, pl, grid, st);
-    case CG_BWD_DST: return tc_launch_t<CG_BWD_DST, 1>(p, pl, grid, st);
+    case CG_FWD: return prof ? tc_launch_t<CG_FWD, 1>(p, pl, grid, st) : tc_launch_t<CG_FWD, 0>(p, pl, grid, st);
+    case CG_BWD_SRC:
+      return prof ? tc_launch_t<CG_BWD_SRC, 1>(p, pl, grid, st) : tc_launch_t<CG_BWD_SRC, 0>(p, pl, grid, st);
+    case CG_BWD_DST:
+      return prof ? tc_launch_t<CG_BWD_DST, 1>(p, pl, grid, st) : tc_launch_t<CG_BWD_DST, 0>(p, pl, grid, st);
   }
   MDL_REQUIRE(false, "cgconv_tc: bad mode");
 }

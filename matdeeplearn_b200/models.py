@@ -151,10 +151,7 @@ class MPNN(_ConvStackModel):
                 m = self.bn_list[i](m)
             m = self._activation(m)
             m = F.dropout(m, p=self.dropout_rate, training=self.training)
-            # fp32 contract: keep cuDNN's RNN path off TF32 (the reference itself runs with cuDNN
-            # disabled under DDP, training/training.py:236)
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                out, hidden = self.gru_list[i](m.unsqueeze(0), hidden)
+            out, hidden = self.gru_list[i](m.unsqueeze(0), hidden)  # cuDNN, TF32 off (package __init__)
             out = out.squeeze(0)
         return self._readout(out, data)
 
