@@ -333,7 +333,8 @@ def run_engine(args, rank, world, local_rank):
             "workload": "CGCNN dim=64 4xCGConv, synthetic bulk graphs, batch 256 per GPU (configs[1])",
             "graphs_per_step": graphs_total, "nodes_per_gpu": N, "edges_per_gpu": E,
             "parallelism": f"dp{world}", "step": "zero_grad+fwd+l1_loss+bwd" +
-            ("+flat grad allreduce" if world > 1 else "") + "+AdamW, one CUDA graph replay",
+            ("+flat grad allreduce(NCCL, eager)+AdamW, two CUDA graph replays around the collective"
+             if world > 1 else "+AdamW, one CUDA graph replay"),
             "l2": "flushed between timed steps (512 MiB read-modify-write)",
             "timing": "sum of per-step CUDA-event durations, max over ranks",
         },
@@ -341,8 +342,8 @@ def run_engine(args, rank, world, local_rank):
         "gpu_launches_per_step": int(step.kernels_per_step),
         "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "path": "TrainStep.from_host(pinned Batch in reference layout): H2D, CSR build, "
-                        "slot permute, fwd, bwd, AdamW, loss.item()"},
+                "path": "TrainStep.from_host(pinned Batch in reference layout): H2D of all 7 tensors, then one "
+                        "CUDA graph replay of CSR build + slot permute + fwd + bwd + AdamW, then loss.item()"},
         "wall_s_timed_region": wall,
     }
     if rank == 0:
@@ -355,7 +356,7 @@ def run_engine(args, rank, world, local_rank):
                                 "kernel": "k_cgconv<BWD_DST>+<BWD_SRC>" if dom is r["bwd_both_passes"] else "k_cgconv<FWD>",
                                 "peak_source": peak_src, "workload": r["workload"]}
             line["roofline_detail"] = r
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             cds, cb = make_workload(0, GRAPHS_PER_GPU)
             threads, table = best_cpu_threads(cds, cb)
             torch.set_num_threads(threads)

@@ -31,6 +31,13 @@ class TrainStep:
                                      capturable=True, fused=True)
         self.kernels_per_step = None
         self._graphs = {}
+        self._host_graphs = {}
+        # warm-up runs on a side stream (standard capture recipe); the resulting stream-mismatch
+        # note from autograd's AccumulateGrad is expected and harmless here
+        try:
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except Exception:
+            pass
 
     # -- pieces ---------------------------------------------------------------
     def _fwd_bwd(self, batch):
@@ -86,7 +93,65 @@ class TrainStep:
         return replay
 
     # -- from pinned host memory (the call a user of the reference makes) -------
-    def from_host(self, host_batch: Batch):
-        dev_batch = host_batch.to(self.device, non_blocking=True)
-        loss = self.eager(dev_batch)
+    def from_host(self, host_batch: Batch, use_graph=True):
+        """One training step starting from a (pinned) host batch in the reference's layout.
+
+        H2D copies of every tensor of the batch, engine layout build (CSR sort, slot
+        permutation), forward, backward, [all-reduce], AdamW, loss read-back.  Everything
+        after the copies is replayed from a CUDA graph cached per batch shape (N, E, B):
+        the layout build is itself a handful of asynchronous kernels, so it sits inside
+        the graph and is re-executed on the new indices at every replay."""
+        if not use_graph:
+            dev_batch = host_batch.to(self.device, non_blocking=True)
+            return float(self.eager(dev_batch).item())
+        B = int(getattr(host_batch, "num_graphs", host_batch.y.shape[0]))
+        key = (host_batch.x.shape[0], host_batch.edge_index.shape[1], B)
+        entry = self._host_graphs.get(key)
+        if entry is None:
+            entry = self._capture_host_step(host_batch, B)
+            self._host_graphs[key] = entry
+        static, replay, loss = entry
+        for name in Batch._TENSOR_KEYS:
+            getattr(static, name).copy_(getattr(host_batch, name), non_blocking=True)
+        replay()
         return float(loss.item())
+
+    def _layout_inside_graph(self, static, B):
+        from .csr import GraphCSR
+        csr = GraphCSR.from_coo(static.edge_index, static.batch, num_nodes=static.x.shape[0], num_graphs=B)
+        static.edge_index._mdl_csr = (static.edge_index._version, csr)  # what models' csr_for() will find
+        if hasattr(static.edge_attr, "_mdl_slots"):
+            del static.edge_attr._mdl_slots                               # re-permute inside the graph
+        return csr
+
+    def _capture_host_step(self, host_batch, B):
+        static = host_batch.to(self.device)
+        static.num_graphs = B
+        distributed = mdist.is_distributed()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._layout_inside_graph(static, B)
+                self.eager(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._layout_inside_graph(static, B)
+            loss = self._fwd_bwd(static)
+            if not distributed:
+                self.opt.step()
+        g2 = None
+        if distributed:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self.opt.step()
+
+        def replay():
+            g1.replay()
+            if g2 is not None:
+                mdist.allreduce_mean_(self.flat.grad)
+                g2.replay()
+
+        return static, replay, loss
