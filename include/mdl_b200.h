@@ -161,6 +161,13 @@ MDL_API int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* d
                                const int32_t* src_eid, float* dhid, float* dXT, float* dXB,
                                int64_t num_nodes, int32_t K, int32_t O, void* stream);
 
+/* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
+ * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).
+ * hyper = device {lr, beta1, beta2, eps, weight_decay}; step = device float step count, advanced by
+ * the call; grad_scale multiplies the gradient first (1/world after a sum all-reduce). ---- */
+MDL_API int mdl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           const float* hyper, float* step, float grad_scale, int64_t n, void* stream);
+
 /* ---- development aid: 16 x uint64 device counters that receive per-phase cycle sums
  * (thread 0 of every CTA) from the tensor-core CGConv kernels; NULL disables. ---- */
 MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr);

@@ -263,7 +263,8 @@ __global__ void k_cg_reduce_dw(const float* __restrict__ part, int nparts, int G
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= G * W2) return;
   float acc = 0.0f;
-  for (int b = 0; b < nparts; ++b) acc += part[(size_t)b * G * W2 + i];
+#pragma unroll 8
+  for (int b = 0; b < nparts; ++b) acc += __ldg(part + (size_t)b * G * W2 + i);  // fixed order; 8 loads in flight
   const int k = i / W2, c = i - k * W2;
   const int col = (c < CC) ? (c_off + c) : (C + c_off + (c - CC));
   dWeT[(size_t)k * (2 * C) + col] = acc;

@@ -23,6 +23,10 @@ namespace mdl {
 constexpr int kTcThreads = 512;  // 16 warps: 4 per scheduler, the epilogue/gather math is latency-bound otherwise
 constexpr int kTcWarps = kTcThreads / 32;
 constexpr int kTcRows = 128;  // slots per round = MMA M
+// k-chunk stride of the A operand tiles: 128 rows x 16 B plus 16 B of padding, so that lanes that
+// read the same row of DIFFERENT chunks (the dWe B-fragments) fall on different banks.  The UMMA
+// descriptor simply carries this value as its leading-dimension byte offset.
+constexpr uint32_t kAChunk = kTcRows * 16 + 16;
 constexpr int kTcTE = 112;    // ownership granularity (leaves head-room for straddling segments)
 
 // optional per-phase cycle accounting (development aid): 16 counters, thread 0 of each CTA adds
@@ -43,7 +47,7 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   int GS = (G + 3) & ~3;
   if (((GS >> 2) & 1) == 0) GS += 4;  // odd number of 16-byte chunks per row: conflict-free float4 column reads
   const int VW = 2 * C + 4;  // [f | s] per slot (+4 floats: conflict-free float4 row access)
-  uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)kTcRows * KP * 4;
+  uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)(KP / 4) * kAChunk;
   uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 4 * kTcRows * 4;
   pl->prof = g_phase_buf;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         hi.x = umma::tf32_hi(v.x); hi.y = umma::tf32_hi(v.y);
         hi.z = umma::tf32_hi(v.z); hi.w = umma::tf32_hi(v.w);
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        const uint32_t off = (uint32_t)j * (kTcRows * 16) + row_off;
+        const uint32_t off = (uint32_t)j * kAChunk + row_off;
         *reinterpret_cast<float4*>(sAhi + off) = hi;
         *reinterpret_cast<float4*>(sAlo + off) = lo;
       }
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     // whose other duties in this window are the lightest)
     if (tid == kTcThreads - 32 && cnt > 0) {
       umma::fence_after_sync();
-      const uint32_t step_a = 2 * kTcRows * 16, step_b = 2 * (uint32_t)NP * 16;
+      const uint32_t step_a = 2 * kAChunk, step_b = 2 * (uint32_t)NP * 16;
       const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
       const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
       uint32_t acc = 0;
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         const uint32_t a = (pass == 2) ? a_lo : a_hi;
         const uint32_t b = (pass == 1) ? b_lo : b_hi;
         for (int kk = 0; kk < (KP >> 3); ++kk) {
-          const uint64_t ad = umma::make_desc(a + kk * step_a, kTcRows * 16, 128);
+          const uint64_t ad = umma::make_desc(a + kk * step_a, kAChunk, 128);
           const uint64_t bd = umma::make_desc(b + kk * step_b, (uint32_t)NP * 16, 128);
           umma::mma_tf32(tmem, ad, bd, idesc, acc);
           acc = 1;
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       const int mgrp = warp & 3, ngrp = warp >> 2;
       const int chunk = ngrp * 4 + (gid >> 1);           // 16-byte chunk of the operand tiles
       const bool col_ok = chunk < (KP >> 2);
-      const uint32_t cb = (uint32_t)chunk * (kTcRows * 16) + (uint32_t)(gid & 1) * 8;
+      const uint32_t cb = (uint32_t)chunk * kAChunk + (uint32_t)(gid & 1) * 8;
       for (int e0 = 0; e0 < cnt; e0 += 8) {
         const int ea_ = e0 + tig, eb_ = e0 + tig + 4;
         float4 a_lo_row = make_float4(0.f, 0.f, 0.f, 0.f), a_hi_row = a_lo_row;

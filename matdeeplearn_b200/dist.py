@@ -44,6 +44,18 @@ class FlatParameters:
     def zero_grad(self):
         self.grad.zero_()
 
+    # ---- cheaper per-step protocol used by engine.TrainStep: instead of zeroing the flat gradient
+    # and letting autograd ADD into ~20 views (one small kernel each), gradients are detached
+    # (autograd then just hands over its result tensors) and packed with ONE concatenation.
+    def release_grads(self):
+        for p in self.params:
+            p.grad = None
+
+    def pack_grads(self):
+        flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(flat, out=self.grad)
+        return self.grad
+
     def bind_grads(self):
         """Re-attach gradient views (needed if someone set .grad to None)."""
         off = 0
@@ -87,3 +99,30 @@ def shard_indices(num_items: int, rank: int, world: int, sizes=None):
         buckets[r].append(i)
         loads[r] += int(sizes[i])
     return sorted(buckets[rank])
+
+
+class FlatAdamW:
+    """torch.optim.AdamW semantics over FlatParameters through mdl_adamw_step (one elementwise
+    kernel over the whole model).  Hyper-parameters live in a device tensor so a scheduler
+    (the reference uses ReduceLROnPlateau, training.py:433-436) can change lr between replays
+    of a captured step."""
+
+    def __init__(self, flat: FlatParameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        from . import _lib
+        self._lib = _lib
+        self.flat = flat
+        dev = flat.param.device
+        self.exp_avg = torch.zeros_like(flat.param)
+        self.exp_avg_sq = torch.zeros_like(flat.param)
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay], dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def set_lr(self, lr):
+        self.hyper[0] = float(lr)
+
+    def step(self, grad_scale=1.0):
+        L, P = self._lib.load(), self._lib.ptr
+        rc = L.mdl_adamw_step(P(self.flat.param), P(self.flat.grad), P(self.exp_avg), P(self.exp_avg_sq),
+                              P(self.hyper), P(self.step_count), float(grad_scale), self.flat.numel,
+                              self._lib.stream())
+        self._lib.check(rc, "mdl_adamw_step")

@@ -27,8 +27,7 @@ class TrainStep:
         self.flat = mdist.FlatParameters(model)
         self.loss_fn = getattr(F, loss)
         self.device = self.flat.param.device
-        self.opt = torch.optim.AdamW([self.flat.leaf], lr=lr, weight_decay=weight_decay,
-                                     capturable=True, fused=True)
+        self.opt = mdist.FlatAdamW(self.flat, lr=lr, weight_decay=weight_decay)
         self.kernels_per_step = None
         self._graphs = {}
         self._host_graphs = {}
@@ -41,10 +40,11 @@ class TrainStep:
 
     # -- pieces ---------------------------------------------------------------
     def _fwd_bwd(self, batch):
-        self.flat.zero_grad()
+        self.flat.release_grads()
         out = self.model(batch)
         loss = self.loss_fn(out, batch.y)
         loss.backward()
+        self.flat.pack_grads()      # one concatenation into the flat gradient buffer
         return loss
 
     def _finish(self):

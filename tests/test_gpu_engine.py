@@ -62,3 +62,25 @@ def test_from_host_graph_equals_eager_and_tracks_oracle():
         l_ref.append(float(loss))
     for a, r in zip(l_eager, l_ref):
         assert abs(a - r) <= 5e-4 * max(1.0, abs(r)), (l_eager, l_ref)
+
+
+def test_flat_adamw_matches_torch_adamw():
+    from matdeeplearn_b200 import dist as mdist
+    torch.manual_seed(3)
+    lin = torch.nn.Sequential(torch.nn.Linear(20, 30), torch.nn.Tanh(), torch.nn.Linear(30, 5))
+    ref = copy.deepcopy(lin).double()
+    lin = lin.to(DEV)
+    flat = mdist.FlatParameters(lin)
+    opt = mdist.FlatAdamW(flat, lr=3e-3, weight_decay=0.02)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=3e-3, weight_decay=0.02)
+    x = torch.randn(64, 20)
+    for it in range(5):
+        flat.release_grads()
+        lin(x.to(DEV)).pow(2).mean().backward()
+        flat.pack_grads()
+        opt.step()
+        ropt.zero_grad()
+        ref(x.double()).pow(2).mean().backward()
+        ropt.step()
+    for p, q in zip(lin.parameters(), ref.parameters()):
+        assert (p.detach().cpu().double() - q.detach()).abs().max().item() < 2e-6
