@@ -47,9 +47,19 @@ class TrainStep:
         self.flat.pack_grads()      # one concatenation into the flat gradient buffer
         return loss
 
+    def _reduce(self):
+        """DDP semantics: mean of the per-rank gradients.  The sum is ONE all-reduce of the flat
+        buffer; the 1/world factor rides along in the optimizer kernel."""
+        if mdist.is_distributed():
+            torch.distributed.all_reduce(self.flat.grad, op=torch.distributed.ReduceOp.SUM)
+
+    def _opt_step(self):
+        world = torch.distributed.get_world_size() if mdist.is_distributed() else 1
+        self.opt.step(grad_scale=1.0 / world)
+
     def _finish(self):
-        mdist.allreduce_mean_(self.flat.grad)
-        self.opt.step()
+        self._reduce()
+        self._opt_step()
 
     def eager(self, batch):
         loss = self._fwd_bwd(batch)
@@ -74,18 +84,19 @@ class TrainStep:
         with torch.cuda.graph(g1):
             loss = self._fwd_bwd(batch)
             if not distributed:
-                self.opt.step()
+                self._opt_step()
         self.kernels_per_step = _lib.launch_count() - n0
         g2 = None
         if distributed:
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
-                self.opt.step()
+                self._opt_step()
+            self.kernels_per_step += 2
 
         def replay():
             g1.replay()
             if g2 is not None:
-                mdist.allreduce_mean_(self.flat.grad)
+                self._reduce()
                 g2.replay()
             return loss
 
@@ -141,17 +152,17 @@ class TrainStep:
             self._layout_inside_graph(static, B)
             loss = self._fwd_bwd(static)
             if not distributed:
-                self.opt.step()
+                self._opt_step()
         g2 = None
         if distributed:
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
-                self.opt.step()
+                self._opt_step()
 
         def replay():
             g1.replay()
             if g2 is not None:
-                mdist.allreduce_mean_(self.flat.grad)
+                self._reduce()
                 g2.replay()
 
         return static, replay, loss
