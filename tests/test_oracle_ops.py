@@ -1,0 +1,135 @@
+"""CPU: the oracle's operator restatements on hand-worked graphs and through the invariants
+the formulas imply (there are no reference tests to lean on)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pyg_ops as O
+
+
+def test_scatter_semantics_match_torch_scatter_documentation():
+    src = torch.tensor([[1.0, -2.0], [3.0, 4.0], [5.0, -6.0]])
+    idx = torch.tensor([2, 0, 2])
+    assert O.scatter(src, idx, 0, 4, "sum").tolist() == [[3, 4], [0, 0], [6, -8], [0, 0]]
+    assert O.scatter(src, idx, 0, 4, "mean").tolist() == [[3, 4], [0, 0], [3, -4], [0, 0]]   # count clamps at 1
+    assert O.scatter(src, idx, 0, 4, "max").tolist() == [[3, 4], [0, 0], [5, -2], [0, 0]]    # empty -> 0
+    assert O.scatter(src, idx, 0, None, "sum").shape[0] == 3                                # dim_size = max+1
+    assert torch.equal(O.global_mean_pool(src, torch.tensor([0, 0, 1])),
+                       torch.tensor([[2.0, 1.0], [5.0, -6.0]]))
+
+
+def test_cgconv_hand_worked_two_node_graph():
+    # nodes 0,1 ; edges 0->1, 1->1 (loop) ; C=1, G=1 ; weights chosen by hand
+    conv = O.CGConv(1, 1, aggr="mean").double()
+    with torch.no_grad():
+        conv.lin_f.weight.copy_(torch.tensor([[0.5, -1.0, 2.0]]))   # [x_i, x_j, e]
+        conv.lin_f.bias.fill_(0.1)
+        conv.lin_s.weight.copy_(torch.tensor([[1.0, 0.25, -0.5]]))
+        conv.lin_s.bias.fill_(-0.2)
+    x = torch.tensor([[2.0], [-1.0]], dtype=torch.float64)
+    ei = torch.tensor([[0, 1], [1, 1]])
+    ea = torch.tensor([[0.3], [1.0]], dtype=torch.float64)
+    out = conv(x, ei, ea)
+
+    def msg(xi, xj, e):
+        f = 0.5 * xi - 1.0 * xj + 2.0 * e + 0.1
+        s = 1.0 * xi + 0.25 * xj - 0.5 * e - 0.2
+        return 1 / (1 + math.exp(-f)) * math.log1p(math.exp(s))
+
+    m01 = msg(-1.0, 2.0, 0.3)   # target i=1, source j=0
+    m11 = msg(-1.0, -1.0, 1.0)
+    assert out[0].item() == pytest.approx(2.0)                       # no in-edges: mean over empty = 0, + x
+    assert out[1].item() == pytest.approx((m01 + m11) / 2 - 1.0, rel=1e-12)
+
+
+def _rand_graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    return ei
+
+
+@pytest.mark.parametrize("make", ["cgconv", "interaction", "nnconv"])
+def test_edge_permutation_invariance_and_block_independence(make):
+    torch.manual_seed(0)
+    n, e, C, G = 12, 40, 8, 5
+    ei = _rand_graph(n, e, 1)
+    x = torch.randn(n, C, dtype=torch.float64)
+    ea = torch.rand(e, G, dtype=torch.float64)
+    ew = torch.rand(e, dtype=torch.float64) * 8
+    if make == "cgconv":
+        m = O.CGConv(C, G, aggr="mean").double()
+        f = lambda x_, ei_, ea_, ew_: m(x_, ei_, ea_)
+    elif make == "interaction":
+        m = O.InteractionBlock(C, G, 6, 8.0).double()
+        f = lambda x_, ei_, ea_, ew_: m(x_, ei_, ew_, ea_)
+    else:
+        net = torch.nn.Sequential(torch.nn.Linear(G, 7), torch.nn.ReLU(), torch.nn.Linear(7, C * C))
+        m = O.NNConv(C, C, net, aggr="mean").double()
+        f = lambda x_, ei_, ea_, ew_: m(x_, ei_, ea_)
+    ref = f(x, ei, ea, ew)
+    perm = torch.randperm(e)
+    torch.testing.assert_close(f(x, ei[:, perm], ea[perm], ew[perm]), ref, rtol=1e-12, atol=1e-12)
+    # block-diagonal union of two graphs == the two graphs processed separately
+    x2 = torch.cat([x, x * 0.5 + 1])
+    ei2 = torch.cat([ei, ei + n], 1)
+    out2 = f(x2, ei2, torch.cat([ea, ea]), torch.cat([ew, ew]))
+    torch.testing.assert_close(out2[:n], ref, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(out2[n:], f(x * 0.5 + 1, ei, ea, ew), rtol=1e-12, atol=1e-12)
+
+
+def test_cgconv_mean_equals_add_times_inverse_degree():
+    torch.manual_seed(1)
+    n, e, C, G = 10, 30, 4, 3
+    ei = _rand_graph(n, e, 2)
+    x = torch.randn(n, C, dtype=torch.float64)
+    ea = torch.rand(e, G, dtype=torch.float64)
+    a = O.CGConv(C, G, aggr="add").double()
+    b = O.CGConv(C, G, aggr="mean").double()
+    b.load_state_dict(a.state_dict())
+    deg = torch.bincount(ei[1], minlength=n).clamp(min=1).double().view(-1, 1)
+    torch.testing.assert_close((a(x, ei, ea) - x) / deg + x, b(x, ei, ea), rtol=1e-12, atol=1e-12)
+
+
+def test_nnconv_equals_explicit_per_edge_matrices():
+    torch.manual_seed(2)
+    n, e, C, G, K = 6, 15, 3, 4, 5
+    ei = _rand_graph(n, e, 3)
+    x = torch.randn(n, C, dtype=torch.float64)
+    ea = torch.rand(e, G, dtype=torch.float64)
+    net = torch.nn.Sequential(torch.nn.Linear(G, K), torch.nn.ReLU(), torch.nn.Linear(K, C * C)).double()
+    m = O.NNConv(C, C, net, aggr="add").double()
+    out = m(x, ei, ea)
+    ref = x @ m.lin.weight.t() + m.bias
+    ref = ref.clone()
+    for k in range(e):
+        theta = net(ea[k]).view(C, C)
+        ref[ei[1, k]] += x[ei[0, k]] @ theta
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_gradients_by_finite_differences():
+    torch.manual_seed(3)
+    n, e, C, G = 5, 12, 3, 2
+    ei = _rand_graph(n, e, 4)
+    ea = torch.rand(e, G, dtype=torch.float64)
+    conv = O.CGConv(C, G, aggr="mean").double()
+    x = torch.randn(n, C, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda t: conv(t, ei, ea), (x,), eps=1e-6, atol=1e-6)
+    blk = O.InteractionBlock(C, G, 4, 8.0).double()
+    ew = torch.rand(e, dtype=torch.float64) * 8
+    assert torch.autograd.gradcheck(lambda t: blk(t, ei, ew, ea), (x,), eps=1e-6, atol=1e-6)
+
+
+def test_interaction_block_cutoff_and_shifted_softplus():
+    assert O.ShiftedSoftplus()(torch.zeros(1)).abs().item() < 1e-7           # ssp(0) = 0
+    blk = O.InteractionBlock(2, 3, 4, cutoff=8.0).double()
+    x = torch.randn(3, 2, dtype=torch.float64)
+    ei = torch.tensor([[0, 1], [2, 2]])
+    ea = torch.rand(2, 3, dtype=torch.float64)
+    # an edge at exactly the cutoff distance contributes nothing (cosine cutoff = 0)
+    a = blk(x, ei, torch.tensor([8.0, 3.0], dtype=torch.float64), ea)
+    b = blk(x, ei[:, 1:], torch.tensor([3.0], dtype=torch.float64), ea[1:])
+    torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-12)
