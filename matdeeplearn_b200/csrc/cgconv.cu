@@ -393,11 +393,19 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
   p.src_slot = src_slot; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg_dst : nullptr;
   p.out = dPQ; p.dW_part = (float*)workspace; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
 
+  // Tensor-core path, default: ONE pass in destination order; dQ[src] is accumulated with 16-byte
+  // vector float atomics (like the reference's own scatter kernels, the summation order then varies
+  // run to run).  MDL_CGCONV_DETERMINISTIC=1 selects the two-pass scheme (second pass over the
+  // by-source view, fixed summation order, bitwise reproducible).
+  const char* det_env = getenv("MDL_CGCONV_DETERMINISTIC");
+  const bool dq_atomic = use_tc(CG_BWD_DST, C, G) && !(det_env && det_env[0] == '1');
+  if (dq_atomic)
+    MDL_CUDA(cudaMemset2DAsync(dPQ + 2 * C, (size_t)4 * C * 4, 0, (size_t)2 * C * 4, (size_t)N, st));
   // pass A: destination order -> dP and dWe
   if (use_tc(CG_BWD_DST, C, G)) {
     p.seg_ptr = dst_ptr;
     int grid = 0;
-    if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid)) return rc;
+    if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid, dq_atomic ? 1 : 0)) return rc;
     const int tot = G * 2 * C;
     k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, grid, G, C, 0, C, dWeT);
     MDL_LAUNCHED();
@@ -421,7 +429,9 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
     }
   }
   // pass B: source order -> dQ
-  if (use_tc(CG_BWD_SRC, C, G)) {
+  if (dq_atomic) {
+    // done inside pass A
+  } else if (use_tc(CG_BWD_SRC, C, G)) {
     p.seg_ptr = src_ptr;
     if (int rc = cgtc_launch(CG_BWD_SRC, p, st, nullptr)) return rc;
   } else {

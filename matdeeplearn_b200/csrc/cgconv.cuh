@@ -56,7 +56,7 @@ __device__ __forceinline__ float sigmoid_fast_(float x) { return __fdividef(1.0f
 // tensor-core path (cgconv_tc.cu).  Returns false if (C, G, mode) does not fit its
 // shared-memory / TMEM plan, in which case the caller uses the SIMT kernel.
 bool cgtc_supported(int mode, int C, int G);
-int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out);
+int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out, int dq_atomic = 0);
 void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
 
 }  // namespace mdl

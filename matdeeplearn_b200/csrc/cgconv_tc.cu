@@ -35,6 +35,7 @@ static unsigned long long* g_phase_buf = nullptr;
 
 struct TcPlan {
   unsigned long long* prof;
+  int dq_atomic;  // BWD_DST also scatters da into dQ[src] with vector float atomics (no BWD_SRC pass)
   int NP, KP, GS, VW, tmem_cols, nitem;
   uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, total;
 };
@@ -50,6 +51,7 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)(KP / 4) * kAChunk;
   uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 4 * kTcRows * 4;
   pl->prof = g_phase_buf;
+  pl->dq_atomic = 0;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
   pl->tmem_cols = 32;
   while (pl->tmem_cols < NP) pl->tmem_cols <<= 1;
@@ -101,6 +103,12 @@ __device__ __forceinline__ float softplus_mufu(float x) {
 }
 
 struct TileInfo { int n_lo, n_hi, e_lo, e_hi; };
+
+// 16-byte vector float reduction into global memory (sm_90+): no return value, resolved in L2
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 // D[16x8] += A[16x8] * B[8x8]  (tf32 inputs, fp32 accumulate; legacy warp-level tensor path)
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
@@ -445,6 +453,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         }
       }
       __syncthreads();  // [S3b]
+      // optional single-pass backward: dQ[src] += da, a whole 512-byte row per warp instruction
+      // (lane l owns floats [4l, 4l+4) of [d a_f | d a_s]); order of the float adds is not fixed
+      if (MODE == CG_BWD_DST && pl.dq_atomic) {
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) {
+          const int e = row0 + i;
+          if (e < cnt) {
+            const float4 v = *(reinterpret_cast<const float4*>(sV + e * VW) + lane);
+            red_add_v4(p.out + (size_t)bSrc[e] * (4 * C) + 2 * C + 4 * lane, v);
+          }
+        }
+      }
     }
 
     // ---- segmented sum over the owned segments that have slots in this round
@@ -586,9 +606,10 @@ bool cgtc_supported(int mode, int C, int G) {
   return tc_plan(mode, C, G, &pl);
 }
 
-int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out) {
+int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out, int dq_atomic) {
   TcPlan pl;
   MDL_REQUIRE(tc_plan(mode, p.C, p.G, &pl), "cgconv_tc: unsupported shape C=%d G=%d", p.C, p.G);
+  pl.dq_atomic = (mode == CG_BWD_DST) ? dq_atomic : 0;
   p.c_off = 0; p.CC = p.C; p.cap = kTcRows; p.te = kTcTE;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTcTE));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;

@@ -87,11 +87,13 @@ def test_scatter_unsorted_index(dev):
         assert_close(got, ref, **FWD, what=red)
 
 
-@pytest.fixture(params=["tc", "simt"])
+@pytest.fixture(params=["tc", "tc_det", "simt"])
 def impl(request, monkeypatch):
-    """Run a case on the tensor-core kernels (default dispatch; shapes that do not
-    fit fall back to SIMT inside the library) and with the SIMT kernels forced."""
-    monkeypatch.setenv("MDL_CGCONV_IMPL", request.param)
+    """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
+    atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
+    tensor-core kernels in deterministic two-pass mode, and with the SIMT kernels forced."""
+    monkeypatch.setenv("MDL_CGCONV_IMPL", "simt" if request.param == "simt" else "tc")
+    monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
     return request.param
 
 
@@ -165,6 +167,26 @@ def test_cgconv_deterministic(dev, impl):
     a = _cgconv_case(dev, n=400, e=5000, C=64, G=50, aggr="mean", seed=5)
     b = _cgconv_case(dev, n=400, e=5000, C=64, G=50, aggr="mean", seed=5)
     assert torch.equal(a, b), "CSR reduction must be bitwise reproducible"
+
+
+def test_cgconv_backward_bitwise_reproducible_in_deterministic_mode(dev, monkeypatch):
+    import matdeeplearn_b200.nn as mnn
+    monkeypatch.setenv("MDL_CGCONV_IMPL", "tc")
+    monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1")
+    torch.manual_seed(9)
+    ei = random_graph(500, 6000, 9).to(dev)
+    x0 = torch.randn(500, 64, device=dev)
+    ea = torch.rand(ei.shape[1], 50, device=dev)
+    conv = mnn.CGConv(64, 50, aggr="mean").to(dev)
+    w = torch.randn(500, 64, device=dev)
+    grads = []
+    for _ in range(2):
+        x = x0.clone().requires_grad_(True)
+        conv.zero_grad()
+        conv(x, ei, ea).backward(w)
+        grads.append([x.grad.clone()] + [p.grad.clone() for p in conv.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
 
 
 def test_cgconv_rejects_cpu_tensors():
