@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     // (c) backward: grad_out rows of this warp's 8 slots, lanes = channels.  For mean aggregation
     // the rows arrive pre-divided by the destination degree (p.gout = grad_out * inv_deg, a node-level
     // elementwise op done by the host wrapper), so nothing here depends on a second load.
-    float g0[(MODE != CG_FWD) ? kRowsPerWarp : 1], g1[(MODE != CG_FWD) ? kRowsPerWarp : 1];
-    if (MODE != CG_FWD) {
+    float g0[(MODE == CG_BWD_SRC) ? kRowsPerWarp : 1], g1[(MODE == CG_BWD_SRC) ? kRowsPerWarp : 1];
+    if (MODE == CG_BWD_SRC) {  // destinations are scattered here: coalesced row loads, applied in the scale pass
 #pragma unroll
       for (int i = 0; i < kRowsPerWarp; ++i) {
         const int e = row0 + i;
@@ -351,6 +351,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
           g0[i] = __ldg(p.gout + (size_t)d * C + lane);
           g1[i] = __ldg(p.gout + (size_t)d * C + 32 + lane);
         }
+      }
+    }
+    // BWD_DST: slots are destination-sorted, so the 32 slots of a warp touch only a few distinct
+    // grad_out rows -- each epilogue thread loads its own 16 channels directly (L1 hits, few
+    // wavefronts) and the factor goes straight into the gate-derivative math: no scale pass.
+    float4 gq[(MODE == CG_BWD_DST) ? 4 : 1];
+    if (MODE == CG_BWD_DST) {
+      const int e = 32 * q + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < cnt) {
+        const float4* gp = reinterpret_cast<const float4*>(p.gout + (size_t)bDst[e] * C + c_begin);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gq[j] = __ldg(gp + j);
       }
     }
     // (d) node projections of this warp's 8 slots: one LDG.128 per lane reads a whole 512-byte
@@ -381,8 +395,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     if (rd == 0 && tid == 64) compute_info(k + 2);  // two tiles ahead (own dependent loads)
     mark(4);
 
-    // ---- overlap window, part 2: LAND.  Next round's indices + ea rows, then this round's P+Q.
-    if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
+    // ---- overlap window, part 2: LAND, in issue order: this round's P+Q first (issued first),
+    // then the next round's indices (issued last) and, from them, its ea rows.
     if (cnt > 0) {
 #pragma unroll
       for (int i = 0; i < kRowsPerWarp; ++i) {
@@ -392,6 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
               make_float4(vp[i].x + vq[i].x, vp[i].y + vq[i].y, vp[i].z + vq[i].z, vp[i].w + vq[i].w);
       }
     }
+    if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
     __syncthreads();  // [S2c] gathered projections visible to the epilogue threads of every warp
     mark(5);
 
@@ -423,9 +438,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
             const float sp = softplus_mufu(as[j]);
             if (MODE == CG_FWD) {
               r0[j] = sg * sp;
-            } else {  // d m / d a_f and d m / d a_s; the grad_out factor follows in the scale pass
-              r0[j] = sp * sg * (1.0f - sg);
-              r1[j] = sg * sigmoid_mufu(as[j]);
+            } else {  // d m / d a_f and d m / d a_s  (x grad_out here for BWD_DST, in the scale pass for BWD_SRC)
+              float g = 1.0f;
+              if (MODE == CG_BWD_DST) {
+                const float4 gv = gq[j4 >> 2];
+                g = j == 0 ? gv.x : j == 1 ? gv.y : j == 2 ? gv.z : gv.w;
+              }
+              r0[j] = g * sp * sg * (1.0f - sg);
+              r1[j] = g * sg * sigmoid_mufu(as[j]);
             }
           }
           *reinterpret_cast<float4*>(rowv + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
@@ -439,8 +459,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     __syncthreads();            // [S3] value tile complete
     mark(8);
 
-    // ---- backward: da = grad_out[dst] / deg[dst] * bracket, applied row-wise (lanes = channels)
-    if (MODE != CG_FWD) {
+    // ---- BWD_SRC: da = grad_out[dst] * bracket, applied row-wise (lanes = channels)
+    if (MODE == CG_BWD_SRC) {
 #pragma unroll
       for (int i = 0; i < kRowsPerWarp; ++i) {
         const int e = row0 + i;
@@ -453,18 +473,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         }
       }
       __syncthreads();  // [S3b]
-      // optional single-pass backward: dQ[src] += da, a whole 512-byte row per warp instruction
-      // (lane l owns floats [4l, 4l+4) of [d a_f | d a_s]); order of the float adds is not fixed
-      if (MODE == CG_BWD_DST && pl.dq_atomic) {
+      mark(11);  // scale pass
+    }
+    // ---- BWD_DST single-pass mode: dQ[src] += da, a whole 512-byte row per warp instruction
+    // (lane l owns floats [4l, 4l+4) of [d a_f | d a_s]); the order of the float adds is not fixed
+    if (MODE == CG_BWD_DST && pl.dq_atomic) {
 #pragma unroll
-        for (int i = 0; i < kRowsPerWarp; ++i) {
-          const int e = row0 + i;
-          if (e < cnt) {
-            const float4 v = *(reinterpret_cast<const float4*>(sV + e * VW) + lane);
-            red_add_v4(p.out + (size_t)bSrc[e] * (4 * C) + 2 * C + 4 * lane, v);
-          }
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int e = row0 + i;
+        if (e < cnt) {
+          const float4 v = *(reinterpret_cast<const float4*>(sV + e * VW) + lane);
+          red_add_v4(p.out + (size_t)bSrc[e] * (4 * C) + 2 * C + 4 * lane, v);
         }
       }
+      mark(12);  // dQ atomics
     }
 
     // ---- segmented sum over the owned segments that have slots in this round

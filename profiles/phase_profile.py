@@ -11,7 +11,8 @@ from matdeeplearn_b200 import _lib, process as pr  # noqa: E402
 from matdeeplearn_b200.csr import GraphCSR, gather_rows  # noqa: E402
 
 NAMES = ["loop/setup", "S1 wait rows", "split hi/lo + S2", "MMA issue", "prefetch issue", "gather P/Q",
-         "wait MMA", "gate math", "S3", "reduce", "dWe", "", "", "", "", "rounds"]
+         "wait MMA", "gate math", "S3", "reduce", "dWe", "scale pass (bwd)", "dQ atomics (bwd)", "", "",
+         "rounds"]
 lib = _lib.load()
 dev = torch.device("cuda:0")
 graphs = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
@@ -49,7 +50,7 @@ def bwd():
                                   1, P(ws), wsb, st), "bwd")
 
 
-for name, fn in (("fwd", fwd), ("bwd (dst pass + src pass)", bwd)):
+for name, fn in (("fwd", fwd), ("bwd", bwd)):
     fn(); torch.cuda.synchronize()
     lib.mdl_debug_set_phase_buffer(P(prof))
     prof.zero_()
@@ -59,6 +60,7 @@ for name, fn in (("fwd", fwd), ("bwd (dst pass + src pass)", bwd)):
     v = prof.cpu().tolist()
     rounds = max(v[15], 1)
     print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, "
-          f"{sum(v[:11]) / rounds:.0f} cycles/round")
-    for i in range(11):
-        print(f"   {NAMES[i]:18s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / max(sum(v[:11]), 1):5.1f}%")
+          f"{sum(v[:13]) / rounds:.0f} cycles/round")
+    for i in range(13):
+        if v[i]:
+            print(f"   {NAMES[i]:18s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / max(sum(v[:13]), 1):5.1f}%")
