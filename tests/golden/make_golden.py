@@ -177,8 +177,36 @@ def golden_models():
         print(f"model_{tag}.npz: out {rec['out_train'][:3]} loss {loss.item():.6f}")
 
 
+def golden_test_data():
+    """BASELINE configs[0]: the reference's bundled data/test_data fixture (Pt10 clusters), first 32
+    structures, default CGCNN_demo hyper-parameters (config.yml:121-136).  Inputs built by the product's
+    host builder from the tarball; outputs by the reference's cgcnn.py glue on the oracle ops, fp64."""
+    tar = "/root/reference/data/test_data/test_data.tar.gz"
+    ds = pr.load_ase_json_tar(tar, limit=32)
+    batch = ds.batch()
+    cfg = dict(dim1=100, dim2=150, pre_fc_count=1, gc_count=4, post_fc_count=3)
+    mod = load_ref("models/cgcnn.py", "ref_cgcnn_td")
+    torch.manual_seed(4321)
+    model = mod.CGCNN(data=ds, **cfg).double()
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    model.train()
+    out = model(batch.double())
+    loss = torch.nn.functional.l1_loss(out, batch.y.double())
+    loss.backward()
+    rec = {"out_train": out.detach().numpy(), "loss": np.array(loss.item())}
+    for k in ("x", "edge_index", "edge_attr", "edge_weight", "batch", "u", "y"):
+        rec["in/" + k] = getattr(batch, k).numpy()
+    for k, v in state0.items():
+        rec["param/" + k] = v.numpy().astype(np.float32) if v.is_floating_point() else v.numpy()
+    for k, p in model.named_parameters():
+        rec["grad/" + k] = p.grad.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "testdata_cgcnn_demo_b32.npz"), **rec)
+    print("testdata_cgcnn_demo_b32.npz: loss", loss.item(), "E", batch.edge_index.shape[1])
+
+
 if __name__ == "__main__":
     install_stubs()
     P = load_ref("process/process.py", "ref_process")
     golden_process(P)
     golden_models()
+    golden_test_data()

@@ -167,3 +167,41 @@ def test_metalayer_fused_edge_model_equals_pyg_call_convention():
     assert_close(out_f, out_p, rtol=1e-5, atol_rel=2e-6, what="fused edge model fwd")
     for a, b in zip(grads_f, grads_p):
         assert_close(a, b, rtol=1e-4, atol_rel=2e-5, what="fused edge model grads")
+
+
+def test_config0_test_data_cgcnn_demo_batch32():
+    """BASELINE configs[0]: real data/test_data Pt clusters, batch 32, default CGCNN_demo
+    (dim1=100 -> the fused kernel's SIMT path).  Fixture: tests/golden/make_golden.py."""
+    import os
+    from matdeeplearn_b200 import models as M
+    from matdeeplearn_b200.data import Batch
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "testdata_cgcnn_demo_b32.npz"))
+    b = Batch(**{k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in/")})
+    b.num_graphs = 32
+    cfg = dict(dim1=100, dim2=150, pre_fc_count=1, gc_count=4, post_fc_count=3)
+    model = M.CGCNN(_DS(b), **cfg)
+    model.load_state_dict({k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")})
+    model = model.to(DEV).train()
+    gb = b.to(DEV)
+    out = model(gb)
+    ref = torch.from_numpy(z["out_train"])
+    _log("config0 test_data out", out, ref)
+    assert_close(out, ref, rtol=1e-4, atol_rel=5e-5, what="config0 forward")
+    torch.nn.functional.l1_loss(out, gb.y).backward()
+    gscale = max(float(np.abs(z[k]).max()) for k in z.files if k.startswith("grad/"))
+    for name, p in model.named_parameters():
+        r = torch.from_numpy(z["grad/" + name])
+        err = _maxerr(p.grad, r)
+        assert err <= 2e-3 * float(r.abs().max()) + 2e-5 * gscale, (name, err)
+
+
+def test_gaussian_smear_kernel_matches_reference_module():
+    from matdeeplearn_b200 import functional as MF
+    pg = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "process_golden.npz"))
+    d = torch.from_numpy(pg["smear_in"]).to(DEV)
+    for G in (50, 100, 200):
+        off = torch.from_numpy(pg[f"smear_offset_{G}"]).to(DEV)
+        got = MF.gaussian_smear(d, off, float(pg[f"smear_coeff_{G}"]))
+        ref = torch.from_numpy(pg[f"smear_{G}"])
+        # same formula in fp32; only expf's last-bit rounding may differ between CPU and GPU libm
+        assert (got.cpu() - ref).abs().max().item() <= 2e-7
