@@ -122,8 +122,14 @@ class CGConvFn(torch.autograd.Function):
                                 C, G, _lib.REDUCE[ctx.reduce], _lib.ptr(ws), ws_bytes, _lib.stream())
         _lib.check(rc, "mdl_cgconv_bwd")
         dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
-        dWn = dPQ.t().mm(x)                                                 # [4C, C]
-        db = dPQ[:, :2 * C].sum(0)
+        # dWn = dPQ^T x  [4C, C] and db = column sums of dP: K = N, split over the whole chip
+        dWn = torch.empty_like(Wn)
+        db = torch.empty(2 * C, dtype=x.dtype, device=x.device)
+        nb = lib.mdl_node_grad_workspace_bytes(N, 4 * C, C, 2 * C)
+        nws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        rc = lib.mdl_node_grad(_lib.ptr(dPQ), _lib.ptr(x), _lib.ptr(dWn), _lib.ptr(db), N, 4 * C, C, 2 * C,
+                               _lib.ptr(nws), nb, _lib.stream())
+        _lib.check(rc, "mdl_node_grad")
         dWe = dWeT.t()                                                      # [2C, G]
         dw_f = torch.cat([dWn[0:C], dWn[2 * C:3 * C], dWe[0:C]], 1)
         dw_s = torch.cat([dWn[C:2 * C], dWn[3 * C:4 * C], dWe[C:2 * C]], 1)
