@@ -350,10 +350,18 @@ def run_engine(args, rank, world, local_rank):
         line["clocks"] = clocks
         if not args.no_roofline:
             r = kernel_roofline(args, dev, flush_buf, peak, peak_src)
-            dom = r["bwd_both_passes"] if r["bwd_both_passes"]["ms"] > r["fwd"]["ms"] else r["fwd"]
+            is_bwd = r["bwd_both_passes"]["ms"] > r["fwd"]["ms"]
+            dom = r["bwd_both_passes"] if is_bwd else r["fwd"]
+            traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            if os.path.exists(tpath):
+                t = json.load(open(tpath))
+                if t.get("graphs") == args.roofline_graphs:
+                    traffic = t.get("bwd_bytes" if is_bwd else "fwd_bytes")
             line["roofline"] = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
-                                "unit": "GB/s", "frac": dom["frac"], "traffic": None,
-                                "kernel": "k_cgconv<BWD_DST>+<BWD_SRC>" if dom is r["bwd_both_passes"] else "k_cgconv<FWD>",
+                                "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
+                                "kernel": "k_cgconv_tc<BWD_DST> (whole CGConv backward: single pass, dP + dWe + dQ)"
+                                if is_bwd else "k_cgconv_tc<FWD>",
                                 "peak_source": peak_src, "workload": r["workload"]}
             line["roofline_detail"] = r
         if not args.no_cpu_baseline and world == 1:
