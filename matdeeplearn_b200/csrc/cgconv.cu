@@ -406,9 +406,8 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
     p.seg_ptr = dst_ptr;
     int grid = 0;
     if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid, dq_atomic ? 1 : 0)) return rc;
-    const int tot = G * 2 * C;
-    k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(p.dW_part, grid, G, C, 0, C, dWeT);
-    MDL_LAUNCHED();
+    const int64_t tot = (int64_t)G * 2 * C;  // partial layout [G][2C] == dWeT layout (no channel chunking)
+    if (int rc = sum_partials(p.dW_part, grid, tot, tot, dWeT, tot, nullptr, st)) return rc;
   } else {
     CgPlan plan;
     MDL_REQUIRE(cg_plan(CG_BWD_DST, C, G, &plan), "cgconv_bwd: C=%d G=%d does not fit", C, G);

@@ -32,16 +32,22 @@ k_node_grad(const float* __restrict__ dY, const float* __restrict__ x, float* __
       for (int i = threadIdx.x; i < tn * C; i += blockDim.x) sx[i] = __ldg(x + t0 * C + i);
       __syncthreads();
       if (r < R) {
-        for (int j = 0; j < tn; ++j) {
-          const float a = __ldg(dY + (t0 + j) * R + r);
-          accb += a;
-          const float* row = sx + j * C + c0;
+        float a[kNgTile];
 #pragma unroll
-          for (int c = 0; c < kNgCols; c += 4) {
-            if (c < cw) {
-              const float4 v = *reinterpret_cast<const float4*>(row + c);
-              acc[c] = fmaf(a, v.x, acc[c]); acc[c + 1] = fmaf(a, v.y, acc[c + 1]);
-              acc[c + 2] = fmaf(a, v.z, acc[c + 2]); acc[c + 3] = fmaf(a, v.w, acc[c + 3]);
+        for (int j = 0; j < kNgTile; ++j)  // all loads of the tile in flight before the first use
+          a[j] = (j < tn) ? __ldg(dY + (t0 + j) * R + r) : 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < kNgTile; ++j) {
+          if (j < tn) {
+            accb += a[j];
+            const float* row = sx + j * C + c0;
+#pragma unroll
+            for (int c = 0; c < kNgCols; c += 4) {
+              if (c < cw) {
+                const float4 v = *reinterpret_cast<const float4*>(row + c);
+                acc[c] = fmaf(a[j], v.x, acc[c]); acc[c + 1] = fmaf(a[j], v.y, acc[c + 1]);
+                acc[c + 2] = fmaf(a[j], v.z, acc[c + 2]); acc[c + 3] = fmaf(a[j], v.w, acc[c + 3]);
+              }
             }
           }
         }
@@ -56,16 +62,35 @@ k_node_grad(const float* __restrict__ dY, const float* __restrict__ x, float* __
   }
 }
 
-// out[i] = sum_b part[b][i], i < len, fixed order
-__global__ void k_sum_partials(const float* __restrict__ part, int nparts, int64_t stride, int64_t len,
-                               float* __restrict__ out0, int64_t len0, float* __restrict__ out1) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= len) return;
+// out[i] = sum_b part[b][i], i < len.  Block = 32 outputs x 8 partial-groups: warp w sums partials
+// w, w+8, ... (coalesced 128-byte reads), the 8 group sums are combined in a fixed order.
+__global__ void __launch_bounds__(256)
+k_sum_partials(const float* __restrict__ part, int nparts, int64_t stride, int64_t len,
+               float* __restrict__ out0, int64_t len0, float* __restrict__ out1) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   float acc = 0.0f;
-#pragma unroll 8
-  for (int b = 0; b < nparts; ++b) acc += __ldg(part + (size_t)b * stride + i);
-  if (i < len0) out0[i] = acc;
-  else if (out1) out1[i - len0] = acc;
+  if (i < len) {
+#pragma unroll 4
+    for (int b = warp; b < nparts; b += 8) acc += __ldg(part + (size_t)b * stride + i);
+  }
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && i < len) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    if (i < len0) out0[i] = t;
+    else if (out1) out1[i - len0] = t;
+  }
+}
+
+int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, float* out0, int64_t len0,
+                 float* out1, cudaStream_t st) {
+  k_sum_partials<<<(int)ceil_div<int64_t>(len, 32), 256, 0, st>>>(part, nparts, stride, len, out0, len0, out1);
+  MDL_LAUNCHED();
+  return MDL_OK;
 }
 
 }  // namespace mdl
@@ -98,8 +123,5 @@ extern "C" int mdl_node_grad(const float* dY, const float* x, float* dW, float* 
   k_node_grad<<<ctas, threads, smem, st>>>(dY, x, (float*)workspace, N, R, C, RB, per);
   MDL_LAUNCHED();
   const int64_t len = (int64_t)R * C + RB;
-  k_sum_partials<<<(int)ceil_div<int64_t>(len, 256), 256, 0, st>>>((const float*)workspace, ctas, len, len, dW,
-                                                                    (int64_t)R * C, db);
-  MDL_LAUNCHED();
-  return MDL_OK;
+  return sum_partials((const float*)workspace, ctas, len, len, dW, (int64_t)R * C, db, st);
 }
