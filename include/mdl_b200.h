@@ -161,14 +161,6 @@ MDL_API int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* d
                                const int32_t* src_eid, float* dhid, float* dXT, float* dXB,
                                int64_t num_nodes, int32_t K, int32_t O, void* stream);
 
-/* ---- weight / bias gradient of a node-level Linear (K = number of nodes), the dense tail of the
- * CGConv backward: dW[r,c] = sum_n dY[n,r] x[n,c], db[r] = sum_n dY[n,r] (r < RB).  Node range split
- * over all SMs, deterministic two-stage sum (autograd of lin_f/lin_s, reference cgcnn.py:142). ---- */
-MDL_API size_t mdl_node_grad_workspace_bytes(int64_t num_nodes, int32_t R, int32_t C, int32_t RB);
-MDL_API int mdl_node_grad(const float* dY, const float* x, float* dW, float* db, int64_t num_nodes,
-                          int32_t R, int32_t C, int32_t RB, void* workspace, size_t workspace_bytes,
-                          void* stream);
-
 /* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
  * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).
  * hyper = device {lr, beta1, beta2, eps, weight_decay}; step = device float step count, advanced by

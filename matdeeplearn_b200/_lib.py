@@ -40,8 +40,6 @@ SIGNATURES = {
     "mdl_edge_gather_add": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),
     "mdl_nnconv_msg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "mdl_nnconv_msg_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
-    "mdl_node_grad_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
-    "mdl_node_grad": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _sz, _p]),
     "mdl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i64, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),

@@ -327,6 +327,37 @@ static int cg_check(int64_t N, int64_t E, int C, int G, int reduce) {
   return MDL_OK;
 }
 
+// out[i] = sum_b part[b][i], i < len.  Block = 32 outputs x 8 partial-groups: warp w sums partials
+// w, w+8, ... (coalesced 128-byte reads), the 8 group sums are combined in a fixed order.
+__global__ void __launch_bounds__(256)
+k_sum_partials(const float* __restrict__ part, int nparts, int64_t stride, int64_t len,
+               float* __restrict__ out0, int64_t len0, float* __restrict__ out1) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  float acc = 0.0f;
+  if (i < len) {
+#pragma unroll 4
+    for (int b = warp; b < nparts; b += 8) acc += __ldg(part + (size_t)b * stride + i);
+  }
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && i < len) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    if (i < len0) out0[i] = t;
+    else if (out1) out1[i - len0] = t;
+  }
+}
+
+int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, float* out0, int64_t len0,
+                 float* out1, cudaStream_t st) {
+  k_sum_partials<<<(int)ceil_div<int64_t>(len, 32), 256, 0, st>>>(part, nparts, stride, len, out0, len0, out1);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
 // MDL_CGCONV_IMPL=simt forces the SIMT kernels (cross-checks, fallback timing)
 static bool use_tc(int mode, int C, int G) {
   const char* env = getenv("MDL_CGCONV_IMPL");

@@ -7,14 +7,10 @@ edge size is done inside the fused kernels and never materialised.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import _lib
 from .csr import GraphCSR
-
-_USE_LIBRARY_NODE_GRAD = os.environ.get("MDL_NODE_GRAD", "") == "library"
 
 
 # ----------------------------------------------------------------------------
@@ -126,18 +122,10 @@ class CGConvFn(torch.autograd.Function):
                                 C, G, _lib.REDUCE[ctx.reduce], _lib.ptr(ws), ws_bytes, _lib.stream())
         _lib.check(rc, "mdl_cgconv_bwd")
         dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
-        # dWn = dPQ^T x  [4C, C] and db = column sums of dP: K = N, split over the whole chip
-        if _USE_LIBRARY_NODE_GRAD:   # A/B switch (MDL_NODE_GRAD=library): cuBLAS GEMM + column sum
-            dWn = dPQ.t().mm(x)
-            db = dPQ[:, :2 * C].sum(0)
-            return CGConvFn._finish(ctx, dx, dWn, db, dWeT, C)
-        dWn = torch.empty_like(Wn)
-        db = torch.empty(2 * C, dtype=x.dtype, device=x.device)
-        nb = lib.mdl_node_grad_workspace_bytes(N, 4 * C, C, 2 * C)
-        nws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-        rc = lib.mdl_node_grad(_lib.ptr(dPQ), _lib.ptr(x), _lib.ptr(dWn), _lib.ptr(db), N, 4 * C, C, 2 * C,
-                               _lib.ptr(nws), nb, _lib.stream())
-        _lib.check(rc, "mdl_node_grad")
+        # node-level dense tail: plain library GEMMs (a hand-written split-over-nodes kernel was
+        # measured slower than cuBLAS + a column sum here and was dropped)
+        dWn = dPQ.t().mm(x)                                                 # [4C, C]
+        db = dPQ[:, :2 * C].sum(0)
         return CGConvFn._finish(ctx, dx, dWn, db, dWeT, C)
 
     @staticmethod
