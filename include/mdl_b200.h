@@ -178,10 +178,7 @@ MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr);
  * No reference counterpart: test infrastructure for the kernels above. ---- */
 MDL_API int mdl_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K,
                               int32_t split, void* stream);
-/* same product with both operands stored MN-major (the layout of a [slot][channel] tile used as the
- * K = slots operand of a weight-gradient GEMM); plain TF32; pad = extra bytes per 16-byte MN chunk row */
-MDL_API int mdl_selftest_umma_mn(const float* A, const float* B, float* D, int32_t N, int32_t K,
-                                 int32_t pad, void* stream);
+/* descriptor-field probe used while bringing up umma.cuh: same staging layout, caller-chosen LBO/SBO */
 MDL_API int mdl_selftest_umma_ex(const float* A, const float* B, float* D, int32_t N, int32_t K,
                                  int32_t split, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b, int32_t sbo_b,
                                  void* stream);

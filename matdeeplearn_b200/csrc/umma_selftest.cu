@@ -81,58 +81,6 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
-// Same product, but BOTH operands stored MN-major (4 consecutive rows of A / of B contiguous,
-// 8 k's 16 bytes apart inside a 128-byte core matrix):
-//   byte(mn, k) = (mn/4)*SBO + (k/8)*128 + (k%8)*16 + (mn%4)*4,   SBO = (K/8)*128 + pad
-// which is how a thread-per-slot epilogue naturally writes a [slot][channel] tile that must later
-// serve as the K = slots operand of the weight-gradient GEMM.  Descriptor: SBO = stride between
-// 16-byte MN chunks, LBO = stride between 8-k groups (128), a_major = b_major = 1 in the idesc.
-__global__ void __launch_bounds__(128, 1)
-k_umma_selftest_mn(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
-                   int pad) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t sbo = (uint32_t)(K / 8) * 128 + (uint32_t)pad;
-  uint8_t* sA = sm;
-  uint8_t* sB = sA + (128 / 4) * sbo;
-  uint32_t ncols = 32;
-  while ((int)ncols < N) ncols <<= 1;
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, ncols);
-  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
-  auto off = [&](int mn, int k) { return (uint32_t)(mn >> 2) * sbo + (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16 + (uint32_t)(mn & 3) * 4; };
-  for (int i = tid; i < 128 * K; i += blockDim.x) { const int r = i / K, k = i - r * K; *reinterpret_cast<float*>(sA + off(r, k)) = A[i]; }
-  for (int i = tid; i < N * K; i += blockDim.x) { const int r = i / K, k = i - r * K; *reinterpret_cast<float*>(sB + off(r, k)) = B[i]; }
-  umma::fence_proxy_async_smem();
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
-    const uint32_t idesc = umma::make_idesc_tf32(128, N) | (1u << 15) | (1u << 16);  // A, B MN-major
-    for (int kk = 0; kk < K / 8; ++kk) {
-      const uint64_t ad = umma::make_desc(umma::smem_u32(sA) + kk * 128, 128, sbo);
-      const uint64_t bd = umma::make_desc(umma::smem_u32(sB) + kk * 128, 128, sbo);
-      umma::mma_tf32(tmem, ad, bd, idesc, kk > 0);
-    }
-    umma::mma_commit(&bar);
-  }
-  umma::mbar_wait(&bar, 0);
-  umma::fence_after_sync();
-  for (int c0 = 0; c0 < N; c0 += 16) {
-    float v[16];
-    umma::tmem_ld16(umma::tmem_addr(tmem, warp, c0), v);
-    umma::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c0 + j < N) D[(size_t)tid * N + c0 + j] = v[j];
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
-}
-
 }  // namespace mdl
 
 using namespace mdl;
@@ -160,19 +108,4 @@ extern "C" int mdl_selftest_umma_ex(
     const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t split, int32_t lbo_a,
     int32_t sbo_a, int32_t lbo_b, int32_t sbo_b, void* stream) {
   return selftest_launch(A, B, D, N, K, split, lbo_a, sbo_a, lbo_b, sbo_b, stream);
-}
-
-// MN-major operand storage (see k_umma_selftest_mn); pad = extra bytes per MN chunk (multiple of 16)
-extern "C" int mdl_selftest_umma_mn(
-    const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t pad, void* stream) {
-  MDL_REQUIRE(A && B && D, "selftest_umma_mn: null pointer");
-  MDL_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K % 8 == 0 && pad >= 0 && pad % 16 == 0,
-              "selftest_umma_mn: bad shape");
-  const size_t sbo = (size_t)(K / 8) * 128 + pad;
-  size_t smem = (size_t)(128 / 4 + N / 4) * sbo;
-  MDL_REQUIRE(smem <= 200 * 1024, "selftest_umma_mn: tile too large");
-  MDL_CUDA(cudaFuncSetAttribute(k_umma_selftest_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_umma_selftest_mn<<<1, 128, smem, as_stream(stream)>>>(A, B, D, N, K, pad);
-  MDL_LAUNCHED();
-  return MDL_OK;
 }

@@ -58,21 +58,3 @@ def test_raw_fp32_operands_are_truncated_not_rounded():
     os.makedirs("gpurun_out", exist_ok=True)
     open("gpurun_out/tf32_narrowing.txt", "w").write(f"err vs truncation {e_trunc:.3e}  err vs round-to-nearest {e_rna:.3e}\n")
     assert e_trunc < 1e-4 and e_trunc < 0.1 * e_rna, (e_trunc, e_rna)
-
-
-@pytest.mark.parametrize("N,K,pad", [(64, 128, 0), (64, 128, 16), (128, 64, 16), (32, 128, 16)])
-def test_umma_mn_major_operands(N, K, pad):
-    from matdeeplearn_b200 import _lib
-    lib = _lib.load()
-    dev = torch.device("cuda:0")
-    torch.manual_seed(N + K + pad)
-    A = torch.randn(128, K)
-    B = torch.randn(N, K)
-    D = torch.full((128, N), float("nan"), device=dev)
-    Ad, Bd = A.to(dev), B.to(dev)
-    _lib.check(lib.mdl_selftest_umma_mn(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, pad, _lib.stream()), "umma_mn")
-    torch.cuda.synchronize()
-    ref = A.double() @ B.double().t()
-    scale = (A.abs().double() @ B.abs().double().t()).max().item()
-    err = (D.cpu().double() - ref).abs().max().item()
-    assert err < 2e-3 * scale, (err, scale)
