@@ -273,8 +273,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     __syncthreads();  // [S1] rows + indices of this round visible; value / operand tiles free
     mark(1);
 
-    // ---- this round's node-side loads go out FIRST (their inputs -- the indices -- are in smem
-    // since S1): they then fly during the operand split, the barrier and the MMA issue below.
+    // ---- split hi/lo into the canonical MMA operand layout
+    {
+      const int e = tid & (kTcRows - 1);
+      const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
+      for (int j = (tid >> 7); j < (KP >> 2); j += kTcThreads / kTcRows) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < cnt && 4 * j < GS) {
+          v = *reinterpret_cast<const float4*>(sEA + e * GS + 4 * j);
+          if (4 * j + 0 >= G) v.x = 0.f;  // padding columns: exact zeros
+          if (4 * j + 1 >= G) v.y = 0.f;
+          if (4 * j + 2 >= G) v.z = 0.f;
+          if (4 * j + 3 >= G) v.w = 0.f;
+        }
+        float4 hi;
+        hi.x = umma::tf32_hi(v.x); hi.y = umma::tf32_hi(v.y);
+        hi.z = umma::tf32_hi(v.z); hi.w = umma::tf32_hi(v.w);
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        const uint32_t off = (uint32_t)j * kAChunk + row_off;
+        *reinterpret_cast<float4*>(sAhi + off) = hi;
+        *reinterpret_cast<float4*>(sAlo + off) = lo;
+      }
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();  // [S2] operands staged; the ea landing zone is free for the next round
+    mark(2);
+
+    // ---- contraction on the tensor core (asynchronous; the issuing lane belongs to the LAST warp,
+    // whose other duties in this window are the lightest)
+    if (tid == kTcThreads - 32 && cnt > 0) {
+      umma::fence_after_sync();
+      const uint32_t step_a = 2 * kAChunk, step_b = 2 * (uint32_t)NP * 16;
+      const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
+      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+      uint32_t acc = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 2) ? a_lo : a_hi;
+        const uint32_t b = (pass == 1) ? b_lo : b_hi;
+        for (int kk = 0; kk < (KP >> 3); ++kk) {
+          const uint64_t ad = umma::make_desc(a + kk * step_a, kAChunk, 128);
+          const uint64_t bd = umma::make_desc(b + kk * step_b, (uint32_t)NP * 16, 128);
+          umma::mma_tf32(tmem, ad, bd, idesc, acc);
+          acc = 1;
+        }
+      }
+      umma::mma_commit(&bar);
+    }
+    mark(3);
+
+    // ---- overlap window, part 1: ISSUE every global load (nothing below waits on memory yet)
     // (b) what the reduce stage will need for this warp's first segment
     const int n0 = n_lo + warp;
     int seg_a = 0, seg_b = 0;
@@ -333,58 +382,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         }
       }
     }
-
-    // ---- split hi/lo into the canonical MMA operand layout
-    {
-      const int e = tid & (kTcRows - 1);
-      const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-      for (int j = (tid >> 7); j < (KP >> 2); j += kTcThreads / kTcRows) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < cnt && 4 * j < GS) {
-          v = *reinterpret_cast<const float4*>(sEA + e * GS + 4 * j);
-          if (4 * j + 0 >= G) v.x = 0.f;  // padding columns: exact zeros
-          if (4 * j + 1 >= G) v.y = 0.f;
-          if (4 * j + 2 >= G) v.z = 0.f;
-          if (4 * j + 3 >= G) v.w = 0.f;
-        }
-        float4 hi;
-        hi.x = umma::tf32_hi(v.x); hi.y = umma::tf32_hi(v.y);
-        hi.z = umma::tf32_hi(v.z); hi.w = umma::tf32_hi(v.w);
-        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        const uint32_t off = (uint32_t)j * kAChunk + row_off;
-        *reinterpret_cast<float4*>(sAhi + off) = hi;
-        *reinterpret_cast<float4*>(sAlo + off) = lo;
-      }
-    }
-    umma::fence_proxy_async_smem();
-    umma::fence_before_sync();
-    __syncthreads();  // [S2] operands staged; the ea landing zone is free for the next round
-    mark(2);
-
-    // ---- contraction on the tensor core (asynchronous; the issuing lane belongs to the LAST warp,
-    // whose other duties in this window are the lightest)
-    if (tid == kTcThreads - 32 && cnt > 0) {
-      umma::fence_after_sync();
-      const uint32_t step_a = 2 * kAChunk, step_b = 2 * (uint32_t)NP * 16;
-      const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
-      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
-      uint32_t acc = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = (pass == 2) ? a_lo : a_hi;
-        const uint32_t b = (pass == 1) ? b_lo : b_hi;
-        for (int kk = 0; kk < (KP >> 3); ++kk) {
-          const uint64_t ad = umma::make_desc(a + kk * step_a, kAChunk, 128);
-          const uint64_t bd = umma::make_desc(b + kk * step_b, (uint32_t)NP * 16, 128);
-          umma::mma_tf32(tmem, ad, bd, idesc, acc);
-          acc = 1;
-        }
-      }
-      umma::mma_commit(&bar);
-    }
-    mark(3);
-
-    // ---- overlap window, part 1: ISSUE the next round's index loads (nothing here waits on memory)
     // (a) indices of the next round -- last: in BWD_SRC they are a dependent chain, which now
     // overlaps with everything issued above
     int ncnt = 0;
