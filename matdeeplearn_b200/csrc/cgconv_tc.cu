@@ -27,7 +27,8 @@ constexpr int kTcRows = 128;  // slots per round = MMA M
 // read the same row of DIFFERENT chunks (the dWe B-fragments) fall on different banks.  The UMMA
 // descriptor simply carries this value as its leading-dimension byte offset.
 constexpr uint32_t kAChunk = kTcRows * 16 + 16;
-constexpr int kTcTE = 112;    // ownership granularity (leaves head-room for straddling segments)
+constexpr int kTcTE = 112;
+constexpr int kInfoCap = 512;  // tile-bound records kept in smem per CTA (refilled if a CTA owns more tiles)    // ownership granularity (leaves head-room for straddling segments)
 
 // optional per-phase cycle accounting (development aid): 16 counters, thread 0 of each CTA adds
 // the cycles it spent between consecutive phase marks.  Enabled by mdl_debug_set_phase_buffer.
@@ -37,7 +38,7 @@ struct TcPlan {
   unsigned long long* prof;
   int dq_atomic;  // BWD_DST also scatters da into dQ[src] with vector float atomics (no BWD_SRC pass)
   int NP, KP, GS, VW, tmem_cols, nitem;
-  uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, total;
+  uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, offInfo, total;
 };
 
 static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
@@ -63,8 +64,9 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   // The value tile has its own region: it is filled (gathered node projections) while the MMAs of
   // the same round are still reading the operand tiles, so it cannot alias them.
   uint32_t end = pl->offEA + ea;
-  if (end + v + idx <= (uint32_t)kMaxDynSmem) {
-    pl->offV = end; pl->offIdx = end + v; pl->total = end + v + idx;
+  const uint32_t info = kInfoCap * 16;  // per-CTA table of tile bounds (TileInfo)
+  if (end + v + idx + info <= (uint32_t)kMaxDynSmem) {
+    pl->offV = end; pl->offIdx = end + v; pl->offInfo = end + v + idx; pl->total = end + v + idx + info;
     return true;
   }
   return false;
@@ -127,7 +129,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ TileInfo sh_tile[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C, G = p.G, W2 = 2 * C;
   const int NP = pl.NP, KP = pl.KP, GS = pl.GS, VW = pl.VW;
@@ -139,22 +140,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   float* sEA = reinterpret_cast<float*>(smem + pl.offEA);  // [128][GS] row-major landing zone
   float* sV = reinterpret_cast<float*>(smem + pl.offV);    // [128][VW]
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);    // [2 buffers][src|dst][128]
+  TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);  // bounds of this CTA's tiles
 
   // tiles of this CTA: blockIdx.x, +gridDim.x, ...
   const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  auto compute_info = [&](int k) {  // one thread
-    TileInfo t;
-    if (k < my_tiles) {
+  // Bounds of tile k of this CTA (two short dependent-load chains).  ALL tiles of the CTA are
+  // resolved up front, one per thread, so the chains run in parallel once instead of serially
+  // on one thread inside every round.
+  int info_base = 0;
+  auto fill_infos = [&](int base) {
+    for (int k = base + tid; k < min(my_tiles, base + kInfoCap); k += kTcThreads) {
+      TileInfo t;
       const int tile = blockIdx.x + k * gridDim.x;
       t.n_lo = first_segment_at_or_after<MODE>(p, tile * kTcTE);
       t.n_hi = (tile == p.n_tiles - 1) ? p.N : first_segment_at_or_after<MODE>(p, (tile + 1) * kTcTE);
       if (t.n_hi < t.n_lo) t.n_hi = t.n_lo;
       t.e_lo = __ldg(p.seg_ptr + t.n_lo);
       t.e_hi = __ldg(p.seg_ptr + t.n_hi);
-    } else {
-      t.n_lo = t.n_hi = t.e_lo = t.e_hi = 0;
+      sInfo[k - base] = t;
     }
-    sh_tile[k % 3] = t;
   };
 
   // ---- one-time setup
@@ -163,8 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     umma::mbar_init(&bar, 1);
     umma::fence_mbar_init();
   }
-  if (tid == 64) compute_info(0);
-  if (tid == 96) compute_info(1);
+  fill_infos(0);
   for (int i = tid; i < NP * KP; i += kTcThreads) {
     const int n = i % NP, k = i / NP;
     const float w = (k < G && n < W2) ? __ldg(p.WeT + (size_t)k * W2 + n) : 0.0f;
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
 
   int k = 0, rd = 0, buf = 0;
   if (my_tiles > 0) {
-    const TileInfo t0 = sh_tile[0];
+    const TileInfo t0 = sInfo[0];
     const int c0 = min(t0.e_hi - t0.e_lo, kTcRows);
     const NextIdx ni = issue_idx(t0.e_lo, c0);
     land_idx_and_rows(ni, c0, 0);
@@ -257,7 +260,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   const int c_begin = part * chh;
 
   while (k < my_tiles) {
-    const TileInfo T = sh_tile[k % 3];
+    if (k + 1 >= info_base + kInfoCap && info_base + kInfoCap < my_tiles) {  // table exhausted: refill
+      __syncthreads();
+      info_base = k;
+      fill_infos(info_base);
+      __syncthreads();
+    }
+    const TileInfo T = sInfo[k - info_base];
     const int rounds = max(1, (T.e_hi - T.e_lo + kTcRows - 1) / kTcRows);
     const int r_lo = T.e_lo + rd * kTcRows;
     const int r_hi = min(T.e_hi, r_lo + kTcRows);
@@ -387,12 +396,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     int ncnt = 0;
     NextIdx ni{0, 0, 0};
     if (nk < my_tiles) {
-      const TileInfo Tn = sh_tile[nk % 3];
+      const TileInfo Tn = sInfo[nk - info_base];
       const int nr_lo = Tn.e_lo + nrd * kTcRows;
       ncnt = min(Tn.e_hi - nr_lo, kTcRows);
       ni = issue_idx(nr_lo, ncnt);
     }
-    if (rd == 0 && tid == 64) compute_info(k + 2);  // two tiles ahead (own dependent loads)
     mark(4);
 
     // ---- overlap window, part 2: LAND, in issue order: this round's P+Q first (issued first),
