@@ -143,11 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);  // bounds of this CTA's tiles
 
   // tiles of this CTA: blockIdx.x, +gridDim.x, ...
-  // CONTIGUOUS tile ranges per CTA: consecutive tiles cover the same graphs, so the node rows a
-  // CTA gathers (P/Q of a graph's ~30 nodes) are re-requested by the SAME SM round after round.
-  const int tiles_per_cta = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile0 = (int)blockIdx.x * tiles_per_cta;
-  const int my_tiles = max(0, min(tiles_per_cta, p.n_tiles - tile0));
+  const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   // Bounds of tile k of this CTA (two short dependent-load chains).  ALL tiles of the CTA are
   // resolved up front, one per thread, so the chains run in parallel once instead of serially
   // on one thread inside every round.
@@ -155,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   auto fill_infos = [&](int base) {
     for (int k = base + tid; k < min(my_tiles, base + kInfoCap); k += kTcThreads) {
       TileInfo t;
-      const int tile = tile0 + k;
+      const int tile = blockIdx.x + k * gridDim.x;
       t.n_lo = first_segment_at_or_after<MODE>(p, tile * kTcTE);
       t.n_hi = (tile == p.n_tiles - 1) ? p.N : first_segment_at_or_after<MODE>(p, (tile + 1) * kTcTE);
       if (t.n_hi < t.n_lo) t.n_hi = t.n_lo;
