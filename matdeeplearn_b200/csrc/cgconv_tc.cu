@@ -59,7 +59,7 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   const int n_dw = (2 * C / 4) * (KP / 8);
   pl->nitem = 1;
   (void)n_dw;
-  if (mode == CG_BWD_DST && KP > 64) return false;  // dWe split: <= 8 SIMT k-chunks + 32 MMA columns
+  if (mode == CG_BWD_DST && KP > 64) return false;  // dWe warp tiling: 4 column groups of 16
   pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
   // The value tile has its own region: it is filled (gathered node projections) while the MMAs of
   // the same round are still reading the operand tiles, so it cannot alias them.
@@ -550,81 +550,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     }
     mark(9);
 
-    // ---- dWe^T[ch, k] += sum_slots da[slot, ch] * ea[slot, k].  The legacy warp-level tensor
-    // path delivers only ~256 tf32 FMA/clk/SM here, i.e. ~85 fp32-faithful (3xTF32) products/clk,
-    // LESS than the 128 fp32 FMA/clk of the SIMT pipe -- so the two pipes split the k-columns and run
-    // concurrently: warps 0-7 take k-chunks [0, ns) with plain fp32 FMAs, warps 8-15 take the last
-    // 32 columns [4*ns, 4*ns+32) with mma.sync m16n8k8 (3xTF32).
-    //   SIMT item  = (4 channels, 4 k) register tile per thread, operands re-assembled as hi + lo.
-    //   MMA warp (mgrp, ngrp) = 32 channels x 16 columns = 2x2 tiles, rows/columns PERMUTED so every
-    //   fragment is a vector load: channel(mi, row gid|gid+8) = mgrp*32 + 4*gid + 2*mi + {0|1},
-    //   column(ni, col gid) = c0 + ngrp*16 + 2*gid + ni; A = da^T from the value tile (split in
-    //   registers), B = ea from the already split operand tiles: element (slot e, column g) sits at
-    //   (g/4)*kAChunk + (e/8)*128 + (e%8)*16 + (g%4)*4 in sAhi / sAlo.
+    // ---- dWe^T[ch, k] += sum_slots da[slot, ch] * ea[slot, k] on the warp-level tensor path
+    // (mma.sync m16n8k8 tf32, 3xTF32).  Warp (mgrp, ngrp) owns 32 channels x 16 k-columns = 2x2
+    // MMA tiles whose rows/columns are PERMUTED so that every fragment is a vector load:
+    //   channel(tile mi, fragment row gid | gid+8) = mgrp*32 + 4*gid + 2*mi + {0 | 1}
+    //   column (tile ni, fragment col gid)        = ngrp*16 + 2*gid + ni
+    // A = da^T from the value tile (float4 per slot, split hi/lo in registers); B = ea straight
+    // from the already split operand tiles (float2 per slot, element (slot e, column g) sits at
+    // (g/4)*2048 + (e/8)*128 + (e%8)*16 + (g%4)*4 in sAhi / sAlo).
     if (MODE == CG_BWD_DST && cnt > 0) {
-      const int ns = (KP >= 32) ? ((KP - 32) >> 2) : 0;  // k-chunks handled by the SIMT half
-      if (warp < 8) {
-        const int item = tid;
-        if (item < 32 * ns) {
-          const int c4 = item & 31, k4 = item >> 5;
-          const uint8_t* h0 = sAhi + (uint32_t)k4 * kAChunk;
-          const uint8_t* l0 = sAlo + (uint32_t)k4 * kAChunk;
-#pragma unroll 2
-          for (int e = 0; e < cnt; ++e) {
-            const uint32_t ro = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-            const float4 da = *reinterpret_cast<const float4*>(sV + e * VW + 4 * c4);
-            const float4 eh = *reinterpret_cast<const float4*>(h0 + ro);
-            const float4 el = *reinterpret_cast<const float4*>(l0 + ro);
-            const float dv[4] = {da.x, da.y, da.z, da.w};
-            const float ev[4] = {eh.x + el.x, eh.y + el.y, eh.z + el.z, eh.w + el.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int w = 0; w < 4; ++w) dacc[u][w] = fmaf(dv[u], ev[w], dacc[u][w]);
-          }
+      const int gid = lane >> 2, tig = lane & 3;
+      const int mgrp = warp & 3, ngrp = warp >> 2;
+      const int chunk = ngrp * 4 + (gid >> 1);           // 16-byte chunk of the operand tiles
+      const bool col_ok = chunk < (KP >> 2);
+      const uint32_t cb = (uint32_t)chunk * kAChunk + (uint32_t)(gid & 1) * 8;
+      for (int e0 = 0; e0 < cnt; e0 += 8) {
+        const int ea_ = e0 + tig, eb_ = e0 + tig + 4;
+        float4 a_lo_row = make_float4(0.f, 0.f, 0.f, 0.f), a_hi_row = a_lo_row;
+        if (ea_ < cnt) a_lo_row = *reinterpret_cast<const float4*>(sV + ea_ * VW + mgrp * 32 + 4 * gid);
+        if (eb_ < cnt) a_hi_row = *reinterpret_cast<const float4*>(sV + eb_ * VW + mgrp * 32 + 4 * gid);
+        float2 bh0 = make_float2(0.f, 0.f), bh1 = bh0, bl0 = bh0, bl1 = bh0;
+        if (col_ok) {
+          const uint32_t rb0 = (uint32_t)(ea_ >> 3) * 128 + (uint32_t)(ea_ & 7) * 16;
+          const uint32_t rb1 = (uint32_t)(eb_ >> 3) * 128 + (uint32_t)(eb_ & 7) * 16;
+          bh0 = *reinterpret_cast<const float2*>(sAhi + cb + rb0);  // rows >= cnt are zero in the tiles
+          bh1 = *reinterpret_cast<const float2*>(sAhi + cb + rb1);
+          bl0 = *reinterpret_cast<const float2*>(sAlo + cb + rb0);
+          bl1 = *reinterpret_cast<const float2*>(sAlo + cb + rb1);
         }
-      } else {
-        const int gid = lane >> 2, tig = lane & 3;
-        const int mgrp = warp & 3, ngrp = (warp >> 2) & 1;
-        const int chunk = ns + ngrp * 4 + (gid >> 1);      // 16-byte chunk of the operand tiles
-        const bool col_ok = chunk < (KP >> 2);
-        const uint32_t cb = (uint32_t)chunk * kAChunk + (uint32_t)(gid & 1) * 8;
-        for (int e0 = 0; e0 < cnt; e0 += 8) {
-          const int ea_ = e0 + tig, eb_ = e0 + tig + 4;
-          float4 a_lo_row = make_float4(0.f, 0.f, 0.f, 0.f), a_hi_row = a_lo_row;
-          if (ea_ < cnt) a_lo_row = *reinterpret_cast<const float4*>(sV + ea_ * VW + mgrp * 32 + 4 * gid);
-          if (eb_ < cnt) a_hi_row = *reinterpret_cast<const float4*>(sV + eb_ * VW + mgrp * 32 + 4 * gid);
-          float2 bh0 = make_float2(0.f, 0.f), bh1 = bh0, bl0 = bh0, bl1 = bh0;
-          if (col_ok) {
-            const uint32_t rb0 = (uint32_t)(ea_ >> 3) * 128 + (uint32_t)(ea_ & 7) * 16;
-            const uint32_t rb1 = (uint32_t)(eb_ >> 3) * 128 + (uint32_t)(eb_ & 7) * 16;
-            bh0 = *reinterpret_cast<const float2*>(sAhi + cb + rb0);  // rows >= cnt are zero in the tiles
-            bh1 = *reinterpret_cast<const float2*>(sAhi + cb + rb1);
-            bl0 = *reinterpret_cast<const float2*>(sAlo + cb + rb0);
-            bl1 = *reinterpret_cast<const float2*>(sAlo + cb + rb1);
-          }
-          const float ar0[4] = {a_lo_row.x, a_lo_row.y, a_lo_row.z, a_lo_row.w};  // slot e0+tig
-          const float ar1[4] = {a_hi_row.x, a_hi_row.y, a_hi_row.z, a_hi_row.w};  // slot e0+tig+4
-          float ah[2][4], al[2][4];
+        const float ar0[4] = {a_lo_row.x, a_lo_row.y, a_lo_row.z, a_lo_row.w};  // slot e0+tig
+        const float ar1[4] = {a_hi_row.x, a_hi_row.y, a_hi_row.z, a_hi_row.w};  // slot e0+tig+4
+        float ah[2][4], al[2][4];
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            // fragment order: (row gid, k tig), (row gid+8, k tig), (row gid, k tig+4), (row gid+8, k tig+4)
-            const float av[4] = {ar0[2 * mi], ar0[2 * mi + 1], ar1[2 * mi], ar1[2 * mi + 1]};
+        for (int mi = 0; mi < 2; ++mi) {
+          // fragment order: (row gid, k tig), (row gid+8, k tig), (row gid, k tig+4), (row gid+8, k tig+4)
+          const float av[4] = {ar0[2 * mi], ar0[2 * mi + 1], ar1[2 * mi], ar1[2 * mi + 1]};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { ah[mi][u] = umma::tf32_hi(av[u]); al[mi][u] = av[u] - ah[mi][u]; }
-          }
-          // pass-major order: four independent accumulators back to back (no dependent MMA chain)
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-              for (int ni = 0; ni < 2; ++ni) {
-                const float b0 = (pass == 1) ? (ni ? bl0.y : bl0.x) : (ni ? bh0.y : bh0.x);
-                const float b1 = (pass == 1) ? (ni ? bl1.y : bl1.x) : (ni ? bh1.y : bh1.x);
-                mma_tf32_16x8x8(dacc[2 * mi + ni], (pass == 2) ? al[mi] : ah[mi], b0, b1);
-              }
+          for (int u = 0; u < 4; ++u) { ah[mi][u] = umma::tf32_hi(av[u]); al[mi][u] = av[u] - ah[mi][u]; }
         }
+        // pass-major order: four independent accumulators back to back (no dependent MMA chain)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+              const float b0 = (pass == 1) ? (ni ? bl0.y : bl0.x) : (ni ? bh0.y : bh0.x);
+              const float b1 = (pass == 1) ? (ni ? bl1.y : bl1.x) : (ni ? bh1.y : bh1.x);
+              mma_tf32_16x8x8(dacc[2 * mi + ni], (pass == 2) ? al[mi] : ah[mi], b0, b1);
+            }
       }
     }
     mark(10);
@@ -633,37 +607,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   }  // work items
 
   if (MODE == CG_BWD_DST) {
+    // C fragment of tile (mi, ni): rows gid | gid+8 -> channels 2*mi | 2*mi+1 of this lane's quad,
+    // cols 2*tig | 2*tig+1 -> fragment columns, i.e. k = ngrp*16 + 2*(2*tig | 2*tig+1) + ni
+    const int gid = lane >> 2, tig = lane & 3;
+    const int mgrp = warp & 3, ngrp = warp >> 2;
     float* part = p.dW_part + (size_t)blockIdx.x * G * W2;
-    const int ns = (KP >= 32) ? ((KP - 32) >> 2) : 0;
-    if (warp < 8) {  // SIMT half: dacc[u][w] = (channel 4*c4+u, k = 4*k4+w)
-      const int item = tid;
-      if (item < 32 * ns) {
-        const int c4 = item & 31, k4 = item >> 5;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int kcol = 4 * k4 + w;
-          if (kcol < G)
-            *reinterpret_cast<float4*>(part + (size_t)kcol * W2 + 4 * c4) =
-                make_float4(dacc[0][w], dacc[1][w], dacc[2][w], dacc[3][w]);
-        }
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int ch = mgrp * 32 + 4 * gid + 2 * mi;
+        const int k0 = ngrp * 16 + 2 * (2 * tig) + ni, k1 = ngrp * 16 + 2 * (2 * tig + 1) + ni;
+        const float* d = dacc[2 * mi + ni];
+        if (k0 < G) { part[(size_t)k0 * W2 + ch] = d[0]; part[(size_t)k0 * W2 + ch + 1] = d[2]; }
+        if (k1 < G) { part[(size_t)k1 * W2 + ch] = d[1]; part[(size_t)k1 * W2 + ch + 1] = d[3]; }
       }
-    } else {
-      // C fragment of tile (mi, ni): rows gid | gid+8 -> channels 2*mi | 2*mi+1 of this lane's quad,
-      // cols 2*tig | 2*tig+1 -> fragment columns, i.e. k = c0 + ngrp*16 + 2*(2*tig | 2*tig+1) + ni
-      const int gid = lane >> 2, tig = lane & 3;
-      const int mgrp = warp & 3, ngrp = (warp >> 2) & 1;
-      const int c0 = 4 * ns;
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni) {
-          const int ch = mgrp * 32 + 4 * gid + 2 * mi;
-          const int k0 = c0 + ngrp * 16 + 2 * (2 * tig) + ni, k1 = c0 + ngrp * 16 + 2 * (2 * tig + 1) + ni;
-          const float* d = dacc[2 * mi + ni];
-          if (k0 < G) { part[(size_t)k0 * W2 + ch] = d[0]; part[(size_t)k0 * W2 + ch + 1] = d[2]; }
-          if (k1 < G) { part[(size_t)k1 * W2 + ch] = d[1]; part[(size_t)k1 * W2 + ch + 1] = d[3]; }
-        }
-    }
   }
   cp_async_wait_all();
   umma::fence_before_sync();
