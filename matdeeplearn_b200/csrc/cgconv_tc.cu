@@ -414,20 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
               make_float4(vp[i].x + vq[i].x, vp[i].y + vq[i].y, vp[i].z + vq[i].z, vp[i].w + vq[i].w);
       }
     }
-    if (nk < my_tiles) {
-      land_idx_and_rows(ni, ncnt, buf ^ 1);
-      // pull the NEXT round's node projections from DRAM into L2 now (no registers, no smem):
-      // its gather, one round from now, then pays an L2 hit instead of a DRAM round trip.
-      // lane -> (row = lane/4, 128-byte line = lane%4) of this warp's 8 rows; P row and Q row.
-      const int prow = lane >> 2, pline = lane & 3;
-      const int pd = __shfl_sync(0xffffffffu, ni.d, prow), ps = __shfl_sync(0xffffffffu, ni.s, prow);
-      if (row0 + prow < ncnt) {
-        const float* a0 = p.PQ + (size_t)pd * (4 * C) + pline * 32;
-        const float* a1 = p.PQ + (size_t)ps * (4 * C) + 2 * C + pline * 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a0));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a1));
-      }
-    }
+    if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
     __syncthreads();  // [S2c] gathered projections visible to the epilogue threads of every warp
     mark(5);
 
