@@ -59,6 +59,11 @@ class Batch(Data):
             us.append(d.u.reshape(1, -1))
             ys.append(d.y.reshape(-1)[:1] if d.y.ndim <= 1 else d.y)
             off += n
+        extras = {}
+        if all(hasattr(d, "d_hat") for d in graphs):
+            # normalised distances behind edge_attr (process.assemble_dataset keeps them): lets a
+            # consumer ship 4 B/edge to the GPU and expand the Gaussian basis there
+            extras["d_hat"] = torch.cat([d.d_hat for d in graphs], 0)
         out = cls(
             x=torch.cat(xs, 0),
             edge_index=torch.cat(eis, 1),
@@ -67,6 +72,7 @@ class Batch(Data):
             batch=torch.cat(bs, 0),
             u=torch.cat(us, 0),
             y=torch.cat(ys, 0),
+            **extras,
         )
         out.num_graphs = len(graphs)
         return out
@@ -120,4 +126,8 @@ class GraphDataset:
 
     def batch(self, idx=None):
         gs = self.graphs if idx is None else [self.graphs[i] for i in idx]
-        return Batch.from_data_list(gs)
+        b = Batch.from_data_list(gs)
+        smear = getattr(self, "smear", None)
+        if smear is not None and hasattr(b, "d_hat"):
+            b.smear = dict(smear)   # (start, stop, resolution, width) of the GaussianSmearing that made edge_attr
+        return b

@@ -60,9 +60,10 @@ def segment_reduce(src, ptr, perm=None, reduce="mean"):
 # ----------------------------------------------------------------------------
 # GaussianSmearing
 # ----------------------------------------------------------------------------
-def gaussian_smear(dist, offset, coeff):
+def gaussian_smear(dist, offset, coeff, out=None):
     dist = dist.contiguous()
-    out = torch.empty((dist.shape[0], offset.shape[0]), dtype=torch.float32, device=dist.device)
+    if out is None:
+        out = torch.empty((dist.shape[0], offset.shape[0]), dtype=torch.float32, device=dist.device)
     rc = _lib.load().mdl_gaussian_smear(_lib.ptr(dist), _lib.ptr(offset.contiguous()), _lib.ptr(out),
                                         dist.shape[0], offset.shape[0], float(coeff), _lib.stream())
     _lib.check(rc, "mdl_gaussian_smear")

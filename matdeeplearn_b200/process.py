@@ -109,6 +109,7 @@ def assemble_dataset(structures, targets, radius=DEFAULT_RADIUS, neighbors=DEFAU
         g.edge_attr = gaussian_expand(g.d_hat, edge_length)
     ds = GraphDataset(graphs)
     ds.edge_range = (lo, hi)
+    ds.smear = dict(start=0.0, stop=1.0, resolution=edge_length, width=0.2)  # reference process.py:500-502
     return ds
 
 

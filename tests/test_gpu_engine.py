@@ -64,6 +64,25 @@ def test_from_host_graph_equals_eager_and_tracks_oracle():
         assert abs(a - r) <= 5e-4 * max(1.0, abs(r)), (l_eager, l_ref)
 
 
+def test_from_host_device_side_gaussian_expansion_matches_materialised_edge_attr():
+    """from_host ships d_hat and expands GaussianSmearing (reference process.py:580-590) on the GPU when
+    the batch carries it; the step must equal the one fed the host-materialised edge_attr."""
+    from matdeeplearn_b200.engine import TrainStep
+    ds, batch, model = _setup()
+    assert hasattr(batch, "d_hat") and batch.smear["resolution"] == batch.edge_attr.shape[1]
+    m1, m2 = copy.deepcopy(model).to(DEV).train(), copy.deepcopy(model).to(DEV).train()
+    s1, s2 = TrainStep(m1, lr=1e-3), TrainStep(m2, lr=1e-3)
+    pinned = batch.pin_memory()
+    la = [s1.from_host(pinned, expand_edge_attr=True) for _ in range(4)]
+    lb = [s2.from_host(pinned, expand_edge_attr=False) for _ in range(4)]
+    assert s2.last_h2d_bytes - s1.last_h2d_bytes == 4 * (batch.edge_attr.numel() - batch.d_hat.numel())
+    for a, c in zip(la, lb):
+        assert abs(a - c) <= 2e-6 * max(1.0, abs(a)), (la, lb)
+    key = [k for k in s1._host_graphs if k[-1]][0]
+    static = s1._host_graphs[key][0]
+    assert (static.edge_attr.cpu() - batch.edge_attr).abs().max().item() < 2e-6
+
+
 def test_flat_adamw_matches_torch_adamw():
     from matdeeplearn_b200 import dist as mdist
     torch.manual_seed(3)
