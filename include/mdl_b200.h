@@ -161,6 +161,75 @@ MDL_API int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* d
                                const int32_t* src_eid, float* dhid, float* dXT, float* dXB,
                                int64_t num_nodes, int32_t K, int32_t O, void* stream);
 
+/* ---- batch assembly from a device-resident dataset -----------------------------------------
+ * Replaces the reference's per-step CPU collate + H2D copy: PyG DataLoader -> Batch.from_data_list
+ * (matdeeplearn/training/training.py:300-307) and data.to(rank) (training.py:39).
+ *
+ * mdl_graph_store: every graph of the processed dataset concatenated on the device, i.e. one
+ * block-diagonal graph in the reference's tensor layout (process.py:504-523), plus the
+ * destination-major layout mdl_csr_from_coo produces over ALL its edges (optional: NULL dst_ptr
+ * means "no layout stored").  edge_attr may be NULL when d_hat (the normalised distance the
+ * Gaussian basis is expanded from, process.py:486-502) is stored instead.
+ * Node ids in src/dst/dst_src/dst_dst are store-global; dst_eid/src_slot are store-global edge /
+ * slot numbers.  All pointers are device pointers; the two structs themselves live on the host. */
+typedef struct mdl_graph_store {
+  int64_t num_graphs, num_nodes, num_edges;
+  int32_t F, G, U, Y;              /* widths of x, edge_attr, u, y rows */
+  const int64_t* node_ptr;         /* [num_graphs+1] */
+  const int64_t* edge_ptr;         /* [num_graphs+1] */
+  const float* x;                  /* [num_nodes, F] */
+  const int32_t* src;              /* [num_edges] edge_index[0] */
+  const int32_t* dst;              /* [num_edges] edge_index[1] */
+  const float* d_hat;              /* [num_edges] or NULL */
+  const float* edge_weight;        /* [num_edges] */
+  const float* edge_attr;          /* [num_edges, G] or NULL */
+  const float* u;                  /* [num_graphs, U] */
+  const float* y;                  /* [num_graphs, Y] */
+  const int32_t* dst_ptr;          /* [num_nodes+1] */
+  const int32_t* dst_src;          /* [num_edges] */
+  const int32_t* dst_dst;          /* [num_edges] */
+  const int32_t* dst_eid;          /* [num_edges] */
+  const int32_t* src_ptr;          /* [num_nodes+1] */
+  const int32_t* src_slot;         /* [num_edges] */
+  const float* inv_deg_dst;        /* [num_nodes] */
+  const float* inv_deg_src;        /* [num_nodes] */
+} mdl_graph_store;
+
+/* One batch = graphs graph_ids[0..B) in that order.  node_off/edge_off are the exclusive prefix
+ * sums of their node/edge counts ([B+1] each, device), N and E the totals.  Outputs are exactly
+ * Batch.from_data_list's tensors (x, edge_index int64 [2,E], edge_weight, edge_attr, batch, u, y;
+ * d_hat and edge_attr optional) and, when dst_ptr != NULL, the arrays mdl_csr_from_coo would
+ * produce for that batch (bit-identical) plus edge_attr in slot order (optional).  When the store
+ * holds no edge_attr it is expanded as exp(smear_coeff * (d_hat - smear_offset[j])^2). */
+typedef struct mdl_batch_out {
+  int64_t B, N, E;
+  const int64_t* graph_ids;
+  const int64_t* node_off;
+  const int64_t* edge_off;
+  float* x;
+  int64_t* edge_index;
+  float* d_hat;                    /* optional */
+  float* edge_weight;
+  float* edge_attr;                /* optional */
+  float* edge_attr_slots;          /* optional, needs the layout outputs */
+  int64_t* batch;
+  float* u;
+  float* y;
+  int32_t* dst_ptr;                /* NULL: skip every layout output below */
+  int32_t* dst_src;
+  int32_t* dst_dst;
+  int32_t* dst_eid;
+  int32_t* src_ptr;
+  int32_t* src_slot;
+  float* inv_deg_dst;
+  float* inv_deg_src;
+  int32_t* graph_ptr;
+  const float* smear_offset;       /* [G] device, or NULL when the store holds edge_attr */
+  float smear_coeff;
+} mdl_batch_out;
+
+MDL_API int mdl_assemble_batch(const mdl_graph_store* store, const mdl_batch_out* out, void* stream);
+
 /* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
  * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).
  * hyper = device {lr, beta1, beta2, eps, weight_decay}; step = device float step count, advanced by

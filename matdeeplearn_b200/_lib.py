@@ -20,6 +20,28 @@ _i32 = C.c_int32
 _f32 = C.c_float
 _sz = C.c_size_t
 
+
+
+class GraphStoreC(C.Structure):
+    """mdl_graph_store (include/mdl_b200.h); field order and types must match the header
+    (tests/test_cabi.py compiles the header with gcc and compares every offset)."""
+    _fields_ = ([("num_graphs", _i64), ("num_nodes", _i64), ("num_edges", _i64),
+                 ("F", _i32), ("G", _i32), ("U", _i32), ("Y", _i32)] +
+                [(n, _p) for n in ("node_ptr", "edge_ptr", "x", "src", "dst", "d_hat", "edge_weight", "edge_attr",
+                                   "u", "y", "dst_ptr", "dst_src", "dst_dst", "dst_eid", "src_ptr", "src_slot",
+                                   "inv_deg_dst", "inv_deg_src")])
+
+
+class BatchOutC(C.Structure):
+    """mdl_batch_out (include/mdl_b200.h)."""
+    _fields_ = ([("B", _i64), ("N", _i64), ("E", _i64)] +
+                [(n, _p) for n in ("graph_ids", "node_off", "edge_off", "x", "edge_index", "d_hat", "edge_weight",
+                                   "edge_attr", "edge_attr_slots", "batch", "u", "y", "dst_ptr", "dst_src",
+                                   "dst_dst", "dst_eid", "src_ptr", "src_slot", "inv_deg_dst", "inv_deg_src",
+                                   "graph_ptr", "smear_offset")] +
+                [("smear_coeff", _f32)])
+
+
 # name -> (restype, argtypes); must list every symbol of include/mdl_b200.h
 SIGNATURES = {
     "mdl_version": (C.c_int, []),
@@ -40,6 +62,7 @@ SIGNATURES = {
     "mdl_edge_gather_add": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),
     "mdl_nnconv_msg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "mdl_nnconv_msg_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
+    "mdl_assemble_batch": (C.c_int, [C.POINTER(GraphStoreC), C.POINTER(BatchOutC), _p]),
     "mdl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i64, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),

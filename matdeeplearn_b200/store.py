@@ -1,0 +1,180 @@
+"""Device-resident dataset + GPU batch assembly.
+
+The reference re-collates every batch on the CPU (PyG DataLoader ->
+Batch.from_data_list, matdeeplearn/training/training.py:300-307) and copies it to
+the device (`data.to(rank)`, training.py:39) at every step.  With a step of about
+a millisecond that host work is the bottleneck, so here the processed dataset is
+uploaded ONCE (GraphStore.from_dataset) as one block-diagonal graph together with
+its destination-major layout, and a batch is an index list turned into tensors by
+one gather kernel (mdl_assemble_batch): the same seven tensors
+Batch.from_data_list produces, bit for bit, plus the GraphCSR and the slot-ordered
+edge_attr the operators would otherwise derive with a sort and a permutation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .csr import GraphCSR
+from .data import Batch
+
+
+class GraphStore:
+    """All graphs of a GraphDataset concatenated in HBM.
+
+    keep_edge_attr: store the materialised [E_total, G] edge_attr (200 B/edge at
+    G=50) instead of re-expanding it from the 4 B/edge normalised distance.  By
+    default the expansion is used whenever the dataset carries `d_hat` and its
+    GaussianSmearing parameters (process.assemble_dataset sets both)."""
+
+    def __init__(self):
+        raise TypeError("use GraphStore.from_dataset")
+
+    @classmethod
+    def from_dataset(cls, ds, device, keep_edge_attr=None):
+        _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("GraphStore lives in GPU memory (no CPU fallback)")
+        self = object.__new__(cls)
+        graphs = ds.graphs
+        smear = getattr(ds, "smear", None)
+        has_dhat = all(hasattr(g, "d_hat") for g in graphs)
+        if keep_edge_attr is None:
+            keep_edge_attr = not (has_dhat and smear is not None)
+        if not keep_edge_attr and not (has_dhat and smear is not None):
+            raise ValueError("dataset has no d_hat/smear parameters: edge_attr must be kept")
+        self.device = device
+        self.num_graphs = len(graphs)
+        self.n_nodes = np.array([g.x.shape[0] for g in graphs], dtype=np.int64)
+        self.n_edges = np.array([g.edge_index.shape[1] for g in graphs], dtype=np.int64)
+        node_ptr = np.concatenate([[0], np.cumsum(self.n_nodes)])
+        edge_ptr = np.concatenate([[0], np.cumsum(self.n_edges)])
+        self.num_nodes, self.num_edges = int(node_ptr[-1]), int(edge_ptr[-1])
+        if self.num_nodes >= 2**31 or self.num_edges >= 2**31:
+            raise ValueError("GraphStore indexes nodes/edges with int32")
+        self.F = graphs[0].x.shape[1]
+        self.G = graphs[0].edge_attr.shape[1]
+        f32 = dict(dtype=torch.float32, device=device)
+        self.node_ptr = torch.from_numpy(node_ptr).to(device)
+        self.edge_ptr = torch.from_numpy(edge_ptr).to(device)
+        self.x = torch.cat([g.x for g in graphs], 0).to(**f32).contiguous()
+        ei = torch.cat([g.edge_index + int(o) for g, o in zip(graphs, node_ptr[:-1])], 1).to(device)
+        self.edge_weight = torch.cat([g.edge_weight for g in graphs], 0).to(**f32).contiguous()
+        self.d_hat = torch.cat([g.d_hat for g in graphs], 0).to(**f32).contiguous() if has_dhat else None
+        self.edge_attr = (torch.cat([g.edge_attr for g in graphs], 0).to(**f32).contiguous()
+                          if keep_edge_attr else None)
+        self.u = torch.cat([g.u.reshape(1, -1) for g in graphs], 0).to(**f32).contiguous()
+        ys = [g.y.reshape(-1)[:1] if g.y.ndim <= 1 else g.y for g in graphs]   # as Batch.from_data_list
+        self.y = torch.cat(ys, 0).to(**f32).contiguous()
+        self.y_shape = tuple(self.y.shape[1:])
+        self.U = self.u.shape[1]
+        self.Y = int(np.prod(self.y_shape)) if self.y_shape else 1
+        self.smear = dict(smear) if smear is not None else None
+        if not keep_edge_attr:
+            self.smear_offset = torch.linspace(smear["start"], smear["stop"], smear["resolution"], **f32)
+            self.smear_coeff = -0.5 / ((smear["stop"] - smear["start"]) * smear["width"]) ** 2
+        else:
+            self.smear_offset, self.smear_coeff = None, 0.0
+        # destination-major layout of the whole store: one sort, ever
+        self.layout = GraphCSR.from_coo(ei, None, num_nodes=self.num_nodes)
+        self.src = ei[0].to(torch.int32).contiguous()
+        self.dst = ei[1].to(torch.int32).contiguous()
+        del ei
+        L = self.layout
+        self._c = _lib.GraphStoreC(
+            self.num_graphs, self.num_nodes, self.num_edges, self.F, self.G, self.U, self.Y,
+            _lib.ptr(self.node_ptr), _lib.ptr(self.edge_ptr), _lib.ptr(self.x), _lib.ptr(self.src),
+            _lib.ptr(self.dst), _lib.ptr(self.d_hat), _lib.ptr(self.edge_weight), _lib.ptr(self.edge_attr),
+            _lib.ptr(self.u), _lib.ptr(self.y), _lib.ptr(L.dst_ptr), _lib.ptr(L.dst_src), _lib.ptr(L.dst_dst),
+            _lib.ptr(L.dst_eid), _lib.ptr(L.src_ptr), _lib.ptr(L.src_slot), _lib.ptr(L.inv_deg_dst),
+            _lib.ptr(L.inv_deg_src))
+        return self
+
+    def __len__(self):
+        return self.num_graphs
+
+    # attributes reference model constructors read from a dataset (cgcnn.py:49-61,81)
+    @property
+    def num_features(self):
+        return self.F
+
+    @property
+    def num_edge_features(self):
+        return self.G
+
+    def nbytes(self):
+        ts = [self.x, self.src, self.dst, self.edge_weight, self.d_hat, self.edge_attr, self.u, self.y,
+              self.node_ptr, self.edge_ptr] + [getattr(self.layout, n) for n in
+                                               ("dst_ptr", "dst_src", "dst_dst", "dst_eid", "src_ptr", "src_slot",
+                                                "inv_deg_dst", "inv_deg_src")]
+        return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+    def batch(self, idx, layout=True, slots=True, d_hat=False):
+        """Assemble graphs `idx` (host sequence / numpy / CPU tensor, in that order) into a Batch on
+        the store's device.  With layout=True the returned batch already carries its GraphCSR (found
+        by csr_for()) and, with slots=True, the slot-ordered edge_attr (found by GraphCSR.to_slots)."""
+        idx = np.asarray(idx.cpu() if torch.is_tensor(idx) else idx, dtype=np.int64).reshape(-1)
+        B = int(idx.shape[0])
+        if B == 0:
+            raise ValueError("empty batch")
+        if idx.min() < 0 or idx.max() >= self.num_graphs:
+            raise IndexError("graph index out of range")
+        dev = self.device
+        # ids and the two exclusive prefix sums travel in one small pinned copy
+        meta = torch.empty((3, B + 1), dtype=torch.int64, pin_memory=True)
+        m = meta.numpy()
+        m[0, :B] = idx
+        m[0, B] = 0
+        m[1, 0] = 0
+        np.cumsum(self.n_nodes[idx], out=m[1, 1:])
+        m[2, 0] = 0
+        np.cumsum(self.n_edges[idx], out=m[2, 1:])
+        N, E = int(m[1, B]), int(m[2, B])
+        meta_d = meta.to(dev, non_blocking=True)
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        out = Batch(
+            x=torch.empty((N, self.F), **f32), edge_index=torch.empty((2, E), **i64),
+            edge_attr=torch.empty((E, self.G), **f32), edge_weight=torch.empty(E, **f32),
+            batch=torch.empty(N, **i64), u=torch.empty((B, self.U), **f32),
+            y=torch.empty((B,) + self.y_shape, **f32))
+        out.num_graphs = B
+        if d_hat:
+            if self.d_hat is None:
+                raise ValueError("store holds no d_hat")
+            out.d_hat = torch.empty(E, **f32)
+        csr = ea_slots = None
+        if layout:
+            csr = object.__new__(GraphCSR)
+            csr.N, csr.E, csr.B = N, E, B
+            csr.dst_ptr, csr.src_ptr = torch.empty(N + 1, **i32), torch.empty(N + 1, **i32)
+            csr.dst_src, csr.dst_dst = torch.empty(E, **i32), torch.empty(E, **i32)
+            csr.dst_eid, csr.src_slot = torch.empty(E, **i32), torch.empty(E, **i32)
+            csr.inv_deg_dst, csr.inv_deg_src = torch.empty(N, **f32), torch.empty(N, **f32)
+            csr.graph_ptr = torch.empty(B + 1, **i32)
+            csr.src_eid = csr.src_nbr = None
+            if slots:
+                ea_slots = torch.empty((E, self.G), **f32)
+        P = _lib.ptr
+        desc = _lib.BatchOutC(
+            B, N, E, meta_d[0].data_ptr(), meta_d[1].data_ptr(), meta_d[2].data_ptr(),
+            P(out.x), P(out.edge_index), P(getattr(out, "d_hat", None)), P(out.edge_weight), P(out.edge_attr),
+            P(ea_slots), P(out.batch), P(out.u), P(out.y),
+            *( [P(csr.dst_ptr), P(csr.dst_src), P(csr.dst_dst), P(csr.dst_eid), P(csr.src_ptr), P(csr.src_slot),
+                P(csr.inv_deg_dst), P(csr.inv_deg_src), P(csr.graph_ptr)] if layout else [None] * 9),
+            P(self.smear_offset), float(self.smear_coeff))
+        rc = _lib.load().mdl_assemble_batch(C.byref(self._c), C.byref(desc), _lib.stream())
+        _lib.check(rc, "mdl_assemble_batch")
+        if self.smear is not None:
+            out.smear = dict(self.smear)
+        if layout:
+            out.edge_index._mdl_csr = (out.edge_index._version, csr)
+            out.batch._mdl_seg = (out.batch._version, csr.graph_ptr, None)
+            if ea_slots is not None:
+                out.edge_attr._mdl_slots = (csr, out.edge_attr._version, ea_slots)
+        return out

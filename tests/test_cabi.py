@@ -45,6 +45,29 @@ def test_ctypes_table_matches_header(lib):
     lib.load()  # binds every prototype; raises AttributeError on a missing symbol
 
 
+def test_struct_layouts_match_the_header(lib, tmp_path):
+    """The header is plain C (gcc compiles it) and the ctypes mirrors of its two descriptor
+    structs agree with the compiler on size and on every field offset."""
+    def fields(cls):
+        return [n for n, _ in cls._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
+    for cname, cls in (("mdl_graph_store", lib.GraphStoreC), ("mdl_batch_out", lib.BatchOutC)):
+        prog.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields(cls):
+            prog.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    prog.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                       check=True).stdout.splitlines())
+    for cname, cls in (("mdl_graph_store", lib.GraphStoreC), ("mdl_batch_out", lib.BatchOutC)):
+        assert int(got[cname]) == ctypes.sizeof(cls)
+        for f in fields(cls):
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
+
+
 def test_no_unexpected_dynamic_dependencies(lib):
     out = subprocess.run(["ldd", lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "libtorch" not in out and "libpython" not in out, "the C ABI must not depend on torch/python"
@@ -60,6 +83,13 @@ def test_host_only_entry_points(lib):
     assert rc != 0 and "multiple of 4" in lib.last_error()
     rc = L.mdl_segment_reduce_fwd(None, None, None, None, None, 3, 0, 0, None)
     assert rc != 0 and "bad shape" in lib.last_error()
+    rc = L.mdl_assemble_batch(None, None, None)
+    assert rc != 0 and "null descriptor" in lib.last_error()
+    store, out = lib.GraphStoreC(), lib.BatchOutC()
+    out.B, out.N, out.E = 2, 10, 20
+    store.F, store.G = 4, 8
+    rc = L.mdl_assemble_batch(ctypes.byref(store), ctypes.byref(out), None)
+    assert rc != 0 and "null arrays" in lib.last_error()
 
 
 def test_product_does_not_import_the_oracle():
