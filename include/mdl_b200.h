@@ -196,7 +196,12 @@ typedef struct mdl_graph_store {
 } mdl_graph_store;
 
 /* One batch = graphs graph_ids[0..B) in that order.  node_off/edge_off are the exclusive prefix
- * sums of their node/edge counts ([B+1] each, device), N and E the totals.  Outputs are exactly
+ * sums of their node/edge counts ([B+1] each, device); their last entries are the batch's node and
+ * edge totals and are read ON THE DEVICE, so one captured launch serves batches of any size up to
+ * the capacities N and E (the row counts of the output arrays; N = node_off[B], E = edge_off[B]
+ * gives the exact batch).  Rows beyond the totals are filled with inert padding: zero features,
+ * batch id B, empty segments in dst_ptr/src_ptr, edges/slots no segment refers to, graph_ptr[B] =
+ * node_off[B] -- segment-driven operators and readouts therefore ignore them.  Outputs are exactly
  * Batch.from_data_list's tensors (x, edge_index int64 [2,E], edge_weight, edge_attr, batch, u, y;
  * d_hat and edge_attr optional) and, when dst_ptr != NULL, the arrays mdl_csr_from_coo would
  * produce for that batch (bit-identical) plus edge_attr in slot order (optional).  When the store
@@ -229,6 +234,26 @@ typedef struct mdl_batch_out {
 } mdl_batch_out;
 
 MDL_API int mdl_assemble_batch(const mdl_graph_store* store, const mdl_batch_out* out, void* stream);
+
+/* ---- masked training-mode BatchNorm1d -------------------------------------------------------
+ * torch.nn.BatchNorm1d as the reference applies it to node features after every conv
+ * (matdeeplearn/models/cgcnn.py:88-92,141-147; torch semantics: biased variance for the
+ * normalisation, unbiased for running_var, running = (1-momentum)*running + momentum*batch),
+ * with the statistics taken over the first *n_valid rows only (n_valid: device int32, NULL = all
+ * N rows) and rows >= *n_valid written as zero (forward) / zero gradient (backward), so that a
+ * capacity-padded batch normalises exactly like the unpadded one.  weight/bias/running_* may be
+ * NULL.  workspace: mdl_batchnorm_workspace_bytes(N, C) bytes, zero-filled once by the caller
+ * (the kernels leave its first word at zero). */
+MDL_API size_t mdl_batchnorm_workspace_bytes(int64_t N, int32_t C);
+MDL_API int mdl_batchnorm_fwd(const float* x, const int32_t* n_valid, int64_t N, int32_t C,
+                              const float* weight, const float* bias, float* running_mean,
+                              float* running_var, float momentum, float eps, float* out,
+                              float* save_mean, float* save_invstd, void* workspace,
+                              size_t workspace_bytes, void* stream);
+MDL_API int mdl_batchnorm_bwd(const float* gout, const float* x, const int32_t* n_valid, int64_t N,
+                              int32_t C, const float* weight, const float* save_mean,
+                              const float* save_invstd, float* gx, float* gweight, float* gbias,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
  * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).

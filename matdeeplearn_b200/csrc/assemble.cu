@@ -30,12 +30,50 @@ __device__ __forceinline__ void copy_shift_i32(int32_t* __restrict__ dst, const 
   for (int64_t i = tid; i < n; i += stride) dst[i] = __ldg(src + i) + shift;
 }
 
+template <typename T>
+__device__ __forceinline__ void fill_span(T* __restrict__ dst, T v, int64_t n, int tid, int stride) {
+  for (int64_t i = tid; i < n; i += stride) dst[i] = v;
+}
+
+// Rows [Nv, N) and edges/slots [Ev, E) of a capacity-padded batch: inert filler.  No segment of either
+// pointer array covers a padded slot (dst_ptr/src_ptr stay at Ev for every padded node), so the
+// segment-driven operators never touch them; padded nodes are empty segments outside every graph.
+__device__ void fill_padding(const mdl_batch_out& o, int F, int G, int64_t Nv, int64_t Ev, int tid, int stride) {
+  const int64_t np = o.N - Nv, ne = o.E - Ev;
+  const int32_t last = (int32_t)(o.N - 1);
+  fill_span(o.x + Nv * F, 0.0f, np * F, tid, stride);
+  fill_span(o.batch + Nv, (int64_t)o.B, np, tid, stride);
+  fill_span(o.edge_index + Ev, (int64_t)last, ne, tid, stride);
+  fill_span(o.edge_index + o.E + Ev, (int64_t)last, ne, tid, stride);
+  if (o.d_hat) fill_span(o.d_hat + Ev, 0.0f, ne, tid, stride);
+  fill_span(o.edge_weight + Ev, 0.0f, ne, tid, stride);
+  if (o.edge_attr) fill_span(o.edge_attr + Ev * G, 0.0f, ne * G, tid, stride);
+  if (o.edge_attr_slots) fill_span(o.edge_attr_slots + Ev * G, 0.0f, ne * G, tid, stride);
+  if (o.dst_ptr) {
+    fill_span(o.dst_ptr + Nv, (int32_t)Ev, np + 1, tid, stride);
+    fill_span(o.src_ptr + Nv, (int32_t)Ev, np + 1, tid, stride);
+    fill_span(o.inv_deg_dst + Nv, 0.0f, np, tid, stride);
+    fill_span(o.inv_deg_src + Nv, 0.0f, np, tid, stride);
+    fill_span(o.dst_src + Ev, last, ne, tid, stride);
+    fill_span(o.dst_dst + Ev, last, ne, tid, stride);
+    for (int64_t i = tid; i < ne; i += stride) {
+      o.dst_eid[Ev + i] = (int32_t)(Ev + i);
+      o.src_slot[Ev + i] = (int32_t)(Ev + i);
+    }
+    if (tid == 0) o.graph_ptr[o.B] = (int32_t)Nv;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_assemble(const AsmArgs a) {
   const mdl_graph_store& s = a.s;
   const mdl_batch_out& o = a.o;
   const int b = blockIdx.x;
   const int tid = blockIdx.y * blockDim.x + threadIdx.x;
   const int stride = gridDim.y * blockDim.x;
+  if (b == o.B) {   // the extra CTA row: padding and the closing pointer entries
+    fill_padding(o, s.F, s.G, __ldg(o.node_off + o.B), __ldg(o.edge_off + o.B), tid, stride);
+    return;
+  }
   const int64_t g = __ldg(o.graph_ids + b);
   const int64_t np = __ldg(s.node_ptr + g), n = __ldg(s.node_ptr + g + 1) - np;
   const int64_t ep = __ldg(s.edge_ptr + g), e = __ldg(s.edge_ptr + g + 1) - ep;
@@ -55,14 +93,7 @@ __global__ void __launch_bounds__(256) k_assemble(const AsmArgs a) {
   // ---- graph-level rows
   if (tid < s.U) o.u[(int64_t)b * s.U + tid] = __ldg(s.u + g * s.U + tid);
   if (tid < s.Y) o.y[(int64_t)b * s.Y + tid] = __ldg(s.y + g * s.Y + tid);
-  if (tid == 0 && o.graph_ptr) {
-    o.graph_ptr[b] = (int32_t)no;
-    if (b == o.B - 1) {
-      o.graph_ptr[o.B] = (int32_t)o.N;
-      o.dst_ptr[o.N] = (int32_t)o.E;
-      o.src_ptr[o.N] = (int32_t)o.E;
-    }
-  }
+  if (tid == 0 && o.graph_ptr) o.graph_ptr[b] = (int32_t)no;
   // ---- edges, reference order
   for (int64_t k = tid; k < e; k += stride) {
     o.edge_index[eo + k] = (int64_t)__ldg(s.src + ep + k) + (no - np);
@@ -119,7 +150,7 @@ extern "C" int mdl_assemble_batch(const mdl_graph_store* store, const mdl_batch_
   MDL_REQUIRE(out->N < (1ll << 31) && out->E < (1ll << 31) && store->num_edges < (1ll << 31) &&
               store->num_nodes < (1ll << 31), "assemble_batch: sizes must fit int32");
   if (out->B == 0) return MDL_OK;
-  MDL_REQUIRE(out->B <= 65535 * 1ll, "assemble_batch: at most 65535 graphs per batch");
+  MDL_REQUIRE(out->B < (1ll << 31) - 1, "assemble_batch: too many graphs");
   MDL_REQUIRE(store->F > 0 && store->G > 0 && store->U >= 0 && store->Y >= 0 && store->U <= 256 && store->Y <= 256,
               "assemble_batch: bad widths");
   MDL_REQUIRE(store->node_ptr && store->edge_ptr && store->x && store->src && store->dst && store->edge_weight &&
@@ -142,7 +173,7 @@ extern "C" int mdl_assemble_batch(const mdl_graph_store* store, const mdl_batch_
   // enough CTAs per graph to fill the machine about four times over
   int parts = (int)std::min<int64_t>(16, std::max<int64_t>(1, ceil_div<int64_t>(4 * kNumSMs, out->B)));
   AsmArgs a{*store, *out};
-  k_assemble<<<dim3((unsigned)out->B, (unsigned)parts), 256, 0, as_stream(stream)>>>(a);
+  k_assemble<<<dim3((unsigned)out->B + 1, (unsigned)parts), 256, 0, as_stream(stream)>>>(a);
   MDL_LAUNCHED();
   return MDL_OK;
 }

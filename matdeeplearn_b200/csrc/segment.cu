@@ -57,10 +57,17 @@ k_segment_fwd(const float* __restrict__ src, const int32_t* __restrict__ ptr,
 template <int REDUCE>
 __global__ void __launch_bounds__(256)
 k_segment_bwd(const float* __restrict__ gout, const int32_t* __restrict__ ptr,
-              const int32_t* __restrict__ perm, float* __restrict__ gsrc, int64_t S, int width) {
+              const int32_t* __restrict__ perm, float* __restrict__ gsrc, int64_t S, int width,
+              int64_t num_rows) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (!perm) {  // rows past the last segment (capacity padding) belong to no segment: zero gradient
+    const int64_t first = (int64_t)__ldg(ptr + S) * width, total = num_rows * width;
+    for (int64_t i = first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x)
+      gsrc[i] = 0.0f;
+  }
   for (int64_t s = warp; s < S; s += nwarps) {
     const int lo = __ldg(ptr + s), hi = __ldg(ptr + s + 1);
     const float w = (REDUCE == MDL_REDUCE_MEAN) ? 1.0f / (float)(hi - lo > 1 ? hi - lo : 1) : 1.0f;
@@ -134,10 +141,10 @@ extern "C" int mdl_segment_reduce_bwd(const float* gout, const int32_t* ptr, con
   int grid = seg_grid(S);
   switch (reduce) {
     case MDL_REDUCE_SUM:
-      k_segment_bwd<MDL_REDUCE_SUM><<<grid, 256, 0, st>>>(gout, ptr, perm, gsrc, S, (int)width);
+      k_segment_bwd<MDL_REDUCE_SUM><<<grid, 256, 0, st>>>(gout, ptr, perm, gsrc, S, (int)width, num_rows);
       break;
     case MDL_REDUCE_MEAN:
-      k_segment_bwd<MDL_REDUCE_MEAN><<<grid, 256, 0, st>>>(gout, ptr, perm, gsrc, S, (int)width);
+      k_segment_bwd<MDL_REDUCE_MEAN><<<grid, 256, 0, st>>>(gout, ptr, perm, gsrc, S, (int)width, num_rows);
       break;
     case MDL_REDUCE_MAX: {
       MDL_REQUIRE(argmax, "segment_reduce_bwd: max needs argmax");

@@ -31,6 +31,7 @@ class TrainStep:
         self.kernels_per_step = None
         self._graphs = {}
         self._host_graphs = {}
+        self._store_graphs = {}
         # warm-up runs on a side stream (standard capture recipe); the resulting stream-mismatch
         # note from autograd's AccumulateGrad is expected and harmless here
         try:
@@ -135,6 +136,82 @@ class TrainStep:
         self.last_h2d_bytes = nbytes
         replay()
         return float(loss.item())
+
+    # -- from a device-resident GraphStore (shuffled epochs at graph-replay speed) ----------
+    def from_store(self, store, idx, sync=True):
+        """One training step on graphs `idx` of a store.GraphStore.
+
+        The batch is assembled on the GPU into capacity-padded buffers of fixed shape, so ONE captured
+        CUDA graph (assembly kernel + forward + backward + AdamW) is replayed for every batch of the
+        epoch whatever its node/edge count; the per-step host work is a 256-element prefix sum and a
+        6 KB copy.  Padding rows are inert (empty segments, masked BatchNorm statistics): the step is
+        the same function of the batch as `eager(store.batch(idx))`.  A batch larger than the
+        capacity takes that exact eager path.  sync=False returns the device loss tensor (overwritten
+        by the next step) instead of a float."""
+        from .models import CGCNN
+        if not isinstance(self.model, CGCNN):
+            raise NotImplementedError("padded replay is wired for CGCNN; use eager(store.batch(idx)) for other models")
+        B = len(idx)
+        key = (id(store), B)
+        entry = self._store_graphs.get(key)
+        if entry is None:
+            entry = self._capture_store_step(store, B, idx)
+            self._store_graphs[key] = entry
+        static, replay, loss = entry
+        if not store.load(static, idx):
+            out = self.eager(store.batch(idx)).detach()
+            return float(out.item()) if sync else out
+        replay()
+        return float(loss.item()) if sync else loss
+
+    def _snapshot(self):
+        bufs = [b for b in self.model.buffers()]
+        return ([t.clone() for t in (self.flat.param, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.step_count)],
+                [b.clone() for b in bufs])
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for t, c in zip((self.flat.param, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.step_count), snap[0]):
+                t.copy_(c)
+            for b, c in zip(self.model.buffers(), snap[1]):
+                b.copy_(c)
+
+    def _capture_store_step(self, store, B, idx):
+        static = store.static_batch(B)
+        if not store.load(static, idx):
+            raise RuntimeError("first batch exceeds the padded capacity; pass a typical batch first")
+        distributed = mdist.is_distributed()
+        snap = self._snapshot()      # the warm-up steps below must not count as training
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                store.assemble(static)
+                self.eager(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        g1 = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g1):
+            store.assemble(static)
+            loss = self._fwd_bwd(static)
+            if not distributed:
+                self._opt_step()
+        self.store_kernels_per_step = _lib.launch_count() - n0 + (1 if distributed else 0)
+        g2 = None
+        if distributed:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._opt_step()
+
+        def replay():
+            g1.replay()
+            if g2 is not None:
+                self._reduce()
+                g2.replay()
+
+        return static, replay, loss
 
     def _layout_inside_graph(self, static, B):
         from .csr import GraphCSR

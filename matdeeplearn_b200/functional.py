@@ -58,6 +58,65 @@ def segment_reduce(src, ptr, perm=None, reduce="mean"):
 
 
 # ----------------------------------------------------------------------------
+# BatchNorm1d (training mode) with a device-side row count
+# ----------------------------------------------------------------------------
+class MaskedBatchNormFn(torch.autograd.Function):
+    """mdl_batchnorm_fwd / _bwd: statistics over the first n_valid[0] rows (None: all rows)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, n_valid, momentum, eps, ws):
+        lib = _lib.load()
+        x = x.contiguous()
+        if x.dim() != 2 or x.dtype != torch.float32:
+            raise RuntimeError("masked batch norm: x must be fp32 [N, C]")
+        N, C = x.shape
+        out = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        rc = lib.mdl_batchnorm_fwd(_lib.ptr(x), _lib.ptr(n_valid), N, C, _lib.ptr(weight), _lib.ptr(bias),
+                                   _lib.ptr(running_mean), _lib.ptr(running_var), float(momentum), float(eps),
+                                   _lib.ptr(out), _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(ws), ws.numel(),
+                                   _lib.stream())
+        _lib.check(rc, "mdl_batchnorm_fwd")
+        ctx.save_for_backward(x, weight, mean, invstd, n_valid, ws)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, mean, invstd, n_valid, ws = ctx.saved_tensors
+        N, C = x.shape
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+        gb = torch.empty(C, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        rc = _lib.load().mdl_batchnorm_bwd(_lib.ptr(g), _lib.ptr(x), _lib.ptr(n_valid), N, C, _lib.ptr(weight),
+                                           _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gx), _lib.ptr(gw),
+                                           _lib.ptr(gb), _lib.ptr(ws), ws.numel(), _lib.stream())
+        _lib.check(rc, "mdl_batchnorm_bwd")
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def masked_batch_norm(bn, x, n_valid=None):
+    """Apply torch.nn.BatchNorm1d module `bn` to x[N,C] with batch statistics over the first
+    n_valid[0] rows (device int32 tensor).  Eval mode is row-wise and goes through the module."""
+    if not bn.training:
+        return bn(x)
+    if bn.momentum is None:
+        raise NotImplementedError("masked batch norm: cumulative-average momentum is not supported")
+    N, C = x.shape
+    need = int(_lib.load().mdl_batchnorm_workspace_bytes(N, C))
+    ws = getattr(bn, "_mdl_ws", None)
+    if ws is None or ws.numel() < need or ws.device != x.device:
+        ws = torch.zeros(need, dtype=torch.uint8, device=x.device)
+        bn._mdl_ws = ws
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return MaskedBatchNormFn.apply(x, bn.weight, bn.bias, rm, rv, n_valid, bn.momentum, bn.eps, ws)
+
+
+# ----------------------------------------------------------------------------
 # GaussianSmearing
 # ----------------------------------------------------------------------------
 def gaussian_smear(dist, offset, coeff, out=None):

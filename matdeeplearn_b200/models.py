@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn as tnn
 
+from . import functional as MF
 from . import nn as mnn
 from .csr import csr_for
 
@@ -96,7 +97,9 @@ class CGCNN(_ConvStackModel):
         for i, conv in enumerate(self.conv_list):
             h = conv(h, data.edge_index, data.edge_attr, csr=csr)
             if self.batch_norm == "True":
-                h = self.bn_list[i](h)
+                nv = getattr(data, "_n_valid", None)
+                # capacity-padded batch (store.GraphStore.static_batch): statistics over real rows only
+                h = self.bn_list[i](h) if nv is None else MF.masked_batch_norm(self.bn_list[i], h, nv)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return self._readout(h, data)
 

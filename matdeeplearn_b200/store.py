@@ -113,18 +113,15 @@ class GraphStore:
                                                 "inv_deg_dst", "inv_deg_src")]
         return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
-    def batch(self, idx, layout=True, slots=True, d_hat=False):
-        """Assemble graphs `idx` (host sequence / numpy / CPU tensor, in that order) into a Batch on
-        the store's device.  With layout=True the returned batch already carries its GraphCSR (found
-        by csr_for()) and, with slots=True, the slot-ordered edge_attr (found by GraphCSR.to_slots)."""
+    # ---- batch assembly ----------------------------------------------------------
+    def _meta(self, idx):
+        """[3, B+1] pinned int64: graph ids, exclusive node prefix, exclusive edge prefix."""
         idx = np.asarray(idx.cpu() if torch.is_tensor(idx) else idx, dtype=np.int64).reshape(-1)
         B = int(idx.shape[0])
         if B == 0:
             raise ValueError("empty batch")
         if idx.min() < 0 or idx.max() >= self.num_graphs:
             raise IndexError("graph index out of range")
-        dev = self.device
-        # ids and the two exclusive prefix sums travel in one small pinned copy
         meta = torch.empty((3, B + 1), dtype=torch.int64, pin_memory=True)
         m = meta.numpy()
         m[0, :B] = idx
@@ -133,8 +130,11 @@ class GraphStore:
         np.cumsum(self.n_nodes[idx], out=m[1, 1:])
         m[2, 0] = 0
         np.cumsum(self.n_edges[idx], out=m[2, 1:])
-        N, E = int(m[1, B]), int(m[2, B])
-        meta_d = meta.to(dev, non_blocking=True)
+        return meta, B, int(m[1, B]), int(m[2, B])
+
+    def _alloc(self, B, N, E, layout, slots, d_hat):
+        """Output tensors for a batch of capacity (N nodes, E edges) + the ctypes descriptor."""
+        dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         i64 = dict(dtype=torch.int64, device=dev)
@@ -160,16 +160,6 @@ class GraphStore:
             csr.src_eid = csr.src_nbr = None
             if slots:
                 ea_slots = torch.empty((E, self.G), **f32)
-        P = _lib.ptr
-        desc = _lib.BatchOutC(
-            B, N, E, meta_d[0].data_ptr(), meta_d[1].data_ptr(), meta_d[2].data_ptr(),
-            P(out.x), P(out.edge_index), P(getattr(out, "d_hat", None)), P(out.edge_weight), P(out.edge_attr),
-            P(ea_slots), P(out.batch), P(out.u), P(out.y),
-            *( [P(csr.dst_ptr), P(csr.dst_src), P(csr.dst_dst), P(csr.dst_eid), P(csr.src_ptr), P(csr.src_slot),
-                P(csr.inv_deg_dst), P(csr.inv_deg_src), P(csr.graph_ptr)] if layout else [None] * 9),
-            P(self.smear_offset), float(self.smear_coeff))
-        rc = _lib.load().mdl_assemble_batch(C.byref(self._c), C.byref(desc), _lib.stream())
-        _lib.check(rc, "mdl_assemble_batch")
         if self.smear is not None:
             out.smear = dict(self.smear)
         if layout:
@@ -177,4 +167,70 @@ class GraphStore:
             out.batch._mdl_seg = (out.batch._version, csr.graph_ptr, None)
             if ea_slots is not None:
                 out.edge_attr._mdl_slots = (csr, out.edge_attr._version, ea_slots)
+        return out, csr, ea_slots
+
+    def _launch(self, out, csr, ea_slots, meta_d, B, N, E):
+        P = _lib.ptr
+        desc = _lib.BatchOutC(
+            B, N, E, meta_d[0].data_ptr(), meta_d[1].data_ptr(), meta_d[2].data_ptr(),
+            P(out.x), P(out.edge_index), P(getattr(out, "d_hat", None)), P(out.edge_weight), P(out.edge_attr),
+            P(ea_slots), P(out.batch), P(out.u), P(out.y),
+            *([P(csr.dst_ptr), P(csr.dst_src), P(csr.dst_dst), P(csr.dst_eid), P(csr.src_ptr), P(csr.src_slot),
+               P(csr.inv_deg_dst), P(csr.inv_deg_src), P(csr.graph_ptr)] if csr is not None else [None] * 9),
+            P(self.smear_offset), float(self.smear_coeff))
+        rc = _lib.load().mdl_assemble_batch(C.byref(self._c), C.byref(desc), _lib.stream())
+        _lib.check(rc, "mdl_assemble_batch")
+
+    def batch(self, idx, layout=True, slots=True, d_hat=False):
+        """Assemble graphs `idx` (host sequence / numpy / CPU tensor, in that order) into a Batch on
+        the store's device.  With layout=True the returned batch already carries its GraphCSR (found
+        by csr_for()) and, with slots=True, the slot-ordered edge_attr (found by GraphCSR.to_slots)."""
+        meta, B, N, E = self._meta(idx)
+        meta_d = meta.to(self.device, non_blocking=True)   # ids + both prefix sums in one small copy
+        out, csr, ea_slots = self._alloc(B, N, E, layout, slots, d_hat)
+        self._launch(out, csr, ea_slots, meta_d, B, N, E)
         return out
+
+    # ---- capacity-padded, fixed-shape batches (one CUDA graph for every batch of an epoch) ----
+    def capacities(self, B, sigmas=6.0, align=64):
+        """(N_cap, E_cap) that a batch of B graphs drawn from this store exceeds with negligible
+        probability: B*mean + sigmas*std*sqrt(B), never more than the B largest graphs together."""
+        caps = []
+        for cnt in (self.n_nodes, self.n_edges):
+            worst = int(np.sort(cnt)[::-1][:B].sum()) if B <= cnt.shape[0] else int(cnt.max()) * B
+            est = B * float(cnt.mean()) + sigmas * float(cnt.std()) * float(np.sqrt(B))
+            cap = min(worst, int(np.ceil(est)))
+            caps.append((cap + align - 1) // align * align + 1)   # +1: at least one padding row
+        return tuple(caps)
+
+    def static_batch(self, B, N_cap=None, E_cap=None, d_hat=False):
+        """Persistent padded batch buffers of fixed shape.  `load(static, idx)` stages the ids of the
+        next batch; `assemble(static)` (capturable in a CUDA graph: it reads ids and sizes from device
+        memory) fills the buffers.  Rows past the real batch are inert padding (include/mdl_b200.h),
+        and `static._n_valid` is the device-side real node count for masked statistics."""
+        if N_cap is None or E_cap is None:
+            N_cap, E_cap = self.capacities(B)
+        out, csr, ea_slots = self._alloc(B, int(N_cap), int(E_cap), True, True, d_hat)
+        out._meta_d = torch.zeros((3, B + 1), dtype=torch.int64, device=self.device)
+        out._n_valid = csr.graph_ptr[B:B + 1]
+        out._parts = (csr, ea_slots)
+        out._valid = (0, 0)
+        return out
+
+    def load(self, static, idx):
+        """Stage batch `idx` into a static batch's id buffer.  False (and nothing staged) if the batch
+        does not fit the capacity."""
+        meta, B, N, E = self._meta(idx)
+        csr = static._parts[0]
+        if B != csr.B:
+            raise ValueError(f"static batch holds {csr.B} graphs, got {B}")
+        if N > csr.N or E > csr.E:
+            return False
+        static._meta_d.copy_(meta, non_blocking=True)
+        static._valid = (N, E)
+        return True
+
+    def assemble(self, static):
+        csr, ea_slots = static._parts
+        self._launch(static, csr, ea_slots, static._meta_d, csr.B, csr.N, csr.E)
+        return static

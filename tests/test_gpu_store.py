@@ -90,3 +90,122 @@ def test_store_argument_checks():
         GraphStore.from_dataset(ds, "cpu")
     b = store.batch([4, 4, 0], layout=False)
     assert not hasattr(b.edge_index, "_mdl_csr") and b.x.shape[0] == 2 * ds[4].x.shape[0] + ds[0].x.shape[0]
+
+
+# ---------------------------------------------------------------- capacity-padded batches
+def test_padded_static_batch_real_rows_match_and_padding_is_inert():
+    from matdeeplearn_b200.csr import GraphCSR
+    from matdeeplearn_b200.store import GraphStore
+    ds = _dataset("bulk", 40)
+    store = GraphStore.from_dataset(ds, DEV)
+    B = 9
+    Nc, Ec = store.capacities(B)
+    static = store.static_batch(B, d_hat=True)
+    rng = np.random.default_rng(3)
+    for trial in range(4):                      # the same buffers refilled with batches of different size
+        idx = rng.integers(0, 40, size=B)
+        assert store.load(static, idx)
+        store.assemble(static)
+        exact = store.batch(idx, d_hat=True)
+        N, E = exact.x.shape[0], exact.edge_index.shape[1]
+        assert static._valid == (N, E) and N < Nc and E < Ec
+        assert int(static._n_valid.item()) == N
+        for k in ("x", "edge_attr", "edge_weight", "batch", "d_hat"):
+            assert torch.equal(getattr(static, k)[: getattr(exact, k).shape[0]], getattr(exact, k)), k
+        assert torch.equal(static.edge_index[:, :E], exact.edge_index)
+        assert torch.equal(static.u, exact.u) and torch.equal(static.y, exact.y)
+        csr, ref = static._parts[0], exact.edge_index._mdl_csr[1]
+        assert (csr.N, csr.E, csr.B) == (Nc, Ec, B)
+        for name in ("dst_src", "dst_dst", "dst_eid", "src_slot"):
+            assert torch.equal(getattr(csr, name)[:E], getattr(ref, name)), name
+        for name in ("dst_ptr", "src_ptr", "inv_deg_dst", "inv_deg_src"):
+            assert torch.equal(getattr(csr, name)[:N], getattr(ref, name)[:N]), name
+        assert torch.equal(csr.graph_ptr, ref.graph_ptr)
+        assert torch.equal(static._parts[1][:E], exact.edge_attr._mdl_slots[2])
+        # padding: zero rows, phantom graph id, empty segments, nothing pointing into real data
+        assert static.x[N:].abs().max().item() == 0 and static.edge_attr[E:].abs().max().item() == 0
+        assert static._parts[1][E:].abs().max().item() == 0
+        assert (static.batch[N:] == B).all()
+        assert (csr.dst_ptr[N:] == E).all() and (csr.src_ptr[N:] == E).all()
+        assert (csr.dst_dst[E:] == Nc - 1).all() and (csr.dst_src[E:] == Nc - 1).all()
+        assert torch.equal(csr.dst_eid[E:].long(), torch.arange(E, Ec, device=DEV))
+        assert (csr.inv_deg_dst[N:] == 0).all()
+
+
+@pytest.mark.parametrize("C,N,n", [(64, 300, 211), (100, 77, 77), (7, 1000, 1), (64, 5000, 4999)])
+def test_masked_batchnorm_equals_torch_on_the_valid_rows(C, N, n):
+    from matdeeplearn_b200 import functional as MF
+    torch.manual_seed(C + N)
+    x = (torch.randn(N, C, device=DEV) * 3 + 5).requires_grad_()
+    g = torch.randn(N, C, device=DEV)
+    bn_a = torch.nn.BatchNorm1d(C).to(DEV).train()
+    bn_b = copy.deepcopy(bn_a)
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5), bn_a.bias.uniform_(-1, 1)
+        bn_b.load_state_dict(bn_a.state_dict())
+    nv = torch.tensor([n], dtype=torch.int32, device=DEV)
+    if n > 1:
+        xr = x.detach()[:n].clone().requires_grad_()
+        ref = bn_b(xr)
+        ref.backward(g[:n])
+    out = MF.masked_batch_norm(bn_a, x, nv)
+    out.backward(g)
+    assert out[n:].abs().max().item() == 0 if n < N else True
+    assert x.grad[n:].abs().max().item() == 0 if n < N else True
+    if n > 1:
+        assert (out[:n] - ref).abs().max().item() < 2e-5
+        assert (x.grad[:n] - xr.grad).abs().max().item() < 2e-5 * max(1.0, xr.grad.abs().max().item())
+        for name in ("weight", "bias"):
+            a, b = getattr(bn_a, name).grad, getattr(bn_b, name).grad
+            assert (a - b).abs().max().item() < 1e-4 * max(1.0, b.abs().max().item()), name
+        assert (bn_a.running_mean - bn_b.running_mean).abs().max().item() < 1e-5
+        assert (bn_a.running_var - bn_b.running_var).abs().max().item() < 1e-4
+        assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 1
+    # second call reuses the self-resetting workspace
+    out2 = MF.masked_batch_norm(bn_a, x.detach(), nv)
+    assert torch.equal(out2, out.detach())
+
+
+def test_from_store_padded_replay_follows_exact_eager_steps():
+    """An epoch of differently-sized batches through ONE captured graph == the same batches, exactly
+    assembled, stepped eagerly."""
+    from matdeeplearn_b200 import models as M
+    from matdeeplearn_b200.engine import TrainStep
+    from matdeeplearn_b200.store import GraphStore
+    ds = _dataset("bulk", 64)
+    store = GraphStore.from_dataset(ds, DEV)
+    torch.manual_seed(0)
+    model = M.CGCNN(ds, dim1=64, dim2=64, pre_fc_count=1, gc_count=3, post_fc_count=2)
+    m1, m2 = copy.deepcopy(model).to(DEV).train(), copy.deepcopy(model).to(DEV).train()
+    s1, s2 = TrainStep(m1, lr=1e-3), TrainStep(m2, lr=1e-3)
+    order = np.random.default_rng(2).permutation(64)
+    chunks = [order[i:i + 16] for i in range(0, 64, 16)] * 2
+    la = [s1.from_store(store, idx) for idx in chunks]
+    lb = [float(s2.eager(store.batch(idx)).item()) for idx in chunks]
+    sizes = {store._meta(idx)[2:] for idx in chunks}
+    assert len(sizes) > 1                      # the batches really differ in shape
+    assert len(s1._store_graphs) == 1          # ...and shared one captured graph
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (la, lb)
+    assert (s1.flat.param - s2.flat.param).abs().max().item() < 5e-5
+    for (n1, b1), (n2, b2) in zip(m1.named_buffers(), m2.named_buffers()):
+        assert (b1.float() - b2.float()).abs().max().item() < 1e-4, n1
+
+
+def test_from_store_over_capacity_batch_takes_the_exact_path():
+    from matdeeplearn_b200 import models as M
+    from matdeeplearn_b200.engine import TrainStep
+    from matdeeplearn_b200.store import GraphStore
+    ds = _dataset("bulk", 64)
+    store = GraphStore.from_dataset(ds, DEV)
+    torch.manual_seed(0)
+    model = M.CGCNN(ds, dim1=64, dim2=64, pre_fc_count=1, gc_count=2, post_fc_count=1).to(DEV).train()
+    step = TrainStep(model, lr=1e-3)
+    small = np.argsort(store.n_nodes)[:8]
+    big = np.argsort(store.n_nodes)[-8:]
+    store.capacities = lambda B, **kw: (int(store.n_nodes[small].sum()) + 8, int(store.n_edges[small].sum()) + 64)
+    l0 = step.from_store(store, small)
+    l1 = step.from_store(store, big)           # does not fit: eager on the exact batch
+    assert np.isfinite(l0) and np.isfinite(l1)
+    static = list(step._store_graphs.values())[0][0]
+    assert not store.load(static, big)
