@@ -276,6 +276,9 @@ MDL_API int mdl_selftest_umma(const float* A, const float* B, float* D, int32_t 
 MDL_API int mdl_selftest_umma_ex(const float* A, const float* B, float* D, int32_t N, int32_t K,
                                  int32_t split, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b, int32_t sbo_b,
                                  void* stream);
+/* same product with A staged in tensor memory (tcgen05.st) and B in shared memory */
+MDL_API int mdl_selftest_umma_ts(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                                 int32_t split, void* stream);
 
 #ifdef __cplusplus
 }

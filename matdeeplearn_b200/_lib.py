@@ -69,6 +69,7 @@ SIGNATURES = {
     "mdl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i64, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
+    "mdl_selftest_umma_ts": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "mdl_selftest_umma_ex": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
 }
 

@@ -109,33 +109,34 @@ __global__ void __launch_bounds__(256) k_assemble(const AsmArgs a) {
     copy_shift_i32(o.src_slot + eo, s.src_slot + ep, e, eshift, tid, stride);
   }
   // ---- edge_attr: copied when the store holds it, else GaussianSmearing(d_hat) on the fly
-  //      (same expression as k_gaussian_smear: expf(coeff * (diff*diff)), reference process.py:588-590)
-  const int64_t eg = e * G;
+  //      (same expression as k_gaussian_smear: expf(coeff * (diff*diff)), reference process.py:588-590).
+  //      One warp per edge row, lanes across the G basis functions: no per-element division, the
+  //      row's distance / source row is fetched once, stores are row-contiguous.
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = tid >> 5, nwarps = stride >> 5;
   if (s.edge_attr) {
-    if (o.edge_attr) copy_span(o.edge_attr + eo * G, s.edge_attr + ep * G, eg, tid, stride);
+    if (o.edge_attr) copy_span(o.edge_attr + eo * G, s.edge_attr + ep * G, e * G, tid, stride);
     if (o.edge_attr_slots) {
-      for (int64_t i = tid; i < eg; i += stride) {
-        int64_t sl = i / G;
-        int j = (int)(i - sl * G);
-        int64_t src_e = __ldg(s.dst_eid + ep + sl);   // store-global reference edge id of this slot
-        o.edge_attr_slots[(eo + sl) * G + j] = __ldg(s.edge_attr + src_e * G + j);
+      for (int64_t sl = warp; sl < e; sl += nwarps) {
+        const float* __restrict__ from = s.edge_attr + (int64_t)__ldg(s.dst_eid + ep + sl) * G;
+        float* __restrict__ to = o.edge_attr_slots + (eo + sl) * G;
+        for (int j = lane; j < G; j += 32) to[j] = __ldg(from + j);
       }
     }
   } else {
-    if (o.edge_attr) {
-      for (int64_t i = tid; i < eg; i += stride) {
-        int64_t k = i / G;
-        int j = (int)(i - k * G);
-        float diff = __ldg(s.d_hat + ep + k) - __ldg(o.smear_offset + j);
-        o.edge_attr[(eo + k) * G + j] = expf(o.smear_coeff * (diff * diff));
-      }
-    }
-    if (o.edge_attr_slots) {
-      for (int64_t i = tid; i < eg; i += stride) {
-        int64_t sl = i / G;
-        int j = (int)(i - sl * G);
-        float diff = __ldg(s.d_hat + __ldg(s.dst_eid + ep + sl)) - __ldg(o.smear_offset + j);
-        o.edge_attr_slots[(eo + sl) * G + j] = expf(o.smear_coeff * (diff * diff));
+    for (int64_t k = warp; k < e; k += nwarps) {
+      const float d_ref = o.edge_attr ? __ldg(s.d_hat + ep + k) : 0.f;
+      const float d_slot = o.edge_attr_slots ? __ldg(s.d_hat + __ldg(s.dst_eid + ep + k)) : 0.f;
+      for (int j = lane; j < G; j += 32) {
+        const float off = __ldg(o.smear_offset + j);
+        if (o.edge_attr) {
+          const float diff = d_ref - off;
+          o.edge_attr[(eo + k) * G + j] = expf(o.smear_coeff * (diff * diff));
+        }
+        if (o.edge_attr_slots) {
+          const float diff = d_slot - off;
+          o.edge_attr_slots[(eo + k) * G + j] = expf(o.smear_coeff * (diff * diff));
+        }
       }
     }
   }

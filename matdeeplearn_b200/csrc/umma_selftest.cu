@@ -81,9 +81,101 @@ k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B, float*
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
+// Same product with the A operand staged in TENSOR MEMORY (tcgen05.st by the thread that owns the
+// row's lane) and B in shared memory: pins the A-from-TMEM convention the transposed edge kernel uses
+// (lane = A row, one 32-bit column per tf32 element, 8 columns per MMA).
+__global__ void __launch_bounds__(128, 1)
+k_umma_selftest_ts(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+                   int split) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b_bytes = N * K * 4;
+  uint8_t* sBhi = sm;
+  uint8_t* sBlo = sBhi + b_bytes;
+  uint32_t ncols = 32;
+  while ((int)ncols < N + 2 * K) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < N * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    const float x = B[i];
+    const float hi = split ? umma::tf32_hi(x) : x;
+    const int off = umma::tile_offset_bytes(r, k, N);
+    *reinterpret_cast<float*>(sBhi + off) = hi;
+    *reinterpret_cast<float*>(sBlo + off) = x - hi;
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t a_hi = tmem + N, a_lo = tmem + N + K;
+  for (int k0 = 0; k0 < K; k0 += 8) {   // thread = lane = row of A
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = A[(size_t)tid * K + k0 + j];
+      hi[j] = split ? umma::tf32_hi(x) : x;
+      lo[j] = x - hi[j];
+    }
+    umma::tmem_st8(umma::tmem_addr(a_hi, warp, k0), hi);
+    umma::tmem_st8(umma::tmem_addr(a_lo, warp, k0), lo);
+  }
+  umma::tmem_st_wait();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_tf32(128, N);
+    const uint32_t step_b = 2 * N * 16;
+    uint32_t acc = 0;
+    for (int pass = 0; pass < (split ? 3 : 1); ++pass) {
+      const uint32_t a = (pass == 2) ? a_lo : a_hi;
+      const uint8_t* b = (pass == 1) ? sBlo : sBhi;
+      for (int kk = 0; kk < K / 8; ++kk) {
+        const uint64_t bd = umma::make_desc(umma::smem_u32(b) + kk * step_b, N * 16, 128);
+        umma::mma_tf32_ts(tmem, a + kk * 8, bd, idesc, acc);
+        acc = 1;
+      }
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(umma::tmem_addr(tmem, warp, c0), v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) D[(size_t)tid * N + c0 + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
 }  // namespace mdl
 
 using namespace mdl;
+
+extern "C" int mdl_selftest_umma_ts(const float* A, const float* B, float* D, int32_t N, int32_t K,
+                                    int32_t split, void* stream) {
+  MDL_REQUIRE(A && B && D, "selftest_umma_ts: null pointer");
+  MDL_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "selftest_umma_ts: N must be a multiple of 16 in [16,256]");
+  MDL_REQUIRE(K >= 8 && K % 8 == 0 && N + 2 * K <= 512, "selftest_umma_ts: K must be a multiple of 8, N+2K <= 512");
+  size_t smem = (size_t)2 * N * K * 4;
+  MDL_REQUIRE(smem <= 200 * 1024, "selftest_umma_ts: tile too large");
+  MDL_CUDA(cudaFuncSetAttribute(k_umma_selftest_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_umma_selftest_ts<<<1, 128, smem, as_stream(stream)>>>(A, B, D, N, K, split);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
 
 static int selftest_launch(const float* A, const float* B, float* D, int32_t N, int32_t K,
                            int32_t split, int lbo_a, int sbo_a, int lbo_b, int sbo_b, void* stream) {

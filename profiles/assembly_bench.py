@@ -84,11 +84,13 @@ def main():
     store = GraphStore.from_dataset(ds, DEV)
     order = np.random.default_rng(1).permutation(n_graphs)
     chunks = [order[i:i + B] for i in range(0, n_graphs, B)]
-    for name in ("device store", "host collate"):
+    for name in ("device store, padded graph replay", "device store", "host collate"):
         torch.manual_seed(0)
         model = M.CGCNN(ds, **cfg).to(DEV).train()
         step = TrainStep(model, lr=1e-3)
         def one(idx):
+            if name == "device store, padded graph replay":
+                return step.from_store(store, idx, sync=False)
             if name == "device store":
                 return step.eager(store.batch(idx))
             hb = ds.batch([int(i) for i in idx]).pin_memory()
@@ -101,7 +103,7 @@ def main():
             loss = one(idx)
         last = float(loss.item())
         dt = time.perf_counter() - t0
-        print(json.dumps({"what": "shuffled epoch, eager steps", "batches_from": name, "graphs": n_graphs,
+        print(json.dumps({"what": "shuffled epoch", "batches_from": name, "graphs": n_graphs,
                           "batch": B, "wall_s": dt, "graphs_per_s": n_graphs / dt, "last_loss": last}), flush=True)
 
 

@@ -28,6 +28,27 @@ def test_umma_selftest(N, K, split):
     assert err < tol, (split, err, scale)
 
 
+@pytest.mark.parametrize("N,K", [(128, 56), (64, 64), (16, 8), (256, 56), (64, 128)])
+@pytest.mark.parametrize("split", [0, 1])
+def test_umma_selftest_a_operand_in_tensor_memory(N, K, split):
+    from matdeeplearn_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(N * 1000 + K + 7)
+    A = torch.randn(128, K)
+    B = torch.randn(N, K)
+    D = torch.full((128, N), float("nan"), device=dev)
+    Ad, Bd = A.to(dev), B.to(dev)
+    rc = lib.mdl_selftest_umma_ts(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, split, _lib.stream())
+    _lib.check(rc, "mdl_selftest_umma_ts")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    err = (D.cpu().double() - ref).abs().max().item()
+    scale = (A.abs().double() @ B.abs().double().t()).max().item()
+    tol = (2e-3 if split == 0 else 2e-6) * scale
+    assert err < tol, (split, err, scale)
+
+
 def _tf32_trunc(x):
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
