@@ -79,20 +79,39 @@ k_bn_stats(const float* __restrict__ x, const int32_t* __restrict__ n_valid, int
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+  // the last CTA merges the per-CTA partials: row lane ty takes partials ty, ty+th, ... (loads batched
+  // so their L2 latencies overlap), then lane 0 merges the th results -- a fixed order either way
+  for (int c0 = 0; c0 < C; c0 += cw) {
+    const int c = c0 + tx;
     Welford w{0.f, 0.f, 0.f};
-    for (unsigned b = 0; b < gridDim.x; ++b) {
-      const float* p = part + (size_t)b * 3 * C;
-      wf_merge(w, Welford{__ldcg(p + c), __ldcg(p + C + c), __ldcg(p + 2 * C + c)});
+    if (c < C) {
+      for (unsigned b0 = ty; b0 < gridDim.x; b0 += 8 * th) {
+        Welford q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned b = b0 + u * th;
+          const float* p = part + (size_t)b * 3 * C;
+          q[u] = (b < gridDim.x) ? Welford{__ldcg(p + c), __ldcg(p + C + c), __ldcg(p + 2 * C + c)}
+                                 : Welford{0.f, 0.f, 0.f};
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wf_merge(w, q[u]);
+      }
     }
-    const float var = w.n > 0.f ? w.m2 / w.n : 0.f;
-    save_mean[c] = w.mean;
-    save_invstd[c] = rsqrtf(var + eps);
-    if (running_mean) {
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * w.mean;
-      const float unbiased = w.n > 1.f ? w.m2 / (w.n - 1.f) : var;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    sh[threadIdx.x] = w;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      for (int k = 1; k < th; ++k) wf_merge(w, sh[k * cw + tx]);
+      const float var = w.n > 0.f ? w.m2 / w.n : 0.f;
+      save_mean[c] = w.mean;
+      save_invstd[c] = rsqrtf(var + eps);
+      if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * w.mean;
+        const float unbiased = w.n > 1.f ? w.m2 / (w.n - 1.f) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
     }
+    __syncthreads();
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
@@ -158,17 +177,40 @@ k_bn_bwd_stats(const float* __restrict__ g, const float* __restrict__ x, const i
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+  for (int c0 = 0; c0 < C; c0 += cw) {
+    const int c = c0 + tx;
     float sg = 0.f, sgx = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) {
-      const float* p = part + (size_t)b * 2 * C;
-      sg += __ldcg(p + c);
-      sgx += __ldcg(p + C + c);
+    if (c < C) {
+      for (unsigned b0 = ty; b0 < gridDim.x; b0 += 8 * th) {
+        float a[8], bx[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned b = b0 + u * th;
+          const float* p = part + (size_t)b * 2 * C;
+          a[u] = (b < gridDim.x) ? __ldcg(p + c) : 0.f;
+          bx[u] = (b < gridDim.x) ? __ldcg(p + C + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          sg += a[u];
+          sgx += bx[u];
+        }
+      }
     }
-    sums[c] = sg;
-    sums[C + c] = sgx;
-    if (gbias) gbias[c] = sg;
-    if (gweight) gweight[c] = sgx;
+    sh[0][threadIdx.x] = sg;
+    sh[1][threadIdx.x] = sgx;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      for (int k = 1; k < th; ++k) {
+        sg += sh[0][k * cw + tx];
+        sgx += sh[1][k * cw + tx];
+      }
+      sums[c] = sg;
+      sums[C + c] = sgx;
+      if (gbias) gbias[c] = sg;
+      if (gweight) gweight[c] = sgx;
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
