@@ -255,16 +255,6 @@ MDL_API int mdl_batchnorm_bwd(const float* gout, const float* x, const int32_t* 
                               const float* save_invstd, float* gx, float* gweight, float* gbias,
                               void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- dense-layer weight gradient over a tall batch ------------------------------------------
- * dW[O,I] = G[N,O]^T X[N,I], db[O] = column sums of G (db may be NULL): what autograd's Linear
- * backward computes for torch.nn.Linear (reference cgcnn.py:64-77,97-111) and for the node
- * projections inside CGConv.  Rows are split over the grid, per-CTA partials are summed in CTA
- * order (deterministic).  workspace: mdl_linear_wgrad_workspace_bytes(N, I, O) bytes. */
-MDL_API size_t mdl_linear_wgrad_workspace_bytes(int64_t N, int32_t I, int32_t O);
-MDL_API int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32_t I, int32_t O,
-                             float* dW, float* db, void* workspace, size_t workspace_bytes,
-                             void* stream);
-
 /* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
  * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).
  * hyper = device {lr, beta1, beta2, eps, weight_decay}; step = device float step count, advanced by

@@ -66,8 +66,6 @@ SIGNATURES = {
     "mdl_batchnorm_workspace_bytes": (_sz, [_i64, _i32]),
     "mdl_batchnorm_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _sz, _p]),
     "mdl_batchnorm_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "mdl_linear_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
-    "mdl_linear_wgrad": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _sz, _p]),
     "mdl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i64, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),

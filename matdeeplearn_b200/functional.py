@@ -58,49 +58,6 @@ def segment_reduce(src, ptr, perm=None, reduce="mean"):
 
 
 # ----------------------------------------------------------------------------
-# Dense layer: weight / bias gradient over a tall batch
-# ----------------------------------------------------------------------------
-def linear_wgrad(x, g, want_bias=True):
-    """dW[O,I] = g^T x, db[O] = g.sum(0) through mdl_linear_wgrad (rows split over the grid)."""
-    lib = _lib.load()
-    x, g = x.contiguous(), g.contiguous()
-    N, I = x.shape
-    O = g.shape[1]
-    dW = torch.empty((O, I), dtype=torch.float32, device=x.device)
-    db = torch.empty(O, dtype=torch.float32, device=x.device) if want_bias else None
-    need = int(lib.mdl_linear_wgrad_workspace_bytes(N, I, O))
-    ws = torch.empty(max(need, 4), dtype=torch.uint8, device=x.device)
-    rc = lib.mdl_linear_wgrad(_lib.ptr(x), _lib.ptr(g), N, I, O, _lib.ptr(dW), _lib.ptr(db), _lib.ptr(ws),
-                              ws.numel(), _lib.stream())
-    _lib.check(rc, "mdl_linear_wgrad")
-    return dW, db
-
-
-class LinearFn(torch.autograd.Function):
-    """y = x W^T + b with the library GEMM forward / input gradient and mdl_linear_wgrad for dW, db."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
-
-    @staticmethod
-    def backward(ctx, g):
-        x, weight = ctx.saved_tensors
-        g = g.contiguous()
-        dx = g.mm(weight) if ctx.needs_input_grad[0] else None
-        dW, db = linear_wgrad(x, g, want_bias=ctx.has_bias)
-        return dx, dW, db
-
-
-def linear(x, weight, bias=None):
-    if x.dim() != 2 or not x.is_cuda or not (x.requires_grad or weight.requires_grad):
-        return torch.nn.functional.linear(x, weight, bias)
-    return LinearFn.apply(x, weight, bias)
-
-
-# ----------------------------------------------------------------------------
 # BatchNorm1d (training mode) with a device-side row count
 # ----------------------------------------------------------------------------
 class MaskedBatchNormFn(torch.autograd.Function):
