@@ -58,6 +58,10 @@ __device__ __forceinline__ float sigmoid_fast_(float x) { return __fdividef(1.0f
 bool cgtc_supported(int mode, int C, int G);
 int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out, int dq_atomic = 0);
 void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
+// transposed-tile tensor-core path (cgconv_tt.cu): channel = TMEM lane, two CTAs per SM
+bool cgtt_supported(int mode, int C, int G);
+int cgtt_launch(int mode, CgParams p, cudaStream_t st);
+void cgtt_set_phase_buffer(unsigned long long* dev_ptr);
 // out0[i] (i < len0) / out1[i - len0] = sum over nparts partial vectors, fixed order (cgconv.cu)
 int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, float* out0, int64_t len0,
                  float* out1, cudaStream_t st);

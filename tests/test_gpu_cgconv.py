@@ -87,12 +87,13 @@ def test_scatter_unsorted_index(dev):
         assert_close(got, ref, **FWD, what=red)
 
 
-@pytest.fixture(params=["tc", "tc_det", "simt"])
+@pytest.fixture(params=["tc", "tc_det", "simt", "tt"])
 def impl(request, monkeypatch):
     """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
     atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
     tensor-core kernels in deterministic two-pass mode, and with the SIMT kernels forced."""
-    monkeypatch.setenv("MDL_CGCONV_IMPL", "simt" if request.param == "simt" else "tc")
+    # "tt": transposed-tile forward kernel (cgconv_tt.cu); the backward stays on the tc kernels
+    monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt", "tt") else "tc")
     monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
     return request.param
 
