@@ -3,20 +3,25 @@
 // Same operator and the same tile-ownership scheme as cgconv_tc.cu, with the contraction
 // transposed so that the CHANNEL, not the edge slot, is the TMEM lane:
 //
-//     D[m, e] = sum_k We[m, k] * ea[e, k]        m = gate*C + c  (128 lanes),  e = slot (128 columns)
+//     D[m, e] = sum_k We[m, k] * ea[e, k]        m = 2*c + gate  (128 lanes),  e = slot (128 columns)
 //
 //   * A operand = the edge weights We, split hi/lo ONCE per CTA and parked in tensor memory
 //     (tcgen05.st by the thread that owns lane m; umma::mma_tf32_ts) -- no shared memory.
 //   * B operand = the round's edge_attr rows [slot][k], K-major: exactly the tile the rows land in.
 //     cp.async writes the raw rows straight into the operand layout, the hi/lo split happens in place.
-//   * epilogue thread = (channel-gate m, half of the slots).  Its loads are COALESCED by construction
-//     (a warp = 32 consecutive channels of one node row = one 128-byte line), so the node
-//     projections P[dst], Q[src] need no staging tile; the sum over a destination's slots runs
+//   * epilogue thread = (lane m, half of the slots).  Its loads are coalesced by construction (a warp
+//     reads 16 consecutive channels of both gates of one node row: two full 64-byte pieces), so the
+//     node projections P[dst], Q[src] need no staging tile; the sum over a destination's slots runs
 //     along the thread's own registers, so there is no value tile and no separate reduce pass.
-//     Warps are gate-homogeneous (sigmoid warps / softplus warps: 2 MUFU per value, no divergence);
-//     the two gates of a channel meet through a 16-slot exchange buffer.
+//     The two gates of a channel sit in ADJACENT lanes and meet through one shuffle per slot pair.
+//     MUFU budget: exp2 for every lane, log2 on the softplus lanes; the sigmoid lanes take their
+//     reciprocal on the FMA pipe (quadratic seed + 2 Newton steps, ~1 ulp), so the transcendental
+//     pipe sees 2 warp instructions per slot exactly as in a gate-homogeneous warp.
+//   * warp 8 is the producer: it issues the MMAs, then the next round's index loads and cp.async
+//     rows as soon as the tensor core has released the operand tiles, and writes the rows of
+//     slot-less owned segments.  The 8 epilogue warps never wait for each other inside a round.
 //
-// Shared memory drops from 219 KB to ~96 KB and TMEM to 256 columns, so TWO CTAs share an SM and
+// Shared memory drops from 219 KB to ~65 KB and TMEM to 256 columns, so TWO CTAs share an SM and
 // the hardware overlaps one CTA's load/split/MMA phases with the other's epilogue.
 //
 // Ownership / ordering of the output rows (deterministic, no atomics): a segment's slots are summed
@@ -29,19 +34,19 @@
 
 namespace mdl {
 
-constexpr int kTtThreads = 256;
-constexpr int kTtWarps = kTtThreads / 32;
+constexpr int kTtEpiThreads = 256;                   // 8 epilogue warps
+constexpr int kTtThreads = kTtEpiThreads + 32;       // + the producer warp
 constexpr int kTtRows = 128;                         // slots per round = MMA N
 constexpr int kTtTE = 112;                           // ownership granularity (as cgconv_tc.cu)
 constexpr uint32_t kTtChunk = kTtRows * 16 + 16;     // k-chunk stride of the operand tiles (bank padding)
 constexpr int kTtInfoCap = 256;
 constexpr int kTtBatch = 16;                         // slots per epilogue batch
-constexpr int kTtC = 64;                             // channels (lane map: 2 gates x 64 = 128 lanes)
+constexpr int kTtC = 64;                             // channels (lane map: 64 channels x 2 gates = 128 lanes)
 
 struct TtPlan {
   unsigned long long* prof;
   int KP;
-  uint32_t offHi, offLo, offX, offComb, offIdx, offInfo, total;
+  uint32_t offHi, offLo, offIdx, offInfo, total;
 };
 
 static bool tt_plan(int C, int G, TtPlan* pl) {
@@ -53,18 +58,18 @@ static bool tt_plan(int C, int G, TtPlan* pl) {
   pl->KP = KP;
   pl->offHi = 0;
   pl->offLo = tile;
-  pl->offX = 2 * tile;                                   // [2 halves][2 buffers][16 slots][128 lanes]
-  pl->offComb = pl->offX + 2 * 2 * kTtBatch * 128 * 4;   // [2 halves][2 parities][64 channels]
-  pl->offIdx = pl->offComb + 2 * 2 * kTtC * 4;           // [2 buffers][src|dst][128]
+  pl->offIdx = 2 * tile;                                 // [2 buffers][src|dst][128]
   pl->offInfo = pl->offIdx + 2 * 2 * kTtRows * 4;
   pl->total = pl->offInfo + kTtInfoCap * 16;
   return pl->total <= 112 * 1024;
 }
 
-// barrier of the 128 threads of one slot half (ids 1 and 2; 0 is __syncthreads)
-__device__ __forceinline__ void bar_sync_half(int h) {
-  if (h == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-  else asm volatile("bar.sync 2, 128;" ::: "memory");
+// 1/u for u in [1, 2] on the FMA pipe: minimax quadratic seed (1% error) + two Newton steps
+__device__ __forceinline__ float rcp_newton_1_2(float u) {
+  float r = fmaf(fmaf(0.3232323232f, u, -1.4545454545f), u, 2.1212121212f);
+  r = fmaf(r, fmaf(-u, r, 1.0f), r);
+  r = fmaf(r, fmaf(-u, r, 1.0f), r);
+  return r;
 }
 
 __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams p, const TtPlan pl) {
@@ -74,14 +79,14 @@ __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int C = kTtC, W2 = 2 * kTtC;
   const int G = p.G, KP = pl.KP;
-  const int q = warp & 3, h = warp >> 2;   // TMEM lane quadrant, slot half
-  const int m = 32 * q + lane;             // lane-channel: gate*64 + c
-  const int gate = q >> 1, c = m & 63;
+  const bool producer = warp == 8;
+  const int q = warp & 3, h = (warp >> 2) & 1;   // TMEM lane quadrant, slot half (epilogue warps)
+  const int m = 32 * q + lane;                   // TMEM lane: 2*c + gate
+  const int gate = m & 1, c = m >> 1;
+  const int col = gate * C + c;                  // column of [f | s] in WeT / P / Q rows
 
   uint8_t* sHi = smem + pl.offHi;
   uint8_t* sLo = smem + pl.offLo;
-  float* sX = reinterpret_cast<float*>(smem + pl.offX);
-  float* sComb = reinterpret_cast<float*>(smem + pl.offComb);
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);
 
@@ -112,12 +117,12 @@ __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams 
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tm_d = tmem, tm_whi = tmem + 128, tm_wlo = tmem + 128 + (uint32_t)KP;
-  if (warp < 4) {  // thread = lane m = column m of WeT [G, 2C]
+  if (warp < 4) {  // thread = lane m = column `col` of WeT [G, 2C]
     for (int k0 = 0; k0 < KP; k0 += 8) {
       float hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float w = (k0 + j < G) ? __ldg(p.WeT + (size_t)(k0 + j) * W2 + m) : 0.0f;
+        const float w = (k0 + j < G) ? __ldg(p.WeT + (size_t)(k0 + j) * W2 + col) : 0.0f;
         hi[j] = umma::tf32_hi(w);
         lo[j] = w - hi[j];
       }
@@ -132,69 +137,70 @@ __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams 
   const uint32_t idesc = umma::make_idesc_tf32(128, kTtRows);
   uint32_t phase = 0;
 
-  // ---- loads of a round: indices (registers), then the ea rows straight into the operand layout
-  constexpr int kRowsPerWarp = kTtRows / kTtWarps;  // 16
-  const int row0 = warp * kRowsPerWarp;
-  struct NextIdx { int s, d; };
+  // ---- producer: indices of a round (4 rows per lane, registers), then its ea rows via cp.async
+  // straight into the operand layout
+  struct Idx4 { int s[4], d[4]; };
   auto issue_idx = [&](int r_lo, int cnt) {
-    NextIdx ni{0, 0};
-    if (lane < kRowsPerWarp && row0 + lane < cnt) {
-      ni.s = __ldg(p.dst_src + r_lo + row0 + lane);
-      ni.d = __ldg(p.dst_dst + r_lo + row0 + lane);
+    Idx4 v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = lane + 32 * u;
+      v.s[u] = v.d[u] = 0;
+      if (e < cnt) {
+        v.s[u] = __ldg(p.dst_src + r_lo + e);
+        v.d[u] = __ldg(p.dst_dst + r_lo + e);
+      }
     }
-    return ni;
+    return v;
   };
-  auto land_idx_and_rows = [&](const NextIdx& ni, int r_lo, int cnt, int buf) {
+  auto land_idx_and_rows = [&](const Idx4& v, int r_lo, int cnt, int buf) {
     int* bS = sIdx + buf * 2 * kTtRows;
     int* bD = bS + kTtRows;
-    if (lane < kRowsPerWarp) {
-      bS[row0 + lane] = ni.s;
-      bD[row0 + lane] = ni.d;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      bS[lane + 32 * u] = v.s[u];
+      bD[lane + 32 * u] = v.d[u];
     }
-    const int wcnt = min(kRowsPerWarp, cnt - row0);
+    // the round's rows are one contiguous span of cnt*G floats (slot order)
+    const float* src = p.ea + (size_t)r_lo * G;
     if ((G & 1) == 0) {  // 8-byte pieces (rows are 8-byte aligned when G is even)
-      const int cpr = G >> 1;
-      for (int i = lane; i < kRowsPerWarp * cpr; i += 32) {
-        const int r = i / cpr, j = i - r * cpr;
-        if (r < wcnt) {
-          const int e = row0 + r;
-          const uint32_t off = (uint32_t)(j >> 1) * kTtChunk + (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16 +
-                               (uint32_t)(j & 1) * 8;
-          cp_async8(sHi + off, p.ea + (size_t)(r_lo + e) * G + 2 * j);
-        }
+      const int cpr = G >> 1, total = cnt * cpr;
+      for (int i = lane; i < total; i += 32) {
+        const int e = i / cpr, j = i - e * cpr;
+        const uint32_t off = (uint32_t)(j >> 1) * kTtChunk + (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16 +
+                             (uint32_t)(j & 1) * 8;
+        cp_async8(sHi + off, src + 2 * i);
       }
     } else {
-      for (int i = lane; i < kRowsPerWarp * G; i += 32) {
-        const int r = i / G, j = i - r * G;
-        if (r < wcnt) {
-          const int e = row0 + r;
-          const uint32_t off = (uint32_t)(j >> 2) * kTtChunk + (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16 +
-                               (uint32_t)(j & 3) * 4;
-          cp_async4(sHi + off, p.ea + (size_t)(r_lo + e) * G + j);
-        }
+      const int total = cnt * G;
+      for (int i = lane; i < total; i += 32) {
+        const int e = i / G, j = i - e * G;
+        const uint32_t off = (uint32_t)(j >> 2) * kTtChunk + (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16 +
+                             (uint32_t)(j & 3) * 4;
+        cp_async4(sHi + off, src + i);
       }
     }
   };
 
   long long t_prev = clock64();
   auto mark = [&](int slot) {
-    if (pl.prof && tid == 0) {
+    if (pl.prof && (tid == 0 || tid == kTtEpiThreads)) {
       const long long now = clock64();
-      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
+      atomicAdd(pl.prof + slot + (producer ? 8 : 0), (unsigned long long)(now - t_prev));
       t_prev = now;
     }
   };
 
   int k = 0, rd = 0, buf = 0;
-  if (my_tiles > 0) {
+  if (producer && my_tiles > 0) {
     const TileInfo t0 = sInfo[0];
     const int c0 = min(t0.e_hi - t0.e_lo, kTtRows);
-    const NextIdx ni = issue_idx(t0.e_lo, c0);
-    land_idx_and_rows(ni, t0.e_lo, c0, 0);
+    const Idx4 v = issue_idx(t0.e_lo, c0);
+    land_idx_and_rows(v, t0.e_lo, c0, 0);
   }
 
-  // carry of the (at most one) segment of the previous half-round of this thread that continued
-  // from before its slot range; applied after a CTA barrier (see header).  Used by f-gate threads.
+  // carry of the (at most one) segment of this thread's previous half-round that had started before
+  // its slot range; applied after a CTA barrier (see header).  Lives in the even (sigmoid) lanes.
   bool carry_on = false, carry_final = false;
   int carry_n = 0;
   float carry_v = 0.f, carry_x = 0.f, carry_sc = 1.f;
@@ -206,7 +212,6 @@ __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams 
       carry_on = false;
     }
   };
-  int par = 0;  // parity of the gate-combine buffer
 
   while (k < my_tiles) {
     if (k + 1 >= info_base + kTtInfoCap && info_base + kTtInfoCap < my_tiles) {
@@ -227,16 +232,16 @@ __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams 
     const int* bDst = bSrc + kTtRows;
 
     mark(0);
-    cp_async_wait_all();
+    if (producer) cp_async_wait_all();
     __syncthreads();  // [S1] rows + indices of this round landed; previous round fully retired
     mark(1);
-    if (h == 1) apply_carry();  // second-half carries of the previous round: after the first halves' (at S3)
+    if (!producer && h == 1) apply_carry();  // second-half carries: after the first halves' (applied at S3)
 
     // ---- split hi/lo in place (raw rows sit in the hi tile)
-    {
+    if (!producer) {
       const int e = tid & (kTtRows - 1);
       const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-      for (int j = (tid >> 7); j < (KP >> 2); j += kTtThreads / kTtRows) {
+      for (int j = (tid >> 7); j < (KP >> 2); j += kTtEpiThreads / kTtRows) {
         const uint32_t off = (uint32_t)j * kTtChunk + row_off;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < cnt) {
@@ -258,132 +263,152 @@ __global__ void __launch_bounds__(kTtThreads, 2) k_cgconv_tt_fwd(const CgParams 
     __syncthreads();  // [S2] operands staged
     mark(2);
 
-    if (tid == 0 && cnt > 0) {
-      umma::fence_after_sync();
-      const uint32_t step_b = 2 * kTtChunk;
-      const uint32_t b_hi = umma::smem_u32(sHi), b_lo = umma::smem_u32(sLo);
-      uint32_t acc = 0;
+    if (producer) {
+      // ================= producer warp =================
+      if (lane == 0 && cnt > 0) {
+        umma::fence_after_sync();
+        const uint32_t step_b = 2 * kTtChunk;
+        const uint32_t b_hi = umma::smem_u32(sHi), b_lo = umma::smem_u32(sLo);
+        uint32_t acc = 0;
 #pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = (pass == 2) ? tm_wlo : tm_whi;
-        const uint32_t b = (pass == 1) ? b_lo : b_hi;
-        for (int kk = 0; kk < (KP >> 3); ++kk) {
-          const uint64_t bd = umma::make_desc(b + kk * step_b, kTtChunk, 128);
-          umma::mma_tf32_ts(tm_d, a + kk * 8, bd, idesc, acc);
-          acc = 1;
-        }
-      }
-      umma::mma_commit(&bar);
-    }
-    mark(3);
-
-    // ---- owned segments without any slot: out = x  (once per tile)
-    if (rd == 0) {
-      for (int i = tid; i < (n_hi - n_lo) * C; i += kTtThreads) {
-        const int n = n_lo + i / C, cc = i % C;
-        if (__ldg(p.seg_ptr + n) == __ldg(p.seg_ptr + n + 1)) p.out[(size_t)n * C + cc] = __ldg(p.x + (size_t)n * C + cc);
-      }
-    }
-
-    // ---- indices of the next round (registers) and the first batch of node projections
-    int ncnt = 0, nr_lo = 0;
-    NextIdx ni{0, 0};
-    if (nk < my_tiles) {
-      const TileInfo Tn = sInfo[nk - info_base];
-      nr_lo = Tn.e_lo + nrd * kTtRows;
-      ncnt = min(Tn.e_hi - nr_lo, kTtRows);
-      ni = issue_idx(nr_lo, ncnt);
-    }
-    const int my_lo = 64 * h, my_hi = min(cnt, 64 * h + 64);
-    float qn[kTtBatch], pn[kTtBatch];
-    auto prefetch = [&](int e0) {
-#pragma unroll
-      for (int j = 0; j < kTtBatch; ++j) {
-        qn[j] = 0.f;
-        pn[j] = 0.f;
-        if (e0 + j < my_hi) {
-          qn[j] = __ldg(p.PQ + (size_t)bSrc[e0 + j] * (4 * C) + 2 * C + m);
-          pn[j] = __ldg(p.PQ + (size_t)bDst[e0 + j] * (4 * C) + m);
-        }
-      }
-    };
-    if (my_lo < my_hi) prefetch(my_lo);
-    mark(4);
-
-    if (cnt > 0) {
-      umma::mbar_wait(&bar, phase);
-      umma::fence_after_sync();
-      phase ^= 1;
-    }
-    mark(5);
-    // operand tiles are free again: the next round's rows start landing under this round's epilogue
-    if (nk < my_tiles) land_idx_and_rows(ni, nr_lo, ncnt, buf ^ 1);
-
-    // ---- epilogue: thread = (lane-channel m, slot half h)
-    if (my_lo < my_hi) {
-      int cur = -1;            // destination node of the running segment
-      bool cur_cont = false;   // it started before this half's slot range
-      float acc = 0.f, cur_x = 0.f, cur_sc = 1.f;
-      auto flush = [&](bool ended) {   // uniform over the 128 threads of the half
-        float* comb = sComb + (h * 2 + par) * C;
-        if (gate == 1) comb[c] = acc;
-        bar_sync_half(h);
-        if (gate == 0) {
-          const float tot = acc + comb[c];
-          if (cur_cont) {
-            carry_on = true; carry_final = ended; carry_n = cur; carry_v = tot; carry_x = cur_x; carry_sc = cur_sc;
-          } else {
-            p.out[(size_t)cur * C + c] = ended ? fmaf(tot, cur_sc, cur_x) : tot;
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = (pass == 2) ? tm_wlo : tm_whi;
+          const uint32_t b = (pass == 1) ? b_lo : b_hi;
+          for (int kk = 0; kk < (KP >> 3); ++kk) {
+            const uint64_t bd = umma::make_desc(b + kk * step_b, kTtChunk, 128);
+            umma::mma_tf32_ts(tm_d, a + kk * 8, bd, idesc, acc);
+            acc = 1;
           }
         }
-        par ^= 1;
-      };
-      for (int e0 = my_lo, b = 0; e0 < my_hi; e0 += kTtBatch, ++b) {
-        float z[kTtBatch];
-        umma::tmem_ld16(umma::tmem_addr(tm_d, q, e0), z);
-        umma::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < kTtBatch; ++j) z[j] += qn[j] + pn[j];
-        if (e0 + kTtBatch < my_hi) prefetch(e0 + kTtBatch);   // next batch's loads fly under this batch's math
-        float* X = sX + (size_t)((h * 2 + (b & 1)) * kTtBatch) * 128;
-#pragma unroll
-        for (int j = 0; j < kTtBatch; ++j) {
-          z[j] = gate ? softplus_mufu(z[j]) : sigmoid_mufu(z[j]);
-          X[j * 128 + m] = z[j];
+        umma::mma_commit(&bar);
+      }
+      __syncwarp();
+      mark(3);
+      // owned segments without any slot: out = x  (once per tile)
+      if (rd == 0) {
+        for (int i = lane; i < (n_hi - n_lo) * C; i += 32) {
+          const int n = n_lo + i / C, cc = i % C;
+          if (__ldg(p.seg_ptr + n) == __ldg(p.seg_ptr + n + 1))
+            p.out[(size_t)n * C + cc] = __ldg(p.x + (size_t)n * C + cc);
         }
-        bar_sync_half(h);
+      }
+      int ncnt = 0, nr_lo = 0;
+      Idx4 nv{};
+      if (nk < my_tiles) {
+        const TileInfo Tn = sInfo[nk - info_base];
+        nr_lo = Tn.e_lo + nrd * kTtRows;
+        ncnt = min(Tn.e_hi - nr_lo, kTtRows);
+        nv = issue_idx(nr_lo, ncnt);
+      }
+      mark(4);
+      if (cnt > 0) {
+        umma::mbar_wait(&bar, phase);
+        umma::fence_after_sync();
+      }
+      mark(5);
+      // operand tiles are free again: the next round's rows land under this round's epilogue
+      if (nk < my_tiles) land_idx_and_rows(nv, nr_lo, ncnt, buf ^ 1);
+      mark(6);
+    } else {
+      // ================= epilogue warps: thread = (TMEM lane m, slot half h) =================
+      const int my_lo = 64 * h, my_hi = min(cnt, 64 * h + 64);
+      float qn[kTtBatch], pn[kTtBatch];
+      auto prefetch = [&](int e0) {
 #pragma unroll
         for (int j = 0; j < kTtBatch; ++j) {
+          qn[j] = 0.f;
+          pn[j] = 0.f;
           if (e0 + j < my_hi) {
-            const int d = bDst[e0 + j];
-            if (d != cur) {
-              if (cur >= 0) flush(true);
-              cur = d;
-              acc = 0.f;
-              cur_cont = (e0 + j == my_lo) && (__ldg(p.seg_ptr + d) < r_lo + my_lo);
-              if (gate == 0) {
-                cur_x = __ldg(p.x + (size_t)d * C + c);
-                cur_sc = p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f;
-              }
-            }
-            if ((j >> 3) == gate) acc = fmaf(z[j], X[j * 128 + (m ^ 64)], acc);
+            qn[j] = __ldg(p.PQ + (size_t)bSrc[e0 + j] * (4 * C) + 2 * C + col);
+            pn[j] = __ldg(p.PQ + (size_t)bDst[e0 + j] * (4 * C) + col);
           }
         }
+      };
+      if (my_lo < my_hi) prefetch(my_lo);
+      mark(3);
+      if (cnt > 0) {
+        umma::mbar_wait(&bar, phase);
+        umma::fence_after_sync();
       }
-      flush(__ldg(p.seg_ptr + cur + 1) <= r_lo + my_hi);
+      mark(4);
+      if (my_lo < my_hi) {
+        int cur = -1, cur_end = 0;   // destination node of the running segment, its end slot
+        bool cur_cont = false;       // it started before this half's slot range
+        float acc = 0.f, cur_x = 0.f, cur_sc = 1.f;
+        auto flush = [&]() {
+          const float tot = acc + __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (gate == 0) {
+            const bool ended = cur_end <= r_lo + my_hi;
+            if (cur_cont) {
+              carry_on = true; carry_final = ended; carry_n = cur; carry_v = tot; carry_x = cur_x; carry_sc = cur_sc;
+            } else {
+              p.out[(size_t)cur * C + c] = ended ? fmaf(tot, cur_sc, cur_x) : tot;
+            }
+          }
+        };
+        for (int e0 = my_lo; e0 < my_hi; e0 += kTtBatch) {
+          float z[kTtBatch];
+          umma::tmem_ld16(umma::tmem_addr(tm_d, q, e0), z);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kTtBatch; ++j) z[j] += qn[j] + pn[j];
+          if (e0 + kTtBatch < my_hi) prefetch(e0 + kTtBatch);   // next batch's loads fly under this batch's math
+          // gate values: sigmoid on even lanes, softplus on odd lanes, one exp2 shared by both forms
+#pragma unroll
+          for (int j = 0; j < kTtBatch; ++j) {
+            const float t = ex2_(-kLog2e * fabsf(z[j]));
+            const float u = 1.0f + t;
+            if (gate == 0) {
+              const float r = rcp_newton_1_2(u);
+              z[j] = z[j] >= 0.f ? r : t * r;
+            } else {
+              z[j] = fmaf(kLn2, lg2_(u), fmaxf(z[j], 0.f));
+            }
+          }
+          // products: the even lane takes slots j < 8 of the batch, the odd lane slots j >= 8
+          float prod[kTtBatch / 2];
+#pragma unroll
+          for (int j = 0; j < kTtBatch / 2; ++j) {
+            const float send = gate ? z[j] : z[j + 8];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            prod[j] = (gate ? z[j + 8] : z[j]) * recv;
+          }
+#pragma unroll
+          for (int j = 0; j < kTtBatch; ++j) {
+            if (e0 + j < my_hi) {
+              const int d = bDst[e0 + j];
+              if (d != cur) {
+                if (cur >= 0) flush();
+                cur = d;
+                acc = 0.f;
+                cur_cont = (e0 + j == my_lo) && (__ldg(p.seg_ptr + d) < r_lo + my_lo);
+                cur_end = __ldg(p.seg_ptr + d + 1);
+                if (gate == 0) {
+                  cur_x = __ldg(p.x + (size_t)d * C + c);
+                  cur_sc = p.inv_deg ? __ldg(p.inv_deg + d) : 1.0f;
+                }
+              }
+              if ((j >> 3) == gate) acc += prod[j & 7];
+            }
+          }
+        }
+        flush();
+      }
+      mark(5);
     }
-    mark(6);
+    if (cnt > 0) phase ^= 1;
     umma::fence_before_sync();   // accumulator reads retire before the next round's MMAs overwrite D
     __syncthreads();             // [S3] every direct row write of this round is visible
-    if (h == 0) apply_carry();
-    mark(7);
+    if (!producer && h == 0) apply_carry();
+    if (!producer) mark(6);
+    else t_prev = clock64();
     if (pl.prof && tid == 0) atomicAdd(pl.prof + 15, 1ull);
     k = nk; rd = nrd; buf ^= 1;
   }
 
-  cp_async_wait_all();
+  if (producer) cp_async_wait_all();
   __syncthreads();
-  if (h == 1) apply_carry();
+  if (!producer && h == 1) apply_carry();
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 256u);

@@ -19,7 +19,9 @@ WeT = torch.randn(G, 2 * C, device=dev) * 0.1
 P, st = _lib.ptr, _lib.stream()
 flush = torch.zeros(64 * 1024 * 1024, device=dev)
 prof = torch.zeros(16, dtype=torch.int64, device=dev)
-NAMES = ["loop", "S1 wait rows", "split + S2", "MMA issue", "empty segs + idx + prefetch0", "wait MMA", "epilogue", "S3 + carry"]
+NAMES = ["loop", "S1 wait rows", "split + S2", "prefetch batch 0", "wait MMA", "epilogue", "S3 + carry", "",
+         "P:loop", "P:S1 (cp.async wait)", "P:S2", "P:MMA issue", "P:empty segs + next idx", "P:wait MMA",
+         "P:rows cp.async issue"]
 res = {}
 for impl in ("tc", "tt"):
     os.environ["MDL_CGCONV_IMPL"] = impl
@@ -39,7 +41,7 @@ for impl in ("tc", "tt"):
         lib.mdl_debug_set_phase_buffer(P(prof)); prof.zero_(); fwd(); torch.cuda.synchronize()
         lib.mdl_debug_set_phase_buffer(None)
         v = prof.cpu().tolist(); rounds = max(v[15], 1)
-        line["cycles_per_round"] = {NAMES[i]: round(v[i] / rounds) for i in range(8)}
+        line["cycles_per_round"] = {NAMES[i]: round(v[i] / rounds) for i in range(15) if NAMES[i]}
         line["rounds"] = rounds
     print(json.dumps(line), flush=True)
 d = (res["tc"] - res["tt"]).abs()
