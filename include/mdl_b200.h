@@ -255,6 +255,31 @@ MDL_API int mdl_batchnorm_bwd(const float* gout, const float* x, const int32_t* 
                               const float* save_invstd, float* gx, float* gweight, float* gbias,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- dense-layer weight gradient over a tall batch, written in place -------------------------
+ * dW[O,I] = G[N,O]^T X[N,I] and db[O] = column sums of G: what autograd's Linear backward computes
+ * for torch.nn.Linear (reference cgcnn.py:64-77,97-111) and for lin_f / lin_s inside PyG's CGConv.
+ * Rows are split over the grid, per-CTA partials are summed in CTA order (deterministic).
+ * The result is delivered through a block map: output row o belongs to block o / block_rows; its
+ * weights go to w[block] + (o % block_rows) * ldw + i, its bias sum to b[block][o % block_rows]
+ * (NULL entries are skipped).  A plain Linear uses one block; CGConv's hoisted projections use
+ * four (P_f, P_s, Q_f, Q_s -> column blocks of lin_f.weight.grad / lin_s.weight.grad), so every
+ * gradient lands where the optimizer reads it (e.g. inside one flat gradient buffer) with no
+ * concatenation.  mdl_copy_mapped scatters an already reduced [O,I] (or transposed [I,O]) result
+ * the same way.  workspace: mdl_linear_wgrad_workspace_bytes(N, I, O) bytes. */
+typedef struct mdl_wgrad_out {
+  int32_t block_rows;
+  int32_t num_blocks;              /* <= 8 */
+  int64_t ldw;                     /* row stride of every w[] block, in floats */
+  float* w[8];
+  float* b[8];
+} mdl_wgrad_out;
+MDL_API size_t mdl_linear_wgrad_workspace_bytes(int64_t N, int32_t I, int32_t O);
+MDL_API int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32_t I, int32_t O,
+                             const mdl_wgrad_out* out, void* workspace, size_t workspace_bytes,
+                             void* stream);
+MDL_API int mdl_copy_mapped(const float* src, int32_t I, int32_t O, int32_t transposed,
+                            const mdl_wgrad_out* out, void* stream);
+
 /* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
  * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).
  * hyper = device {lr, beta1, beta2, eps, weight_decay}; step = device float step count, advanced by

@@ -42,6 +42,11 @@ class BatchOutC(C.Structure):
                 [("smear_coeff", _f32)])
 
 
+class WgradOutC(C.Structure):
+    """mdl_wgrad_out (include/mdl_b200.h)."""
+    _fields_ = [("block_rows", _i32), ("num_blocks", _i32), ("ldw", _i64), ("w", _p * 8), ("b", _p * 8)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/mdl_b200.h
 SIGNATURES = {
     "mdl_version": (C.c_int, []),
@@ -66,6 +71,9 @@ SIGNATURES = {
     "mdl_batchnorm_workspace_bytes": (_sz, [_i64, _i32]),
     "mdl_batchnorm_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _sz, _p]),
     "mdl_batchnorm_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mdl_linear_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "mdl_linear_wgrad": (C.c_int, [_p, _p, _i64, _i32, _i32, C.POINTER(WgradOutC), _p, _sz, _p]),
+    "mdl_copy_mapped": (C.c_int, [_p, _i32, _i32, _i32, C.POINTER(WgradOutC), _p]),
     "mdl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i64, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),

@@ -37,6 +37,7 @@ class FlatParameters:
             off += n
         self.params = params
         self.numel = total
+        self.direct = False
         # a leaf the optimizer can own: same storage as every view above
         self.leaf = torch.nn.Parameter(self.param, requires_grad=True)
         self.leaf.grad = self.grad
@@ -47,13 +48,45 @@ class FlatParameters:
     # ---- cheaper per-step protocol used by engine.TrainStep: instead of zeroing the flat gradient
     # and letting autograd ADD into ~20 views (one small kernel each), gradients are detached
     # (autograd then just hands over its result tensors) and packed with ONE concatenation.
+    def enable_direct(self):
+        """Direct delivery: every parameter advertises its slice of the flat gradient buffer
+        (`_mdl_grad_dest`); the engine's autograd Functions (functional.CGConvFn / LinearFn /
+        MaskedBatchNormFn) then write weight and bias gradients straight into it and return None,
+        so nothing is concatenated afterwards.  Parameters whose gradient still arrives through
+        autograd are copied in by pack_grads()."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p._mdl_grad_dest = self.grad[off:off + n].view_as(p)
+            p._mdl_written = False
+            off += n
+        self.direct = True
+
     def release_grads(self):
         for p in self.params:
             p.grad = None
+            if self.direct:
+                p._mdl_written = False
 
     def pack_grads(self):
-        flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
-        torch.cat(flat, out=self.grad)
+        if not self.direct:
+            flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+            torch.cat(flat, out=self.grad)
+            return self.grad
+        dst, src, extra = [], [], []
+        for p in self.params:
+            if p._mdl_written:
+                if p.grad is not None:          # a second use of the parameter went through autograd: add
+                    extra.append((p._mdl_grad_dest, p.grad))
+            elif p.grad is not None:
+                dst.append(p._mdl_grad_dest)
+                src.append(p.grad)
+            else:
+                p._mdl_grad_dest.zero_()
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for d, g in extra:
+            d.add_(g)
         return self.grad
 
     def bind_grads(self):

@@ -25,6 +25,7 @@ class TrainStep:
     def __init__(self, model, lr=2e-3, loss="l1_loss", weight_decay=1e-2):
         self.model = model
         self.flat = mdist.FlatParameters(model)
+        self.flat.enable_direct()   # weight/bias gradients land in the flat buffer, nothing to concatenate
         self.loss_fn = getattr(F, loss)
         self.device = self.flat.param.device
         self.opt = mdist.FlatAdamW(self.flat, lr=lr, weight_decay=weight_decay)

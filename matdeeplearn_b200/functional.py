@@ -16,6 +16,83 @@ from .csr import GraphCSR
 # ----------------------------------------------------------------------------
 # segmented reduce (pools, scatter_mean by source, node -> graph)
 # ----------------------------------------------------------------------------
+# ----------------------------------------------------------------------------
+# direct gradient delivery (dist.FlatParameters.enable_direct)
+# ----------------------------------------------------------------------------
+def _grad_dest(p):
+    """Where parameter p's gradient lives when the engine owns a flat gradient buffer and p has not
+    been written this step; None otherwise (the Function then returns the gradient to autograd)."""
+    if p is None:
+        return None
+    d = getattr(p, "_mdl_grad_dest", None)
+    if d is None or getattr(p, "_mdl_written", False):
+        return None
+    return d
+
+
+def _ptr_off(t, floats=0):
+    return None if t is None else t.data_ptr() + 4 * floats
+
+
+def _wgrad_map(block_rows, ldw, w_ptrs, b_ptrs):
+    m = _lib.WgradOutC()
+    m.block_rows, m.num_blocks, m.ldw = block_rows, len(w_ptrs), ldw
+    for k, (w, b) in enumerate(zip(w_ptrs, b_ptrs)):
+        m.w[k] = w
+        m.b[k] = b
+    return m
+
+
+def linear_wgrad_into(x, g, wmap):
+    """dW = g^T x, db = g.sum(0) delivered through the block map `wmap` (mdl_linear_wgrad)."""
+    import ctypes
+    lib = _lib.load()
+    x, g = x.contiguous(), g.contiguous()
+    N, I = x.shape
+    O = g.shape[1]
+    need = int(lib.mdl_linear_wgrad_workspace_bytes(N, I, O))
+    ws = torch.empty(max(need, 4), dtype=torch.uint8, device=x.device)
+    rc = lib.mdl_linear_wgrad(_lib.ptr(x), _lib.ptr(g), N, I, O, ctypes.byref(wmap), _lib.ptr(ws), ws.numel(),
+                              _lib.stream())
+    _lib.check(rc, "mdl_linear_wgrad")
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b: library GEMMs for y and dx; with direct delivery, dW and db come from
+    mdl_linear_wgrad and land in the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.wb = (weight, bias)
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        wparam, bparam = ctx.wb
+        g = g.contiguous()
+        dx = g.mm(weight) if ctx.needs_input_grad[0] else None
+        wd = _grad_dest(wparam)
+        bd = _grad_dest(bparam) if bparam is not None else None
+        if wd is not None and (bparam is None or bd is not None) and x.shape[0] > 0:
+            O, I = weight.shape
+            linear_wgrad_into(x, g, _wgrad_map(O, I, [_ptr_off(wd)], [_ptr_off(bd)]))
+            wparam._mdl_written = True
+            if bparam is not None:
+                bparam._mdl_written = True
+            return dx, None, None
+        return dx, g.t().mm(x), (g.sum(0) if bparam is not None else None)
+
+
+def linear(x, weight, bias=None):
+    """torch.nn.functional.linear; routed through LinearFn when the engine delivers gradients directly."""
+    if (x.dim() == 2 and x.is_cuda and torch.is_grad_enabled() and weight.requires_grad
+            and getattr(weight, "_mdl_grad_dest", None) is not None):
+        return LinearFn.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 class SegmentReduceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, ptr, perm, reduce, num_segments):
@@ -80,6 +157,7 @@ class MaskedBatchNormFn(torch.autograd.Function):
         _lib.check(rc, "mdl_batchnorm_fwd")
         ctx.save_for_backward(x, weight, mean, invstd, n_valid, ws)
         ctx.has_bias = bias is not None
+        ctx.wb = (weight, bias)
         return out
 
     @staticmethod
@@ -88,12 +166,24 @@ class MaskedBatchNormFn(torch.autograd.Function):
         N, C = x.shape
         g = g.contiguous()
         gx = torch.empty_like(x)
-        gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
-        gb = torch.empty(C, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        wparam, bparam = ctx.wb
+        wd = _grad_dest(wparam) if weight is not None else None
+        bd = _grad_dest(bparam) if ctx.has_bias else None
+        direct = (weight is None or wd is not None) and (not ctx.has_bias or bd is not None)
+        if direct:
+            gw, gb = wd, bd
+        else:
+            gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+            gb = torch.empty(C, dtype=torch.float32, device=x.device) if ctx.has_bias else None
         rc = _lib.load().mdl_batchnorm_bwd(_lib.ptr(g), _lib.ptr(x), _lib.ptr(n_valid), N, C, _lib.ptr(weight),
                                            _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gx), _lib.ptr(gw),
                                            _lib.ptr(gb), _lib.ptr(ws), ws.numel(), _lib.stream())
         _lib.check(rc, "mdl_batchnorm_bwd")
+        if direct:
+            for prm in (wparam, bparam):
+                if prm is not None:
+                    prm._mdl_written = True
+            return gx, None, None, None, None, None, None, None, None
         return gx, gw, gb, None, None, None, None, None, None
 
 
@@ -158,6 +248,7 @@ class CGConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, PQ, Wn, WeT, ea_slots)
         ctx.csr, ctx.reduce = csr, reduce
         ctx.has_bias = (b_f is not None, b_s is not None)
+        ctx.params = (w_f, b_f, w_s, b_s)
         return out
 
     @staticmethod
@@ -184,6 +275,26 @@ class CGConvFn(torch.autograd.Function):
         dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
         # node-level dense tail: plain library GEMMs (a hand-written split-over-nodes kernel was
         # measured slower than cuBLAS + a column sum here and was dropped)
+        w_f, b_f, w_s, b_s = ctx.params
+        dwf, dws = _grad_dest(w_f), _grad_dest(w_s)
+        dbf = _grad_dest(b_f) if ctx.has_bias[0] else None
+        dbs = _grad_dest(b_s) if ctx.has_bias[1] else None
+        if (dwf is not None and dws is not None and (not ctx.has_bias[0] or dbf is not None)
+                and (not ctx.has_bias[1] or dbs is not None)):
+            # direct delivery: [P_f | P_s | Q_f | Q_s] column blocks of dPQ^T x, the bias sums and the
+            # transposed edge block go straight into lin_f / lin_s .weight / .bias gradient storage
+            import ctypes
+            G = dWeT.shape[0]
+            ld = 2 * C + G
+            linear_wgrad_into(x, dPQ, _wgrad_map(
+                C, ld, [_ptr_off(dwf), _ptr_off(dws), _ptr_off(dwf, C), _ptr_off(dws, C)],
+                [_ptr_off(dbf), _ptr_off(dbs), None, None]))
+            m2 = _wgrad_map(C, ld, [_ptr_off(dwf, 2 * C), _ptr_off(dws, 2 * C)], [None, None])
+            rc = _lib.load().mdl_copy_mapped(_lib.ptr(dWeT), G, 2 * C, 1, ctypes.byref(m2), _lib.stream())
+            _lib.check(rc, "mdl_copy_mapped")
+            for prm in (w_f, w_s) + ((b_f,) if ctx.has_bias[0] else ()) + ((b_s,) if ctx.has_bias[1] else ()):
+                prm._mdl_written = True
+            return dx, None, None, None, None, None, None, None
         dWn = dPQ.t().mm(x)                                                 # [4C, C]
         db = dPQ[:, :2 * C].sum(0)
         return CGConvFn._finish(ctx, dx, dWn, db, dWeT, C)

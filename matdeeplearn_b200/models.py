@@ -65,16 +65,26 @@ class _ConvStackModel(tnn.Module):
     def _embed(self, data):
         h = data.x
         for lin in self.pre_lin_list:
-            h = self._activation(lin(h))
+            h = self._activation(MF.linear(h, lin.weight, lin.bias))
         return h
+
+    def _bn(self, i, h, data):
+        """BatchNorm after conv i.  The engine's own kernels take over when the batch is capacity-padded
+        (statistics over the real rows only) or when gradients are delivered straight into the flat
+        buffer (dist.FlatParameters.enable_direct); otherwise the torch module runs."""
+        bn = self.bn_list[i]
+        nv = getattr(data, "_n_valid", None)
+        own = nv is not None or (bn.training and h.is_cuda and bn.weight is not None
+                                 and getattr(bn.weight, "_mdl_grad_dest", None) is not None)
+        return MF.masked_batch_norm(bn, h, nv) if own else bn(h)
 
     def _readout(self, h, data):
         pool = getattr(mnn, self.pool)
         if self.pool_order == "early":
             h = pool(h, data.batch)
         for lin in self.post_lin_list:
-            h = self._activation(lin(h))
-        h = self.lin_out(h)
+            h = self._activation(MF.linear(h, lin.weight, lin.bias))
+        h = MF.linear(h, self.lin_out.weight, self.lin_out.bias)
         if self.pool_order == "late":
             h = pool(h, data.batch)
         return h.view(-1) if h.shape[1] == 1 else h
@@ -97,9 +107,7 @@ class CGCNN(_ConvStackModel):
         for i, conv in enumerate(self.conv_list):
             h = conv(h, data.edge_index, data.edge_attr, csr=csr)
             if self.batch_norm == "True":
-                nv = getattr(data, "_n_valid", None)
-                # capacity-padded batch (store.GraphStore.static_batch): statistics over real rows only
-                h = self.bn_list[i](h) if nv is None else MF.masked_batch_norm(self.bn_list[i], h, nv)
+                h = self._bn(i, h, data)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return self._readout(h, data)
 
@@ -122,7 +130,7 @@ class SchNet(_ConvStackModel):
         for i, conv in enumerate(self.conv_list):
             h = h + conv(h, data.edge_index, data.edge_weight, data.edge_attr, csr=csr)  # residual outside the block
             if self.batch_norm == "True":
-                h = self.bn_list[i](h)
+                h = self._bn(i, h, data)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return self._readout(h, data)
 
@@ -151,7 +159,7 @@ class MPNN(_ConvStackModel):
         for i, conv in enumerate(self.conv_list):
             m = conv(out, data.edge_index, data.edge_attr, csr=csr)
             if self.batch_norm == "True":
-                m = self.bn_list[i](m)
+                m = self._bn(i, m, data)
             m = self._activation(m)
             m = F.dropout(m, p=self.dropout_rate, training=self.training)
             out, hidden = self.gru_list[i](m.unsqueeze(0), hidden)  # cuDNN, TF32 off (package __init__)
@@ -181,7 +189,7 @@ class _MegnetStack(tnn.Module):
             if not (i == 0 and first_done):
                 h = getattr(F, self.act)(lin(h))
             if self.batch_norm == "True":
-                h = self.bn_list[i](h)
+                h = self._bn(i, h, data)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return h
 

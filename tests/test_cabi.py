@@ -51,7 +51,9 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
     def fields(cls):
         return [n for n, _ in cls._fields_]
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
-    for cname, cls in (("mdl_graph_store", lib.GraphStoreC), ("mdl_batch_out", lib.BatchOutC)):
+    structs = (("mdl_graph_store", lib.GraphStoreC), ("mdl_batch_out", lib.BatchOutC),
+               ("mdl_wgrad_out", lib.WgradOutC))
+    for cname, cls in structs:
         prog.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
         for f in fields(cls):
             prog.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
@@ -62,7 +64,7 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)
     got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True,
                                                        check=True).stdout.splitlines())
-    for cname, cls in (("mdl_graph_store", lib.GraphStoreC), ("mdl_batch_out", lib.BatchOutC)):
+    for cname, cls in structs:
         assert int(got[cname]) == ctypes.sizeof(cls)
         for f in fields(cls):
             assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)

@@ -103,3 +103,56 @@ def test_flat_adamw_matches_torch_adamw():
         ropt.step()
     for p, q in zip(lin.parameters(), ref.parameters()):
         assert (p.detach().cpu().double() - q.detach()).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("N,I,O", [(7862, 64, 256), (300, 114, 64), (256, 64, 1), (1, 8, 8), (5000, 100, 150)])
+def test_linear_wgrad_kernel_matches_autograd(N, I, O):
+    from matdeeplearn_b200 import functional as MF
+    torch.manual_seed(N + I)
+    x, g = torch.randn(N, I, device=DEV), torch.randn(N, O, device=DEV)
+    dW = torch.full((O, I), float("nan"), device=DEV)
+    db = torch.full((O,), float("nan"), device=DEV)
+    MF.linear_wgrad_into(x, g, MF._wgrad_map(O, I, [dW.data_ptr()], [db.data_ptr()]))
+    ref_w = g.double().t().mm(x.double())
+    ref_b = g.double().sum(0)
+    assert (dW.double() - ref_w).abs().max().item() <= 2e-6 * (g.abs().double().t().mm(x.abs().double())).max().item()
+    assert (db.double() - ref_b).abs().max().item() <= 2e-6 * g.abs().double().sum(0).max().item()
+
+
+def test_linear_wgrad_block_map_scatters_into_column_blocks():
+    """CGConv's use: four row blocks of dPQ^T x go to column blocks of two [C, 2C+G] matrices."""
+    from matdeeplearn_b200 import functional as MF
+    torch.manual_seed(4)
+    N, C, G = 1000, 64, 50
+    x, dPQ = torch.randn(N, C, device=DEV), torch.randn(N, 4 * C, device=DEV)
+    Wf = torch.zeros(C, 2 * C + G, device=DEV)
+    Ws = torch.zeros(C, 2 * C + G, device=DEV)
+    bf, bs = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ld = 2 * C + G
+    MF.linear_wgrad_into(x, dPQ, MF._wgrad_map(
+        C, ld, [Wf.data_ptr(), Ws.data_ptr(), Wf.data_ptr() + 4 * C, Ws.data_ptr() + 4 * C],
+        [bf.data_ptr(), bs.data_ptr(), None, None]))
+    ref = dPQ.t().mm(x)
+    for got, blk in ((Wf[:, :C], 0), (Ws[:, :C], 1), (Wf[:, C:2 * C], 2), (Ws[:, C:2 * C], 3)):
+        assert (got - ref[blk * C:(blk + 1) * C]).abs().max().item() < 1e-3
+    assert Wf[:, 2 * C:].abs().max().item() == 0                    # untouched columns
+    assert (bf - dPQ[:, :C].sum(0)).abs().max().item() < 1e-3
+    assert (bs - dPQ[:, C:2 * C].sum(0)).abs().max().item() < 1e-3
+
+
+def test_direct_gradient_delivery_equals_autograd_gradients():
+    """TrainStep writes every weight/bias gradient straight into the flat buffer (no .grad tensors,
+    no concatenation); the buffer must hold what plain autograd would have produced."""
+    from matdeeplearn_b200.engine import TrainStep
+    ds, batch, model = _setup()
+    m1, m2 = copy.deepcopy(model).to(DEV).train(), copy.deepcopy(model).to(DEV).train()
+    b = batch.to(DEV)
+    step = TrainStep(m1, lr=0.0)
+    step._fwd_bwd(b)
+    assert all(p.grad is None for p in m1.parameters())          # nothing went through .grad
+    loss = torch.nn.functional.l1_loss(m2(b), b.y)
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in m2.parameters()])
+    got = step.flat.grad
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 2e-5 * scale
