@@ -189,7 +189,7 @@ class _MegnetStack(tnn.Module):
             if not (i == 0 and first_done):
                 h = getattr(F, self.act)(lin(h))
             if self.batch_norm == "True":
-                h = self._bn(i, h, data)
+                h = self.bn_list[i](h)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return h
 
