@@ -62,8 +62,19 @@ k_bn_stats(const float* __restrict__ x, const int32_t* __restrict__ n_valid, int
   for (int c0 = 0; c0 < C; c0 += cw) {
     const int c = c0 + tx;
     Welford w{0.f, 0.f, 0.f};
-    if (c < C)
-      for (int64_t r = r0 + ty; r < r1; r += th) wf_add(w, __ldg(x + r * C + c));
+    if (c < C) {
+      for (int64_t rb = r0 + ty; rb < r1; rb += 8 * th) {   // 8 rows in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t r = rb + (int64_t)u * th;
+          v[u] = (r < r1) ? __ldg(x + r * C + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (rb + (int64_t)u * th < r1) wf_add(w, v[u]);
+      }
+    }
     sh[threadIdx.x] = w;
     __syncthreads();
     if (ty == 0 && c < C) {
@@ -153,10 +164,20 @@ k_bn_bwd_stats(const float* __restrict__ g, const float* __restrict__ x, const i
     float sg = 0.f, sgx = 0.f;
     if (c < C) {
       const float m = __ldg(mean + c), is = __ldg(invstd + c);
-      for (int64_t r = r0 + ty; r < r1; r += th) {
-        const float gv = __ldg(g + r * C + c);
-        sg += gv;
-        sgx += gv * ((__ldg(x + r * C + c) - m) * is);
+      for (int64_t rb = r0 + ty; rb < r1; rb += 8 * th) {   // 8 rows in flight per thread
+        float gv[8], xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t r = rb + (int64_t)u * th;
+          const bool ok = r < r1;
+          gv[u] = ok ? __ldg(g + r * C + c) : 0.f;
+          xv[u] = ok ? __ldg(x + r * C + c) : m;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          sg += gv[u];
+          sgx += gv[u] * ((xv[u] - m) * is);
+        }
       }
     }
     sh[0][threadIdx.x] = sg;

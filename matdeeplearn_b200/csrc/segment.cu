@@ -24,17 +24,34 @@ k_segment_fwd(const float* __restrict__ src, const int32_t* __restrict__ ptr,
       int arg[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[j] = (REDUCE == MDL_REDUCE_MAX) ? -INFINITY : 0.0f; arg[j] = -1; }
-      for (int r = lo; r < hi; ++r) {
-        const int64_t row = perm ? __ldg(perm + r) : r;
-        const float* p = src + row * width + c0 + lane;
+      // rows in batches of four: all loads of a batch are issued before the first is consumed (the
+      // sum stays in row order, so the result does not depend on the batching)
+      for (int r0 = lo; r0 < hi; r0 += 4) {
+        float v[4][4];
+        int64_t rows[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (c0 + lane + 32 * j < width) {
-            float v = __ldg(p + 32 * j);
-            if (REDUCE == MDL_REDUCE_MAX) {
-              if (v > acc[j]) { acc[j] = v; arg[j] = (int)row; }
-            } else {
-              acc[j] += v;
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          rows[u] = (r < hi) ? (perm ? (int64_t)__ldg(perm + r) : (int64_t)r) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* p = src + (rows[u] < 0 ? 0 : rows[u]) * width + c0 + lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[u][j] = (rows[u] >= 0 && c0 + lane + 32 * j < width) ? __ldg(p + 32 * j) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (rows[u] < 0) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c0 + lane + 32 * j < width) {
+              if (REDUCE == MDL_REDUCE_MAX) {
+                if (v[u][j] > acc[j]) { acc[j] = v[u][j]; arg[j] = (int)rows[u]; }
+              } else {
+                acc[j] += v[u][j];
+              }
             }
           }
         }

@@ -21,24 +21,54 @@ constexpr int kWgThreads = 256;
 __host__ __device__ inline int wg_stride(int n) { return ((n + 7) & ~7) + 4; }  // floats, 16-byte multiple
 
 static int wg_grid(int64_t N) {
-  int64_t g = ceil_div<int64_t>(N, 2 * kWgRows);   // at least two chunks per CTA: halves the partials
+  int64_t g = ceil_div<int64_t>(N, 2 * kWgRows);   // two chunks per CTA when possible: halves the partials
   if (g > 2 * kNumSMs) g = 2 * kNumSMs;
   return (int)(g > 0 ? g : 1);
 }
 
+__device__ __forceinline__ void wg_cp_async(void* dst, const void* src, int bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+
+// stage rows [r0, r0+rows) of a row-major [*, W] matrix into smem rows of stride `ld`: a warp per row,
+// every piece an asynchronous copy (nothing waits on a load inside the loop); rows beyond `rows` are zeroed
+__device__ __forceinline__ void wg_stage(float* dst, int ld, const float* __restrict__ src, int W, int64_t r0,
+                                         int rows, int vec, int warp, int lane) {
+  const int pieces = W / vec;
+  for (int r = warp; r < kWgRows; r += kWgThreads / 32) {
+    float* drow = dst + r * ld;
+    if (r < rows) {
+      const float* srow = src + (r0 + r) * W;
+      for (int c = lane; c < pieces; c += 32) wg_cp_async(drow + c * vec, srow + c * vec, vec * 4);
+    } else {
+      for (int c = lane; c < W; c += 32) drow[c] = 0.f;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWgThreads, 2)
 k_linear_wgrad(const float* __restrict__ X, const float* __restrict__ G, int64_t N, int I, int O,
-               float* __restrict__ part) {
+               int vx, int vg, float* __restrict__ part) {
   extern __shared__ __align__(16) float wsm[];
   const int sx = wg_stride(I), sg = wg_stride(O);
-  float* sX = wsm;                  // [kWgRows][sx]
-  float* sG = wsm + kWgRows * sx;   // [kWgRows][sg]
+  const int buf_floats = kWgRows * (sx + sg);   // one stage: X chunk [kWgRows][sx] then G chunk [kWgRows][sg]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_i = (I + 7) >> 3, tiles_o = (O + 7) >> 3, ntiles = tiles_i * tiles_o;
   const int64_t nchunks = ceil_div<int64_t>(N, kWgRows);
   float* mine = part + (size_t)blockIdx.x * ((size_t)O * I + O);
-  for (int i = threadIdx.x; i < kWgRows * sx; i += kWgThreads) sX[i] = 0.f;   // pad columns stay zero
-  for (int i = threadIdx.x; i < kWgRows * sg; i += kWgThreads) sG[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * buf_floats; i += kWgThreads) wsm[i] = 0.f;   // pad columns stay zero
+  __syncthreads();
+  auto stage = [&](int64_t ch, int b) {
+    const int64_t r0 = ch * kWgRows;
+    const int rows = (int)min((int64_t)kWgRows, N - r0);
+    float* sX = wsm + b * buf_floats;
+    wg_stage(sX, sx, X, I, r0, rows, vx, warp, lane);
+    wg_stage(sX + kWgRows * sx, sg, G, O, r0, rows, vg, warp, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   for (int t0 = 0; t0 < ntiles; t0 += kWgThreads) {
     const int t = t0 + threadIdx.x;
     const bool live = t < ntiles;
@@ -51,16 +81,16 @@ k_linear_wgrad(const float* __restrict__ X, const float* __restrict__ G, int64_t
 #pragma unroll
       for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
     }
-    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-      const int64_t r0 = ch * kWgRows;
-      const int rows = (int)min((int64_t)kWgRows, N - r0);
+    int b = 0;
+    if ((int64_t)blockIdx.x < nchunks) stage(blockIdx.x, 0);
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, b ^= 1) {
+      const bool more = ch + gridDim.x < nchunks;
+      if (more) stage(ch + gridDim.x, b ^ 1);   // next chunk lands under this chunk's FMAs
+      if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
-      for (int r = warp; r < kWgRows; r += kWgThreads / 32) {   // a warp per row: coalesced, no division
-        const bool ok = r < rows;
-        for (int c = lane; c < I; c += 32) sX[r * sx + c] = ok ? __ldg(X + (r0 + r) * I + c) : 0.f;
-        for (int c = lane; c < O; c += 32) sG[r * sg + c] = ok ? __ldg(G + (r0 + r) * O + c) : 0.f;
-      }
-      __syncthreads();
+      const float* sX = wsm + b * buf_floats;
+      const float* sG = sX + kWgRows * sx;
       if (live) {
 #pragma unroll 2
         for (int r = 0; r < kWgRows; ++r) {
@@ -74,10 +104,11 @@ k_linear_wgrad(const float* __restrict__ X, const float* __restrict__ G, int64_t
           for (int a = 0; a < 8; ++a) {
             accb[a] += gv[a];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(gv[a], xv[b], acc[a][b]);
+            for (int bb = 0; bb < 8; ++bb) acc[a][bb] = fmaf(gv[a], xv[bb], acc[a][bb]);
           }
         }
       }
+      __syncthreads();   // this stage is free to be overwritten by the copy issued next iteration
     }
     if (live) {
 #pragma unroll
@@ -85,9 +116,9 @@ k_linear_wgrad(const float* __restrict__ X, const float* __restrict__ G, int64_t
         const int o = to * 8 + a;
         if (o >= O) continue;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int i = ti * 8 + b;
-          if (i < I) mine[(size_t)o * I + i] = acc[a][b];
+        for (int bb = 0; bb < 8; ++bb) {
+          const int i = ti * 8 + bb;
+          if (i < I) mine[(size_t)o * I + i] = acc[a][bb];
         }
         if (ti == 0) mine[(size_t)O * I + o] = accb[a];
       }
@@ -172,7 +203,7 @@ extern "C" int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32
   if (int rc = wg_check_map(out, O, "linear_wgrad")) return rc;
   MDL_REQUIRE(X && G && workspace, "linear_wgrad: null pointer");
   MDL_REQUIRE(workspace_bytes >= wg_ws_bytes(N, I, O), "linear_wgrad: workspace too small");
-  const size_t smem = (size_t)kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
+  const size_t smem = (size_t)2 * kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
   MDL_REQUIRE(smem <= 100 * 1024, "linear_wgrad: layer too wide (I + O <= ~750)");
   static bool attr_set = false;
   if (!attr_set) {
@@ -182,7 +213,12 @@ extern "C" int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32
   cudaStream_t st = as_stream(stream);
   const int grid = wg_grid(N);
   float* part = reinterpret_cast<float*>(workspace);
-  k_linear_wgrad<<<grid, kWgThreads, smem, st>>>(X, G, N, I, O, part);
+  // widest asynchronous copy the row and base alignment allow (rows start at multiples of W floats)
+  auto vec = [](const float* p, int W) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    return (W % 4 == 0 && a % 16 == 0) ? 4 : (W % 2 == 0 && a % 8 == 0) ? 2 : 1;
+  };
+  k_linear_wgrad<<<grid, kWgThreads, smem, st>>>(X, G, N, I, O, vec(X, I), vec(G, O), part);
   MDL_LAUNCHED();
   const int64_t len = (int64_t)O * I + O;
   k_wgrad_reduce<<<(int)ceil_div<int64_t>(len, 32), 256, 0, st>>>(part, grid, I, O, *out);
