@@ -100,6 +100,13 @@ MDL_API int mdl_segment_reduce_bwd(const float* grad_out, const int32_t* ptr, co
                            const int32_t* argmax, float* grad_src, int64_t num_segments,
                            int64_t num_rows, int64_t width, int32_t reduce, void* stream);
 
+/* The reference layer's parameters -- lin_f / lin_s of torch_geometric CGConv, weight [C, 2C+G] over
+ * cat[x_i, x_j, e] and bias [C] (NULL = no bias) -- repacked in one launch into the operands of the
+ * hoisted form used below:  Wn [4C, C] (rows P_f | P_s | Q_f | Q_s: PQ = x Wn^T + bias),
+ * bias [4C] (zero on the Q rows) and WeT [G, 2C]. */
+MDL_API int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const float* w_s, const float* b_s,
+                                    int32_t C, int32_t G, float* Wn, float* bias, float* WeT, void* stream);
+
 /* ---- CGConv, PyG CGConv(channels=C, dim=G, aggr, batch_norm=False) as
  * constructed at reference matdeeplearn/models/cgcnn.py:80-82 and called at
  * cgcnn.py:136-145.  The caller splits lin_f/lin_s column-wise into

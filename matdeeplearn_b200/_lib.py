@@ -60,6 +60,7 @@ SIGNATURES = {
     "mdl_segment_reduce_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),
     "mdl_segment_reduce_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p]),
     "mdl_cgconv_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "mdl_cgconv_pack_weights": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "mdl_cgconv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "mdl_cgconv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
     "mdl_spmm_edge": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),

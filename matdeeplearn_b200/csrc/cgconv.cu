@@ -487,6 +487,41 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
   return MDL_OK;
 }
 
+namespace mdl {
+// lin_f / lin_s of the reference layer ([C, 2C+G] each, cat order x_i | x_j | e) -> the hoisted operands
+__global__ void k_cgconv_pack(const float* __restrict__ w_f, const float* __restrict__ b_f,
+                              const float* __restrict__ w_s, const float* __restrict__ b_s, int C, int G,
+                              float* __restrict__ Wn, float* __restrict__ bias, float* __restrict__ WeT) {
+  const int ld = 2 * C + G;
+  const int n_wn = 4 * C * C, n_b = 4 * C, n_we = G * 2 * C;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_wn + n_b + n_we; t += gridDim.x * blockDim.x) {
+    if (t < n_wn) {
+      const int r = t / C, i = t - r * C, blk = r / C, c = r - blk * C;
+      const float* w = (blk & 1) ? w_s : w_f;
+      Wn[t] = __ldg(w + (size_t)c * ld + (blk >> 1) * C + i);
+    } else if (t < n_wn + n_b) {
+      const int r = t - n_wn, blk = r / C, c = r - blk * C;
+      const float* b = (blk == 0) ? b_f : (blk == 1) ? b_s : nullptr;
+      bias[r] = b ? __ldg(b + c) : 0.0f;
+    } else {
+      const int u = t - n_wn - n_b, g = u / (2 * C), col = u - g * 2 * C;
+      const float* w = (col < C) ? w_f : w_s;
+      WeT[u] = __ldg(w + (size_t)(col < C ? col : col - C) * ld + 2 * C + g);
+    }
+  }
+}
+}  // namespace mdl
+
+extern "C" int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const float* w_s, const float* b_s,
+                                       int32_t C, int32_t G, float* Wn, float* bias, float* WeT, void* stream) {
+  MDL_REQUIRE(C > 0 && G > 0 && w_f && w_s && Wn && bias && WeT, "cgconv_pack_weights: bad arguments");
+  const int total = 4 * C * C + 4 * C + G * 2 * C;
+  k_cgconv_pack<<<std::min(ceil_div(total, 256), 2 * kNumSMs), 256, 0, as_stream(stream)>>>(w_f, b_f, w_s, b_s, C, G,
+                                                                                             Wn, bias, WeT);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
 // development aid: 16 x uint64 device counters receiving per-phase cycle sums of the
 // tensor-core kernels (NULL disables).  Not part of the reference-facing surface.
 extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {

@@ -233,12 +233,14 @@ class CGConvFn(torch.autograd.Function):
         G = ea_slots.shape[1]
         assert w_f.shape == (C, 2 * C + G) and w_s.shape == (C, 2 * C + G)
         # column split of lin(cat[x_i, x_j, e]) = W_i x_i + W_j x_j + W_e e + b
-        Wn = torch.cat([w_f[:, :C], w_s[:, :C], w_f[:, C:2 * C], w_s[:, C:2 * C]], 0)  # [4C, C]
-        zeros = x.new_zeros(C)
-        bias = torch.cat([b_f if b_f is not None else zeros, b_s if b_s is not None else zeros,
-                          zeros, zeros])
+        Wn = torch.empty((4 * C, C), dtype=torch.float32, device=x.device)    # rows P_f | P_s | Q_f | Q_s
+        bias = torch.empty(4 * C, dtype=torch.float32, device=x.device)
+        WeT = torch.empty((G, 2 * C), dtype=torch.float32, device=x.device)
+        w_fc, w_sc = w_f.contiguous(), w_s.contiguous()
+        rc = lib.mdl_cgconv_pack_weights(_lib.ptr(w_fc), _lib.ptr(b_f), _lib.ptr(w_sc), _lib.ptr(b_s), C, G,
+                                         _lib.ptr(Wn), _lib.ptr(bias), _lib.ptr(WeT), _lib.stream())
+        _lib.check(rc, "mdl_cgconv_pack_weights")
         PQ = torch.addmm(bias, x, Wn.t())                                              # [N, 4C]
-        WeT = torch.cat([w_f[:, 2 * C:], w_s[:, 2 * C:]], 0).t().contiguous()          # [G, 2C]
         out = torch.empty_like(x)
         rc = lib.mdl_cgconv_fwd(_lib.ptr(x), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
                                 _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src), _lib.ptr(csr.dst_dst),
