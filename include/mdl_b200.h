@@ -168,6 +168,31 @@ MDL_API int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* d
                                const int32_t* src_eid, float* dhid, float* dXT, float* dXB,
                                int64_t num_nodes, int32_t K, int32_t O, void* stream);
 
+/* ---- graph builder on the GPU --------------------------------------------------------------
+ * The per-structure part of the reference's process_data (matdeeplearn/process/process.py:284-305
+ * distances + threshold_sort + dense_to_sparse + add_self_loops, :540-560 threshold_sort, :365-388
+ * and :594-605 node features).  Structures are concatenated: pos [num_nodes,3] f64, numbers
+ * [num_nodes] i32, node_ptr [num_graphs+1] i64, cell [num_graphs,3] f64 orthorhombic box lengths
+ * (NULL or 0 entries = not periodic along that axis).
+ *
+ * mdl_build_neighbors: one CTA per structure (max_nodes = the largest structure, <= ~2300 atoms).
+ *   Row i keeps its neighbors+1 closest columns within `radius` by (distance, column) -- numpy's
+ *   stable ordinal rank --, drops exact-zero distances, and writes them in ascending column order:
+ *   nbr_col/nbr_w [num_nodes, neighbors+1] (column local to the structure, weight = float(distance)),
+ *   cnt [num_nodes].  Distances are fp64 without FMA contraction (bit-equal to numpy).
+ * mdl_build_emit: scatters the table into src/dst/edge_weight at first_edge[node] (the caller's
+ *   prefix sum of cnt, laid out so that each structure's loops follow its edges), writes the loop
+ *   (node,node,0) at loop_pos[node], and sets the two one-hot entries of x[node] (x zero-filled by
+ *   the caller): column numbers[node]-1 and column z_width + cnt[node] + 1. */
+MDL_API int mdl_build_neighbors(const double* pos, const double* cell, const int64_t* node_ptr,
+                                int64_t num_graphs, int32_t max_nodes, double radius, int32_t neighbors,
+                                int32_t* nbr_col, float* nbr_w, int32_t* cnt, void* stream);
+MDL_API int mdl_build_emit(const int32_t* nbr_col, const float* nbr_w, const int32_t* cnt,
+                           const int64_t* first_edge, const int64_t* loop_pos,
+                           const int64_t* node_graph_start, const int32_t* numbers, int64_t num_nodes,
+                           int32_t neighbors, int32_t z_width, int32_t F, int32_t* src, int32_t* dst,
+                           float* w, float* x, void* stream);
+
 /* ---- batch assembly from a device-resident dataset -----------------------------------------
  * Replaces the reference's per-step CPU collate + H2D copy: PyG DataLoader -> Batch.from_data_list
  * (matdeeplearn/training/training.py:300-307) and data.to(rank) (training.py:39).

@@ -84,7 +84,9 @@ def pairwise_distances(pos, cell_lengths=None):
     if cell_lengths is not None:
         L = np.asarray(cell_lengths, dtype=np.float64)
         d -= np.round(d / L) * L
-    return np.sqrt(np.einsum("ijk,ijk->ij", d, d))
+    # (dx^2 + dy^2) + dz^2 in that order, plain multiplies and adds: einsum would pick an FMA kernel whose
+    # rounding depends on the host CPU; the GPU builder (csrc/builder.cu) reproduces THIS expression bit for bit
+    return np.sqrt((d * d).sum(-1))
 
 
 def assemble_dataset(structures, targets, radius=DEFAULT_RADIUS, neighbors=DEFAULT_NEIGHBORS,
@@ -136,8 +138,9 @@ def _random_structure(rng, n, density, min_sep=1.6, n_species=20):
     return numbers, pos, np.array([L, L, L])
 
 
-def synthetic_dataset(kind="bulk", num_graphs=256, seed=BENCH_SEED, edge_length=DEFAULT_EDGE_LENGTH):
-    """kind="bulk": n ~ clip(round(N(30,8)),4,60), density 0.06 A^-3
+def synthetic_structures(kind="bulk", num_graphs=256, seed=BENCH_SEED):
+    """(structures, targets) of the synthetic workloads: structures = [(numbers, positions, box lengths)].
+       kind="bulk": n ~ clip(round(N(30,8)),4,60), density 0.06 A^-3
        kind="mof" : n ~ clip(round(N(200,40)),80,400), density 0.025 A^-3"""
     rng = np.random.default_rng(seed)
     if kind == "bulk":
@@ -151,6 +154,12 @@ def synthetic_dataset(kind="bulk", num_graphs=256, seed=BENCH_SEED, edge_length=
         n = int(np.clip(np.rint(rng.normal(mean, std)), lo, hi))
         structs.append(_random_structure(rng, n, rho))
         ys.append(rng.normal())
+    return structs, ys
+
+
+def synthetic_dataset(kind="bulk", num_graphs=256, seed=BENCH_SEED, edge_length=DEFAULT_EDGE_LENGTH):
+    """The synthetic workload run through the host builder (see synthetic_structures)."""
+    structs, ys = synthetic_structures(kind, num_graphs, seed)
     return assemble_dataset(structs, ys, edge_length=edge_length)
 
 

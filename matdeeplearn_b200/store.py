@@ -79,11 +79,15 @@ class GraphStore:
             self.smear_coeff = -0.5 / ((smear["stop"] - smear["start"]) * smear["width"]) ** 2
         else:
             self.smear_offset, self.smear_coeff = None, 0.0
-        # destination-major layout of the whole store: one sort, ever
+        self._seal(ei)
+        return self
+
+    def _seal(self, ei):
+        """Common tail: destination-major layout of the whole store (one sort, ever) and the C descriptor.
+        ei: int64 [2, E_total] with store-global node ids, reference edge order."""
         self.layout = GraphCSR.from_coo(ei, None, num_nodes=self.num_nodes)
         self.src = ei[0].to(torch.int32).contiguous()
         self.dst = ei[1].to(torch.int32).contiguous()
-        del ei
         L = self.layout
         self._c = _lib.GraphStoreC(
             self.num_graphs, self.num_nodes, self.num_edges, self.F, self.G, self.U, self.Y,
@@ -92,6 +96,87 @@ class GraphStore:
             _lib.ptr(self.u), _lib.ptr(self.y), _lib.ptr(L.dst_ptr), _lib.ptr(L.dst_src), _lib.ptr(L.dst_dst),
             _lib.ptr(L.dst_eid), _lib.ptr(L.src_ptr), _lib.ptr(L.src_slot), _lib.ptr(L.inv_deg_dst),
             _lib.ptr(L.inv_deg_src))
+
+    @classmethod
+    def from_structures(cls, structures, targets, device, radius=8.0, neighbors=12, edge_length=50,
+                        z_width=100):
+        """Build the store from raw structures ON THE GPU (csrc/builder.cu): what the reference's
+        process_data does per structure on the host (process.py:284-305, 365-388, 540-560, 594-605) --
+        distances, radius + k-nearest selection, row-major edges + loops, one-hot node features --
+        followed by the dataset-global min-max edge normalisation (process.py:626-653).  The Gaussian
+        basis is never materialised: batches expand it from the normalised distance (csrc/assemble.cu).
+
+        structures: iterable of (numbers, positions [n,3], cell_lengths [3] or None), the same input
+        process.assemble_dataset takes; the result is tensor-for-tensor the store that
+        GraphStore.from_dataset(process.assemble_dataset(...)) would hold (tested bit-exact)."""
+        lib = _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("GraphStore lives in GPU memory (no CPU fallback)")
+        structures = list(structures)
+        self = object.__new__(cls)
+        self.device = device
+        self.num_graphs = len(structures)
+        self.n_nodes = np.array([len(s[0]) for s in structures], dtype=np.int64)
+        node_ptr = np.concatenate([[0], np.cumsum(self.n_nodes)])
+        self.num_nodes = int(node_ptr[-1])
+        pos = np.concatenate([np.asarray(s[1], dtype=np.float64).reshape(-1, 3) for s in structures], 0)
+        numbers = np.concatenate([np.asarray(s[0], dtype=np.int32).reshape(-1) for s in structures])
+        cell = np.stack([np.zeros(3) if s[2] is None else np.asarray(s[2], dtype=np.float64).reshape(3)
+                         for s in structures])
+        K = neighbors + 1
+        self.F, self.G = z_width + neighbors + 2, edge_length
+        f32 = dict(dtype=torch.float32, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        pos_d = torch.from_numpy(pos).to(device)
+        num_d = torch.from_numpy(numbers).to(device)
+        cell_d = torch.from_numpy(cell).to(device)
+        self.node_ptr = torch.from_numpy(node_ptr).to(device)
+        nbr_col = torch.empty((self.num_nodes, K), **i32)
+        nbr_w = torch.empty((self.num_nodes, K), **f32)
+        cnt = torch.empty(self.num_nodes, **i32)
+        rc = lib.mdl_build_neighbors(_lib.ptr(pos_d), _lib.ptr(cell_d), _lib.ptr(self.node_ptr), self.num_graphs,
+                                     int(self.n_nodes.max()), float(radius), neighbors, _lib.ptr(nbr_col),
+                                     _lib.ptr(nbr_w), _lib.ptr(cnt), _lib.stream())
+        _lib.check(rc, "mdl_build_neighbors")
+        # edge offsets: a structure's edges in row-major order, then its loops
+        cnt64 = cnt.long()
+        csum = torch.cat([cnt64.new_zeros(1), torch.cumsum(cnt64, 0)])          # [num_nodes+1]
+        kept_before = csum[self.node_ptr[:-1]]                                    # non-loop edges before graph g
+        kept_in = csum[self.node_ptr[1:]] - kept_before
+        edge_ptr = torch.cat([cnt64.new_zeros(1), torch.cumsum(kept_in + torch.from_numpy(self.n_nodes).to(device), 0)])
+        node_graph = torch.repeat_interleave(torch.arange(self.num_graphs, device=device),
+                                             torch.from_numpy(self.n_nodes).to(device))
+        g_start = self.node_ptr[node_graph]
+        first_edge = (edge_ptr[node_graph] + (csum[:-1] - kept_before[node_graph])).contiguous()
+        loop_pos = (edge_ptr[node_graph] + kept_in[node_graph] +
+                    (torch.arange(self.num_nodes, device=device) - g_start)).contiguous()
+        edge_ptr_h = edge_ptr.cpu().numpy()                                        # one sync: sizes to the host
+        self.edge_ptr = edge_ptr.contiguous()
+        self.n_edges = np.diff(edge_ptr_h)
+        self.num_edges = int(edge_ptr_h[-1])
+        if self.num_nodes >= 2**31 or self.num_edges >= 2**31:
+            raise ValueError("GraphStore indexes nodes/edges with int32")
+        src = torch.empty(self.num_edges, **i32)
+        dst = torch.empty(self.num_edges, **i32)
+        self.edge_weight = torch.empty(self.num_edges, **f32)
+        self.x = torch.zeros((self.num_nodes, self.F), **f32)
+        rc = lib.mdl_build_emit(_lib.ptr(nbr_col), _lib.ptr(nbr_w), _lib.ptr(cnt), _lib.ptr(first_edge),
+                                _lib.ptr(loop_pos), _lib.ptr(g_start.contiguous()), _lib.ptr(num_d), self.num_nodes,
+                                neighbors, z_width, self.F, _lib.ptr(src), _lib.ptr(dst), _lib.ptr(self.edge_weight),
+                                _lib.ptr(self.x), _lib.stream())
+        _lib.check(rc, "mdl_build_emit")
+        lo, hi = float(self.edge_weight.min()), float(self.edge_weight.max())      # dataset-global range
+        self.edge_range = (lo, hi)
+        self.d_hat = ((self.edge_weight - lo) / (hi - lo)).contiguous()
+        self.edge_attr = None
+        self.u = torch.zeros((self.num_graphs, 3), **f32)
+        self.y = torch.as_tensor(np.asarray(targets, dtype=np.float32).reshape(-1)).to(device)
+        self.y_shape, self.U, self.Y = (), 3, 1
+        self.smear = dict(start=0.0, stop=1.0, resolution=edge_length, width=0.2)
+        self.smear_offset = torch.linspace(0.0, 1.0, edge_length, **f32)
+        self.smear_coeff = -0.5 / 0.2 ** 2
+        self._seal(torch.stack([src.long(), dst.long()]))
         return self
 
     def __len__(self):
