@@ -319,7 +319,7 @@ MDL_API int mdl_copy_mapped(const float* src, int32_t I, int32_t O, int32_t tran
 MDL_API int mdl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                            const float* hyper, float* step, float grad_scale, int64_t n, void* stream);
 
-/* ---- development aid: 16 x uint64 device counters that receive per-phase cycle sums
+/* ---- development aid: 32 x uint64 device counters that receive per-phase cycle sums
  * (thread 0 of every CTA) from the tensor-core CGConv kernels; NULL disables. ---- */
 MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr);
 

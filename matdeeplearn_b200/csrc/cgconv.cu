@@ -522,7 +522,7 @@ extern "C" int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const
   return MDL_OK;
 }
 
-// development aid: 16 x uint64 device counters receiving per-phase cycle sums of the
+// development aid: 32 x uint64 device counters receiving per-phase cycle sums of the
 // tensor-core kernels (NULL disables).  Not part of the reference-facing surface.
 extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
   cgtc_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));

@@ -38,8 +38,9 @@ static unsigned long long* g_phase_buf = nullptr;
 struct TcPlan {
   unsigned long long* prof;
   int dq_atomic;  // BWD_DST also scatters da into dQ[src] with vector float atomics (no BWD_SRC pass)
+  int window;     // stage the round's contiguous P / Q node-row ranges in shared memory when they fit
   int NP, KP, GS, VW, tmem_cols, nitem;
-  uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, offInfo, total;
+  uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, offRange, offInfo, total;
 };
 
 static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
@@ -51,9 +52,11 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   if (((GS >> 2) & 1) == 0) GS += 4;  // odd number of 16-byte chunks per row: conflict-free float4 column reads
   const int VW = 2 * C + 4;  // [f | s] per slot (+4 floats: conflict-free float4 row access)
   uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)(KP / 4) * kAChunk;
-  uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4, idx = 4 * kTcRows * 4;
+  uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4;
+  const uint32_t idx = 4 * kTcRows * 4 + 32;  // indices [2][src|dst][128] + node ranges [2][4]
   pl->prof = g_phase_buf;
   pl->dq_atomic = 0;
+  pl->window = 1;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
   pl->tmem_cols = 32;
   while (pl->tmem_cols < NP) pl->tmem_cols <<= 1;
@@ -67,7 +70,8 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   uint32_t end = pl->offEA + ea;
   const uint32_t info = kInfoCap * 16;  // per-CTA table of tile bounds (TileInfo)
   if (end + v + idx + info <= (uint32_t)kMaxDynSmem) {
-    pl->offV = end; pl->offIdx = end + v; pl->offInfo = end + v + idx; pl->total = end + v + idx + info;
+    pl->offV = end; pl->offIdx = end + v; pl->offRange = end + v + idx - 32; pl->offInfo = end + v + idx;
+    pl->total = end + v + idx + info;
     return true;
   }
   return false;
@@ -92,7 +96,7 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[
 // Persistent CTA, software-pipelined over "rounds" of <=128 slots:
 //   while round r's MMAs run and its epilogue executes, round r+1's indices and ea rows are
 //   already in flight (cp.async) and the node projections for round r are being gathered.
-template <int MODE, int PROFILE>
+template <int MODE, int PROFILE, int GATE>
 __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, const TcPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -109,6 +113,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   float* sV = reinterpret_cast<float*>(smem + pl.offV);    // [128][VW]
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);    // [2 buffers][src|dst][128]
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);  // bounds of this CTA's tiles
+  // node ranges touched by a round, [2 buffers][src min, src max, dst min, dst max]: edges of a crystal
+  // graph stay inside the graph, so the P / Q rows a round gathers lie in two short CONTIGUOUS node
+  // ranges.  When both fit, they are streamed into the (still idle) value tile with coalesced
+  // 16-byte cp.async and the epilogue reads them from shared memory: a few KB from L2 per round
+  // instead of one 512-byte row per slot and operand, and no register staging.
+  int* sRange = reinterpret_cast<int*>(smem + pl.offRange);
 
   // tiles of this CTA: blockIdx.x, +gridDim.x, ...
   const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -135,6 +145,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     umma::mbar_init(&bar, 1);
     umma::fence_mbar_init();
   }
+  if (tid < 8) sRange[tid] = (tid & 1) ? -1 : 0x7fffffff;
   fill_infos(0);
   for (int i = tid; i < NP * KP; i += kTcThreads) {
     const int n = i % NP, k = i / NP;
@@ -176,25 +187,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       bS[row0 + lane] = ni.s;
       bD[row0 + lane] = ni.d;
     }
-    // the warp's 8 rows as one flat list of 8-byte (even G) or 4-byte chunks: every lane issues
-    // ceil(8*chunks/32) cp.async instead of one mostly idle 32-lane pass per row
-    const int wcnt = min(kRowsPerWarp, cnt - row0);  // rows of this warp that exist (may be <= 0)
-    if ((G & 1) == 0) {
-      const int cpr = G >> 1;
-      for (int base = 0; base < kRowsPerWarp * cpr; base += 32) {  // warp-uniform trip count (shfl inside)
-        const int i = base + lane;
-        const bool ok = i < kRowsPerWarp * cpr;
-        const int r = ok ? i / cpr : 0, c = i - r * cpr;
-        const int sl = __shfl_sync(0xffffffffu, ni.slot, r);
-        if (ok && r < wcnt) cp_async8(sEA + (row0 + r) * GS + 2 * c, p.ea + (size_t)sl * G + 2 * c);
+    if (pl.window && row0 < cnt) {  // warp-uniform; at least lane 0 holds a real slot
+      const bool real = lane < kRowsPerWarp && row0 + lane < cnt;
+      const int s_lo = __reduce_min_sync(0xffffffffu, real ? ni.s : 0x7fffffff);
+      const int s_hi = __reduce_max_sync(0xffffffffu, real ? ni.s : -1);
+      const int d_lo = __reduce_min_sync(0xffffffffu, real ? ni.d : 0x7fffffff);
+      const int d_hi = __reduce_max_sync(0xffffffffu, real ? ni.d : -1);
+      if (lane == 0) {
+        atomicMin(sRange + 4 * buf + 0, s_lo);
+        atomicMax(sRange + 4 * buf + 1, s_hi);
+        atomicMin(sRange + 4 * buf + 2, d_lo);
+        atomicMax(sRange + 4 * buf + 3, d_hi);
       }
-    } else {
-      for (int base = 0; base < kRowsPerWarp * G; base += 32) {
-        const int i = base + lane;
-        const bool ok = i < kRowsPerWarp * G;
-        const int r = ok ? i / G : 0, c = i - r * G;
-        const int sl = __shfl_sync(0xffffffffu, ni.slot, r);
-        if (ok && r < wcnt) cp_async4(sEA + (row0 + r) * GS + c, p.ea + (size_t)sl * G + c);
+    }
+    // the warp's 8 rows, lanes across the 8-byte (even G) or 4-byte chunks of a row
+    const int wcnt = min(kRowsPerWarp, cnt - row0);  // rows of this warp that exist (may be <= 0)
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int sl = __shfl_sync(0xffffffffu, ni.slot, r);
+      if (r < wcnt) {
+        float* d = sEA + (row0 + r) * GS;
+        const float* g = p.ea + (size_t)sl * G;
+        if ((G & 1) == 0) {
+#pragma unroll 1
+          for (int c = 2 * lane; c < G; c += 64) cp_async8(d + c, g + c);
+        } else {
+#pragma unroll 1
+          for (int c = lane; c < G; c += 32) cp_async4(d + c, g + c);
+        }
       }
     }
   };
@@ -250,6 +270,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     __syncthreads();  // [S1] rows + indices of this round visible; value / operand tiles free
     mark(1);
 
+    // ---- indices of the next round: issued first, landed after the MMA issue (in BWD_SRC they are a
+    // dependent chain); everything up to there overlaps their latency
+    int ncnt = 0;
+    NextIdx ni{0, 0, 0};
+    if (nk < my_tiles) {
+      const TileInfo Tn = sInfo[nk - info_base];
+      const int nr_lo = Tn.e_lo + nrd * kTcRows;
+      ncnt = min(Tn.e_hi - nr_lo, kTcRows);
+      ni = issue_idx(nr_lo, ncnt);
+    }
+    mark(16);
+
+    // ---- node terms of this round, staged into the (idle) value tile by cp.async (CTA-uniform choice):
+    //   window   rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
+    //   per slot row e = the operand of the UNSORTED side (Q[src[e]]; P[dst[e]] in BWD_SRC); the sorted
+    //            side repeats a few rows per warp and is read straight from global in the epilogue
+    bool win = false;
+    if (cnt > 0) {
+      int4 rg = make_int4(0, 0, 0, 0);
+      int nq = kTcRows, np_ = kTcRows;
+      if (pl.window) {  // ranges are only maintained in window mode
+        rg = *reinterpret_cast<const int4*>(sRange + 4 * buf);
+        nq = rg.y - rg.x + 1; np_ = rg.w - rg.z + 1;
+      }
+      if (nq + np_ <= kTcRows) {
+        win = true;
+        const int total = (nq + np_) * 32;  // 16-byte chunks: 2C floats per row
+        for (int i = tid; i < total; i += kTcThreads) {
+          const int r = i >> 5, c = i & 31;
+          const float* g = (r < nq) ? p.PQ + (size_t)(rg.x + r) * (4 * C) + 2 * C + 4 * c
+                                    : p.PQ + (size_t)(rg.z + r - nq) * (4 * C) + 4 * c;
+          cp_async16(sV + r * VW + 4 * c, g);
+        }
+      } else {
+        const int* bNode = (MODE == CG_BWD_SRC) ? bDst : bSrc;
+        const float* base = p.PQ + ((MODE == CG_BWD_SRC) ? 0 : 2 * C);
+        for (int i = tid; i < cnt * 32; i += kTcThreads) {
+          const int r = i >> 5, c = i & 31;
+          cp_async16(sV + r * VW + 4 * c, base + (size_t)bNode[r] * (4 * C) + 4 * c);
+        }
+      }
+    }
+
+    mark(17);
     // ---- split hi/lo into the canonical MMA operand layout
     {
       const int e = tid & (kTcRows - 1);
@@ -272,8 +336,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         *reinterpret_cast<float4*>(sAlo + off) = lo;
       }
     }
+    mark(18);
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
+    mark(19);
     __syncthreads();  // [S2] operands staged; the ea landing zone is free for the next round
     mark(2);
 
@@ -344,90 +410,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
         for (int j = 0; j < 4; ++j) gq[j] = __ldg(gp + j);
       }
     }
-    // (d) node projections of this warp's 8 slots: one LDG.128 per lane reads a whole 512-byte
-    // P row ([f | s], 4 full lines) resp. Q row -- lane l owns floats [4l, 4l+4) of the row.
-    float4 vp[kRowsPerWarp], vq[kRowsPerWarp];
-    if (cnt > 0) {
-#pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) {
-        const int e = row0 + i;
-        vp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        vq[i] = vp[i];
-        if (e < cnt) {
-          vp[i] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)bDst[e] * (4 * C)) + lane);
-          vq[i] = __ldg(reinterpret_cast<const float4*>(p.PQ + (size_t)bSrc[e] * (4 * C) + 2 * C) + lane);
-        }
-      }
-    }
-    // (a) indices of the next round -- last: in BWD_SRC they are a dependent chain, which now
-    // overlaps with everything issued above
-    int ncnt = 0;
-    NextIdx ni{0, 0, 0};
-    if (nk < my_tiles) {
-      const TileInfo Tn = sInfo[nk - info_base];
-      const int nr_lo = Tn.e_lo + nrd * kTcRows;
-      ncnt = min(Tn.e_hi - nr_lo, kTcRows);
-      ni = issue_idx(nr_lo, ncnt);
-    }
     mark(4);
 
-    // ---- overlap window, part 2: LAND, in issue order: this round's P+Q first (issued first),
-    // then the next round's indices (issued last) and, from them, its ea rows.
-    if (cnt > 0) {
-#pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) {
-        const int e = row0 + i;
-        if (e < cnt)
-          *(reinterpret_cast<float4*>(sV + e * VW) + lane) =
-              make_float4(vp[i].x + vq[i].x, vp[i].y + vq[i].y, vp[i].z + vq[i].z, vp[i].w + vq[i].w);
-      }
-    }
+    // ---- overlap window, part 2: LAND: this round's node rows, then the next round's indices and,
+    // from them, its ea rows.
+    cp_async_wait_all();  // this round's node rows (the only cp.async group in flight at this point)
+    mark(20);
     if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
+    mark(21);
     __syncthreads();  // [S2c] gathered projections visible to the epilogue threads of every warp
     mark(5);
 
-    // ---- epilogue: thread = slot (TMEM lane); a = accumulator + gathered projections
+    // ---- epilogue, part 1: thread = slot (TMEM lane); a = accumulator + (P[dst] + Q[src]), the node
+    // terms read from the window rows (or, without a window, from the slot's own value-tile row)
+    float f[16], sacc[16];
+    const int e_ep = 32 * q + lane;
+    const bool live = e_ep < cnt;
     if (cnt > 0) {
-      const int e = 32 * q + lane;
-      const bool live = e < cnt;
       umma::mbar_wait(&bar, phase);
       umma::fence_after_sync();
       phase ^= 1;
       mark(6);
-      float f[16], sacc[16];
       umma::tmem_ld16(umma::tmem_addr(tmem, q, c_begin), f);
       umma::tmem_ld16(umma::tmem_addr(tmem, q, C + c_begin), sacc);
       umma::tmem_ld_wait();
+      mark(22);
       if (live) {
-        float* rowv = sV + e * VW;
+        const int sd = bDst[e_ep], ss = bSrc[e_ep];
+        auto add_rows = [&](const float* r0, const float* r1) {  // a += r0[.] + r1[.]   ([f | s] rows)
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const int c = c_begin + j4;
-          const float4 bf = *reinterpret_cast<const float4*>(rowv + c);
-          const float4 bs = *reinterpret_cast<const float4*>(rowv + C + c);
-          const float af[4] = {f[j4] + bf.x, f[j4 + 1] + bf.y, f[j4 + 2] + bf.z, f[j4 + 3] + bf.w};
-          const float as[4] = {sacc[j4] + bs.x, sacc[j4 + 1] + bs.y, sacc[j4 + 2] + bs.z, sacc[j4 + 3] + bs.w};
-          float r0[4], r1[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float sg = sigmoid_mufu(af[j]);
-            const float sp = softplus_mufu(as[j]);
-            if (MODE == CG_FWD) {
-              r0[j] = sg * sp;
-            } else {  // d m / d a_f and d m / d a_s  (x grad_out here for BWD_DST, in the scale pass for BWD_SRC)
-              float g = 1.0f;
-              if (MODE == CG_BWD_DST) {
-                const float4 gv = gq[j4 >> 2];
-                g = j == 0 ? gv.x : j == 1 ? gv.y : j == 2 ? gv.z : gv.w;
-              }
-              r0[j] = g * sp * sg * (1.0f - sg);
-              r1[j] = g * sg * sigmoid_mufu(as[j]);
-            }
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 pf = *reinterpret_cast<const float4*>(r0 + j4);
+            const float4 ps = *reinterpret_cast<const float4*>(r0 + C + j4);
+            const float4 qf = *reinterpret_cast<const float4*>(r1 + j4);
+            const float4 qs = *reinterpret_cast<const float4*>(r1 + C + j4);
+            f[j4] += pf.x + qf.x; f[j4 + 1] += pf.y + qf.y; f[j4 + 2] += pf.z + qf.z; f[j4 + 3] += pf.w + qf.w;
+            sacc[j4] += ps.x + qs.x; sacc[j4 + 1] += ps.y + qs.y;
+            sacc[j4 + 2] += ps.z + qs.z; sacc[j4 + 3] += ps.w + qs.w;
           }
-          *reinterpret_cast<float4*>(rowv + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
-          if (MODE != CG_FWD)
-            *reinterpret_cast<float4*>(rowv + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+        };
+        if (win) {
+          const int4 rg = *reinterpret_cast<const int4*>(sRange + 4 * buf);
+          add_rows(sV + (rg.y - rg.x + 1 + sd - rg.z) * VW + c_begin, sV + (ss - rg.x) * VW + c_begin);
+        } else {
+          const float* direct = (MODE == CG_BWD_SRC) ? p.PQ + (size_t)ss * (4 * C) + 2 * C + c_begin
+                                                     : p.PQ + (size_t)sd * (4 * C) + c_begin;
+          add_rows(direct, sV + e_ep * VW + c_begin);
         }
+      }
+    }
+    mark(23);
+    __syncthreads();  // [S2d] every read of the staged node rows done: the value tile may be overwritten
+    if (tid < 4) sRange[4 * buf + tid] = (tid & 1) ? -1 : 0x7fffffff;  // refilled two rounds from now
+    mark(13);
+    // ---- epilogue, part 2: gate math, per-slot values parked in the value tile
+    if (live) {
+      float* rowv = sV + e_ep * VW;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const int c = c_begin + j4;
+        float r0[4], r1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float sg = GATE ? sigmoid_mixed(f[j4 + j]) : sigmoid_mufu(f[j4 + j]);
+          if (MODE == CG_FWD) {
+            r0[j] = sg * softplus_mufu(sacc[j4 + j]);
+          } else {  // d m / d a_f and d m / d a_s  (x grad_out here for BWD_DST, in the scale pass for BWD_SRC)
+            float sp, sgs;
+            softplus_sigmoid_mufu(sacc[j4 + j], sp, sgs);
+            float g = 1.0f;
+            if (MODE == CG_BWD_DST) {
+              const float4 gv = gq[j4 >> 2];
+              g = j == 0 ? gv.x : j == 1 ? gv.y : j == 2 ? gv.z : gv.w;
+            }
+            r0[j] = g * sp * sg * (1.0f - sg);
+            r1[j] = g * sg * sgs;
+          }
+        }
+        *reinterpret_cast<float4*>(rowv + c) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+        if (MODE != CG_FWD)
+          *reinterpret_cast<float4*>(rowv + C + c) = make_float4(r1[0], r1[1], r1[2], r1[3]);
       }
     }
     mark(7);
@@ -557,7 +619,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       }
     }
     mark(10);
-    if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 15, 1ull);
+    if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
     k = nk; rd = nrd; buf ^= 1;
   }  // work items
 
@@ -584,15 +646,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)pl.tmem_cols);
 }
 
-template <int MODE, int PROFILE>
+template <int MODE, int PROFILE, int GATE>
 static int tc_launch_t(const CgParams& p, const TcPlan& pl, int grid, cudaStream_t st) {
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_tc<MODE, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_tc<MODE, PROFILE, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMaxDynSmem));
     configured.store(1, std::memory_order_release);
   }
-  k_cgconv_tc<MODE, PROFILE><<<grid, kTcThreads, pl.total, st>>>(p, pl);
+  k_cgconv_tc<MODE, PROFILE, GATE><<<grid, kTcThreads, pl.total, st>>>(p, pl);
   MDL_LAUNCHED();
   return MDL_OK;
 }
@@ -608,18 +670,25 @@ int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out, int dq_ato
   TcPlan pl;
   MDL_REQUIRE(tc_plan(mode, p.C, p.G, &pl), "cgconv_tc: unsupported shape C=%d G=%d", p.C, p.G);
   pl.dq_atomic = (mode == CG_BWD_DST) ? dq_atomic : 0;
+  const char* wenv = getenv("MDL_CGCONV_WINDOW");  // "0": always gather per slot (A/B and test switch)
+  pl.window = !(wenv && wenv[0] == '0');
   p.c_off = 0; p.CC = p.C; p.cap = kTcRows; p.te = kTcTE;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTcTE));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
   if (grid_out) *grid_out = grid;
   const bool prof = pl.prof != nullptr;  // instrumented instantiation only while a phase buffer is set
+  const char* genv = getenv("MDL_CGCONV_GATE");  // "mufu": every reciprocal on the transcendental pipe
+  const bool mixed = !(genv && genv[0] == 'm' && genv[1] == 'u');
+#define MDL_TC_CASE(M)                                                                        \
+  case M:                                                                                     \
+    return prof ? (mixed ? tc_launch_t<M, 1, 1>(p, pl, grid, st) : tc_launch_t<M, 1, 0>(p, pl, grid, st)) \
+                : (mixed ? tc_launch_t<M, 0, 1>(p, pl, grid, st) : tc_launch_t<M, 0, 0>(p, pl, grid, st));
   switch (mode) {
-    case CG_FWD: return prof ? tc_launch_t<CG_FWD, 1>(p, pl, grid, st) : tc_launch_t<CG_FWD, 0>(p, pl, grid, st);
-    case CG_BWD_SRC:
-      return prof ? tc_launch_t<CG_BWD_SRC, 1>(p, pl, grid, st) : tc_launch_t<CG_BWD_SRC, 0>(p, pl, grid, st);
-    case CG_BWD_DST:
-      return prof ? tc_launch_t<CG_BWD_DST, 1>(p, pl, grid, st) : tc_launch_t<CG_BWD_DST, 0>(p, pl, grid, st);
+    MDL_TC_CASE(CG_FWD)
+    MDL_TC_CASE(CG_BWD_SRC)
+    MDL_TC_CASE(CG_BWD_DST)
   }
+#undef MDL_TC_CASE
   MDL_REQUIRE(false, "cgconv_tc: bad mode");
 }
 

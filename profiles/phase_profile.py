@@ -10,9 +10,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matdeeplearn_b200 import _lib, process as pr  # noqa: E402
 from matdeeplearn_b200.csr import GraphCSR, gather_rows  # noqa: E402
 
-NAMES = ["loop/setup", "S1 wait rows", "split hi/lo + S2", "MMA issue", "prefetch issue", "gather P/Q",
-         "wait MMA", "gate math", "S3", "reduce", "dWe", "scale pass (bwd)", "dQ atomics (bwd)", "", "",
-         "rounds"]
+NAMES = {0: "loop top", 1: "S1 (wait ea rows + barrier)", 16: "next idx issue", 17: "node rows cp.async issue",
+         18: "split hi/lo", 19: "proxy fence", 2: "S2 barrier", 3: "MMA issue", 4: "seg/grad loads issue",
+         20: "node rows wait", 21: "next idx land + ea rows issue", 5: "S2c barrier", 6: "wait MMA",
+         22: "TMEM ld", 23: "node terms add", 13: "S2d barrier", 7: "gate math", 8: "S3 barrier",
+         11: "scale pass (bwd_src)", 12: "dQ atomics (bwd)", 9: "reduce", 10: "dWe"}
 lib = _lib.load()
 dev = torch.device("cuda:0")
 graphs = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
@@ -35,7 +37,7 @@ dPQ = torch.empty(N, 4 * C, device=dev)
 dWeT = torch.empty(G, 2 * C, device=dev)
 wsb = lib.mdl_cgconv_workspace_bytes(N, E, C, G)
 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-prof = torch.zeros(16, dtype=torch.int64, device=dev)
+prof = torch.zeros(32, dtype=torch.int64, device=dev)
 P, st = _lib.ptr, _lib.stream()
 
 
@@ -58,9 +60,34 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
     a.record(); fn(); c.record(); torch.cuda.synchronize()
     lib.mdl_debug_set_phase_buffer(None)
     v = prof.cpu().tolist()
-    rounds = max(v[15], 1)
-    print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, "
-          f"{sum(v[:13]) / rounds:.0f} cycles/round")
-    for i in range(13):
+    rounds = max(v[31], 1)
+    tot = max(sum(v[:31]), 1)
+    print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, {tot / rounds:.0f} cycles/round")
+    for i, nm in NAMES.items():  # in program order
         if v[i]:
-            print(f"   {NAMES[i]:18s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / max(sum(v[:13]), 1):5.1f}%")
+            print(f"   {nm:34s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / tot:5.1f}%")
+
+# A/B of the kernel switches on the same inputs: cold L2 (512 MiB flush), CUDA events, mean of 10
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, n=10):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(n):
+        flush.add_(1)
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); c.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(c))
+    return sum(ts) / n, min(ts)
+
+
+bytes_fwd = 8 * N * C + 8 * E + 4 * E * G
+for win, gate in (("1", "mixed"), ("0", "mixed"), ("1", "mufu"), ("0", "mufu")):
+    os.environ["MDL_CGCONV_WINDOW"] = win
+    os.environ["MDL_CGCONV_GATE"] = gate
+    f_ms, f_min = timed(fwd)
+    b_ms, b_min = timed(bwd)
+    print(f"A/B window={win} gate={gate}: fwd {f_ms:.3f} ms (min {f_min:.3f}, {bytes_fwd / f_ms / 1e6:.0f} GB/s algorithmic)"
+          f"  bwd {b_ms:.3f} ms (min {b_min:.3f})")

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import assert_close, random_graph, contiguous_batch_vector
+from tests.util import assert_close, random_graph, contiguous_batch_vector, block_diagonal_graph
 
 pytestmark = pytest.mark.gpu
 
@@ -87,12 +87,14 @@ def test_scatter_unsorted_index(dev):
         assert_close(got, ref, **FWD, what=red)
 
 
-@pytest.fixture(params=["tc", "tc_det", "simt", "tt"])
+@pytest.fixture(params=["tc", "tc_det", "tc_nowin", "simt", "tt"])
 def impl(request, monkeypatch):
     """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
     atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
     tensor-core kernels in deterministic two-pass mode, and with the SIMT kernels forced."""
     # "tt": transposed-tile forward kernel (cgconv_tt.cu); the backward stays on the tc kernels
+    # "tc_nowin": tensor-core kernels with the shared-memory node-row window off (per-slot rows only)
+    monkeypatch.setenv("MDL_CGCONV_WINDOW", "0" if request.param == "tc_nowin" else "1")
     monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt", "tt") else "tc")
     monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
     return request.param
@@ -107,11 +109,12 @@ def _log_err(tag, got, ref):
         f.write(f"{tag}: max|err|={err:.3e} scale={scale:.3e} rel={err / max(scale, 1e-30):.3e}\n")
 
 
-def _cgconv_case(dev, n, e, C, G, aggr, hub=None, iso=0, seed=0, tag=""):
+def _cgconv_case(dev, n, e, C, G, aggr, hub=None, iso=0, seed=0, tag="", ei=None):
     import matdeeplearn_b200.nn as mnn
     from oracle import pyg_ops as O
     torch.manual_seed(seed)
-    ei = random_graph(n, e, seed, hub, iso)
+    if ei is None:
+        ei = random_graph(n, e, seed, hub, iso)
     E = ei.shape[1]
     x = torch.randn(n, C, dtype=torch.float64)
     ea = torch.rand(E, G, dtype=torch.float64)
@@ -153,6 +156,22 @@ def test_cgconv_add_aggr(dev, impl):
 def test_cgconv_hub_and_isolated(dev, impl):
     # in-degree 400 (> several rounds of 128 slots) and 7 nodes with no edges at all
     _cgconv_case(dev, n=600, e=4000, C=64, G=50, aggr="mean", hub=(11, 400), iso=7, tag=impl)
+
+
+@pytest.mark.parametrize("sizes,k", [([30] * 40, 12), ([4, 60, 9, 33, 58, 17, 41] * 9, 12), ([5] * 300, 3),
+                                     ([100, 20, 130, 7, 64, 64], 12), ([1] * 200 + [25] * 8, 6)])
+def test_cgconv_crystal_batches(dev, impl, sizes, k):
+    """Block-diagonal batches: the rounds' source / destination rows sit in short contiguous node
+    ranges, which is the case the shared-memory window serves (and where it must hand over to the
+    per-slot rows: blocks above the 128-row capacity, rounds that straddle several blocks)."""
+    ei = block_diagonal_graph(sizes, k, seed=len(sizes))
+    got = _cgconv_case(dev, n=sum(sizes), e=0, C=64, G=50, aggr="mean", seed=3, tag=impl, ei=ei)
+    if impl in ("tc", "tc_nowin"):
+        import os
+        os.environ["MDL_CGCONV_WINDOW"] = "1" if impl == "tc_nowin" else "0"
+        other = _cgconv_case(dev, n=sum(sizes), e=0, C=64, G=50, aggr="mean", seed=3, ei=ei)
+        os.environ["MDL_CGCONV_WINDOW"] = "0" if impl == "tc_nowin" else "1"
+        assert torch.equal(got, other), "window and per-slot staging must give bit-identical forwards"
 
 
 def test_cgconv_tiny(dev, impl):

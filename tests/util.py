@@ -46,3 +46,21 @@ def contiguous_batch_vector(n_nodes, n_graphs, seed):
     cuts = np.sort(rng.choice(np.arange(1, n_nodes), size=n_graphs - 1, replace=False))
     sizes = np.diff(np.concatenate([[0], cuts, [n_nodes]]))
     return torch.repeat_interleave(torch.arange(n_graphs), torch.tensor(sizes))
+
+
+def block_diagonal_graph(sizes, edges_per_node, seed):
+    """Crystal-batch-shaped COO: independent blocks of the given node counts, every edge inside its
+    block, one self-loop per node appended per block (as the reference builder does).  Returns
+    int64 [2,E] in the reference's per-graph row-major order."""
+    rng = np.random.default_rng(seed)
+    out, base = [], 0
+    for n in sizes:
+        pairs = set()
+        want = min(n * edges_per_node, n * (n - 1))
+        while len(pairs) < want:
+            a, b = int(rng.integers(n)), int(rng.integers(n))
+            if a != b:
+                pairs.add((a, b))
+        out += [(base + a, base + b) for a, b in sorted(pairs)] + [(base + i, base + i) for i in range(n)]
+        base += n
+    return torch.tensor(out, dtype=torch.int64).t().contiguous()
