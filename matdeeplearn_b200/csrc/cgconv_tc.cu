@@ -39,6 +39,7 @@ struct TcPlan {
   unsigned long long* prof;
   int dq_atomic;  // BWD_DST also scatters da into dQ[src] with vector float atomics (no BWD_SRC pass)
   int window;     // stage the round's contiguous P / Q node-row ranges in shared memory when they fit
+  int ea_bulk;    // a round's edge rows are one contiguous block of ea: fetch it with ONE bulk (TMA) copy
   int NP, KP, GS, VW, tmem_cols, nitem;
   uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, offRange, offInfo, total;
 };
@@ -52,11 +53,12 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   if (((GS >> 2) & 1) == 0) GS += 4;  // odd number of 16-byte chunks per row: conflict-free float4 column reads
   const int VW = 2 * C + 4;  // [f | s] per slot (+4 floats: conflict-free float4 row access)
   uint32_t b = (uint32_t)NP * KP * 4, a = (uint32_t)(KP / 4) * kAChunk;
-  uint32_t ea = (uint32_t)kTcRows * GS * 4, v = (uint32_t)kTcRows * VW * 4;
-  const uint32_t idx = 4 * kTcRows * 4 + 32;  // indices [2][src|dst][128] + node ranges [2][4]
+  uint32_t ea = (uint32_t)kTcRows * GS * 4 + 16, v = (uint32_t)kTcRows * VW * 4;  // +16: bulk-copy alignment slack
+  const uint32_t idx = 4 * kTcRows * 4 + 512;  // indices [2][src|dst][128] + per-warp node ranges [2][16][4]
   pl->prof = g_phase_buf;
   pl->dq_atomic = 0;
   pl->window = 1;
+  pl->ea_bulk = 0;
   pl->NP = NP; pl->KP = KP; pl->GS = GS; pl->VW = VW;
   pl->tmem_cols = 32;
   while (pl->tmem_cols < NP) pl->tmem_cols <<= 1;
@@ -70,7 +72,7 @@ static bool tc_plan(int mode, int C, int G, TcPlan* pl) {
   uint32_t end = pl->offEA + ea;
   const uint32_t info = kInfoCap * 16;  // per-CTA table of tile bounds (TileInfo)
   if (end + v + idx + info <= (uint32_t)kMaxDynSmem) {
-    pl->offV = end; pl->offIdx = end + v; pl->offRange = end + v + idx - 32; pl->offInfo = end + v + idx;
+    pl->offV = end; pl->offIdx = end + v; pl->offRange = end + v + idx - 512; pl->offInfo = end + v + idx;
     pl->total = end + v + idx + info;
     return true;
   }
@@ -96,10 +98,12 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[
 // Persistent CTA, software-pipelined over "rounds" of <=128 slots:
 //   while round r's MMAs run and its epilogue executes, round r+1's indices and ea rows are
 //   already in flight (cp.async) and the node projections for round r are being gathered.
-template <int MODE, int PROFILE, int GATE>
+template <int MODE, int PROFILE, int GATE, int EA_BULK>
 __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, const TcPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar;       // MMA completion (tcgen05.commit)
+  __shared__ uint64_t bar_rows;  // this round's node rows (bulk copies into the value tile)
+  __shared__ uint64_t bar_ea;    // next round's edge rows (one bulk copy into the landing zone)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C, G = p.G, W2 = 2 * C;
@@ -113,11 +117,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   float* sV = reinterpret_cast<float*>(smem + pl.offV);    // [128][VW]
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);    // [2 buffers][src|dst][128]
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);  // bounds of this CTA's tiles
-  // node ranges touched by a round, [2 buffers][src min, src max, dst min, dst max]: edges of a crystal
-  // graph stay inside the graph, so the P / Q rows a round gathers lie in two short CONTIGUOUS node
-  // ranges.  When both fit, they are streamed into the (still idle) value tile with coalesced
-  // 16-byte cp.async and the epilogue reads them from shared memory: a few KB from L2 per round
-  // instead of one 512-byte row per slot and operand, and no register staging.
+  // node ranges touched by a round, [2 buffers][16 warps][src min, src max, dst min, dst max] (one
+  // record per warp for its 8 slots, combined by whoever needs the range): edges of a crystal graph
+  // stay inside the graph, so the P / Q rows a round gathers lie in two short CONTIGUOUS node ranges.
+  // When both fit, they are streamed into the (still idle) value tile by bulk copies and the epilogue
+  // reads them from shared memory: a few KB from L2 per round instead of one 512-byte row per slot
+  // and operand, and no register staging.
   int* sRange = reinterpret_cast<int*>(smem + pl.offRange);
 
   // tiles of this CTA: blockIdx.x, +gridDim.x, ...
@@ -143,9 +148,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, (uint32_t)pl.tmem_cols);
   if (tid == 32) {
     umma::mbar_init(&bar, 1);
+    umma::mbar_init(&bar_rows, 1);
+    umma::mbar_init(&bar_ea, 1);
     umma::fence_mbar_init();
   }
-  if (tid < 8) sRange[tid] = (tid & 1) ? -1 : 0x7fffffff;
+
   fill_infos(0);
   for (int i = tid; i < NP * KP; i += kTcThreads) {
     const int n = i % NP, k = i / NP;
@@ -187,19 +194,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
       bS[row0 + lane] = ni.s;
       bD[row0 + lane] = ni.d;
     }
-    if (pl.window && row0 < cnt) {  // warp-uniform; at least lane 0 holds a real slot
+    if (pl.window) {  // this warp's record (neutral when it holds no real slot)
       const bool real = lane < kRowsPerWarp && row0 + lane < cnt;
       const int s_lo = __reduce_min_sync(0xffffffffu, real ? ni.s : 0x7fffffff);
-      const int s_hi = __reduce_max_sync(0xffffffffu, real ? ni.s : -1);
+      const int s_hi = __reduce_max_sync(0xffffffffu, real ? ni.s : -0x40000000);
       const int d_lo = __reduce_min_sync(0xffffffffu, real ? ni.d : 0x7fffffff);
-      const int d_hi = __reduce_max_sync(0xffffffffu, real ? ni.d : -1);
-      if (lane == 0) {
-        atomicMin(sRange + 4 * buf + 0, s_lo);
-        atomicMax(sRange + 4 * buf + 1, s_hi);
-        atomicMin(sRange + 4 * buf + 2, d_lo);
-        atomicMax(sRange + 4 * buf + 3, d_hi);
-      }
+      const int d_hi = __reduce_max_sync(0xffffffffu, real ? ni.d : -0x40000000);
+      if (lane == 0) *reinterpret_cast<int4*>(sRange + (buf * kTcWarps + warp) * 4) = make_int4(s_lo, s_hi, d_lo, d_hi);
     }
+    if (EA_BULK) return;  // the edge rows arrive by one bulk copy (issue_ea_bulk)
     // the warp's 8 rows, lanes across the 8-byte (even G) or 4-byte chunks of a row
     const int wcnt = min(kRowsPerWarp, cnt - row0);  // rows of this warp that exist (may be <= 0)
 #pragma unroll
@@ -216,6 +219,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
           for (int c = lane; c < G; c += 32) cp_async4(d + c, g + c);
         }
       }
+    }
+  };
+
+  // Bulk variant of the edge-row fetch (FWD / BWD_DST: slots r_lo.. are consecutive rows of ea, i.e.
+  // one contiguous block).  The block starts at any 4-byte offset; it is copied from the 16-byte
+  // boundary below it, so element (e, k) lands at sEA[ea_off + e*G + k], ea_off = (r_lo*G) & 3.  The
+  // copy length is rounded up to 16 bytes when ea continues for >= 12 bytes behind the block,
+  // otherwise down, and thread 0 moves the last few floats by hand.
+  auto ea_bulk_bytes = [&](int r_lo, int cnt) -> uint32_t {
+    if (cnt <= 0) return 0u;
+    const long long first = (long long)r_lo * G;
+    const uint32_t bytes = (uint32_t)(((int)(first & 3) + cnt * G) * 4);
+    const bool more = ((long long)p.E * G - (first + (long long)cnt * G)) >= 3;
+    return more ? ((bytes + 15u) & ~15u) : (bytes & ~15u);
+  };
+  auto issue_ea_bulk = [&](int r_lo, int cnt) {  // thread 0 only
+    const long long first = (long long)r_lo * G;
+    const int off = (int)(first & 3);
+    const float* src = p.ea + (first - off);
+    const uint32_t bytes = (uint32_t)((off + cnt * G) * 4), nb = ea_bulk_bytes(r_lo, cnt);
+    if (nb) {
+      umma::mbar_arrive_expect_tx(&bar_ea, nb);
+      umma::bulk_g2s(sEA, src, nb, &bar_ea);
+    }
+    for (uint32_t t = nb / 4; t < bytes / 4; ++t) sEA[t] = __ldg(src + t);  // tail at the very end of ea
+  };
+  uint32_t ph_rows = 0, ph_ea = 0;
+  int dbg_round = 0;
+  // debugging aid (instrumented build only): a wait that does not complete within 2^20 polls records
+  // (barrier id, CTA, round, thread) in the phase buffer and carries on instead of trapping
+  auto wait_dbg = [&](uint64_t* b, uint32_t parity, int id) {
+    if (!PROFILE || !pl.prof) { umma::mbar_wait(b, parity); return; }
+    const uint32_t addr = umma::smem_u32(b);
+    for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
+      uint32_t done;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+      if (done) return;
+    }
+    if (atomicCAS(pl.prof + 25, 0ull, 1ull) == 0ull) {
+      pl.prof[26] = (unsigned long long)id;
+      pl.prof[27] = blockIdx.x;
+      pl.prof[28] = (unsigned long long)dbg_round;
+      pl.prof[29] = (unsigned long long)tid;
+      pl.prof[30] = parity;
     }
   };
 
@@ -241,6 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     const int c0 = min(t0.e_hi - t0.e_lo, kTcRows);
     const NextIdx ni = issue_idx(t0.e_lo, c0);
     land_idx_and_rows(ni, c0, 0);
+    if (EA_BULK && tid == 0) issue_ea_bulk(t0.e_lo, c0);
   }
 
   const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
@@ -266,8 +318,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     const int* bDst = bSrc + kTcRows;
 
     mark(0);
-    cp_async_wait_all();
-    __syncthreads();  // [S1] rows + indices of this round visible; value / operand tiles free
+    if (!EA_BULK) cp_async_wait_all();
+    umma::fence_proxy_async_smem();  // generic accesses of the value tile (last round) before bulk writes into it
+    __syncthreads();  // [S1] indices of this round visible; value / operand tiles free
     mark(1);
 
     // ---- indices of the next round: issued first, landed after the MMA issue (in BWD_SRC they are a
@@ -287,40 +340,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     //   per slot row e = the operand of the UNSORTED side (Q[src[e]]; P[dst[e]] in BWD_SRC); the sorted
     //            side repeats a few rows per warp and is read straight from global in the epilogue
     bool win = false;
+    int w_smin = 0, w_dmin = 0, w_nq = 0;
     if (cnt > 0) {
       int4 rg = make_int4(0, 0, 0, 0);
       int nq = kTcRows, np_ = kTcRows;
       if (pl.window) {  // ranges are only maintained in window mode
-        rg = *reinterpret_cast<const int4*>(sRange + 4 * buf);
+        int4 w = make_int4(0x7fffffff, -0x40000000, 0x7fffffff, -0x40000000);
+        if (lane < kTcWarps) w = *reinterpret_cast<const int4*>(sRange + (buf * kTcWarps + lane) * 4);
+        rg.x = __reduce_min_sync(0xffffffffu, w.x); rg.y = __reduce_max_sync(0xffffffffu, w.y);
+        rg.z = __reduce_min_sync(0xffffffffu, w.z); rg.w = __reduce_max_sync(0xffffffffu, w.w);
         nq = rg.y - rg.x + 1; np_ = rg.w - rg.z + 1;
       }
-      if (nq + np_ <= kTcRows) {
-        win = true;
-        const int total = (nq + np_) * 32;  // 16-byte chunks: 2C floats per row
-        for (int i = tid; i < total; i += kTcThreads) {
-          const int r = i >> 5, c = i & 31;
-          const float* g = (r < nq) ? p.PQ + (size_t)(rg.x + r) * (4 * C) + 2 * C + 4 * c
-                                    : p.PQ + (size_t)(rg.z + r - nq) * (4 * C) + 4 * c;
-          cp_async16(sV + r * VW + 4 * c, g);
-        }
-      } else {
-        const int* bNode = (MODE == CG_BWD_SRC) ? bDst : bSrc;
-        const float* base = p.PQ + ((MODE == CG_BWD_SRC) ? 0 : 2 * C);
-        for (int i = tid; i < cnt * 32; i += kTcThreads) {
-          const int r = i >> 5, c = i & 31;
-          cp_async16(sV + r * VW + 4 * c, base + (size_t)bNode[r] * (4 * C) + 4 * c);
+      win = nq + np_ <= kTcRows;
+      w_smin = rg.x; w_dmin = rg.z; w_nq = nq;
+      const int nrows = win ? nq + np_ : cnt;  // one 512-byte bulk copy per row, one thread each
+      // The expectation is registered here, next to the copies (copies of other warps may complete first:
+      // the transaction count of the phase simply goes negative until this arrives).  Registering it
+      // ahead of [S1] instead failed intermittently on the GPU (profiles/r1_bulk_copy_race.txt).
+      if (tid == 0) umma::mbar_arrive_expect_tx(&bar_rows, (uint32_t)nrows * (uint32_t)(2 * C * 4));
+      // one bulk copy per 512-byte row; a bulk copy is a warp-serial instruction (~70 cycles each when
+      // one warp issues a batch), so the rows are dealt out to lane 0 of all 16 warps
+      if (lane == 0) {
+        for (int r = warp; r < nrows; r += kTcWarps) {
+          const float* g;
+          if (win) {
+            g = (r < nq) ? p.PQ + (size_t)(rg.x + r) * (4 * C) + 2 * C : p.PQ + (size_t)(rg.z + r - nq) * (4 * C);
+          } else {
+            g = (MODE == CG_BWD_SRC) ? p.PQ + (size_t)bDst[r] * (4 * C) : p.PQ + (size_t)bSrc[r] * (4 * C) + 2 * C;
+          }
+          umma::bulk_g2s(sV + r * VW, g, (uint32_t)(2 * C * 4), &bar_rows);
         }
       }
     }
-
     mark(17);
+    int ea_off = 0;
+    if (EA_BULK) {
+      ea_off = (int)(((long long)r_lo * G) & 3);
+      if (ea_bulk_bytes(r_lo, cnt)) {  // CTA-uniform
+        wait_dbg(&bar_ea, ph_ea, 1);
+        ph_ea ^= 1;
+      }
+    }
+    mark(24);
     // ---- split hi/lo into the canonical MMA operand layout
     {
       const int e = tid & (kTcRows - 1);
       const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
       for (int j = (tid >> 7); j < (KP >> 2); j += kTcThreads / kTcRows) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < cnt && 4 * j < GS) {
+        if (EA_BULK) {
+          if (e < cnt && 4 * j < G) {  // dense rows (stride G) at a 4- or 8-byte offset: 8-byte loads for even G
+            const float* r = sEA + ea_off + e * G + 4 * j;
+            if ((G & 1) == 0) {
+              const float2 a = *reinterpret_cast<const float2*>(r);
+              v.x = a.x; v.y = a.y;
+              if (4 * j + 2 < G) { const float2 b2 = *reinterpret_cast<const float2*>(r + 2); v.z = b2.x; v.w = b2.y; }
+            } else {
+              v.x = r[0];
+              if (4 * j + 1 < G) v.y = r[1];
+              if (4 * j + 2 < G) v.z = r[2];
+              if (4 * j + 3 < G) v.w = r[3];
+            }
+          }
+        } else if (e < cnt && 4 * j < GS) {
           v = *reinterpret_cast<const float4*>(sEA + e * GS + 4 * j);
           if (4 * j + 0 >= G) v.x = 0.f;  // padding columns: exact zeros
           if (4 * j + 1 >= G) v.y = 0.f;
@@ -342,6 +424,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     mark(19);
     __syncthreads();  // [S2] operands staged; the ea landing zone is free for the next round
     mark(2);
+    if (EA_BULK && tid == 0 && nk < my_tiles) {
+      const TileInfo Tn = sInfo[nk - info_base];
+      const int nr_lo = Tn.e_lo + nrd * kTcRows;
+      issue_ea_bulk(nr_lo, min(Tn.e_hi - nr_lo, kTcRows));
+    }
 
     // ---- contraction on the tensor core (asynchronous; the issuing lane belongs to the LAST warp,
     // whose other duties in this window are the lightest)
@@ -414,12 +501,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
 
     // ---- overlap window, part 2: LAND: this round's node rows, then the next round's indices and,
     // from them, its ea rows.
-    cp_async_wait_all();  // this round's node rows (the only cp.async group in flight at this point)
-    mark(20);
     if (nk < my_tiles) land_idx_and_rows(ni, ncnt, buf ^ 1);
     mark(21);
-    __syncthreads();  // [S2c] gathered projections visible to the epilogue threads of every warp
-    mark(5);
 
     // ---- epilogue, part 1: thread = slot (TMEM lane); a = accumulator + (P[dst] + Q[src]), the node
     // terms read from the window rows (or, without a window, from the slot's own value-tile row)
@@ -427,7 +510,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     const int e_ep = 32 * q + lane;
     const bool live = e_ep < cnt;
     if (cnt > 0) {
-      umma::mbar_wait(&bar, phase);
+      wait_dbg(&bar_rows, ph_rows, 2);  // node rows landed (each thread observes the barrier itself)
+      ph_rows ^= 1;
+      mark(20);
+      wait_dbg(&bar, phase, 3);
       umma::fence_after_sync();
       phase ^= 1;
       mark(6);
@@ -450,8 +536,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
           }
         };
         if (win) {
-          const int4 rg = *reinterpret_cast<const int4*>(sRange + 4 * buf);
-          add_rows(sV + (rg.y - rg.x + 1 + sd - rg.z) * VW + c_begin, sV + (ss - rg.x) * VW + c_begin);
+          add_rows(sV + (w_nq + sd - w_dmin) * VW + c_begin, sV + (ss - w_smin) * VW + c_begin);
         } else {
           const float* direct = (MODE == CG_BWD_SRC) ? p.PQ + (size_t)ss * (4 * C) + 2 * C + c_begin
                                                      : p.PQ + (size_t)sd * (4 * C) + c_begin;
@@ -461,7 +546,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     }
     mark(23);
     __syncthreads();  // [S2d] every read of the staged node rows done: the value tile may be overwritten
-    if (tid < 4) sRange[4 * buf + tid] = (tid & 1) ? -1 : 0x7fffffff;  // refilled two rounds from now
     mark(13);
     // ---- epilogue, part 2: gate math, per-slot values parked in the value tile
     if (live) {
@@ -620,7 +704,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
     }
     mark(10);
     if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
-    k = nk; rd = nrd; buf ^= 1;
+    k = nk; rd = nrd; buf ^= 1; ++dbg_round;
   }  // work items
 
   if (MODE == CG_BWD_DST) {
@@ -646,15 +730,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_cgconv_tc(const CgParams p, c
   if (warp == 0) umma::tmem_dealloc(tmem, (uint32_t)pl.tmem_cols);
 }
 
-template <int MODE, int PROFILE, int GATE>
+template <int MODE, int PROFILE, int GATE, int EA_BULK>
 static int tc_launch_t(const CgParams& p, const TcPlan& pl, int grid, cudaStream_t st) {
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_acquire)) {
-    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_tc<MODE, PROFILE, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_tc<MODE, PROFILE, GATE, EA_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMaxDynSmem));
     configured.store(1, std::memory_order_release);
   }
-  k_cgconv_tc<MODE, PROFILE, GATE><<<grid, kTcThreads, pl.total, st>>>(p, pl);
+  k_cgconv_tc<MODE, PROFILE, GATE, EA_BULK><<<grid, kTcThreads, pl.total, st>>>(p, pl);
   MDL_LAUNCHED();
   return MDL_OK;
 }
@@ -679,15 +763,21 @@ int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out, int dq_ato
   const bool prof = pl.prof != nullptr;  // instrumented instantiation only while a phase buffer is set
   const char* genv = getenv("MDL_CGCONV_GATE");  // "mufu": every reciprocal on the transcendental pipe
   const bool mixed = !(genv && genv[0] == 'm' && genv[1] == 'u');
-#define MDL_TC_CASE(M)                                                                        \
-  case M:                                                                                     \
-    return prof ? (mixed ? tc_launch_t<M, 1, 1>(p, pl, grid, st) : tc_launch_t<M, 1, 0>(p, pl, grid, st)) \
-                : (mixed ? tc_launch_t<M, 0, 1>(p, pl, grid, st) : tc_launch_t<M, 0, 0>(p, pl, grid, st));
+  const char* benv = getenv("MDL_CGCONV_EA");  // "rows": per-row cp.async instead of the bulk copy
+  const bool bulk = mode != CG_BWD_SRC && (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 && !(benv && benv[0] == 'r');
+  MDL_REQUIRE((reinterpret_cast<uintptr_t>(p.PQ) & 15) == 0, "cgconv_tc: PQ must be 16-byte aligned");
+#define MDL_TC_G(M, PR, GT) (bulk ? tc_launch_t<M, PR, GT, 1>(p, pl, grid, st) : tc_launch_t<M, PR, GT, 0>(p, pl, grid, st))
+#define MDL_TC_CASE(M) \
+  case M:              \
+    return prof ? (mixed ? MDL_TC_G(M, 1, 1) : MDL_TC_G(M, 1, 0)) : (mixed ? MDL_TC_G(M, 0, 1) : MDL_TC_G(M, 0, 0));
   switch (mode) {
     MDL_TC_CASE(CG_FWD)
-    MDL_TC_CASE(CG_BWD_SRC)
     MDL_TC_CASE(CG_BWD_DST)
+    case CG_BWD_SRC:
+      return prof ? (mixed ? tc_launch_t<CG_BWD_SRC, 1, 1, 0>(p, pl, grid, st) : tc_launch_t<CG_BWD_SRC, 1, 0, 0>(p, pl, grid, st))
+                  : (mixed ? tc_launch_t<CG_BWD_SRC, 0, 1, 0>(p, pl, grid, st) : tc_launch_t<CG_BWD_SRC, 0, 0, 0>(p, pl, grid, st));
   }
+#undef MDL_TC_G
 #undef MDL_TC_CASE
   MDL_REQUIRE(false, "cgconv_tc: bad mode");
 }

@@ -10,9 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matdeeplearn_b200 import _lib, process as pr  # noqa: E402
 from matdeeplearn_b200.csr import GraphCSR, gather_rows  # noqa: E402
 
-NAMES = {0: "loop top", 1: "S1 (wait ea rows + barrier)", 16: "next idx issue", 17: "node rows cp.async issue",
-         18: "split hi/lo", 19: "proxy fence", 2: "S2 barrier", 3: "MMA issue", 4: "seg/grad loads issue",
-         20: "node rows wait", 21: "next idx land + ea rows issue", 5: "S2c barrier", 6: "wait MMA",
+NAMES = {0: "loop top", 1: "S1 (fence + barrier)", 16: "next idx issue", 17: "node rows bulk issue",
+         24: "wait ea rows", 18: "split hi/lo", 19: "proxy fence", 2: "S2 barrier", 3: "MMA issue (+ next ea bulk)",
+         4: "seg/grad loads issue", 21: "next idx land (+ ea rows cp.async)", 20: "wait node rows", 6: "wait MMA",
          22: "TMEM ld", 23: "node terms add", 13: "S2d barrier", 7: "gate math", 8: "S3 barrier",
          11: "scale pass (bwd_src)", 12: "dQ atomics (bwd)", 9: "reduce", 10: "dWe"}
 lib = _lib.load()
@@ -53,6 +53,8 @@ def bwd():
 
 
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
+    if os.environ.get("ONLY", name) != name:
+        continue
     fn(); torch.cuda.synchronize()
     lib.mdl_debug_set_phase_buffer(P(prof))
     prof.zero_()
@@ -61,12 +63,17 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
     lib.mdl_debug_set_phase_buffer(None)
     v = prof.cpu().tolist()
     rounds = max(v[31], 1)
-    tot = max(sum(v[:31]), 1)
+    if v[25]:
+        print(f"!! wait timed out: barrier id {v[26]} (1 ea, 2 node rows, 3 mma), CTA {v[27]}, round {v[28]}, "
+              f"thread {v[29]}, parity {v[30]}")
+    tot = max(sum(v[:25]), 1)
     print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, {tot / rounds:.0f} cycles/round")
     for i, nm in NAMES.items():  # in program order
         if v[i]:
             print(f"   {nm:34s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / tot:5.1f}%")
 
+if os.environ.get("PHASE_ONLY"):
+    sys.exit(0)
 # A/B of the kernel switches on the same inputs: cold L2 (512 MiB flush), CUDA events, mean of 10
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -84,10 +91,12 @@ def timed(fn, n=10):
 
 
 bytes_fwd = 8 * N * C + 8 * E + 4 * E * G
-for win, gate in (("1", "mixed"), ("0", "mixed"), ("1", "mufu"), ("0", "mufu")):
+for win, gate, ea_mode in (("1", "mixed", "bulk"), ("0", "mixed", "bulk"), ("1", "mufu", "bulk"), ("1", "mixed", "rows"),
+                           ("0", "mufu", "rows")):
     os.environ["MDL_CGCONV_WINDOW"] = win
     os.environ["MDL_CGCONV_GATE"] = gate
+    os.environ["MDL_CGCONV_EA"] = ea_mode
     f_ms, f_min = timed(fwd)
     b_ms, b_min = timed(bwd)
-    print(f"A/B window={win} gate={gate}: fwd {f_ms:.3f} ms (min {f_min:.3f}, {bytes_fwd / f_ms / 1e6:.0f} GB/s algorithmic)"
+    print(f"A/B window={win} gate={gate} ea={ea_mode}: fwd {f_ms:.3f} ms (min {f_min:.3f}, {bytes_fwd / f_ms / 1e6:.0f} GB/s algorithmic)"
           f"  bwd {b_ms:.3f} ms (min {b_min:.3f})")

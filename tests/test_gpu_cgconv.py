@@ -87,14 +87,16 @@ def test_scatter_unsorted_index(dev):
         assert_close(got, ref, **FWD, what=red)
 
 
-@pytest.fixture(params=["tc", "tc_det", "tc_nowin", "simt", "tt"])
+@pytest.fixture(params=["tc", "tc_det", "tc_nowin", "tc_rows", "simt", "tt"])
 def impl(request, monkeypatch):
     """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
     atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
     tensor-core kernels in deterministic two-pass mode, and with the SIMT kernels forced."""
     # "tt": transposed-tile forward kernel (cgconv_tt.cu); the backward stays on the tc kernels
     # "tc_nowin": tensor-core kernels with the shared-memory node-row window off (per-slot rows only)
+    # "tc_rows": edge rows by per-row cp.async instead of one bulk (TMA) copy per round
     monkeypatch.setenv("MDL_CGCONV_WINDOW", "0" if request.param == "tc_nowin" else "1")
+    monkeypatch.setenv("MDL_CGCONV_EA", "rows" if request.param == "tc_rows" else "bulk")
     monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt", "tt") else "tc")
     monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
     return request.param
