@@ -398,7 +398,13 @@ extern "C" int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, 
   p.dst_dst = dst_dst; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg_dst : nullptr;
   p.out = out; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
   if (use_tt(CG_FWD, C, G)) return cgtt_launch(CG_FWD, p, as_stream(stream));
-  if (use_tc(CG_FWD, C, G)) return cgtc_launch(CG_FWD, p, as_stream(stream), nullptr);
+  if (use_tc(CG_FWD, C, G)) {
+    // default: the software-pipelined forward kernel (cgconv_fwd.cu); MDL_CGCONV_IMPL=tc keeps the
+    // round-serial tensor-core kernel (A/B, and the shapes / alignments the pipelined one declines)
+    const char* env = getenv("MDL_CGCONV_IMPL");
+    if (!(env && strcmp(env, "tc") == 0) && cgfwd_supported(p)) return cgfwd_launch(p, as_stream(stream));
+    return cgtc_launch(CG_FWD, p, as_stream(stream), nullptr);
+  }
   p.cap = plan.cap; p.te = plan.te;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(E, plan.te));
   for (int c_off = 0; c_off < C; c_off += plan.CC) {
@@ -527,5 +533,6 @@ extern "C" int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const
 extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
   cgtc_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgtt_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
+  cgfwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   return MDL_OK;
 }

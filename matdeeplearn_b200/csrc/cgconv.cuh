@@ -58,6 +58,10 @@ __device__ __forceinline__ float sigmoid_fast_(float x) { return __fdividef(1.0f
 bool cgtc_supported(int mode, int C, int G);
 int cgtc_launch(int mode, CgParams p, cudaStream_t st, int* grid_out, int dq_atomic = 0);
 void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
+// software-pipelined forward kernel (cgconv_fwd.cu): contraction one round ahead of the epilogue
+bool cgfwd_supported(const CgParams& p);
+int cgfwd_launch(CgParams p, cudaStream_t st);
+void cgfwd_set_phase_buffer(unsigned long long* dev_ptr);
 // transposed-tile tensor-core path (cgconv_tt.cu): channel = TMEM lane, two CTAs per SM
 bool cgtt_supported(int mode, int C, int G);
 int cgtt_launch(int mode, CgParams p, cudaStream_t st);

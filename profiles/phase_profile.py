@@ -52,9 +52,16 @@ def bwd():
                                   1, P(ws), wsb, st), "bwd")
 
 
+PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 5: "idx/rows/seg loads issue", 6: "wait MMA(r)", 2: "wait ea(r+1)",
+              3: "split(r+1)", 4: "row+idx STS, fences, S2", 7: "MMA(r+1) + ea(r+2) issue", 8: "TMEM ld + node terms",
+              9: "S2d barrier", 10: "gate math", 11: "S3 barrier", 12: "reduce"}
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if os.environ.get("ONLY", name) != name:
         continue
+    if name == "fwd" and os.environ.get("MDL_CGCONV_IMPL", "pipe") == "pipe":
+        NAMES_ = PIPE_NAMES
+    else:
+        NAMES_ = NAMES
     fn(); torch.cuda.synchronize()
     lib.mdl_debug_set_phase_buffer(P(prof))
     prof.zero_()
@@ -68,7 +75,7 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
               f"thread {v[29]}, parity {v[30]}")
     tot = max(sum(v[:25]), 1)
     print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, {tot / rounds:.0f} cycles/round")
-    for i, nm in NAMES.items():  # in program order
+    for i, nm in NAMES_.items():  # in program order
         if v[i]:
             print(f"   {nm:34s} {v[i] / rounds:9.0f} cyc/round  {100 * v[i] / tot:5.1f}%")
 
@@ -91,12 +98,13 @@ def timed(fn, n=10):
 
 
 bytes_fwd = 8 * N * C + 8 * E + 4 * E * G
-for win, gate, ea_mode in (("1", "mixed", "bulk"), ("0", "mixed", "bulk"), ("1", "mufu", "bulk"), ("1", "mixed", "rows"),
-                           ("0", "mufu", "rows")):
+for impl, win, gate, ea_mode in (("pipe", "1", "mixed", "bulk"), ("pipe", "0", "mixed", "bulk"), ("tc", "1", "mixed", "bulk"),
+                                 ("tc", "0", "mixed", "bulk"), ("tc", "1", "mufu", "bulk"), ("tc", "1", "mixed", "rows")):
+    os.environ["MDL_CGCONV_IMPL"] = impl
     os.environ["MDL_CGCONV_WINDOW"] = win
     os.environ["MDL_CGCONV_GATE"] = gate
     os.environ["MDL_CGCONV_EA"] = ea_mode
     f_ms, f_min = timed(fwd)
     b_ms, b_min = timed(bwd)
-    print(f"A/B window={win} gate={gate} ea={ea_mode}: fwd {f_ms:.3f} ms (min {f_min:.3f}, {bytes_fwd / f_ms / 1e6:.0f} GB/s algorithmic)"
+    print(f"A/B impl={impl} window={win} gate={gate} ea={ea_mode}: fwd {f_ms:.3f} ms (min {f_min:.3f}, {bytes_fwd / f_ms / 1e6:.0f} GB/s algorithmic)"
           f"  bwd {b_ms:.3f} ms (min {b_min:.3f})")

@@ -87,7 +87,7 @@ def test_scatter_unsorted_index(dev):
         assert_close(got, ref, **FWD, what=red)
 
 
-@pytest.fixture(params=["tc", "tc_det", "tc_nowin", "tc_rows", "simt", "tt"])
+@pytest.fixture(params=["pipe", "pipe_nowin", "tc", "tc_det", "tc_nowin", "tc_rows", "simt", "tt"])
 def impl(request, monkeypatch):
     """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
     atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
@@ -95,9 +95,11 @@ def impl(request, monkeypatch):
     # "tt": transposed-tile forward kernel (cgconv_tt.cu); the backward stays on the tc kernels
     # "tc_nowin": tensor-core kernels with the shared-memory node-row window off (per-slot rows only)
     # "tc_rows": edge rows by per-row cp.async instead of one bulk (TMA) copy per round
-    monkeypatch.setenv("MDL_CGCONV_WINDOW", "0" if request.param == "tc_nowin" else "1")
+    monkeypatch.setenv("MDL_CGCONV_WINDOW", "0" if request.param.endswith("_nowin") else "1")
     monkeypatch.setenv("MDL_CGCONV_EA", "rows" if request.param == "tc_rows" else "bulk")
-    monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt", "tt") else "tc")
+    # "pipe": default dispatch (software-pipelined forward kernel, cgconv_fwd.cu; tc backward)
+    monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt", "tt") else
+                       ("pipe" if request.param.startswith("pipe") else "tc"))
     monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
     return request.param
 
@@ -168,11 +170,11 @@ def test_cgconv_crystal_batches(dev, impl, sizes, k):
     per-slot rows: blocks above the 128-row capacity, rounds that straddle several blocks)."""
     ei = block_diagonal_graph(sizes, k, seed=len(sizes))
     got = _cgconv_case(dev, n=sum(sizes), e=0, C=64, G=50, aggr="mean", seed=3, tag=impl, ei=ei)
-    if impl in ("tc", "tc_nowin"):
+    if impl in ("tc", "tc_nowin", "pipe", "pipe_nowin"):
         import os
-        os.environ["MDL_CGCONV_WINDOW"] = "1" if impl == "tc_nowin" else "0"
+        os.environ["MDL_CGCONV_WINDOW"] = "1" if impl.endswith("_nowin") else "0"
         other = _cgconv_case(dev, n=sum(sizes), e=0, C=64, G=50, aggr="mean", seed=3, ei=ei)
-        os.environ["MDL_CGCONV_WINDOW"] = "0" if impl == "tc_nowin" else "1"
+        os.environ["MDL_CGCONV_WINDOW"] = "0" if impl.endswith("_nowin") else "1"
         assert torch.equal(got, other), "window and per-slot staging must give bit-identical forwards"
 
 
