@@ -28,8 +28,10 @@ namespace mdl {
 
 namespace {
 
-constexpr int kThreadsF = 512;
+constexpr int kThreadsF = 512;                    // epilogue ("consumer") threads: 16 warps
 constexpr int kWarpsF = kThreadsF / 32;
+constexpr int kS2Threads = kThreadsF + 32;        // + one warp that only issues MMAs and bulk copies
+constexpr int kLaunchF = kThreadsF + 128;         // registers are re-balanced per warpgroup: launch a whole one for it
 constexpr int kRowsF = 128;                       // slots per round = MMA M
 constexpr int kTileSlots = 112;                   // ownership granularity (as cgconv_tc.cu)
 constexpr int kInfoCapF = 512;
@@ -67,13 +69,18 @@ struct Round {
 };
 
 template <int PROFILE>
-__global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams p, const FwdPlan pl) {
+__global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams p, const FwdPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_mma;  // tcgen05.commit of a round's MMAs
   __shared__ uint64_t bar_ea;   // bulk copy of a round's edge rows
   __shared__ uint32_t tmem_base_s;
+  __shared__ int sMail[4];  // consumers -> issuer warp at [S2]: {round staged?, its cnt, next round's r_lo, cnt (or -1)}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP;
+  // barriers: 0 = whole CTA (setup / teardown), 1 = whole CTA at [S2] (hands the staged tiles to the
+  // issuer warp), 2 = the 512 consumer threads only
+  auto sync_consumers = [] { asm volatile("bar.sync 2, %0;" ::"n"(kThreadsF) : "memory"); };
+  auto sync_s2 = [] { asm volatile("bar.sync 1, %0;" ::"n"(kS2Threads) : "memory"); };
 
   uint8_t* sBhi = smem + pl.offBhi;
   uint8_t* sBlo = smem + pl.offBlo;
@@ -87,6 +94,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
   const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   int info_base = 0;
   auto fill_infos = [&](int base) {
+    if (tid >= kThreadsF) return;
     for (int k = base + tid; k < min(my_tiles, base + kInfoCapF); k += kThreadsF) {
       TileInfo t;
       const int tile = blockIdx.x + k * gridDim.x;
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
     umma::fence_mbar_init();
   }
   fill_infos(0);
-  for (int i = tid; i < kNP * KP; i += kThreadsF) {
+  for (int i = tid; i < kNP * KP; i += kLaunchF) {
     const int n = i % kNP, k = i / kNP;
     const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) : 0.0f;
     const float hi = umma::tf32_hi(w);
@@ -202,14 +210,18 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
       mark(3);
     }
     mid();
+    if (tid == 0) {
+      const Round Y = valid(X) ? next_round(X) : X;
+      sMail[0] = valid(X); sMail[1] = X.cnt;
+      sMail[2] = Y.r_lo; sMail[3] = (valid(X) && valid(Y)) ? Y.cnt : -1;
+    }
     umma::fence_proxy_async_smem();
     umma::fence_before_sync();
-    __syncthreads();  // [S2] operand tiles, staged node rows and next indices visible; landing zone free
+    sync_s2();  // [S2] operand tiles, staged node rows, next indices visible; landing zone free; issuer warp released
     mark(4);
   };
   // the 21 MMAs of a round into accumulator column `acc_col` (ONE thread; the tiles were staged by front())
-  auto issue_mma = [&](const Round& X, uint32_t acc_col) {
-    if (!valid(X) || X.cnt <= 0) return;
+  auto issue_mma = [&](uint32_t acc_col) {
     umma::fence_after_sync();
     const uint32_t step_a = 2 * kAChunkF, step_b = 2 * (uint32_t)kNP * 16;
     const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
@@ -228,7 +240,29 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
     }
     umma::mma_commit(&bar_mma);
   };
-  constexpr int kIssuer = kThreadsF - 32;  // lane 0 of the last warp: MMAs and bulk copies (see the loop)
+
+  // ---- the issuer warp: per staged round, the MMAs into the alternating accumulator and the bulk copy
+  // of the FOLLOWING round's edge rows (the landing zone is free once the split is done).  tcgen05.mma
+  // issue blocks for most of the MMAs' run time (~2.4k cycles per round measured), which is why this
+  // is not an epilogue warp's side job.
+  if (warp >= kWarpsF) {
+    // 640 threads leave 96 registers each at launch; this warpgroup hands most of its share to the
+    // epilogue warpgroups (512 x 120 + 128 x 32 = 64 K)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    for (uint32_t i = 0; warp == kWarpsF; ++i) {
+      sync_s2();
+      const int staged = sMail[0], xcnt = sMail[1], y_lo = sMail[2], ycnt = sMail[3];
+      if (!staged) break;
+      if (lane == 0) {
+        if (ycnt >= 0) issue_ea_bulk(y_lo, ycnt);  // first: the MMA issue below blocks for ~2k cycles
+        if (xcnt > 0) issue_mma((i & 1) * kNP);
+      }
+      __syncwarp();
+    }
+    __syncthreads();  // teardown barrier of the CTA
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 
   const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
   const int c_begin = part * 16;
@@ -239,31 +273,30 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
   int buf = 0;
   uint32_t it = 0;
   if (valid(cur)) {
-    if (tid == kIssuer) issue_ea_bulk(cur.r_lo, cur.cnt);
+    if (tid == 0) issue_ea_bulk(cur.r_lo, cur.cnt);
     if (tid < 2 * kRowsF) {
       const int e = tid & (kRowsF - 1);
       if (e < cur.cnt) sIdx[tid] = __ldg((tid < kRowsF ? p.dst_src : p.dst_dst) + cur.r_lo + e);
     }
     front(cur, [] {});
-    if (tid == kIssuer) {
-      issue_mma(cur, 0u);
-      if (valid(nxt)) issue_ea_bulk(nxt.r_lo, nxt.cnt);
-    }
+  } else {
+    if (tid == 0) sMail[0] = 0;
+    sync_s2();  // releases the issuer warp, which leaves
   }
 
   while (valid(cur)) {
     if (cur.k + 2 >= info_base + kInfoCapF && info_base + kInfoCapF < my_tiles) {  // table exhausted: refill
-      __syncthreads();
+      sync_consumers();
       info_base = cur.k;
       fill_infos(info_base);
-      __syncthreads();
+      sync_consumers();
     }
     const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
     const int n_lo = sInfo[cur.k - info_base].n_lo, n_hi = sInfo[cur.k - info_base].n_hi;
     const int* bSrc = sIdx + buf * 2 * kRowsF;
     const int* bDst = bSrc + kRowsF;
     mark(0);
-    __syncthreads();  // [S1] value tile free (last round's sums done); this round's indices visible
+    sync_consumers();  // [S1] value tile free (last round's sums done); this round's indices visible
     mark(1);
 
     // ---- indices of the next round: one coalesced load per thread (slots are consecutive)
@@ -300,12 +333,14 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
       else g = p.PQ + (size_t)bSrc[r] * (4 * kC) + 2 * kC;
       return reinterpret_cast<const float4*>(g);
     };
+    mark(13);
     float4 rr[kRowRegs];  // rows 0..63 stay in flight across the split; rows 64.. (rare) are copied in mid
 #pragma unroll
     for (int i = 0; i < kRowRegs; ++i) {
       const int c = tid + kThreadsF * i, r = c >> 5, col = c & 31;
       if (r < nrows) rr[i] = __ldg(row_src(r) + col);
     }
+    mark(14);
     // ---- reduce-stage node data of this warp's first segment
     const int n0 = n_lo + warp;
     int seg_a = 0, seg_b = 0;
@@ -349,9 +384,6 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
       umma::tmem_ld16(umma::tmem_addr(tmem, q, acc_col + kC + c_begin), sacc);
       umma::tmem_ld_wait();
     }
-    // The next round's MMAs go out only now: a warp's tcgen05.ld queues behind the MMAs the same warp
-    // issued, so the issuing warp reads its own accumulator slice first (measured: 2k cycles otherwise).
-    if (tid == kIssuer) issue_mma(nxt, ((it + 1) & 1) * kNP);
     mark(7);
     if (cnt > 0) {
       if (live) {
@@ -374,7 +406,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
     }
     mark(8);
     umma::fence_before_sync();  // accumulator reads done before a later round's MMAs overwrite it
-    __syncthreads();            // [S2d] every read of the staged node rows done: the value tile may be overwritten
+    sync_consumers();           // [S2d] every read of the staged node rows done: the value tile may be overwritten
     mark(9);
     // ---- epilogue, part 2: gate math, per-slot messages parked in the value tile
     if (live) {
@@ -388,16 +420,10 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_cgconv_fwd_pipe(const CgParams
       }
     }
     mark(10);
-    __syncthreads();  // [S3] value tile complete
+    sync_consumers();  // [S3] value tile complete
     mark(11);
 
     // ---- segmented sum over the owned segments that have slots in this round (slot order: deterministic)
-    // the last warp rarely owns a segment here (~10 per round): it starts the bulk copy of the edge
-    // rows after next (landing zone free since [S2]); a bulk copy costs its issuer ~500 cycles
-    if (tid == kIssuer) {
-      const Round nn = next_round(nxt);
-      if (valid(nxt) && valid(nn)) issue_ea_bulk(nn.r_lo, nn.cnt);
-    }
     for (int n = n0; n < n_hi; n += kWarpsF) {
       int a, b;
       if (n == n0) { a = seg_a; b = seg_b; }
@@ -439,7 +465,7 @@ int fwd_launch_t(const CgParams& p, const FwdPlan& pl, int grid, cudaStream_t st
     MDL_CUDA(cudaFuncSetAttribute(k_cgconv_fwd_pipe<PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     configured.store(1, std::memory_order_release);
   }
-  k_cgconv_fwd_pipe<PROFILE><<<grid, kThreadsF, pl.total, st>>>(p, pl);
+  k_cgconv_fwd_pipe<PROFILE><<<grid, kLaunchF, pl.total, st>>>(p, pl);
   MDL_LAUNCHED();
   return MDL_OK;
 }

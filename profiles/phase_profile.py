@@ -52,9 +52,10 @@ def bwd():
                                   1, P(ws), wsb, st), "bwd")
 
 
-PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 5: "idx/rows/seg loads issue", 6: "wait MMA(r)", 2: "wait ea(r+1)",
+PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue", 6: "wait MMA(r)", 2: "wait ea(r+1)",
               3: "split(r+1)", 4: "row+idx STS, fences, S2", 7: "MMA(r+1) + ea(r+2) issue", 8: "TMEM ld + node terms",
-              9: "S2d barrier", 10: "gate math", 11: "S3 barrier", 12: "reduce"}
+              9: "S2d barrier", 10: "gate math", 11: "S3 barrier", 12: "reduce",
+              20: "(issuer thread: MMA issue)", 21: "(issuer thread: ea bulk issue)"}
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if os.environ.get("ONLY", name) != name:
         continue
@@ -73,7 +74,7 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if v[25]:
         print(f"!! wait timed out: barrier id {v[26]} (1 ea, 2 node rows, 3 mma), CTA {v[27]}, round {v[28]}, "
               f"thread {v[29]}, parity {v[30]}")
-    tot = max(sum(v[:25]), 1)
+    tot = max(sum(v[:20]), 1)
     print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, {tot / rounds:.0f} cycles/round")
     for i, nm in NAMES_.items():  # in program order
         if v[i]:
