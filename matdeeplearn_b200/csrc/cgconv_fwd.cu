@@ -35,8 +35,10 @@ constexpr int kLaunchF = kThreadsF + 128;         // registers are re-balanced p
 constexpr int kRowsF = 128;                       // slots per round = MMA M
 constexpr int kTileSlots = 112;                   // ownership granularity (as cgconv_tc.cu)
 constexpr int kInfoCapF = 512;
-constexpr uint32_t kAChunkF = kRowsF * 16 + 16;   // k-chunk stride of the A tiles (padded, see cgconv_tc.cu)
-constexpr int kC = 64, kNP = 2 * kC, kVW = 2 * kC + 4;
+constexpr int kC = 64, kNP = 2 * kC;
+constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tile ([f | s] rows + 16 B: bank spread)
+constexpr int kVP = kC + 4;                       // row stride of the per-slot message tile
+constexpr int kTmemCols = 512;                    // 2 accumulators (2 x 128) + A operand hi / lo (2 x KP <= 256)
 constexpr int kRowRegs = 4;                       // 16-byte node-row chunks a thread keeps in flight across the split (64 rows)
 
 unsigned long long* g_fwd_phase_buf = nullptr;
@@ -44,20 +46,22 @@ unsigned long long* g_fwd_phase_buf = nullptr;
 struct FwdPlan {
   unsigned long long* prof;
   int window, KP;
-  uint32_t offBhi, offBlo, offAhi, offAlo, offEA, offV, offIdx, offInfo, total;
+  uint32_t offBhi, offBlo, offEA, offW, offV, offIdx, offInfo, total;
 };
 
 bool fwd_plan(int C, int G, FwdPlan* pl) {
   if (C != kC || G < 1) return false;
   const int KP = (G + 7) & ~7;
-  const uint32_t b = (uint32_t)kNP * KP * 4, a = (uint32_t)(KP / 4) * kAChunkF;
+  if (2 * kNP + 2 * KP > kTmemCols) return false;
+  const uint32_t b = (uint32_t)kNP * KP * 4;
   const uint32_t ea = (((uint32_t)kRowsF * G * 4 + 32) + 15u) & ~15u;  // dense rows + alignment slack of the bulk copy
-  const uint32_t v = (uint32_t)kRowsF * kVW * 4, idx = 4 * kRowsF * 4, info = kInfoCapF * 16;
+  const uint32_t w = (uint32_t)kRowsF * kVW * 4, v = (uint32_t)kRowsF * kVP * 4;
+  const uint32_t idx = 4 * kRowsF * 4, info = kInfoCapF * 16;
   pl->prof = g_fwd_phase_buf;
   pl->window = 1;
   pl->KP = KP;
-  pl->offBhi = 0; pl->offBlo = b; pl->offAhi = 2 * b; pl->offAlo = 2 * b + a; pl->offEA = 2 * b + 2 * a;
-  pl->offV = pl->offEA + ea; pl->offIdx = pl->offV + v; pl->offInfo = pl->offIdx + idx;
+  pl->offBhi = 0; pl->offBlo = b; pl->offEA = 2 * b;
+  pl->offW = pl->offEA + ea; pl->offV = pl->offW + w; pl->offIdx = pl->offV + v; pl->offInfo = pl->offIdx + idx;
   pl->total = pl->offInfo + info;
   return pl->total <= (uint32_t)kMaxDynSmem;
 }
@@ -84,10 +88,9 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
 
   uint8_t* sBhi = smem + pl.offBhi;
   uint8_t* sBlo = smem + pl.offBlo;
-  uint8_t* sAhi = smem + pl.offAhi;
-  uint8_t* sAlo = smem + pl.offAlo;
   float* sEA = reinterpret_cast<float*>(smem + pl.offEA);  // dense [cnt][G] block at a 0..12 byte offset
-  float* sV = reinterpret_cast<float*>(smem + pl.offV);    // [128][VW]: node rows, then per-slot values
+  float* sW = reinterpret_cast<float*>(smem + pl.offW);    // [128][VW]: staged node rows (window or per slot)
+  float* sV = reinterpret_cast<float*>(smem + pl.offV);    // [128][VP]: per-slot messages
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);    // [2 buffers][src | dst][128]
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);
 
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
   auto next_round = [&](const Round& R) -> Round { return R.last ? make_round(R.k + 1, 0) : make_round(R.k, R.rd + 1); };
 
   // ---- one-time setup: TMEM (two accumulators), barriers, tile table, resident W_e split hi/lo
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 2 * kNP);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
   if (tid == 32) {
     umma::mbar_init(&bar_mma, 1);
     umma::mbar_init(&bar_ea, 1);
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc = umma::make_idesc_tf32(kRowsF, kNP);
+  const uint32_t tmA_hi = tmem + 2 * kNP, tmA_lo = tmA_hi + (uint32_t)KP;  // A operand (edge rows) in tensor memory
   uint32_t ph_mma = 0, ph_ea = 0;
 
   // ---- edge rows of a round: one bulk copy from the 16-byte boundary below the block (see cgconv_tc.cu)
@@ -182,31 +186,36 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
         ph_ea ^= 1;
       }
       mark(2);
+      // thread = slot = TMEM lane (quadrant warp & 3); the four warps of a quadrant share the row's
+      // 8-column chunks.  The split halves go straight to tensor memory (A operand of the MMAs): no
+      // operand tiles in shared memory, and the MMAs read half as much of it.
       const int e = tid & (kRowsF - 1);
-      const uint32_t row_off = (uint32_t)(e >> 3) * 128 + (uint32_t)(e & 7) * 16;
-      for (int j = (tid >> 7); j < (KP >> 2); j += kThreadsF / kRowsF) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < X.cnt && 4 * j < G) {  // dense rows (stride G) at a 4- or 8-byte offset: 8-byte loads for even G
-          const float* r = sEA + ea_off + e * G + 4 * j;
-          if ((G & 1) == 0) {
-            const float2 a = *reinterpret_cast<const float2*>(r);
-            v.x = a.x; v.y = a.y;
-            if (4 * j + 2 < G) { const float2 b2 = *reinterpret_cast<const float2*>(r + 2); v.z = b2.x; v.w = b2.y; }
+      const float* row = sEA + ea_off + e * G;
+      for (int ch = (tid >> 7); ch < (KP >> 3); ch += kThreadsF / kRowsF) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+        if (e < X.cnt) {
+          if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
+#pragma unroll
+            for (int t = 0; t < 8; t += 2)
+              if (8 * ch + t < G) {
+                const float2 a = *reinterpret_cast<const float2*>(row + 8 * ch + t);
+                v[t] = a.x; v[t + 1] = a.y;
+              }
           } else {
-            v.x = r[0];
-            if (4 * j + 1 < G) v.y = r[1];
-            if (4 * j + 2 < G) v.z = r[2];
-            if (4 * j + 3 < G) v.w = r[3];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              if (8 * ch + t < G) v[t] = row[8 * ch + t];
           }
         }
-        float4 hi;
-        hi.x = umma::tf32_hi(v.x); hi.y = umma::tf32_hi(v.y);
-        hi.z = umma::tf32_hi(v.z); hi.w = umma::tf32_hi(v.w);
-        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        const uint32_t off = (uint32_t)j * kAChunkF + row_off;
-        *reinterpret_cast<float4*>(sAhi + off) = hi;
-        *reinterpret_cast<float4*>(sAlo + off) = lo;
+        float hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+        umma::tmem_st8(umma::tmem_addr(tmA_hi, warp, 8 * ch), hi);
+        umma::tmem_st8(umma::tmem_addr(tmA_lo, warp, 8 * ch), lo);
       }
+      umma::tmem_st_wait();
       mark(3);
     }
     mid();
@@ -223,18 +232,16 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
   // the 21 MMAs of a round into accumulator column `acc_col` (ONE thread; the tiles were staged by front())
   auto issue_mma = [&](uint32_t acc_col) {
     umma::fence_after_sync();
-    const uint32_t step_a = 2 * kAChunkF, step_b = 2 * (uint32_t)kNP * 16;
-    const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo);
+    const uint32_t step_b = 2 * (uint32_t)kNP * 16;
     const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
     uint32_t acc = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t a = (pass == 2) ? a_lo : a_hi;
+      const uint32_t a = (pass == 2) ? tmA_lo : tmA_hi;
       const uint32_t b = (pass == 1) ? b_lo : b_hi;
       for (int kk = 0; kk < (KP >> 3); ++kk) {
-        const uint64_t ad = umma::make_desc(a + kk * step_a, kAChunkF, 128);
         const uint64_t bd = umma::make_desc(b + kk * step_b, (uint32_t)kNP * 16, 128);
-        umma::mma_tf32(tmem + acc_col, ad, bd, idesc, acc);
+        umma::mma_tf32_ts(tmem + acc_col, a + kk * 8, bd, idesc, acc);
         acc = 1;
       }
     }
@@ -366,61 +373,54 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
 #pragma unroll
       for (int i = 0; i < kRowRegs; ++i) {
         const int c = tid + kThreadsF * i, r = c >> 5, col = c & 31;
-        if (r < nrows) *(reinterpret_cast<float4*>(sV + r * kVW) + col) = rr[i];
+        if (r < nrows) *(reinterpret_cast<float4*>(sW + r * kVW) + col) = rr[i];
       }
       for (int c = tid + kThreadsF * kRowRegs; c < nrows * 32; c += kThreadsF)
-        *(reinterpret_cast<float4*>(sV + (c >> 5) * kVW) + (c & 31)) = __ldg(row_src(c >> 5) + (c & 31));
+        *(reinterpret_cast<float4*>(sW + (c >> 5) * kVW) + (c & 31)) = __ldg(row_src(c >> 5) + (c & 31));
       if (valid(nxt) && tid < 2 * kRowsF) sIdx[(buf ^ 1) * 2 * kRowsF + tid] = nidx;
     };
     front(nxt, mid);
 
-    // ---- epilogue, part 1: thread = slot (TMEM lane); a = accumulator + P[dst] + Q[src]
-    float f[16], sacc[16];
+    // ---- epilogue: thread = slot (TMEM lane), 16 channels; a = accumulator + P[dst] + Q[src] (node rows
+    // from the staged tile), gates, message parked in the message tile.  Row reads (LDS pipe) and gate
+    // math (MUFU pipe) of different warps overlap: one phase, no barrier in between.
     const int e_ep = 32 * q + lane;
     const bool live = e_ep < cnt;
     if (cnt > 0) {
+      float f[16], sacc[16];
       const uint32_t acc_col = (it & 1) * kNP;
       umma::tmem_ld16(umma::tmem_addr(tmem, q, acc_col + c_begin), f);
       umma::tmem_ld16(umma::tmem_addr(tmem, q, acc_col + kC + c_begin), sacc);
       umma::tmem_ld_wait();
-    }
-    mark(7);
-    if (cnt > 0) {
+      mark(7);
       if (live) {
         const int sd = bDst[e_ep], ss = bSrc[e_ep];
-        auto add_rows = [&](const float* r0, const float* r1) {  // a += r0[.] + r1[.]   ([f | s] rows)
+        const float* r0 = win ? sW + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
+        const float* r1 = win ? sW + (ss - w_smin) * kVW + c_begin : sW + e_ep * kVW + c_begin;
+        float* rowv = sV + e_ep * kVP + c_begin;
+        auto run = [&](auto ld0) {  // ld0: how the P row is read (shared or global memory)
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 pf = *reinterpret_cast<const float4*>(r0 + j4);
-            const float4 ps = *reinterpret_cast<const float4*>(r0 + kC + j4);
+            const float4 pf = ld0(r0 + j4), ps = ld0(r0 + kC + j4);
             const float4 qf = *reinterpret_cast<const float4*>(r1 + j4);
             const float4 qs = *reinterpret_cast<const float4*>(r1 + kC + j4);
-            f[j4] += pf.x + qf.x; f[j4 + 1] += pf.y + qf.y; f[j4 + 2] += pf.z + qf.z; f[j4 + 3] += pf.w + qf.w;
-            sacc[j4] += ps.x + qs.x; sacc[j4 + 1] += ps.y + qs.y;
-            sacc[j4 + 2] += ps.z + qs.z; sacc[j4 + 3] += ps.w + qs.w;
+            const float af[4] = {f[j4] + (pf.x + qf.x), f[j4 + 1] + (pf.y + qf.y), f[j4 + 2] + (pf.z + qf.z),
+                                 f[j4 + 3] + (pf.w + qf.w)};
+            const float as[4] = {sacc[j4] + (ps.x + qs.x), sacc[j4 + 1] + (ps.y + qs.y), sacc[j4 + 2] + (ps.z + qs.z),
+                                 sacc[j4 + 3] + (ps.w + qs.w)};
+            float m[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m[j] = sigmoid_mixed(af[j]) * softplus_mufu(as[j]);
+            *reinterpret_cast<float4*>(rowv + j4) = make_float4(m[0], m[1], m[2], m[3]);
           }
         };
-        if (win) add_rows(sV + (w_nq + sd - w_dmin) * kVW + c_begin, sV + (ss - w_smin) * kVW + c_begin);
-        else add_rows(p.PQ + (size_t)sd * (4 * kC) + c_begin, sV + e_ep * kVW + c_begin);
-      }
-    }
-    mark(8);
-    umma::fence_before_sync();  // accumulator reads done before a later round's MMAs overwrite it
-    sync_consumers();           // [S2d] every read of the staged node rows done: the value tile may be overwritten
-    mark(9);
-    // ---- epilogue, part 2: gate math, per-slot messages parked in the value tile
-    if (live) {
-      float* rowv = sV + e_ep * kVW + c_begin;
-#pragma unroll
-      for (int j4 = 0; j4 < 16; j4 += 4) {
-        float m[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = sigmoid_mixed(f[j4 + j]) * softplus_mufu(sacc[j4 + j]);
-        *reinterpret_cast<float4*>(rowv + j4) = make_float4(m[0], m[1], m[2], m[3]);
+        if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
+        else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
       }
     }
     mark(10);
-    sync_consumers();  // [S3] value tile complete
+    umma::fence_before_sync();  // accumulator reads done before a later round's MMAs overwrite it
+    sync_consumers();           // [S3] message tile complete
     mark(11);
 
     // ---- segmented sum over the owned segments that have slots in this round (slot order: deterministic)
@@ -442,8 +442,8 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
       }
       float acc0 = first ? 0.0f : o[lane], acc1 = first ? 0.0f : o[32 + lane];
       for (int s = lo; s < hi; ++s) {
-        acc0 += sV[(s - r_lo) * kVW + lane];
-        acc1 += sV[(s - r_lo) * kVW + 32 + lane];
+        acc0 += sV[(s - r_lo) * kVP + lane];
+        acc1 += sV[(s - r_lo) * kVP + 32 + lane];
       }
       o[lane] = lastp ? fmaf(acc0, sc, x0) : acc0;
       o[32 + lane] = lastp ? fmaf(acc1, sc, x1) : acc1;
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
 
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 2 * kNP);
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
 template <int PROFILE>

@@ -52,10 +52,9 @@ def bwd():
                                   1, P(ws), wsb, st), "bwd")
 
 
-PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue", 6: "wait MMA(r)", 2: "wait ea(r+1)",
-              3: "split(r+1)", 4: "row+idx STS, fences, S2", 7: "MMA(r+1) + ea(r+2) issue", 8: "TMEM ld + node terms",
-              9: "S2d barrier", 10: "gate math", 11: "S3 barrier", 12: "reduce",
-              20: "(issuer thread: MMA issue)", 21: "(issuer thread: ea bulk issue)"}
+PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue",
+              6: "wait MMA(r)", 2: "wait ea(r+1)", 3: "split(r+1) -> TMEM", 4: "row+idx STS, fences, S2",
+              7: "TMEM ld", 10: "node terms + gate math", 11: "S3 barrier", 12: "reduce"}
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if os.environ.get("ONLY", name) != name:
         continue
