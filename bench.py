@@ -388,7 +388,9 @@ def run_engine(args, rank, world, local_rank):
             line["roofline"] = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
                                 "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
                                 "kernel": "k_cgconv_tc<BWD_DST> (whole CGConv backward: single pass, dP + dWe + dQ)"
-                                if is_bwd else "k_cgconv_tc<FWD>",
+                                if is_bwd else "k_cgconv_fwd_pipe",
+                                "note": "dominant = the slower of the two fused edge kernels; roofline_detail.fwd is the "
+                                        "fused gather->message->scatter_add forward kernel (k_cgconv_fwd_pipe)",
                                 "peak_source": peak_src, "workload": r["workload"]}
             line["roofline_detail"] = r
         if not args.no_cpu_baseline and world == 1:

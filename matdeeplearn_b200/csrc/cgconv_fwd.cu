@@ -351,13 +351,13 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
     // ---- reduce-stage node data of this warp's first segment
     const int n0 = n_lo + warp;
     int seg_a = 0, seg_b = 0;
-    float seg_sc = 1.0f, seg_x0 = 0.0f, seg_x1 = 0.0f;
+    float seg_sc = 1.0f;
+    float2 seg_x = make_float2(0.0f, 0.0f);  // lane l owns channels 2l, 2l+1
     if (n0 < n_hi) {
       seg_a = __ldg(p.seg_ptr + n0);
       seg_b = __ldg(p.seg_ptr + n0 + 1);
       if (p.inv_deg) seg_sc = __ldg(p.inv_deg + n0);
-      seg_x0 = __ldg(p.x + (size_t)n0 * kC + lane);
-      seg_x1 = __ldg(p.x + (size_t)n0 * kC + 32 + lane);
+      seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
     }
     mark(5);
 
@@ -433,20 +433,19 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
       if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
       const bool first = empty_seg || (a >= r_lo);
       const bool lastp = empty_seg || (b <= r_hi);
-      float* o = p.out + (size_t)n * kC;
-      float sc = seg_sc, x0 = seg_x0, x1 = seg_x1;
+      float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
+      float sc = seg_sc;
+      float2 x = seg_x;
       if (n != n0) {
         sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
-        x0 = __ldg(p.x + (size_t)n * kC + lane);
-        x1 = __ldg(p.x + (size_t)n * kC + 32 + lane);
+        x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
       }
-      float acc0 = first ? 0.0f : o[lane], acc1 = first ? 0.0f : o[32 + lane];
+      float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
       for (int s = lo; s < hi; ++s) {
-        acc0 += sV[(s - r_lo) * kVP + lane];
-        acc1 += sV[(s - r_lo) * kVP + 32 + lane];
+        const float2 v = *(reinterpret_cast<const float2*>(sV + (s - r_lo) * kVP) + lane);
+        acc.x += v.x; acc.y += v.y;
       }
-      o[lane] = lastp ? fmaf(acc0, sc, x0) : acc0;
-      o[32 + lane] = lastp ? fmaf(acc1, sc, x1) : acc1;
+      *o = lastp ? make_float2(fmaf(acc.x, sc, x.x), fmaf(acc.y, sc, x.y)) : acc;
     }
     mark(12);
     if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
@@ -479,7 +478,8 @@ void cgfwd_set_phase_buffer(unsigned long long* dev_ptr) { g_fwd_phase_buf = dev
 bool cgfwd_supported(const CgParams& p) {
   FwdPlan pl;
   return fwd_plan(p.C, p.G, &pl) && (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 &&
-         (reinterpret_cast<uintptr_t>(p.PQ) & 15) == 0;
+         (reinterpret_cast<uintptr_t>(p.PQ) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.out) & 7) == 0 && (int64_t)p.N * 4 * p.C < (int64_t)1 << 31;
 }
 
 int cgfwd_launch(CgParams p, cudaStream_t st) {

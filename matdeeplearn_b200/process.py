@@ -106,8 +106,11 @@ def assemble_dataset(structures, targets, radius=DEFAULT_RADIUS, neighbors=DEFAU
                            u=torch.zeros(1, 3), y=torch.tensor(float(y), dtype=torch.float32)))
     lo = min(float(g.edge_weight.min()) for g in graphs)
     hi = max(float(g.edge_weight.max()) for g in graphs)
+    # tensor / tensor: an IEEE division on every backend (tensor / python-scalar becomes a multiplication
+    # by the reciprocal in some of torch's kernels, e.g. on CUDA, which is 1 ulp off for some elements)
+    span = torch.tensor(hi - lo, dtype=torch.float32)
     for g in graphs:
-        g.d_hat = (g.edge_weight - lo) / (hi - lo)
+        g.d_hat = (g.edge_weight - lo) / span
         g.edge_attr = gaussian_expand(g.d_hat, edge_length)
     ds = GraphDataset(graphs)
     ds.edge_range = (lo, hi)

@@ -168,7 +168,8 @@ class GraphStore:
         _lib.check(rc, "mdl_build_emit")
         lo, hi = float(self.edge_weight.min()), float(self.edge_weight.max())      # dataset-global range
         self.edge_range = (lo, hi)
-        self.d_hat = ((self.edge_weight - lo) / (hi - lo)).contiguous()
+        # tensor / tensor = IEEE division, bit-identical to the host builder (process.assemble_dataset)
+        self.d_hat = ((self.edge_weight - lo) / torch.tensor(hi - lo, **f32)).contiguous()
         self.edge_attr = None
         self.u = torch.zeros((self.num_graphs, 3), **f32)
         self.y = torch.as_tensor(np.asarray(targets, dtype=np.float32).reshape(-1)).to(device)
