@@ -161,11 +161,14 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
     const int off = (int)(first & 3);
     const float* src = p.ea + (first - off);
     const uint32_t bytes = (uint32_t)((off + cnt * G) * 4), nb = ea_bulk_bytes(r_lo, cnt);
+    (void)bytes;
     if (nb) {
       umma::mbar_arrive_expect_tx(&bar_ea, nb);
       umma::bulk_g2s(sEA, src, nb, &bar_ea);
     }
-    for (uint32_t t = nb / 4; t < bytes / 4; ++t) sEA[t] = __ldg(src + t);  // the last floats of ea
+    // The last block of ea is copied rounded DOWN to 16 bytes; its last (<= 3) floats are read from
+    // global memory by the split itself (front()).  Storing them here would race with the split: the
+    // mbarrier only orders the bulk copy's bytes, and no barrier joins this thread and the readers.
   };
 
   long long t_prev = PROFILE ? clock64() : 0;
@@ -191,6 +194,9 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
       // operand tiles in shared memory, and the MMAs read half as much of it.
       const int e = tid & (kRowsF - 1);
       const float* row = sEA + ea_off + e * G;
+      // first float (index into the landing zone) the bulk copy did NOT deliver: only in the last block of ea
+      const int landed = (int)(ea_bulk_bytes(X.r_lo, X.cnt) >> 2);
+      const bool patch = e < X.cnt && landed < ea_off + (e + 1) * G;  // this row reaches past the delivered part
       for (int ch = (tid >> 7); ch < (KP >> 3); ch += kThreadsF / kRowsF) {
         float v[8];
 #pragma unroll
@@ -207,6 +213,13 @@ __global__ void __launch_bounds__(kLaunchF, 1) k_cgconv_fwd_pipe(const CgParams 
 #pragma unroll
             for (int t = 0; t < 8; ++t)
               if (8 * ch + t < G) v[t] = row[8 * ch + t];
+          }
+        }
+        if (patch) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int k = 8 * ch + t;
+            if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)X.r_lo + e) * G + k);
           }
         }
         float hi[8], lo[8];

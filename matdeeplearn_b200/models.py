@@ -112,6 +112,30 @@ class CGCNN(_ConvStackModel):
         return self._readout(h, data)
 
 
+class GCN(_ConvStackModel):
+    """reference matdeeplearn/models/gcn.py:17-178 (conv -> BN -> act -> dropout, gcn.py:139-152)"""
+
+    def __init__(self, data, dim1=64, dim2=64, pre_fc_count=1, gc_count=3, post_fc_count=1,
+                 pool="global_mean_pool", pool_order="early", batch_norm="True",
+                 batch_track_stats="True", act="relu", dropout_rate=0.0, **kwargs):
+        super().__init__(data, dim1, dim2, pre_fc_count, gc_count, post_fc_count, pool,
+                         pool_order, batch_norm, batch_track_stats, act, dropout_rate)
+        for _ in range(gc_count):
+            self.conv_list.append(mnn.GCNConv(self.gc_dim, self.gc_dim, improved=True, add_self_loops=False))
+            self._add_bn()
+
+    def forward(self, data):
+        csr = _prepare(data)
+        h = self._embed(data)
+        for i, conv in enumerate(self.conv_list):
+            h = conv(h, data.edge_index, data.edge_weight, csr=csr)
+            if self.batch_norm == "True":
+                h = self._bn(i, h, data)
+            h = self._activation(h)
+            h = F.dropout(h, p=self.dropout_rate, training=self.training)
+        return self._readout(h, data)
+
+
 class SchNet(_ConvStackModel):
     """reference matdeeplearn/models/schnet.py:16-172"""
 

@@ -134,6 +134,41 @@ class CGConv(nn.Module):
 # ----------------------------------------------------------------------------
 # SchNet interaction (torch_geometric.nn.models.schnet.InteractionBlock / CFConv)
 # ----------------------------------------------------------------------------
+class GCNConv(nn.Module):
+    """PyG GCNConv in the one configuration the reference builds (gcn.py:80-82:
+    improved=True, add_self_loops=False; called with the raw distances as edge_weight):
+    x' = D^-1/2 A D^-1/2 (x W^T) + b.  Same parameter names as PyG 2.0.1 (`lin.weight`, `bias`).
+    The degree and the weighted neighbour sum run on the CSR kernels (segment sum, mdl_spmm_edge);
+    the per-edge coefficient is expanded to the row width for the latter (first version: [E,F])."""
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, add_self_loops=True,
+                 normalize=True, bias=True):
+        super().__init__()
+        if add_self_loops or not normalize or cached:
+            raise NotImplementedError("GCNConv: only add_self_loops=False, normalize=True, cached=False "
+                                      "(reference gcn.py:80-82)")
+        self.in_channels, self.out_channels, self.improved = in_channels, out_channels, improved
+        self.lin = nn.Linear(in_channels, out_channels, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        nn.init.xavier_uniform_(self.lin.weight)
+
+    def forward(self, x, edge_index, edge_weight=None, csr: GraphCSR | None = None):
+        _require_cuda(x, "GCNConv")
+        n = x.shape[0]
+        if csr is None:
+            csr = csr_for(edge_index, num_nodes=n)
+        row, col = edge_index[0], edge_index[1]
+        if edge_weight is None:
+            edge_weight = torch.ones(row.numel(), dtype=x.dtype, device=x.device)
+        deg = scatter(edge_weight.view(-1, 1), col, 0, n, "sum").view(-1)
+        dinv = deg.pow(-0.5)
+        dinv = dinv.masked_fill(dinv == float("inf"), 0.0)
+        norm = dinv.index_select(0, row) * edge_weight * dinv.index_select(0, col)
+        h = self.lin(x)
+        out = MF.cfconv_aggregate(h, norm.view(-1, 1).expand(-1, h.shape[1]).contiguous(), csr)
+        return out + self.bias if self.bias is not None else out
+
+
 class ShiftedSoftplus(nn.Module):
     def __init__(self):
         super().__init__()

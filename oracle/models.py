@@ -9,6 +9,7 @@ CUDA-backed models in matdeeplearn_b200.models.
   SchNet  reference matdeeplearn/models/schnet.py:16-172
   MPNN    reference matdeeplearn/models/mpnn.py:17-188
   MEGNet  reference matdeeplearn/models/megnet.py:16-371
+  GCN     reference matdeeplearn/models/gcn.py:17-178
 Set2Set pooling is out of scope.
 """
 import torch
@@ -84,6 +85,30 @@ class CGCNN(_Skeleton):
             out = conv(out, data.edge_index, data.edge_attr)
             if self.batch_norm == "True":
                 out = self.bn_list[i](out)
+            out = F.dropout(out, p=self.dropout_rate, training=self.training)
+        return self._post(out, data)
+
+
+class GCN(_Skeleton):
+    """reference gcn.py: conv(out, edge_index, edge_weight) -> BN -> act -> dropout (gcn.py:139-152)"""
+
+    def __init__(self, data, dim1=64, dim2=64, pre_fc_count=1, gc_count=3, post_fc_count=1,
+                 pool="global_mean_pool", pool_order="early", batch_norm="True",
+                 batch_track_stats="True", act="relu", dropout_rate=0.0, **kwargs):
+        super().__init__(data, dim1, dim2, pre_fc_count, gc_count, post_fc_count, pool,
+                         pool_order, batch_norm, batch_track_stats, act, dropout_rate)
+        self.conv_list = nn.ModuleList(
+            [P.GCNConv(self.gc_dim, self.gc_dim, improved=True, add_self_loops=False) for _ in range(gc_count)])
+        self.bn_list = nn.ModuleList(
+            [self._bn() for _ in range(gc_count)] if batch_norm == "True" else [])
+
+    def forward(self, data):
+        out = self._pre(data)
+        for i, conv in enumerate(self.conv_list):
+            out = conv(out, data.edge_index, data.edge_weight)
+            if self.batch_norm == "True":
+                out = self.bn_list[i](out)
+            out = getattr(F, self.act)(out)
             out = F.dropout(out, p=self.dropout_rate, training=self.training)
         return self._post(out, data)
 

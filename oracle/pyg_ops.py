@@ -107,6 +107,38 @@ class CGConv(nn.Module):
 
 
 # ----------------------------------------------------------------------------
+# GCNConv  (constructed at reference matdeeplearn/models/gcn.py:80-82 as
+# GCNConv(gc_dim, gc_dim, improved=True, add_self_loops=False); called gcn.py:141-150
+# with (x, edge_index, edge_weight) -- edge_weight is the RAW distance, 0 on the loops)
+# ----------------------------------------------------------------------------
+class GCNConv(nn.Module):
+    """x' = D^-1/2 A D^-1/2 (x W^T) + b with A_ij = edge_weight, D_i = sum_{j->i} edge_weight
+    (PyG 2.0.1 GCNConv + gcn_norm; without added self-loops `improved` changes nothing)."""
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, add_self_loops=True,
+                 normalize=True, bias=True):
+        super().__init__()
+        assert not add_self_loops and normalize and not cached, "only the reference's configuration is restated"
+        self.in_channels, self.out_channels, self.improved = in_channels, out_channels, improved
+        self.lin = nn.Linear(in_channels, out_channels, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        nn.init.xavier_uniform_(self.lin.weight)  # PyG: glorot weight, zero bias
+
+    def forward(self, x, edge_index, edge_weight=None):
+        row, col = edge_index[0], edge_index[1]
+        n = x.size(0)
+        if edge_weight is None:
+            edge_weight = torch.ones(row.numel(), dtype=x.dtype, device=x.device)
+        deg = scatter(edge_weight, col, 0, n, "sum")
+        dinv = deg.pow(-0.5)
+        dinv = dinv.masked_fill(dinv == float("inf"), 0.0)
+        norm = dinv.index_select(0, row) * edge_weight * dinv.index_select(0, col)
+        h = self.lin(x)
+        out = scatter(norm.view(-1, 1) * h.index_select(0, row), col, 0, n, "sum")
+        return out + self.bias if self.bias is not None else out
+
+
+# ----------------------------------------------------------------------------
 # SchNet InteractionBlock / CFConv  (constructed at reference
 # matdeeplearn/models/schnet.py:81; called schnet.py:134-143 with
 # (x, edge_index, edge_weight, edge_attr))

@@ -10,7 +10,7 @@ one with importlib:
     OneHotDegree, NormalizeEdge run AS-IS.  The three PyG utilities they call
     (dense_to_sparse, degree, add_self_loops) are stubbed with their documented
     semantics (nonzero scan / bincount / append loops).
-  * matdeeplearn/models/{cgcnn,schnet,mpnn,megnet}.py -> the model glue (pre/post
+  * matdeeplearn/models/{cgcnn,schnet,mpnn,megnet,gcn}.py -> the model glue (pre/post
     FC, BN placement, residuals, GRU threading, MEGNet wiring) runs AS-IS, with
     torch_geometric.nn.{CGConv,NNConv,MetaLayer,global_*_pool},
     InteractionBlock and torch_scatter.scatter* bound to oracle/pyg_ops.py.
@@ -74,7 +74,7 @@ def install_stubs():
     tg.transforms = _module("torch_geometric.transforms")
     tg.nn = _module("torch_geometric.nn", Set2Set=_Dummy, global_mean_pool=O.global_mean_pool,
                     global_add_pool=O.global_add_pool, global_max_pool=O.global_max_pool,
-                    CGConv=O.CGConv, NNConv=O.NNConv, MetaLayer=O.MetaLayer, GCNConv=_Dummy)
+                    CGConv=O.CGConv, NNConv=O.NNConv, MetaLayer=O.MetaLayer, GCNConv=O.GCNConv)
     tg.nn.models = _module("torch_geometric.nn.models")
     tg.nn.models.schnet = _module("torch_geometric.nn.models.schnet", InteractionBlock=O.InteractionBlock)
     _module("torch_scatter", scatter=O.scatter, scatter_mean=O.scatter_mean, scatter_add=O.scatter_add,
@@ -143,20 +143,26 @@ MODEL_CFGS = {
                             post_fc_count=1, batch_norm="False", pool="global_max_pool"),
     "MEGNet_fc1": dict(dim1=32, dim2=24, dim3=28, pre_fc_count=1, gc_count=2, gc_fc_count=1,
                        post_fc_count=1),
+    "GCN": dict(dim1=32, dim2=24, pre_fc_count=1, gc_count=3, post_fc_count=2),
+    "GCN_nobn_late": dict(dim1=32, dim2=24, pre_fc_count=1, gc_count=2, post_fc_count=1, batch_norm="False",
+                          pool="global_add_pool", pool_order="late"),
 }
 
 
-def golden_models():
+def golden_models(only=None):
     ds = pr.synthetic_dataset("bulk", 6, seed=5, edge_length=50)
     batch = ds.batch()
-    np.savez_compressed(os.path.join(OUT, "batch_inputs.npz"),
-                        x=batch.x.numpy(), edge_index=batch.edge_index.numpy(),
-                        edge_attr=batch.edge_attr.numpy(), edge_weight=batch.edge_weight.numpy(),
-                        batch=batch.batch.numpy(), u=batch.u.numpy(), y=batch.y.numpy())
-    mods = {n: load_ref(f"models/{n}.py", f"ref_{n}") for n in ("cgcnn", "schnet", "mpnn", "megnet")}
+    if only is None:
+        np.savez_compressed(os.path.join(OUT, "batch_inputs.npz"),
+                            x=batch.x.numpy(), edge_index=batch.edge_index.numpy(),
+                            edge_attr=batch.edge_attr.numpy(), edge_weight=batch.edge_weight.numpy(),
+                            batch=batch.batch.numpy(), u=batch.u.numpy(), y=batch.y.numpy())
+    mods = {n: load_ref(f"models/{n}.py", f"ref_{n}") for n in ("cgcnn", "schnet", "mpnn", "megnet", "gcn")}
     classes = {"CGCNN": mods["cgcnn"].CGCNN, "SchNet": mods["schnet"].SchNet,
-               "MPNN": mods["mpnn"].MPNN, "MEGNet": mods["megnet"].MEGNet}
+               "MPNN": mods["mpnn"].MPNN, "MEGNet": mods["megnet"].MEGNet, "GCN": mods["gcn"].GCN}
     for tag, cfg in MODEL_CFGS.items():
+        if only is not None and tag.split("_")[0] not in only:
+            continue
         cls = classes[tag.split("_")[0]]
         torch.manual_seed(1234)
         model = cls(data=ds, **cfg).double()
@@ -206,7 +212,10 @@ def golden_test_data():
 
 if __name__ == "__main__":
     install_stubs()
-    P = load_ref("process/process.py", "ref_process")
-    golden_process(P)
-    golden_models()
-    golden_test_data()
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":  # e.g. --only GCN : add fixtures of one model family
+        golden_models(only=set(sys.argv[2:]))
+    else:
+        P = load_ref("process/process.py", "ref_process")
+        golden_process(P)
+        golden_models()
+        golden_test_data()

@@ -110,6 +110,39 @@ def test_interaction_block_matches_oracle():
         assert_close(pg.grad, pr.grad, rtol=1e-4, atol_rel=2e-5, what=f"InteractionBlock d{name}")
 
 
+@pytest.mark.parametrize("n,e,iso", [(300, 3000, 0), (200, 900, 6)])
+def test_gcnconv_matches_oracle(n, e, iso):
+    """GCNConv(improved=True, add_self_loops=False) with distance-like edge weights, zero on the loops
+    (reference gcn.py:80-82, 141); isolated nodes have degree 0 -> coefficient 0, output = bias."""
+    import matdeeplearn_b200.nn as mnn
+    from oracle import pyg_ops as O
+    torch.manual_seed(2)
+    ei = random_graph(n, e, 7, None, iso)
+    E = ei.shape[1]
+    x = torch.randn(n, 48, dtype=torch.float64)
+    ew = torch.rand(E, dtype=torch.float64) * 8.0
+    ew[ei[0] == ei[1]] = 0.0
+    ref_m = O.GCNConv(48, 48, improved=True, add_self_loops=False).double()
+    with torch.no_grad():
+        ref_m.bias.uniform_(-0.5, 0.5)
+    m = mnn.GCNConv(48, 48, improved=True, add_self_loops=False)
+    m.load_state_dict({k: v.float() for k, v in ref_m.state_dict().items()})
+    m = m.to(DEV)
+    xr = x.clone().requires_grad_(True)
+    ref = ref_m(xr, ei, ew)
+    xg = x.float().to(DEV).requires_grad_(True)
+    got = m(xg, ei.to(DEV), ew.float().to(DEV))
+    _log("GCNConv fwd", got, ref)
+    assert_close(got, ref, rtol=1e-5, atol_rel=5e-6, what="GCNConv fwd")
+    w = torch.randn_like(ref)
+    ref.backward(w)
+    got.backward(w.float().to(DEV))
+    assert_close(xg.grad, xr.grad, rtol=1e-4, atol_rel=2e-5, what="GCNConv dx")
+    for name, pr in ref_m.named_parameters():
+        pg = dict(m.named_parameters())[name]
+        assert_close(pg.grad, pr.grad, rtol=1e-4, atol_rel=2e-5, what=f"GCNConv d{name}")
+
+
 @pytest.mark.parametrize("C,K,G", [(64, 64, 50), (16, 20, 37), (100, 100, 50)])
 def test_nnconv_matches_oracle(C, K, G):
     import matdeeplearn_b200.nn as mnn

@@ -31,5 +31,5 @@ def test_models_refuse_cpu_batches():
 def test_model_lookup_by_name_like_reference():
     # reference training/training.py:250: getattr(models, model_name)(data=dataset, **params)
     from matdeeplearn_b200 import models as M
-    for name in ("CGCNN", "SchNet", "MPNN", "MEGNet"):
+    for name in ("CGCNN", "SchNet", "MPNN", "MEGNet", "GCN"):
         assert callable(getattr(M, name))
