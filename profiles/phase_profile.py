@@ -73,7 +73,7 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if v[25]:
         print(f"!! wait timed out: barrier id {v[26]} (1 ea, 2 node rows, 3 mma), CTA {v[27]}, round {v[28]}, "
               f"thread {v[29]}, parity {v[30]}")
-    tot = max(sum(v[:20]), 1)
+    tot = max(sum(v[i] for i, nm in NAMES_.items() if not nm.startswith("(")), 1)
     print(f"== {name}: N={N} E={E}  {a.elapsed_time(c):.3f} ms, {rounds} rounds, {tot / rounds:.0f} cycles/round")
     for i, nm in NAMES_.items():  # in program order
         if v[i]:
