@@ -39,8 +39,6 @@ class _ConvStackModel(tnn.Module):
         super().__init__()
         if gc_count <= 0:
             raise AssertionError("Need at least 1 GC layer")
-        if pool == "set2set":
-            raise NotImplementedError("Set2Set readout is outside the engine's scope (SURVEY.md 8f)")
         self.batch_track_stats = not (batch_track_stats == "False")
         self.batch_norm = batch_norm
         self.pool, self.pool_order, self.act = pool, pool_order, act
@@ -51,9 +49,18 @@ class _ConvStackModel(tnn.Module):
             tnn.Linear(n_in if i == 0 else dim1, dim1) for i in range(pre_fc_count))
         self.conv_list = tnn.ModuleList()
         self.bn_list = tnn.ModuleList()
+        # Set2Set doubles the width it pools (reference cgcnn.py:95-119)
+        s2s = pool == "set2set"
+        post_in = 2 * self.gc_dim if (s2s and pool_order == "early") else self.gc_dim
+        out_dim = _target_dim(data)
         self.post_lin_list = tnn.ModuleList(
-            tnn.Linear(self.gc_dim if i == 0 else dim2, dim2) for i in range(post_fc_count))
-        self.lin_out = tnn.Linear(dim2 if post_fc_count > 0 else self.gc_dim, _target_dim(data))
+            tnn.Linear(post_in if i == 0 else dim2, dim2) for i in range(post_fc_count))
+        self.lin_out = tnn.Linear(dim2 if post_fc_count > 0 else post_in, out_dim)
+        if s2s and pool_order == "early":
+            self.set2set = mnn.Set2Set(self.gc_dim, processing_steps=3)
+        elif s2s and pool_order == "late":
+            self.set2set = mnn.Set2Set(out_dim, processing_steps=3, num_layers=1)
+            self.lin_out_2 = tnn.Linear(out_dim * 2, out_dim)
 
     def _add_bn(self):
         if self.batch_norm == "True":
@@ -79,7 +86,10 @@ class _ConvStackModel(tnn.Module):
         return MF.masked_batch_norm(bn, h, nv) if own else bn(h)
 
     def _readout(self, h, data):
-        pool = getattr(mnn, self.pool)
+        s2s = self.pool == "set2set"
+        if s2s and getattr(data, "_n_valid", None) is not None:
+            raise NotImplementedError("Set2Set on capacity-padded batches (its softmax would see the padding rows)")
+        pool = self.set2set if s2s else getattr(mnn, self.pool)
         if self.pool_order == "early":
             h = pool(h, data.batch)
         for lin in self.post_lin_list:
@@ -87,6 +97,8 @@ class _ConvStackModel(tnn.Module):
         h = MF.linear(h, self.lin_out.weight, self.lin_out.bias)
         if self.pool_order == "late":
             h = pool(h, data.batch)
+            if s2s:
+                h = MF.linear(h, self.lin_out_2.weight, self.lin_out_2.bias)
         return h.view(-1) if h.shape[1] == 1 else h
 
 
@@ -279,8 +291,6 @@ class MEGNet(tnn.Module):
         super().__init__()
         if gc_count <= 0:
             raise AssertionError("Need at least 1 GC layer")
-        if pool == "set2set":
-            raise NotImplementedError("Set2Set readout is outside the engine's scope (SURVEY.md 8f)")
         track = not (batch_track_stats == "False")
         self.batch_norm, self.pool, self.act = batch_norm, pool, act
         self.pool_order, self.dropout_rate = pool_order, dropout_rate

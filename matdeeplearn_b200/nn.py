@@ -134,6 +134,43 @@ class CGConv(nn.Module):
 # ----------------------------------------------------------------------------
 # SchNet interaction (torch_geometric.nn.models.schnet.InteractionBlock / CFConv)
 # ----------------------------------------------------------------------------
+def segment_softmax(src, index, num_segments):
+    """torch_geometric.utils.softmax over sorted segments: exp(src - max_seg) / (sum_seg + 1e-16);
+    the segment max / sum are the CSR reduction kernels."""
+    smax = scatter(src, index, 0, num_segments, "max").index_select(0, index)
+    out = (src - smax).exp()
+    ssum = scatter(out, index, 0, num_segments, "sum").index_select(0, index)
+    return out / (ssum + 1e-16)
+
+
+class Set2Set(nn.Module):
+    """PyG Set2Set readout as the reference builds it (cgcnn.py:114-119: processing_steps=3,
+    num_layers=1): q_t = LSTM(q*_{t-1}); a = softmax_graph(x . q_t); r_t = sum_graph a x;
+    q*_t = [q_t || r_t].  Same parameter names as PyG (`lstm.*`).  The per-graph softmax and the
+    weighted sum run on the segmented-reduction kernels; the LSTM cell is a [B, 2C] dense op (library)."""
+
+    def __init__(self, in_channels, processing_steps, num_layers=1):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, 2 * in_channels
+        self.processing_steps, self.num_layers = processing_steps, num_layers
+        self.lstm = nn.LSTM(self.out_channels, in_channels, num_layers)
+
+    def forward(self, x, batch, size=None):
+        _require_cuda(x, "Set2Set")
+        B = int(size) if size is not None else int(batch.max().item()) + 1
+        h = (x.new_zeros((self.num_layers, B, self.in_channels)),
+             x.new_zeros((self.num_layers, B, self.in_channels)))
+        q_star = x.new_zeros(B, self.out_channels)
+        for _ in range(self.processing_steps):
+            q, h = self.lstm(q_star.unsqueeze(0), h)
+            q = q.view(B, self.in_channels)
+            e = (x * q.index_select(0, batch)).sum(dim=-1, keepdim=True)
+            a = segment_softmax(e, batch, B)
+            r = scatter(a * x, batch, 0, B, "sum")
+            q_star = torch.cat([q, r], dim=-1)
+        return q_star
+
+
 class GCNConv(nn.Module):
     """PyG GCNConv in the one configuration the reference builds (gcn.py:80-82:
     improved=True, add_self_loops=False; called with the raw distances as edge_weight):

@@ -10,7 +10,7 @@ CUDA-backed models in matdeeplearn_b200.models.
   MPNN    reference matdeeplearn/models/mpnn.py:17-188
   MEGNet  reference matdeeplearn/models/megnet.py:16-371
   GCN     reference matdeeplearn/models/gcn.py:17-178
-Set2Set pooling is out of scope.
+Set2Set readout: cgcnn.py:95-119,150-168 (and the same lines of schnet / mpnn / gcn).
 """
 import torch
 import torch.nn.functional as F
@@ -36,15 +36,21 @@ class _Skeleton(nn.Module):
                  pool_order, batch_norm, batch_track_stats, act, dropout_rate):
         super().__init__()
         assert gc_count > 0
-        assert pool != "set2set", "Set2Set readout is out of scope"
         self.batch_track_stats = batch_track_stats != "False"
         self.batch_norm, self.pool, self.act = batch_norm, pool, act
         self.pool_order, self.dropout_rate = pool_order, dropout_rate
         self.gc_dim = dim1 if pre_fc_count > 0 else data.num_features
         self.output_dim = _out_dim(data)
         self.pre_lin_list = _mlp_stack(pre_fc_count, data.num_features, dim1)
-        self.post_lin_list = _mlp_stack(post_fc_count, self.gc_dim, dim2)
-        self.lin_out = nn.Linear(dim2 if post_fc_count > 0 else self.gc_dim, self.output_dim)
+        # Set2Set doubles the width it pools (reference cgcnn.py:95-110)
+        post_in = 2 * self.gc_dim if (pool == "set2set" and pool_order == "early") else self.gc_dim
+        self.post_lin_list = _mlp_stack(post_fc_count, post_in, dim2)
+        self.lin_out = nn.Linear(dim2 if post_fc_count > 0 else post_in, self.output_dim)
+        if pool == "set2set" and pool_order == "early":
+            self.set2set = P.Set2Set(self.gc_dim, processing_steps=3)
+        elif pool == "set2set" and pool_order == "late":
+            self.set2set = P.Set2Set(self.output_dim, processing_steps=3, num_layers=1)
+            self.lin_out_2 = nn.Linear(self.output_dim * 2, self.output_dim)
 
     def _bn(self):
         return nn.BatchNorm1d(self.gc_dim, track_running_stats=self.batch_track_stats)
@@ -56,7 +62,8 @@ class _Skeleton(nn.Module):
         return out
 
     def _post(self, out, data):
-        pool = getattr(P, self.pool)
+        s2s = self.pool == "set2set"
+        pool = self.set2set if s2s else getattr(P, self.pool)
         if self.pool_order == "early":
             out = pool(out, data.batch)
         for lin in self.post_lin_list:
@@ -64,6 +71,8 @@ class _Skeleton(nn.Module):
         out = self.lin_out(out)
         if self.pool_order == "late":
             out = pool(out, data.batch)
+            if s2s:
+                out = self.lin_out_2(out)
         return out.view(-1) if out.shape[1] == 1 else out
 
 

@@ -81,6 +81,43 @@ def global_max_pool(x, batch, size=None):
 
 
 # ----------------------------------------------------------------------------
+# Set2Set readout (constructed at reference cgcnn.py:114-119 and twins:
+# Set2Set(post_fc_dim, processing_steps=3) early, Set2Set(output_dim, 3, num_layers=1) late)
+# ----------------------------------------------------------------------------
+def segment_softmax(src, index, num_segments):
+    """PyG 2.0.1 torch_geometric.utils.softmax: exp(src - max_seg) / (sum_seg + 1e-16)."""
+    smax = scatter(src, index, 0, num_segments, "max").index_select(0, index)
+    out = (src - smax).exp()
+    ssum = scatter(out, index, 0, num_segments, "sum").index_select(0, index)
+    return out / (ssum + 1e-16)
+
+
+class Set2Set(nn.Module):
+    """q_t = LSTM(q*_{t-1}); a = softmax_graph(x . q_t); r_t = sum_graph a x; q*_t = [q_t || r_t]
+    (PyG 2.0.1 Set2Set; output width 2 * in_channels)."""
+
+    def __init__(self, in_channels, processing_steps, num_layers=1):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, 2 * in_channels
+        self.processing_steps, self.num_layers = processing_steps, num_layers
+        self.lstm = nn.LSTM(self.out_channels, in_channels, num_layers)
+
+    def forward(self, x, batch):
+        B = _num_graphs(batch)
+        h = (x.new_zeros((self.num_layers, B, self.in_channels)),
+             x.new_zeros((self.num_layers, B, self.in_channels)))
+        q_star = x.new_zeros(B, self.out_channels)
+        for _ in range(self.processing_steps):
+            q, h = self.lstm(q_star.unsqueeze(0), h)
+            q = q.view(B, self.in_channels)
+            e = (x * q.index_select(0, batch)).sum(dim=-1, keepdim=True)
+            a = segment_softmax(e, batch, B)
+            r = scatter(a * x, batch, 0, B, "sum")
+            q_star = torch.cat([q, r], dim=-1)
+        return q_star
+
+
+# ----------------------------------------------------------------------------
 # CGConv  (constructed at reference matdeeplearn/models/cgcnn.py:80-82 as
 # CGConv(gc_dim, num_edge_features, aggr="mean", batch_norm=False))
 # ----------------------------------------------------------------------------

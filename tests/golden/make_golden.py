@@ -72,7 +72,7 @@ def install_stubs():
     tg.utils = _module("torch_geometric.utils", dense_to_sparse=dense_to_sparse, degree=degree,
                        add_self_loops=add_self_loops)
     tg.transforms = _module("torch_geometric.transforms")
-    tg.nn = _module("torch_geometric.nn", Set2Set=_Dummy, global_mean_pool=O.global_mean_pool,
+    tg.nn = _module("torch_geometric.nn", Set2Set=O.Set2Set, global_mean_pool=O.global_mean_pool,
                     global_add_pool=O.global_add_pool, global_max_pool=O.global_max_pool,
                     CGConv=O.CGConv, NNConv=O.NNConv, MetaLayer=O.MetaLayer, GCNConv=O.GCNConv)
     tg.nn.models = _module("torch_geometric.nn.models")
@@ -144,6 +144,9 @@ MODEL_CFGS = {
     "MEGNet_fc1": dict(dim1=32, dim2=24, dim3=28, pre_fc_count=1, gc_count=2, gc_fc_count=1,
                        post_fc_count=1),
     "GCN": dict(dim1=32, dim2=24, pre_fc_count=1, gc_count=3, post_fc_count=2),
+    "CGCNN_set2set": dict(dim1=32, dim2=24, pre_fc_count=1, gc_count=2, post_fc_count=1, pool="set2set"),
+    "GCN_set2set_late": dict(dim1=32, dim2=24, pre_fc_count=1, gc_count=2, post_fc_count=1, pool="set2set",
+                             pool_order="late"),
     "GCN_nobn_late": dict(dim1=32, dim2=24, pre_fc_count=1, gc_count=2, post_fc_count=1, batch_norm="False",
                           pool="global_add_pool", pool_order="late"),
 }
@@ -161,7 +164,7 @@ def golden_models(only=None):
     classes = {"CGCNN": mods["cgcnn"].CGCNN, "SchNet": mods["schnet"].SchNet,
                "MPNN": mods["mpnn"].MPNN, "MEGNet": mods["megnet"].MEGNet, "GCN": mods["gcn"].GCN}
     for tag, cfg in MODEL_CFGS.items():
-        if only is not None and tag.split("_")[0] not in only:
+        if only is not None and tag.split("_")[0] not in only and tag not in only:
             continue
         cls = classes[tag.split("_")[0]]
         torch.manual_seed(1234)
