@@ -133,3 +133,52 @@ def test_interaction_block_cutoff_and_shifted_softplus():
     a = blk(x, ei, torch.tensor([8.0, 3.0], dtype=torch.float64), ea)
     b = blk(x, ei[:, 1:], torch.tensor([3.0], dtype=torch.float64), ea[1:])
     torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-12)
+
+
+def test_gcnconv_hand_worked_against_dense_normalised_adjacency():
+    # out = D^-1/2 A D^-1/2 (x W^T) + b with A[i, j] = weight of edge j -> i, D = row sums of A
+    # (PyG gcn_norm without added self-loops; a node whose in-weights sum to 0 gets coefficient 0)
+    torch.manual_seed(0)
+    n, C = 5, 3
+    ei = torch.tensor([[0, 1, 2, 3, 1, 4, 4], [1, 0, 1, 1, 2, 2, 4]])   # node 3 has no in-edges, 4 only a loop
+    ew = torch.tensor([2.0, 0.5, 1.5, 4.0, 3.0, 1.0, 0.0], dtype=torch.float64)  # loop weight 0 (raw distance)
+    x = torch.randn(n, C, dtype=torch.float64)
+    conv = O.GCNConv(C, C, improved=True, add_self_loops=False).double()
+    with torch.no_grad():
+        conv.bias.copy_(torch.tensor([0.1, -0.2, 0.3]))
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A[ei[1], ei[0]] = ew
+    deg = A.sum(1)
+    dinv = torch.where(deg > 0, deg.pow(-0.5), torch.zeros_like(deg))
+    ref = (dinv[:, None] * A * dinv[None, :]) @ (x @ conv.lin.weight.t()) + conv.bias
+    out = conv(x, ei, ew)
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(out[3], conv.bias) and torch.allclose(out[4], conv.bias)   # degree 0 -> bias only
+    assert not out.isnan().any()
+
+
+def test_segment_softmax_and_set2set_hand_worked():
+    src = torch.tensor([[1.0], [2.0], [0.5], [-1.0], [3.0]], dtype=torch.float64)
+    batch = torch.tensor([0, 0, 1, 1, 1])
+    a = O.segment_softmax(src, batch, 2)
+    assert torch.allclose(a[:2, 0], torch.softmax(src[:2, 0], 0)) and torch.allclose(a[2:, 0], torch.softmax(src[2:, 0], 0))
+    assert torch.allclose(O.scatter(a, batch, 0, 2, "sum"), torch.ones(2, 1, dtype=torch.float64))
+    # Set2Set against an explicit per-graph loop over the same LSTM
+    torch.manual_seed(1)
+    C = 4
+    s2s = O.Set2Set(C, processing_steps=3).double()
+    x = torch.randn(5, C, dtype=torch.float64)
+    got = s2s(x, batch)
+    rows = []
+    for g in range(2):
+        xg = x[batch == g]
+        h = (torch.zeros(1, 1, C, dtype=torch.float64), torch.zeros(1, 1, C, dtype=torch.float64))
+        q_star = torch.zeros(1, 2 * C, dtype=torch.float64)
+        for _ in range(3):
+            q, h = s2s.lstm(q_star.unsqueeze(0), h)
+            q = q.view(1, C)
+            att = torch.softmax(xg @ q.t(), 0)
+            q_star = torch.cat([q, (att * xg).sum(0, keepdim=True)], -1)
+        rows.append(q_star)
+    assert got.shape == (2, 2 * C)
+    assert torch.allclose(got, torch.cat(rows, 0), rtol=1e-10, atol=1e-12)
