@@ -77,13 +77,58 @@ def gaussian_expand(d_hat, resolution=DEFAULT_EDGE_LENGTH, start=0.0, stop=1.0, 
     return torch.exp(coeff * (diff * diff))
 
 
-def pairwise_distances(pos, cell_lengths=None):
-    """Euclidean, or minimum-image for an orthorhombic periodic box."""
+def orthorhombic_lengths(cell):
+    """[3] box lengths if `cell` is a length vector or a diagonal 3x3 matrix, else None."""
+    c = np.asarray(cell, dtype=np.float64)
+    if c.shape == (3,):
+        return c
+    if c.shape == (3, 3) and np.array_equal(c, np.diag(np.diag(c))):
+        return np.diag(c).copy()
+    return None
+
+
+def _general_minimum_image(d, cell):
+    """Minimum-image vectors for a general (triclinic) cell, rows of `cell` = lattice vectors.
+    What the reference gets from ASE (`get_all_distances(mic=True)`, process.py:284-287): the shortest
+    of all lattice translates of each difference vector.  Wrap the fractional coordinates into
+    [-0.5, 0.5), then search every integer shift that can still shorten a wrapped vector: the wrapped
+    vector is no longer than R0 = (|a1|+|a2|+|a3|)/2, so a better image needs a lattice vector shorter
+    than 2 R0, i.e. |shift_i| <= ceil(2 R0 / h_i) with h_i the cell's height along axis i."""
+    inv = np.linalg.inv(cell)
+    frac = d @ inv
+    frac -= np.round(frac)
+    w = frac @ cell
+    vol = abs(np.linalg.det(cell))
+    r0 = 0.5 * np.linalg.norm(cell, axis=1).sum()
+    heights = np.array([vol / np.linalg.norm(np.cross(cell[(i + 1) % 3], cell[(i + 2) % 3])) for i in range(3)])
+    n = np.minimum(np.ceil(2.0 * r0 / heights).astype(int), 4)   # 4: guard for needle-shaped cells
+    best = w.copy()
+    best_d2 = (w * w).sum(-1)
+    for i in range(-n[0], n[0] + 1):
+        for j in range(-n[1], n[1] + 1):
+            for k in range(-n[2], n[2] + 1):
+                if i == j == k == 0:
+                    continue
+                c = w + (i * cell[0] + j * cell[1] + k * cell[2])
+                d2 = (c * c).sum(-1)
+                m = d2 < best_d2
+                best[m] = c[m]
+                best_d2[m] = d2[m]
+    return best
+
+
+def pairwise_distances(pos, cell=None):
+    """Euclidean, or minimum-image for a periodic cell: `cell` = [3] box lengths / diagonal 3x3
+    (orthorhombic; the expression the GPU builder reproduces bit for bit) or a general 3x3 matrix
+    whose rows are the lattice vectors (host builder only)."""
     pos = np.asarray(pos, dtype=np.float64)
     d = pos[:, None, :] - pos[None, :, :]
-    if cell_lengths is not None:
-        L = np.asarray(cell_lengths, dtype=np.float64)
-        d -= np.round(d / L) * L
+    if cell is not None:
+        L = orthorhombic_lengths(cell)
+        if L is not None:
+            d -= np.round(d / L) * L
+        else:
+            d = _general_minimum_image(d, np.asarray(cell, dtype=np.float64).reshape(3, 3))
     # (dx^2 + dy^2) + dz^2 in that order, plain multiplies and adds: einsum would pick an FMA kernel whose
     # rounding depends on the host CPU; the GPU builder (csrc/builder.cu) reproduces THIS expression bit for bit
     return np.sqrt((d * d).sum(-1))
@@ -91,7 +136,8 @@ def pairwise_distances(pos, cell_lengths=None):
 
 def assemble_dataset(structures, targets, radius=DEFAULT_RADIUS, neighbors=DEFAULT_NEIGHBORS,
                      edge_length=DEFAULT_EDGE_LENGTH):
-    """structures: iterable of (numbers, positions, cell_lengths-or-None).
+    """structures: iterable of (numbers, positions, cell-or-None); cell = [3] box lengths or a 3x3
+    matrix of lattice vectors (rows), see pairwise_distances.
 
     Returns GraphDataset whose graphs carry x, edge_index, edge_weight (raw
     Angstrom), edge_attr (Gaussian basis of the globally min-max normalised
@@ -186,9 +232,7 @@ def parse_ase_json(text):
     if any(pbc):
         c = rec["cell"]
         c = _decode_ndarray(c) if isinstance(c, dict) else np.asarray(c, dtype=float)
-        if not np.allclose(c, np.diag(np.diag(c))):
-            raise NotImplementedError("non-orthorhombic periodic cells need the GPU builder row (section 8f)")
-        cell = np.diag(c)
+        cell = np.diag(c).copy() if np.allclose(c, np.diag(np.diag(c))) else c  # lengths, or the full matrix
     return numbers, pos, cell
 
 

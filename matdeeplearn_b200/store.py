@@ -22,6 +22,23 @@ from .csr import GraphCSR
 from .data import Batch
 
 
+def _box_lengths(structures):
+    """[num_structures, 3] float64 box lengths for the GPU builder (zeros = not periodic).  It handles
+    orthorhombic cells only; general cells go through process.assemble_dataset + GraphStore.from_dataset."""
+    from .process import orthorhombic_lengths
+    rows = []
+    for s in structures:
+        if s[2] is None:
+            rows.append(np.zeros(3))
+            continue
+        L = orthorhombic_lengths(s[2])
+        if L is None:
+            raise NotImplementedError("GraphStore.from_structures: the GPU builder handles orthorhombic cells; "
+                                      "build general cells with process.assemble_dataset + from_dataset")
+        rows.append(np.asarray(L, dtype=np.float64).reshape(3))
+    return np.stack(rows) if rows else np.zeros((0, 3))
+
+
 class GraphStore:
     """All graphs of a GraphDataset concatenated in HBM.
 
@@ -122,8 +139,7 @@ class GraphStore:
         self.num_nodes = int(node_ptr[-1])
         pos = np.concatenate([np.asarray(s[1], dtype=np.float64).reshape(-1, 3) for s in structures], 0)
         numbers = np.concatenate([np.asarray(s[0], dtype=np.int32).reshape(-1) for s in structures])
-        cell = np.stack([np.zeros(3) if s[2] is None else np.asarray(s[2], dtype=np.float64).reshape(3)
-                         for s in structures])
+        cell = _box_lengths(structures)
         K = neighbors + 1
         self.F, self.G = z_width + neighbors + 2, edge_length
         f32 = dict(dtype=torch.float32, device=device)
