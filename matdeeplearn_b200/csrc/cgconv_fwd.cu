@@ -5,21 +5,26 @@
 // its phases back to back (split -> MMA -> epilogue -> reduce) and the tensor core's ~1.7k cycles sit
 // on the critical path.  Here the contraction runs ONE ROUND AHEAD into a second TMEM accumulator:
 //
-//   iteration r:   [S1]  node rows of round r requested (LDG -> registers)
+//   iteration r:   [S1]  node rows of round r requested (LDG.128 -> registers), indices of round r+1 requested
 //                        wait MMA(r)                         (issued an iteration ago: long finished)
-//                        split ea(r+1) -> operand tiles      (its bulk copy was issued an iteration ago)
+//                        split ea(r+1): landing zone -> hi / lo -> tcgen05.st (the A operand lives in TENSOR
+//                        MEMORY: no operand tiles in shared memory; its bulk copy was issued an iteration ago)
 //                        node rows / next indices -> smem
-//                  [S2]  MMA(r+1) issued into the other accumulator; bulk copy of ea(r+2) issued
-//                        epilogue(r): TMEM -> + P[dst] + Q[src] -> gates -> value tile -> segment sums
+//                  [S2]  issuer warp (its own warp, it does nothing else): bulk copy of ea(r+2), then the 21 MMAs
+//                        of round r+1 into the other accumulator -- issuing them blocks a thread for ~2.4k cycles
+//                        epilogue(r): tcgen05.ld -> + P[dst] + Q[src] (node-row tile) -> gates -> message tile
+//                  [S3]  per-segment sums of round r -> out
 //
 // so the tensor core, the bulk copy engine and the L2 round trips of the node rows all run under the
-// epilogue of the previous round.  The backward kernels cannot use this schedule with the same shared
-// memory: their dW_e stage reads round r's operand tiles at the END of the round.
+// epilogue of the previous round.  640 threads: 16 epilogue warps + one warpgroup for the issuer warp, with
+// setmaxnreg moving registers from the latter to the former (112 / 32).  The backward kernels cannot use this
+// schedule with the same shared memory: their dW_e stage reads round r's operand tiles at the END of the round.
 //
 // Node terms: the P / Q rows a round needs lie in two short contiguous node ranges (edges never leave
-// their crystal graph); when both fit in 128 rows they are staged in the (idle) value tile and the
-// epilogue reads them from shared memory ("window"), else Q[src[e]] is staged per slot and P[dst[e]]
-// (few distinct rows per warp, slots are destination-sorted) is read straight from global memory.
+// their crystal graph); when both fit in 128 rows they are staged in the node-row tile (separate from the
+// message tile, so row reads and gate math share one phase) and the epilogue reads them from shared memory
+// ("window"), else Q[src[e]] is staged per slot and P[dst[e]] (few distinct rows per warp, slots are
+// destination-sorted) is read straight from global memory.
 #include "cgconv.cuh"
 #include "umma.cuh"
 #include "edge_dev.cuh"
