@@ -77,31 +77,40 @@ def gaussian_expand(d_hat, resolution=DEFAULT_EDGE_LENGTH, start=0.0, stop=1.0, 
     return torch.exp(coeff * (diff * diff))
 
 
-def orthorhombic_lengths(cell):
-    """[3] box lengths if `cell` is a length vector or a diagonal 3x3 matrix, else None."""
+def orthorhombic_lengths(cell, pbc=None):
+    """[3] box lengths if `cell` is a length vector or a diagonal 3x3 matrix, else None.  A length of 0
+    means "not periodic along this axis" (what the GPU builder tests per axis); `pbc` (3 booleans, ASE's
+    per-axis flags) zeroes the lengths of the free axes."""
     c = np.asarray(cell, dtype=np.float64)
-    if c.shape == (3,):
-        return c
-    if c.shape == (3, 3) and np.array_equal(c, np.diag(np.diag(c))):
-        return np.diag(c).copy()
-    return None
+    if c.shape == (3, 3):
+        if not np.array_equal(c, np.diag(np.diag(c))):
+            return None
+        c = np.diag(c)
+    elif c.shape != (3,):
+        return None
+    c = c.copy()
+    if pbc is not None:
+        c[~np.asarray(pbc, dtype=bool)] = 0.0
+    return c
 
 
-def _general_minimum_image(d, cell):
+def _general_minimum_image(d, cell, pbc=None):
     """Minimum-image vectors for a general (triclinic) cell, rows of `cell` = lattice vectors.
     What the reference gets from ASE (`get_all_distances(mic=True)`, process.py:284-287): the shortest
     of all lattice translates of each difference vector.  Wrap the fractional coordinates into
     [-0.5, 0.5), then search every integer shift that can still shorten a wrapped vector: the wrapped
     vector is no longer than R0 = (|a1|+|a2|+|a3|)/2, so a better image needs a lattice vector shorter
     than 2 R0, i.e. |shift_i| <= ceil(2 R0 / h_i) with h_i the cell's height along axis i."""
+    per = np.ones(3, dtype=bool) if pbc is None else np.asarray(pbc, dtype=bool)
     inv = np.linalg.inv(cell)
     frac = d @ inv
-    frac -= np.round(frac)
+    frac[..., per] -= np.round(frac[..., per])   # free axes (slabs, wires) keep their coordinate
     w = frac @ cell
     vol = abs(np.linalg.det(cell))
     r0 = 0.5 * np.linalg.norm(cell, axis=1).sum()
     heights = np.array([vol / np.linalg.norm(np.cross(cell[(i + 1) % 3], cell[(i + 2) % 3])) for i in range(3)])
     n = np.minimum(np.ceil(2.0 * r0 / heights).astype(int), 4)   # 4: guard for needle-shaped cells
+    n[~per] = 0
     best = w.copy()
     best_d2 = (w * w).sum(-1)
     for i in range(-n[0], n[0] + 1):
@@ -117,18 +126,21 @@ def _general_minimum_image(d, cell):
     return best
 
 
-def pairwise_distances(pos, cell=None):
+def pairwise_distances(pos, cell=None, pbc=None):
     """Euclidean, or minimum-image for a periodic cell: `cell` = [3] box lengths / diagonal 3x3
-    (orthorhombic; the expression the GPU builder reproduces bit for bit) or a general 3x3 matrix
-    whose rows are the lattice vectors (host builder only)."""
+    (orthorhombic; the expression the GPU builder reproduces bit for bit; length 0 = free axis) or a
+    general 3x3 matrix whose rows are the lattice vectors (host builder only).  `pbc`: ASE's per-axis
+    periodicity flags (default: periodic along every axis of a given cell)."""
     pos = np.asarray(pos, dtype=np.float64)
     d = pos[:, None, :] - pos[None, :, :]
-    if cell is not None:
-        L = orthorhombic_lengths(cell)
+    if cell is not None and (pbc is None or np.any(pbc)):
+        L = orthorhombic_lengths(cell, pbc)
         if L is not None:
-            d -= np.round(d / L) * L
+            for ax in range(3):  # per axis, as the GPU builder: wrap only where the box is periodic
+                if L[ax] > 0.0:
+                    d[..., ax] -= np.round(d[..., ax] / L[ax]) * L[ax]
         else:
-            d = _general_minimum_image(d, np.asarray(cell, dtype=np.float64).reshape(3, 3))
+            d = _general_minimum_image(d, np.asarray(cell, dtype=np.float64).reshape(3, 3), pbc)
     # (dx^2 + dy^2) + dz^2 in that order, plain multiplies and adds: einsum would pick an FMA kernel whose
     # rounding depends on the host CPU; the GPU builder (csrc/builder.cu) reproduces THIS expression bit for bit
     return np.sqrt((d * d).sum(-1))
@@ -136,16 +148,17 @@ def pairwise_distances(pos, cell=None):
 
 def assemble_dataset(structures, targets, radius=DEFAULT_RADIUS, neighbors=DEFAULT_NEIGHBORS,
                      edge_length=DEFAULT_EDGE_LENGTH):
-    """structures: iterable of (numbers, positions, cell-or-None); cell = [3] box lengths or a 3x3
-    matrix of lattice vectors (rows), see pairwise_distances.
+    """structures: iterable of (numbers, positions, cell-or-None[, pbc]); cell = [3] box lengths or a
+    3x3 matrix of lattice vectors (rows), pbc = optional per-axis flags, see pairwise_distances.
 
     Returns GraphDataset whose graphs carry x, edge_index, edge_weight (raw
     Angstrom), edge_attr (Gaussian basis of the globally min-max normalised
     distance), d_hat (that normalised distance; engine extra), u, y.
     """
     graphs = []
-    for (numbers, pos, cell), y in zip(structures, targets):
-        D = pairwise_distances(pos, cell)
+    for st, y in zip(structures, targets):
+        numbers, pos, cell = st[0], st[1], st[2]
+        D = pairwise_distances(pos, cell, st[3] if len(st) > 3 else None)
         ei, ew = knn_radius_edges(D, radius, neighbors)
         x = node_features(numbers, ei, neighbors)
         graphs.append(Data(x=x, edge_index=ei, edge_weight=ew,
@@ -233,6 +246,8 @@ def parse_ase_json(text):
         c = rec["cell"]
         c = _decode_ndarray(c) if isinstance(c, dict) else np.asarray(c, dtype=float)
         cell = np.diag(c).copy() if np.allclose(c, np.diag(np.diag(c))) else c  # lengths, or the full matrix
+        if not all(pbc):
+            return numbers, pos, cell, tuple(bool(b) for b in pbc)   # slab / wire: free axes
     return numbers, pos, cell
 
 

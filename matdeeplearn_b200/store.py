@@ -31,7 +31,7 @@ def _box_lengths(structures):
         if s[2] is None:
             rows.append(np.zeros(3))
             continue
-        L = orthorhombic_lengths(s[2])
+        L = orthorhombic_lengths(s[2], s[3] if len(s) > 3 else None)
         if L is None:
             raise NotImplementedError("GraphStore.from_structures: the GPU builder handles orthorhombic cells; "
                                       "build general cells with process.assemble_dataset + from_dataset")

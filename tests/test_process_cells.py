@@ -84,3 +84,48 @@ def test_gpu_builder_cell_argument():
     s_tri = (np.array([1, 2]), np.zeros((2, 3)), np.array([[5.0, 0, 0], [1.0, 6.0, 0], [0, 0, 7.0]]))
     with pytest.raises(NotImplementedError):
         _box_lengths([s_tri])
+
+
+def test_slab_periodicity_is_per_axis():
+    # periodic in x, y; free along z (pbc = T, T, F): two atoms 9 A apart in z in a 10 A box are 9 A apart, not 1 A
+    L = np.array([5.0, 5.0, 10.0])
+    pos = np.array([[0.5, 0.5, 0.5], [4.8, 0.5, 9.5]])
+    full = pr.pairwise_distances(pos, L)
+    slab = pr.pairwise_distances(pos, L, pbc=(True, True, False))
+    assert full[0, 1] == pytest.approx(np.sqrt(0.7 ** 2 + 1.0 ** 2))
+    assert slab[0, 1] == pytest.approx(np.sqrt(0.7 ** 2 + 9.0 ** 2))
+    assert np.array_equal(pr.pairwise_distances(pos, np.array([5.0, 5.0, 0.0])), slab)   # length 0 = free axis
+    assert np.array_equal(pr.pairwise_distances(pos, L, pbc=(False, False, False)), pr.pairwise_distances(pos))
+    got = _box_lengths([(np.array([1, 2]), pos, L, (True, True, False))])
+    assert np.array_equal(got, np.array([[5.0, 5.0, 0.0]]))
+
+
+def test_triclinic_slab_matches_restricted_brute_force():
+    rng = np.random.default_rng(11)
+    cell = np.array([[6.0, 0, 0], [2.5, 5.0, 0], [0.5, 0.8, 14.0]])
+    pos = rng.uniform(0, 1, (15, 3)) @ cell
+    got = pr.pairwise_distances(pos, cell, pbc=(True, True, False))
+    d = pos[:, None, :] - pos[None, :, :]
+    best = np.full(d.shape[:2], np.inf)
+    for i in range(-3, 4):
+        for j in range(-3, 4):
+            c = d + i * cell[0] + j * cell[1]
+            best = np.minimum(best, np.sqrt((c * c).sum(-1)))
+    assert np.allclose(got, best, atol=1e-12)
+
+
+def test_ase_json_cells_and_flags():
+    import json
+    def rec(cell, pbc):
+        return json.dumps({"1": {"numbers": {"__ndarray__": [[2], "int64", [78, 78]]},
+                                 "positions": {"__ndarray__": [[2, 3], "float64", [0, 0, 0, 1.0, 1.0, 1.0]]},
+                                 "cell": {"__ndarray__": [[3, 3], "float64", cell]}, "pbc": pbc}, "ids": [1], "nextid": 2})
+    ortho = [5.0, 0, 0, 0, 6.0, 0, 0, 0, 7.0]
+    tri = [5.0, 0, 0, 1.0, 6.0, 0, 0, 0, 7.0]
+    assert pr.parse_ase_json(rec(ortho, [False, False, False]))[2] is None
+    n, p, c = pr.parse_ase_json(rec(ortho, [True, True, True]))
+    assert np.array_equal(c, [5.0, 6.0, 7.0])
+    out = pr.parse_ase_json(rec(tri, [True, True, False]))
+    assert len(out) == 4 and out[2].shape == (3, 3) and out[3] == (True, True, False)
+    ds = pr.assemble_dataset([out], [1.0])
+    assert ds[0].edge_index.shape[1] >= 2   # two loops at least; the graph builds
