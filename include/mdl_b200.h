@@ -336,6 +336,11 @@ MDL_API int mdl_selftest_umma_ex(const float* A, const float* B, float* D, int32
 /* same product with A staged in tensor memory (tcgen05.st) and B in shared memory */
 MDL_API int mdl_selftest_umma_ts(const float* A, const float* B, float* D, int32_t N, int32_t K,
                                  int32_t split, void* stream);
+/* layout probe: raw shared-memory images of both operand tiles + descriptor fields, nmma K=8 MMAs */
+MDL_API int mdl_selftest_umma_probe(const float* rawA, int32_t a_floats, const float* rawB, int32_t b_floats,
+                                    float* D, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
+                                    int32_t sbo_b, int32_t a_mn, int32_t b_mn, int32_t nmma, int32_t step_a,
+                                    int32_t step_b, int32_t layout_a, int32_t layout_b, void* stream);
 
 #ifdef __cplusplus
 }

@@ -368,13 +368,6 @@ static bool use_tc(int mode, int C, int G) {
   return cgtc_supported(mode, C, G);
 }
 
-// MDL_CGCONV_IMPL=tt selects the transposed-tile kernel where it applies
-static bool use_tt(int mode, int C, int G) {
-  const char* env = getenv("MDL_CGCONV_IMPL");
-  if (!env || strcmp(env, "tt") != 0) return false;
-  return cgtt_supported(mode, C, G);
-}
-
 }  // namespace mdl
 
 using namespace mdl;
@@ -400,7 +393,6 @@ extern "C" int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, 
   p.x = x; p.PQ = PQ; p.ea = ea; p.WeT = WeT; p.seg_ptr = dst_ptr; p.dst_src = dst_src;
   p.dst_dst = dst_dst; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg_dst : nullptr;
   p.out = out; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
-  if (use_tt(CG_FWD, C, G)) return cgtt_launch(CG_FWD, p, as_stream(stream));
   if (use_tc(CG_FWD, C, G)) {
     // default: the software-pipelined forward kernel (cgconv_fwd.cu); MDL_CGCONV_IMPL=tc keeps the
     // round-serial tensor-core kernel (A/B, and the shapes / alignments the pipelined one declines)
@@ -535,7 +527,6 @@ extern "C" int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const
 // tensor-core kernels (NULL disables).  Not part of the reference-facing surface.
 extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
   cgtc_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
-  cgtt_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgfwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   return MDL_OK;
 }

@@ -62,10 +62,6 @@ void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
 bool cgfwd_supported(const CgParams& p);
 int cgfwd_launch(CgParams p, cudaStream_t st);
 void cgfwd_set_phase_buffer(unsigned long long* dev_ptr);
-// transposed-tile tensor-core path (cgconv_tt.cu): channel = TMEM lane, two CTAs per SM
-bool cgtt_supported(int mode, int C, int G);
-int cgtt_launch(int mode, CgParams p, cudaStream_t st);
-void cgtt_set_phase_buffer(unsigned long long* dev_ptr);
 // out0[i] (i < len0) / out1[i - len0] = sum over nparts partial vectors, fixed order (cgconv.cu)
 int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, float* out0, int64_t len0,
                  float* out1, cudaStream_t st);

@@ -160,9 +160,80 @@ k_umma_selftest_ts(const float* __restrict__ A, const float* __restrict__ B, flo
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
+
+// Layout probe (development aid): the caller supplies the RAW shared-memory images of both operand tiles and
+// the descriptor fields (LBO / SBO / layout type / major bits); nmma K = 8 MMAs are issued on them.  With
+// index-coded tile contents and one-hot rows on the other side, D spells out which shared-memory word the
+// tensor core reads for every (row, k).  Finding of round 2 (profiles/r2_umma_mn_probe.txt): kind::tf32 with
+// an MN-major operand returns zeros for the no-swizzle, 32B, 64B and 128B layout types -- MN-major tf32
+// needs SWIZZLE_128B_BASE32B -- so the K = E weight-gradient contractions stage their operands K-major.
+__global__ void __launch_bounds__(128, 1)
+k_umma_probe(const float* __restrict__ rawA, int a_floats, const float* __restrict__ rawB, int b_floats,
+             float* __restrict__ D, int N, uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b,
+             uint32_t idesc_extra, int nmma, uint32_t step_a, uint32_t step_b, uint32_t layout_a, uint32_t layout_b) {
+  extern __shared__ __align__(128) uint8_t sm[];  // dynamic smem starts 1024-aligned on sm_100 (only static 16 B here)
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* sA = reinterpret_cast<float*>(sm);
+  float* sB = sA + ((a_floats + 255) & ~255);   // both tiles 1024-byte aligned (swizzled layouts)
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < a_floats; i += blockDim.x) sA[i] = rawA[i];
+  for (int i = tid; i < b_floats; i += blockDim.x) sB[i] = rawB[i];
+  umma::fence_proxy_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_tf32(128, N) | idesc_extra;
+    for (int i = 0; i < nmma; ++i)
+      umma::mma_tf32(tmem, umma::make_desc(umma::smem_u32(sA) + i * step_a, lbo_a, sbo_a) | ((uint64_t)layout_a << 61),
+                     umma::make_desc(umma::smem_u32(sB) + i * step_b, lbo_b, sbo_b) | ((uint64_t)layout_b << 61), idesc,
+                     i > 0);
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(umma::tmem_addr(tmem, warp, c0), v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) D[(size_t)tid * N + c0 + j] = v[j];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
 }  // namespace mdl
 
 using namespace mdl;
+
+extern "C" int mdl_selftest_umma_probe(const float* rawA, int32_t a_floats, const float* rawB, int32_t b_floats,
+                                       float* D, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
+                                       int32_t sbo_b, int32_t a_mn, int32_t b_mn, int32_t nmma, int32_t step_a,
+                                       int32_t step_b, int32_t layout_a, int32_t layout_b, void* stream) {
+  MDL_REQUIRE(rawA && rawB && D, "umma_probe: null pointer");
+  MDL_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "umma_probe: N must be a multiple of 16 in [16,256]");
+  const size_t smem = ((size_t)((a_floats + 255) & ~255) + b_floats) * 4;
+  MDL_REQUIRE(smem <= 200 * 1024, "umma_probe: tiles too large");
+  MDL_CUDA(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k_umma_probe<<<1, 128, smem, as_stream(stream)>>>(rawA, a_floats, rawB, b_floats, D, N, lbo_a, sbo_a, lbo_b, sbo_b,
+                                                     (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u), nmma,
+                                                     (uint32_t)step_a, (uint32_t)step_b, (uint32_t)layout_a,
+                                                     (uint32_t)layout_b);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
 
 extern "C" int mdl_selftest_umma_ts(const float* A, const float* B, float* D, int32_t N, int32_t K,
                                     int32_t split, void* stream) {

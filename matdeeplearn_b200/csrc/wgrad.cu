@@ -204,11 +204,12 @@ extern "C" int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32
   MDL_REQUIRE(X && G && workspace, "linear_wgrad: null pointer");
   MDL_REQUIRE(workspace_bytes >= wg_ws_bytes(N, I, O), "linear_wgrad: workspace too small");
   const size_t smem = (size_t)2 * kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
-  MDL_REQUIRE(smem <= 100 * 1024, "linear_wgrad: layer too wide (I + O <= ~750)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    MDL_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
+  // two stages of 32 rows of X and G: I + O <= ~780 floats per row pair (one CTA per SM above ~100 KB)
+  MDL_REQUIRE(smem <= 200 * 1024, "linear_wgrad: layer too wide (needs %zu bytes of shared memory, I + O <= ~780)", smem);
+  static std::atomic<int> attr_set{0};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    MDL_CUDA(cudaFuncSetAttribute(k_linear_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set.store(1, std::memory_order_release);
   }
   cudaStream_t st = as_stream(stream);
   const int grid = wg_grid(N);

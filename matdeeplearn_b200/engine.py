@@ -9,6 +9,8 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from collections import OrderedDict
+
 from . import _lib, dist as mdist
 from .csr import csr_for
 from .data import Batch
@@ -31,8 +33,15 @@ class TrainStep:
         self.opt = mdist.FlatAdamW(self.flat, lr=lr, weight_decay=weight_decay)
         self.kernels_per_step = None
         self._graphs = {}
-        self._host_graphs = {}
+        self._host_graphs = OrderedDict()   # LRU: one static batch + graph pool per (N, E, B) shape
+        self.max_host_graphs = 8
         self._store_graphs = {}
+        if mdist.is_distributed():
+            # what DDP's constructor does (reference training.py:262-266): every replica starts from rank 0's
+            # parameters and buffers, whatever seed the caller built the model with
+            mdist.broadcast_(self.flat.param)
+            for b in model.buffers():
+                mdist.broadcast_(b)
         # warm-up runs on a side stream (standard capture recipe); the resulting stream-mismatch
         # note from autograd's AccumulateGrad is expected and harmless here
         try:
@@ -73,6 +82,7 @@ class TrainStep:
         assert batch.x.is_cuda
         csr_for(batch.edge_index, batch.batch, num_nodes=batch.x.shape[0],
                 num_graphs=getattr(batch, "num_graphs", None))  # layout built outside the graph
+        snap = self._snapshot()      # warm-up steps are not training steps
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -80,6 +90,7 @@ class TrainStep:
                 self.eager(batch)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._restore(snap)
         distributed = mdist.is_distributed()
         g1 = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
@@ -128,6 +139,10 @@ class TrainStep:
         if entry is None:
             entry = self._capture_host_step(host_batch, B, smear if lazy else None)
             self._host_graphs[key] = entry
+            while len(self._host_graphs) > self.max_host_graphs:   # least recently used shape goes
+                self._host_graphs.popitem(last=False)
+        else:
+            self._host_graphs.move_to_end(key)
         static, replay, loss, names = entry
         nbytes = 0
         for name in names:
@@ -237,6 +252,7 @@ class TrainStep:
                 # raw-pointer write: _layout_inside_graph drops the cached slot-order copy right after
                 MF.gaussian_smear(static.d_hat, offset, coeff, out=static.edge_attr)
         distributed = mdist.is_distributed()
+        snap = self._snapshot()      # the warm-up steps below must not count as training
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -247,6 +263,7 @@ class TrainStep:
                 self.eager(static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._restore(snap)
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             if expand is not None:

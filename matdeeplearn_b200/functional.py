@@ -107,7 +107,7 @@ class SegmentReduceFn(torch.autograd.Function):
         out = torch.empty((num_segments,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
         red = _lib.REDUCE[reduce]
         argmax = None
-        if red == 2 and src.requires_grad:
+        if red == 2 and ctx.needs_input_grad[0]:
             argmax = torch.empty((num_segments, width), dtype=torch.int32, device=src.device)
         rc = lib.mdl_segment_reduce_fwd(_lib.ptr(src), _lib.ptr(ptr), _lib.ptr(perm), _lib.ptr(out),
                                         _lib.ptr(argmax), num_segments, width, red, _lib.stream())
@@ -121,7 +121,8 @@ class SegmentReduceFn(torch.autograd.Function):
         ptr, perm, argmax = ctx.saved_tensors
         red, rows, width, S, shape = ctx.meta
         g = g.contiguous()
-        gsrc = torch.empty(shape, dtype=g.dtype, device=g.device)
+        # with a permutation, rows no segment refers to (capacity padding) are not written by the kernel
+        gsrc = (torch.zeros if perm is not None else torch.empty)(shape, dtype=g.dtype, device=g.device)
         rc = _lib.load().mdl_segment_reduce_bwd(_lib.ptr(g), _lib.ptr(ptr), _lib.ptr(perm),
                                                 _lib.ptr(argmax), _lib.ptr(gsrc), S, rows, width,
                                                 red, _lib.stream())
@@ -195,9 +196,11 @@ def masked_batch_norm(bn, x, n_valid=None):
     if bn.momentum is None:
         raise NotImplementedError("masked batch norm: cumulative-average momentum is not supported")
     N, C = x.shape
-    need = int(_lib.load().mdl_batchnorm_workspace_bytes(N, C))
+    # Sized ONCE for the saturated grid (the row count only changes how many CTAs write partials), so the
+    # buffer is never reallocated: CUDA graphs captured earlier keep a valid pointer whatever N comes later.
     ws = getattr(bn, "_mdl_ws", None)
-    if ws is None or ws.numel() < need or ws.device != x.device:
+    if ws is None or ws.device != x.device:
+        need = int(_lib.load().mdl_batchnorm_workspace_bytes(1 << 40, C))
         ws = torch.zeros(need, dtype=torch.uint8, device=x.device)
         bn._mdl_ws = ws
     rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)

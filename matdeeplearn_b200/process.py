@@ -109,8 +109,10 @@ def _general_minimum_image(d, cell, pbc=None):
     vol = abs(np.linalg.det(cell))
     r0 = 0.5 * np.linalg.norm(cell, axis=1).sum()
     heights = np.array([vol / np.linalg.norm(np.cross(cell[(i + 1) % 3], cell[(i + 2) % 3])) for i in range(3)])
-    n = np.minimum(np.ceil(2.0 * r0 / heights).astype(int), 4)   # 4: guard for needle-shaped cells
+    n = np.ceil(2.0 * r0 / heights).astype(int)
     n[~per] = 0
+    if n.max() > 8:   # (2n+1)^3 image shifts: a needle-shaped / badly reduced cell; refuse rather than truncate the search
+        raise ValueError(f"minimum image: cell too skewed (needs image shifts up to {n.tolist()}); reduce the cell first")
     best = w.copy()
     best_d2 = (w * w).sum(-1)
     for i in range(-n[0], n[0] + 1):

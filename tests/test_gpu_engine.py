@@ -27,11 +27,11 @@ def test_resident_graph_replay_equals_eager():
     s1, s2 = TrainStep(m1, lr=1e-3), TrainStep(m2, lr=1e-3)
     b = batch.to(DEV)
     b.num_graphs = 12
-    eager_losses = [float(s1.eager(b)) for _ in range(3 + 4)]   # resident() warms up 3 eager steps
-    replay = s2.resident(b, warmup=3)
+    eager_losses = [float(s1.eager(b)) for _ in range(4)]
+    replay = s2.resident(b, warmup=3)     # the warm-up steps are rolled back: capture is not training
     graph_losses = [float(replay()) for _ in range(4)]
     assert s2.kernels_per_step and s2.kernels_per_step > 0
-    for a, c in zip(eager_losses[3:], graph_losses):
+    for a, c in zip(eager_losses, graph_losses):
         assert abs(a - c) <= 1e-6 * max(1.0, abs(a)), (eager_losses, graph_losses)
 
 
@@ -43,10 +43,10 @@ def test_from_host_graph_equals_eager_and_tracks_oracle():
     s1, s2 = TrainStep(m1, lr=1e-3), TrainStep(m2, lr=1e-3)
     pinned = batch.pin_memory()
     pinned.num_graphs = 12
-    # graph capture warms up with 2 eager steps on the first call
+    # graph capture warms up with 2 eager steps on the first call and rolls them back
     l_eager = [s1.from_host(pinned, use_graph=False) for _ in range(6)]
     l_graph = [s2.from_host(pinned, use_graph=True) for _ in range(4)]
-    for a, c in zip(l_eager[2:], l_graph):
+    for a, c in zip(l_eager, l_graph):
         assert abs(a - c) <= 1e-6 * max(1.0, abs(a)), (l_eager, l_graph)
     # CPU oracle trajectory (same init, same optimizer)
     ref = OM.CGCNN(ds, **CFG)
@@ -156,3 +156,43 @@ def test_direct_gradient_delivery_equals_autograd_gradients():
     got = step.flat.grad
     scale = ref.abs().max().item()
     assert (got - ref).abs().max().item() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("dim1", [100, 128])
+def test_train_step_wide_cgcnn_direct_gradients(dim1):
+    """TrainStep (direct gradient delivery) on the reference's default width (config.yml CGCNN_demo: dim1=100)
+    and on 128: the weight-gradient kernel must take [N,C] x [N,4C] there, and the flat buffer must hold
+    what plain autograd produces."""
+    from matdeeplearn_b200 import models as M, process as pr
+    from matdeeplearn_b200.engine import TrainStep
+    ds = pr.synthetic_dataset("bulk", 12, seed=11)
+    batch = ds.batch()
+    torch.manual_seed(1)
+    model = M.CGCNN(ds, dim1=dim1, dim2=64, pre_fc_count=1, gc_count=2, post_fc_count=1)
+    m1, m2 = copy.deepcopy(model).to(DEV).train(), copy.deepcopy(model).to(DEV).train()
+    b = batch.to(DEV)
+    step = TrainStep(m1, lr=1e-3)
+    step._fwd_bwd(b)
+    loss = torch.nn.functional.l1_loss(m2(b), b.y)
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in m2.parameters()])
+    assert (step.flat.grad - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    losses = [float(step.eager(b)) for _ in range(3)]
+    assert all(l == l for l in losses)
+
+
+def test_from_host_many_shapes_is_bounded_and_does_not_overtrain():
+    """Every new (N, E) shape captures a graph: the warm-up must not advance the optimizer, and the cache of
+    captured shapes is bounded (LRU)."""
+    from matdeeplearn_b200 import process as pr
+    from matdeeplearn_b200.engine import TrainStep
+    ds, batch, model = _setup()
+    m1 = copy.deepcopy(model).to(DEV).train()
+    s1 = TrainStep(m1, lr=1e-3)
+    s1.max_host_graphs = 2
+    for k, n in enumerate((5, 7, 9, 11)):
+        sub = pr.synthetic_dataset("bulk", n, seed=20 + k).batch().pin_memory()
+        sub.num_graphs = n
+        s1.from_host(sub)
+        assert int(s1.opt.step_count.item()) == k + 1
+    assert len(s1._host_graphs) == 2

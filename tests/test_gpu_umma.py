@@ -79,3 +79,4 @@ def test_raw_fp32_operands_are_truncated_not_rounded():
     os.makedirs("gpurun_out", exist_ok=True)
     open("gpurun_out/tf32_narrowing.txt", "w").write(f"err vs truncation {e_trunc:.3e}  err vs round-to-nearest {e_rna:.3e}\n")
     assert e_trunc < 1e-4 and e_trunc < 0.1 * e_rna, (e_trunc, e_rna)
+
