@@ -28,11 +28,33 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-MODEL_CFG = dict(dim1=64, dim2=64, pre_fc_count=1, gc_count=4, post_fc_count=1,
-                 pool="global_mean_pool", pool_order="early", batch_norm="True",
-                 batch_track_stats="True", act="relu", dropout_rate=0.0)
-GRAPHS_PER_GPU = 256
-LR = 0.002  # config.yml CGCNN_demo
+_COMMON = dict(pre_fc_count=1, post_fc_count=1, pool="global_mean_pool", pool_order="early", batch_norm="True",
+               batch_track_stats="True", act="relu", dropout_rate=0.0)
+# BASELINE.json configs[1..4]; `graphs` = graphs per GPU under weak scaling (the reference's per-rank batch_size,
+# training.py:291-307), the global batch under --scaling strong
+CONFIGS = {
+    1: dict(model="CGCNN", kind="bulk", graphs=256, cfg=dict(dim1=64, dim2=64, gc_count=4, **_COMMON),
+            what="CGCNN dim=64 4xCGConv, synthetic bulk graphs, batch 256 (configs[1])"),
+    2: dict(model="SchNet", kind="bulk", graphs=256,
+            cfg=dict(dim1=128, dim2=128, dim3=128, cutoff=8, gc_count=4, **_COMMON),
+            what="SchNet dim=128 4 interactions, synthetic bulk graphs, batch 256 (configs[2])"),
+    3: dict(model="MEGNet", kind="mof", graphs=64,
+            cfg=dict(dim1=128, dim2=128, dim3=128, gc_count=3, gc_fc_count=2, **_COMMON),
+            what="MEGNet dim=128 3 blocks (gc_fc 2), synthetic MOF-shaped graphs, batch 64 (configs[3])"),
+    4: dict(model="MPNN", kind="bulk", graphs=256, cfg=dict(dim1=64, dim2=64, dim3=64, gc_count=4, **_COMMON),
+            sweep=(50, 100, 200),
+            what="MPNN dim=64 4xNNConv+GRU, synthetic bulk graphs, batch 256, edge_length 50 (sweep 50/100/200 beside "
+                 "it) (configs[4])"),
+}
+MODEL_CFG = CONFIGS[1]["cfg"]
+LR = 0.002  # config.yml *_demo
+
+
+def workload_string(cfgno, scaling, world):
+    """ONE string for both arms (the driver compares them)."""
+    c = CONFIGS[cfgno]
+    per = "per GPU (weak scaling)" if scaling == "weak" else f"global, split over {world} GPU(s) (strong scaling)"
+    return f"{c['what']}; batch {per}"
 
 
 def parse():
@@ -41,6 +63,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[k]")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's batch per GPU (reference DistributedSampler semantics); strong: one "
+                         "global batch split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated-kernel roofline leg")
     ap.add_argument("--roofline-graphs", type=int, default=16384)
@@ -104,56 +130,95 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_workload(rank, graphs):
+def make_workload(rank, graphs, kind="bulk", edge_length=50):
     from matdeeplearn_b200 import process as pr
-    ds = pr.synthetic_dataset("bulk", graphs, seed=pr.BENCH_SEED + rank)
+    ds = pr.synthetic_dataset(kind, graphs, seed=pr.BENCH_SEED + rank, edge_length=edge_length)
     return ds, ds.batch()
 
 
+def graphs_per_rank(cfgno, scaling, world):
+    g = CONFIGS[cfgno]["graphs"]
+    return g if scaling == "weak" else max(1, g // world)
+
+
 # ------------------------------------------------------------------ CPU leg
-def cpu_reference_steps(ds, batch, steps, warmup):
-    """The reference's CPU path: oracle restatement of the PyG op sequence on all
-    host cores (the reference itself cannot be installed: BASELINE.md section 2)."""
+def cpu_workload(args, world):
+    """The CPU arm's step = the WHOLE job's work: world x (per-rank batch), i.e. the same graphs the N GPUs
+    step through together, processed by one host (per-rank batches one after the other, each with the
+    reference's per-rank BatchNorm statistics)."""
+    c = CONFIGS[args.config]
+    per = graphs_per_rank(args.config, args.scaling, world)
+    G = c.get("sweep", (50,))[0]
+    return [make_workload(r, per, c["kind"], G) for r in range(world)], per
+
+
+def cpu_step_times(args, world, steps, warmup, threads=None, budget_s=None):
+    """budget_s: bound the run -- a step then covers only as many of the rank-batches as fit (a bounded sample of
+    the job's graphs; throughput = graphs actually processed / time)."""
     from oracle import models as OM
+    c = CONFIGS[args.config]
+    shards, per = cpu_workload(args, world)
+    if threads:
+        torch.set_num_threads(threads)
     torch.manual_seed(0)
-    model = OM.CGCNN(ds, **MODEL_CFG)
+    model = getattr(OM, c["model"])(shards[0][0], **c["cfg"])
     opt = torch.optim.AdamW(model.parameters(), lr=LR)
     model.train()
+    times_all = []
     times = []
     for i in range(warmup + steps):
+        if budget_s is not None and i == 1 and len(shards) > 1:   # first (warm-up) step timed: cut the sample to fit
+            keep = int(budget_s / max(times_all[0] / len(shards), 1e-9) / (warmup + steps))
+            shards = shards[:max(1, min(len(shards), keep))]
         t0 = time.perf_counter()
-        opt.zero_grad()
-        out = model(batch)
-        loss = F.l1_loss(out, batch.y)
-        loss.backward()
-        opt.step()
+        for _, batch in shards:       # one optimizer step per rank-batch: the same work, serialised on the host
+            opt.zero_grad()
+            loss = F.l1_loss(model(batch), batch.y)
+            loss.backward()
+            opt.step()
+        times_all.append(time.perf_counter() - t0)
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return times
+            times.append(times_all[-1])
+    E = sum(int(b.edge_index.shape[1]) for _, b in shards)
+    return times, per * len(shards), E
+
+
+def best_cpu_threads(args, world):
+    """Host thread count that maximises the CPU path's throughput; bounded sweep on ONE rank-batch."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    one = argparse.Namespace(**{**vars(args), "scaling": "weak"})
+    best, table = None, {}
+    for c in cands:
+        ts, graphs, _ = cpu_step_times(one, 1, 1, 1, threads=c)
+        table[c] = graphs / float(np.mean(ts))
+        if best is None or table[c] > table[best]:
+            best = c
+    return best, table
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    ds, batch = make_workload(0, GRAPHS_PER_GPU)
-    E = batch.edge_index.shape[1]
-    cores, table = best_cpu_threads(ds, batch)
-    torch.set_num_threads(cores)
-    times = cpu_reference_steps(ds, batch, args.steps, max(args.warmup, 1))
+    cores, table = best_cpu_threads(args, world)
+    times, graphs, E = cpu_step_times(args, world, args.steps, max(args.warmup, 1), threads=cores, budget_s=150.0)
     ms = 1e3 * float(np.mean(times))
-    value = GRAPHS_PER_GPU / (ms / 1e3)
+    value = graphs / (ms / 1e3)
+    c = CONFIGS[args.config]
     line = {
-        "impl": "reference", "metric": "graphs_per_sec_cgcnn_train_step", "value": value,
-        "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": f"graphs_per_sec_{c['model'].lower()}_train_step", "value": value,
+        "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "edges_per_sec": E / (ms / 1e3),
-        "config": {"workload": "CGCNN dim=64 4xCGConv, synthetic bulk graphs, batch 256 (configs[1])",
-                   "graphs_per_step": GRAPHS_PER_GPU, "edges_per_step": E,
+        "config": {"workload": workload_string(args.config, args.scaling, world),
+                   "graphs_per_step": graphs, "edges_per_step": E,
                    "note": "reference CPU path = PyG-equivalent op sequence restated in oracle/ "
-                           "(torch_geometric/torch_scatter not installable offline); rank 0 only"},
+                           "(torch_geometric/torch_scatter not installable offline); rank 0 only; one step = the "
+                           "whole job's graphs (n_gpus x per-rank batch) on this host"},
         "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": cores, "kind": "port",
                          "host_cores": os.cpu_count(), "thread_sweep_graphs_per_s": table,
-                         "sample": f"{args.steps} full train steps of the 256-graph batch, best thread count"},
+                         "sample": f"{args.steps} full train steps (zero_grad+fwd+l1_loss+bwd+AdamW) over {graphs} graphs, "
+                                   "best thread count"},
         "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -258,23 +323,59 @@ def kernel_roofline(args, dev, flush_buf, peak, peak_src):
     return res
 
 
-def best_cpu_threads(ds, batch):
-    """Host thread count that maximises the CPU path's throughput (more threads than
-    the batch can feed only adds synchronisation cost); bounded sweep."""
-    cores = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
-    best, table = None, {}
-    for c in cands:
-        torch.set_num_threads(c)
-        ts = cpu_reference_steps(ds, batch, 2, 1)
-        table[c] = GRAPHS_PER_GPU / float(np.mean(ts))
-        if best is None or table[c] > table[best]:
-            best = c
-    return best, table
+def aux_roofline(args, dev, flush_buf, peak):
+    """configs[2..4]: the CSR gather -> message -> segment-sum kernel of the config's operator, alone, on a
+    working set >> L2, cold L2, CUDA events (forward launch).  Algorithmic bytes: SURVEY.md 8(d) per-edge /
+    per-node figures of that kernel's own inputs and outputs (stated in `form`)."""
+    from matdeeplearn_b200 import functional as MF, process as pr
+    from matdeeplearn_b200.csr import GraphCSR
+    c = CONFIGS[args.config]
+    base = 256 if c["kind"] == "bulk" else 32
+    reps = 32 if c["kind"] == "bulk" else 16
+    ds = pr.synthetic_dataset(c["kind"], base, seed=pr.BENCH_SEED + 1000)
+    b = ds.batch().to(dev)
+    n0 = b.x.shape[0]
+    ei = torch.cat([b.edge_index + i * n0 for i in range(reps)], 1).contiguous()
+    bv = torch.cat([b.batch + i * base for i in range(reps)]).contiguous()
+    N, E = n0 * reps, ei.shape[1]
+    csr = GraphCSR.from_coo(ei, bv, num_graphs=base * reps)
+    torch.manual_seed(0)
+    if args.config == 2:
+        Fw = 128
+        h, W = torch.randn(N, Fw, device=dev), torch.randn(E, Fw, device=dev)
+        fn = lambda: MF.cfconv_aggregate(h, W, csr)                       # noqa: E731
+        nbytes, kernel = 4 * E * Fw + 8 * N * Fw + 8 * E, "k_spmm_edge (CFConv gather * filter -> destination sum)"
+        form = "4*E*F (filter rows) + 4*N*F (h) + 4*N*F (out) + 8*E (indices), F=128"
+    elif args.config == 3:
+        D = 128
+        base_t, A, B_ = torch.randn(E, D, device=dev), torch.randn(N, D, device=dev), torch.randn(N, D, device=dev)
+        U, bias = torch.randn(base * reps, D, device=dev), torch.randn(D, device=dev)
+        fn = lambda: MF.edge_gather_add(base_t, A, B_, U, bias, ei, bv, csr, True)   # noqa: E731
+        nbytes, kernel = 8 * E * D + 8 * N * D + 16 * E, "k_edge_gather_add (MEGNet edge update, first layer)"
+        form = "4*E*D read + 4*E*D write + 2*4*N*D (node projections) + 16*E (int64 indices), D=128"
+    else:
+        K, O = 64, 64
+        hid, XT, XB = torch.randn(E, K, device=dev), torch.randn(N, K * O, device=dev), torch.randn(N, O, device=dev)
+        fn = lambda: MF.nnconv_message(hid, XT, XB, csr)                  # noqa: E731
+        nbytes, kernel = 4 * E * K + 4 * E * O + 4 * N * (K * O + O) + 4 * E, "k_nnconv_msg (NNConv re-associated message)"
+        form = "4*E*K (hidden) + 4*E*O (messages) + 4*N*(K*O+O) (per-node products) + 4*E (edge ids), K=O=64"
+    with torch.no_grad():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush_l2(flush_buf)
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e))
+    ms = float(np.mean(ts))
+    return {"kernel": kernel, "workload": f"{base * reps} {c['kind']} graphs (N={N}, E={E}), cold L2", "ms": ms,
+            "algorithmic_bytes": nbytes, "form": form, "achieved_gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
 
 
 def run_engine(args, rank, world, local_rank):
-    from matdeeplearn_b200 import _lib, models as M, dist as mdist
+    from matdeeplearn_b200 import _lib, models as M
     from matdeeplearn_b200.engine import TrainStep
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -284,124 +385,159 @@ def run_engine(args, rank, world, local_rank):
         flush_buf = torch.zeros(128 * 1024 * 1024, device=dev)
         print(json.dumps(kernel_roofline(args, dev, flush_buf, peak, peak_src)), flush=True)
         return
-    ds, host_batch = make_workload(rank, GRAPHS_PER_GPU)
-    host_batch.num_graphs = GRAPHS_PER_GPU
-    N, E = host_batch.x.shape[0], host_batch.edge_index.shape[1]
-    torch.manual_seed(0)
-    model = M.CGCNN(ds, **MODEL_CFG).to(dev)
-    model.train()
-    step = TrainStep(model, lr=LR * world)
-    mdist.broadcast_(step.flat.param)
+    c = CONFIGS[args.config]
+    per = graphs_per_rank(args.config, args.scaling, world)
+    sweep = c.get("sweep", (50,))
     flush_buf = torch.zeros(128 * 1024 * 1024, device=dev)  # 512 MiB
-
-    # ---- device-resident, graph-replayed step (value)
-    dev_batch = host_batch.to(dev)
-    dev_batch.num_graphs = GRAPHS_PER_GPU
-    replay = step.resident(dev_batch, warmup=3)
-    for _ in range(max(args.warmup, 3)):
-        replay()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    total_ms, wall = timed_steps(replay, args.steps, flush_buf, world)
-    # ---- end to end from pinned host buffers through the public API (e2e)
-    pinned = host_batch.pin_memory()
-    pinned.num_graphs = GRAPHS_PER_GPU
-    pinned.smear = getattr(host_batch, "smear", None)
-    e2e_steps = max(5, min(args.steps, 30))
-    # (i) the batch's 7 reference tensors copied as they are (edge_attr materialised on the host)
-    for _ in range(3):
-        step.from_host(pinned, expand_edge_attr=False)
-    e2e_full_ms, _ = timed_steps(lambda: step.from_host(pinned, expand_edge_attr=False), e2e_steps, flush_buf, world)
-    h2d_full = step.last_h2d_bytes
-    # (ii) default public path: normalised distances shipped, Gaussian basis expanded on the GPU
-    for _ in range(3):
-        step.from_host(pinned)
-    e2e_ms, _ = timed_steps(lambda: step.from_host(pinned), e2e_steps, flush_buf, world)
-    h2d = step.last_h2d_bytes
-    # (iii) dataset resident in HBM (store.GraphStore): per step a fresh permutation of the rank's graphs is
-    #       assembled on the GPU into padded buffers and the captured step replayed; nothing crosses PCIe
-    #       but 6 KB of ids.  Not the e2e number (no host batch), reported beside it.
-    from matdeeplearn_b200.store import GraphStore
-    store = GraphStore.from_dataset(ds, dev)
-    perm_rng = np.random.default_rng(1234 + rank)
-    perms = [perm_rng.permutation(GRAPHS_PER_GPU) for _ in range(e2e_steps + 3)]
-    for i in range(3):
-        step.from_store(store, perms[i])
-    it = iter(perms[3:])
-    store_ms, _ = timed_steps(lambda: step.from_store(store, next(it)), e2e_steps, flush_buf, world)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = total_ms / args.steps
-    graphs_total = GRAPHS_PER_GPU * world
-    e_total = torch.tensor([float(E)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e_total)
-    edges_total = float(e_total.item())
-    value = graphs_total / (ms_per_step / 1e3)
-    e2e_value = graphs_total / (e2e_ms / e2e_steps / 1e3)
+    head, sweep_out = None, {}
+    for G in sweep:
+        ds, host_batch = make_workload(rank, per, c["kind"], G)
+        host_batch.num_graphs = per
+        N, E = host_batch.x.shape[0], host_batch.edge_index.shape[1]
+        torch.manual_seed(0)
+        model = getattr(M, c["model"])(ds, **c["cfg"]).to(dev)
+        model.train()
+        step = TrainStep(model, lr=LR * world)     # broadcasts rank 0's parameters (DDP constructor semantics)
+        # ---- device-resident, graph-replayed step (value)
+        dev_batch = host_batch.to(dev)
+        dev_batch.num_graphs = per
+        replay = step.resident(dev_batch, warmup=3)
+        for _ in range(max(args.warmup, 3)):
+            replay()
+        first = head is None
+        if first and rank == 0:
+            sampler.start()
+        total_ms, wall = timed_steps(replay, args.steps, flush_buf, world)
+        e_total = torch.tensor([float(E)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(e_total)
+        rec = {"G": G, "ms_per_step": total_ms / args.steps, "graphs_per_s": per * world / (total_ms / args.steps / 1e3),
+               "edges_per_s": float(e_total.item()) / (total_ms / args.steps / 1e3), "nodes_per_gpu": N, "edges_per_gpu": E,
+               "kernels_per_step": int(step.kernels_per_step)}
+        sweep_out[str(G)] = rec
+        if not first:
+            del model, step, replay
+            torch.cuda.empty_cache()
+            continue
+        head = dict(rec, wall=wall)
+        # ---- end to end from pinned host buffers through the public API (e2e)
+        pinned = host_batch.pin_memory()
+        pinned.num_graphs = per
+        pinned.smear = getattr(host_batch, "smear", None)
+        e2e_steps = max(5, min(args.steps, 30))
+        graph_ok = True
+        try:
+            for _ in range(3):
+                step.from_host(pinned, expand_edge_attr=False)
+        except Exception as exc:  # a model whose step cannot be captured from host buffers: eager step, said so below
+            graph_ok = False
+            head["e2e_capture_error"] = repr(exc)[:200]
+            torch.cuda.synchronize()
+        call = (lambda **kw: step.from_host(pinned, **kw)) if graph_ok else (lambda **kw: step.from_host(pinned, use_graph=False))
+        # (i) the batch's 7 reference tensors copied as they are (edge_attr materialised on the host)
+        for _ in range(2):
+            call(expand_edge_attr=False)
+        e2e_full_ms, _ = timed_steps(lambda: call(expand_edge_attr=False), e2e_steps, flush_buf, world)
+        h2d_full = getattr(step, "last_h2d_bytes", 0)
+        # (ii) product extra: normalised distances shipped, Gaussian basis expanded on the GPU
+        for _ in range(3):
+            call()
+        e2e_ms, _ = timed_steps(lambda: call(), e2e_steps, flush_buf, world)
+        h2d = getattr(step, "last_h2d_bytes", 0)
+        head.update(e2e_steps=e2e_steps, e2e_full_ms=e2e_full_ms, e2e_ms=e2e_ms, h2d_full=h2d_full, h2d=h2d, graph_ok=graph_ok)
+        # (iii) dataset resident in HBM (store.GraphStore), padded replay: CGCNN only
+        if c["model"] == "CGCNN":
+            from matdeeplearn_b200.store import GraphStore
+            store = GraphStore.from_dataset(ds, dev)
+            perm_rng = np.random.default_rng(1234 + rank)
+            perms = [perm_rng.permutation(per) for _ in range(e2e_steps + 3)]
+            for i in range(3):
+                step.from_store(store, perms[i])
+            it = iter(perms[3:])
+            store_ms, _ = timed_steps(lambda: step.from_store(store, next(it)), e2e_steps, flush_buf, world)
+            head["store_ms"] = store_ms
+        head["clocks"] = sampler.stop() if rank == 0 else None
+        del model, step, replay
+        torch.cuda.empty_cache()
 
+    graphs_total = per * world
+    ms_per_step = head["ms_per_step"]
+    es = head["e2e_steps"]
+    # the headline e2e is the reference-layout call (all 7 tensors of the PyG batch copied, edge_attr [E,G] included)
+    e2e_value = graphs_total / (head["e2e_full_ms"] / es / 1e3)
+    how = ("one CUDA graph replay of CSR build + slot permute + fwd + bwd" + ("" if world == 1 else " + NCCL all-reduce")
+           + " + AdamW") if head["graph_ok"] else "eager step (capture from host buffers failed for this model)"
     line = {
-        "metric": "graphs_per_sec_cgcnn_train_step", "value": value, "unit": "graphs/s",
+        "metric": f"graphs_per_sec_{c['model'].lower()}_train_step", "value": head["graphs_per_s"], "unit": "graphs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "edges_per_sec": edges_total / (ms_per_step / 1e3),
+        "edges_per_sec": head["edges_per_s"],
         "config": {
-            "workload": "CGCNN dim=64 4xCGConv, synthetic bulk graphs, batch 256 per GPU (configs[1])",
-            "graphs_per_step": graphs_total, "nodes_per_gpu": N, "edges_per_gpu": E,
+            "workload": workload_string(args.config, args.scaling, world),
+            "graphs_per_step": graphs_total, "nodes_per_gpu": head["nodes_per_gpu"], "edges_per_gpu": head["edges_per_gpu"],
             "parallelism": f"dp{world}", "step": "zero_grad+fwd+l1_loss+bwd" +
             ("+flat grad allreduce(NCCL, eager)+AdamW, two CUDA graph replays around the collective"
-             if world > 1 else "+AdamW, one CUDA graph replay"),
+             if world > 1 else "+AdamW, one CUDA graph replay") +
+            " (the metric text says fwd+bwd; the optimizer step is included, as in the reference's train() body)",
             "l2": "flushed between timed steps (512 MiB read-modify-write)",
             "timing": "sum of per-step CUDA-event durations, max over ranks",
         },
-        "gpu_launches": int(step.kernels_per_step) * args.steps,
-        "gpu_launches_per_step": int(step.kernels_per_step),
-        "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                "path": "TrainStep.from_host(pinned Batch): H2D of x, edge_index, edge_weight, batch, u, y and the "
-                        "normalised distances d_hat [E] (edge_attr = GaussianSmearing(d_hat) is expanded on the GPU), "
-                        "then one CUDA graph replay of smear + CSR build + slot permute + fwd + bwd + AdamW, then "
-                        "loss.item()",
-                "materialised_edge_attr": {
-                    "value": graphs_total / (e2e_full_ms / e2e_steps / 1e3), "h2d_bytes_per_step": int(h2d_full),
-                    "path": "same call with expand_edge_attr=False: all 7 reference tensors copied, edge_attr "
-                            "[E,50] included"}},
-        "store_step": {"value": graphs_total / (store_ms / e2e_steps / 1e3), "unit": "graphs/s", "steps": e2e_steps,
-                       "path": "TrainStep.from_store(GraphStore, idx): dataset resident in HBM, batch = index list -> "
-                               "one assembly kernel into capacity-padded buffers + the step, one CUDA graph replay; "
-                               "loss.item() each step"},
-        "wall_s_timed_region": wall,
+        "gpu_launches": head["kernels_per_step"] * args.steps,
+        "gpu_launches_per_step": head["kernels_per_step"],
+        "gpu_launches_note": "kernels launched by libmdl_b200.so inside the captured step (mdl_launch_count); library "
+                             "(cuBLAS / ATen) launches in the same step are not counted",
+        "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(head["h2d_full"]),
+                "d2h_bytes_per_step": 4, "steps": es,
+                "path": "TrainStep.from_host(pinned Batch, expand_edge_attr=False): H2D of the 7 tensors of the "
+                        "reference's batch (x, edge_index, edge_attr [E,G], edge_weight, batch, u, y), then " + how +
+                        ", then loss.item()",
+                "distances_shipped": {
+                    "value": graphs_total / (head["e2e_ms"] / es / 1e3), "h2d_bytes_per_step": int(head["h2d"]),
+                    "path": "product extra (batches made by process.assemble_dataset carry d_hat): 4 B/edge shipped, "
+                            "GaussianSmearing (reference process.py:580-590) expanded on the GPU inside the graph"}},
+        "wall_s_timed_region": head["wall"],
     }
+    if "e2e_capture_error" in head:
+        line["e2e"]["capture_error"] = head["e2e_capture_error"]
+    if "store_ms" in head:
+        line["store_step"] = {"value": graphs_total / (head["store_ms"] / es / 1e3), "unit": "graphs/s", "steps": es,
+                              "path": "TrainStep.from_store(GraphStore, idx): dataset resident in HBM, batch = index "
+                                      "list -> one assembly kernel into capacity-padded buffers + the step, one CUDA "
+                                      "graph replay; loss.item() each step"}
+    if len(sweep) > 1:
+        line["edge_length_sweep"] = sweep_out
+        line["epoch_100k_graphs_s"] = {g: 100000.0 / r["graphs_per_s"] for g, r in sweep_out.items()}
     if rank == 0:
-        line["clocks"] = clocks
+        line["clocks"] = head["clocks"]
         if not args.no_roofline:
-            r = kernel_roofline(args, dev, flush_buf, peak, peak_src)
-            is_bwd = r["bwd_both_passes"]["ms"] > r["fwd"]["ms"]
-            dom = r["bwd_both_passes"] if is_bwd else r["fwd"]
-            traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture
-            tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-            if os.path.exists(tpath):
-                t = json.load(open(tpath))
-                if t.get("graphs") == args.roofline_graphs:
-                    traffic = t.get("bwd_bytes" if is_bwd else "fwd_bytes")
-            line["roofline"] = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
-                                "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
-                                "kernel": "k_cgconv_tc<BWD_DST> (whole CGConv backward: single pass, dP + dWe + dQ)"
-                                if is_bwd else "k_cgconv_fwd_pipe",
-                                "note": "dominant = the slower of the two fused edge kernels; roofline_detail.fwd is the "
-                                        "fused gather->message->scatter_add forward kernel (k_cgconv_fwd_pipe)",
-                                "peak_source": peak_src, "workload": r["workload"]}
-            line["roofline_detail"] = r
+            if args.config == 1:
+                r = kernel_roofline(args, dev, flush_buf, peak, peak_src)
+                f, bw = r["fwd"], r["bwd_both_passes"]
+                line["roofline"] = {"bound": "hbm", "achieved": f["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                                    "frac": f["frac"], "traffic": None,
+                                    "kernel": "k_cgconv_fwd_pipe (fused gather -> message -> scatter_add, the kernel the "
+                                              "north star's roofline target names)",
+                                    "fwd_frac": f["frac"], "bwd_frac": bw["frac"],
+                                    "bwd": {"kernel": "k_cgconv_bwd_pipe (whole CGConv backward: single pass, dP + dW_e + dQ)",
+                                            "achieved": bw["achieved_gbs"], "frac": bw["frac"], "ms": bw["ms"]},
+                                    "form": "operator-surface: 8NC + 8E + 4EG bytes forward, + 4NC backward (SURVEY.md 8d)",
+                                    "traffic_note": "dram bytes per launch are in profiles/ (ncu --set full), not re-measured here",
+                                    "peak_source": peak_src, "workload": r["workload"]}
+                line["roofline_detail"] = r
+            else:
+                r = aux_roofline(args, dev, flush_buf, peak)
+                line["roofline"] = {"bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                                    "frac": r["frac"], "traffic": None, "kernel": r["kernel"], "form": r["form"],
+                                    "peak_source": peak_src, "workload": r["workload"], "ms": r["ms"]}
         if not args.no_cpu_baseline and world == 1:
-            cds, cb = make_workload(0, GRAPHS_PER_GPU)
-            threads, table = best_cpu_threads(cds, cb)
-            torch.set_num_threads(threads)
-            ts = cpu_reference_steps(cds, cb, args.cpu_steps, 1)
-            v = GRAPHS_PER_GPU / float(np.mean(ts))
+            threads, table = best_cpu_threads(args, 1)
+            ts, graphs, _ = cpu_step_times(args, 1, args.cpu_steps, 1, threads=threads)
+            v = graphs / float(np.mean(ts))
             line["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": threads, "kind": "port",
                                     "host_cores": os.cpu_count(), "thread_sweep_graphs_per_s": table,
-                                    "sample": f"{args.cpu_steps} full train steps of the same 256-graph batch "
+                                    "sample": f"{args.cpu_steps} full train steps of the same {graphs}-graph batch "
                                               "(oracle = PyG-equivalent op sequence, torch CPU), best thread count"}
         print(json.dumps(line), flush=True)
 

@@ -445,7 +445,11 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
   if (use_tc(CG_BWD_DST, C, G)) {
     p.seg_ptr = dst_ptr;
     int grid = 0;
-    if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid, dq_atomic ? 1 : 0)) return rc;
+    // default single-pass kernel: dW_e on tcgen05 (cgconv_bwd.cu); MDL_CGCONV_BWD=tc keeps the mma.sync one (A/B)
+    const char* benv = getenv("MDL_CGCONV_BWD");
+    if (dq_atomic && !(benv && strcmp(benv, "tc") == 0) && cgbwd_supported(p)) {
+      if (int rc = cgbwd_launch(p, st, &grid)) return rc;
+    } else if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid, dq_atomic ? 1 : 0)) return rc;
     const int64_t tot = (int64_t)G * 2 * C;  // partial layout [G][2C] == dWeT layout (no channel chunking)
     if (int rc = sum_partials(p.dW_part, grid, tot, tot, dWeT, tot, nullptr, st)) return rc;
   } else {
@@ -528,5 +532,6 @@ extern "C" int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const
 extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
   cgtc_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgfwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
+  cgbwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   return MDL_OK;
 }

@@ -62,6 +62,10 @@ void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
 bool cgfwd_supported(const CgParams& p);
 int cgfwd_launch(CgParams p, cudaStream_t st);
 void cgfwd_set_phase_buffer(unsigned long long* dev_ptr);
+// single-pass backward with dW_e on tcgen05 (cgconv_bwd.cu)
+bool cgbwd_supported(const CgParams& p);
+int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out);
+void cgbwd_set_phase_buffer(unsigned long long* dev_ptr);
 // out0[i] (i < len0) / out1[i - len0] = sum over nparts partial vectors, fixed order (cgconv.cu)
 int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, float* out0, int64_t len0,
                  float* out1, cudaStream_t st);

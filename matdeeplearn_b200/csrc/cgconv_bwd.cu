@@ -1,0 +1,549 @@
+// cgconv_bwd.cu -- single-pass CGConv backward (dP, dQ, dW_e) with BOTH contractions on tcgen05.
+//
+// Reference: autograd through PyG's CGConv (matdeeplearn/models/cgcnn.py:80-82,136-145); SURVEY.md Appendix E.1.
+// Same tile ownership, staging, gate recompute and deterministic per-destination sums as k_cgconv_tc<BWD_DST>
+// (cgconv_tc.cu); what changes:
+//   * 640 threads as in cgconv_fwd.cu: 16 epilogue warps + an issuer warp (every tcgen05.mma and bulk copy),
+//     setmaxnreg 112 / 32; barrier 1 hands work to the issuer through a double-buffered mailbox
+//     (kind 0 = gate recompute, 1 = dW_e, 2 = leave).
+//   * gate recompute: A operand (edge rows, hi/lo) in tensor memory, B = W_e in shared memory (as the forward).
+//   * dW_e^T[m, k] += sum_slot da[slot, m] * ea[slot, k]  as  D[M = 128 gate-channels][N = 64] accumulated in TMEM
+//     over the CTA's whole life (read once at the end):  A = da^T from TENSOR MEMORY (lane = gate-channel m,
+//     column = slot; written after [S3] by a column-wise re-read of the value tile), B = ea^T in shared memory,
+//     K-major [k][slot] hi/lo, written by the split pass (conflict-free with the 16-byte chunk padding).
+//     3 x 16 MMAs of 128x64x8 per round, asynchronous, instead of ~10.5k cycles of mma.sync in the epilogue warps.
+//     (kind::tf32 cannot read an MN-major operand in the plain layouts -- profiles/r2_umma_mn_probe.txt -- so the
+//     slot-contiguous operand is staged explicitly.)
+//   * TMEM: [0,128) recompute accumulator | [128,192) dW_e accumulator | [192,448) operand columns: the edge-row
+//     operand (2 x KP) of the recompute first, da^T (2 x 128) after it -- the former is dead when the latter is written.
+//   * the operand region and the ea^T tiles are busy until the round's dW_e MMAs retire: the NEXT round waits on
+//     bar_dwe before its split (they run under the dQ atomics, the per-destination sums and the next round's loads).
+#include "cgconv.cuh"
+#include "umma.cuh"
+#include "edge_dev.cuh"
+
+namespace mdl {
+namespace {
+
+constexpr int kThreads = 512, kWarps = 16, kS2 = kThreads + 32, kLaunch = kThreads + 128;
+constexpr int kRows = 128, kTile = 112, kInfoCap = 128;
+constexpr int kC = 64, kNP = 2 * kC, kVW = 2 * kC + 4;
+constexpr int kKT = 64;                                  // k rows of the ea^T tiles (G <= 64)
+constexpr uint32_t kTChunk = kKT * 16 + 16;              // bytes per 4-slot chunk of an ea^T tile (padded)
+constexpr uint32_t kColAcc = 0, kColDwe = 128, kColOp = 192, kTmemCols = 512;
+
+unsigned long long* g_bwd_phase_buf = nullptr;
+
+struct Plan {
+  unsigned long long* prof;
+  int window, KP;
+  uint32_t offBhi, offBlo, offThi, offTlo, offEA, offV, offIdx, offInfo, total;
+};
+
+inline bool plan(int C, int G, Plan* pl) {
+  if (C != kC || G < 1 || G > kKT) return false;
+  const int KP = (G + 7) & ~7;
+  const uint32_t b = (uint32_t)kNP * KP * 4, t = (uint32_t)(kRows / 4) * kTChunk;
+  const uint32_t ea = (((uint32_t)kRows * G * 4 + 32) + 15u) & ~15u, v = (uint32_t)kRows * kVW * 4;
+  const uint32_t idx = 4 * kRows * 4, info = kInfoCap * 16;
+  pl->prof = g_bwd_phase_buf; pl->window = 1; pl->KP = KP;
+  pl->offBhi = 0; pl->offBlo = b; pl->offThi = 2 * b; pl->offTlo = 2 * b + t; pl->offEA = 2 * b + 2 * t;
+  pl->offV = pl->offEA + ea; pl->offIdx = pl->offV + v; pl->offInfo = pl->offIdx + idx;
+  pl->total = pl->offInfo + info;
+  return pl->total <= (uint32_t)kMaxDynSmem;
+}
+
+struct Round { int k, rd, r_lo, cnt; bool last; };
+
+template <int PROFILE>
+__global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p, const Plan pl) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_mma, bar_dwe, bar_ea;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int sMail[2][4];  // double-buffered {kind, cnt, next r_lo, next cnt (or -1)}: consumers -> issuer warp
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = p.G, KP = pl.KP;
+  uint8_t* sBhi = smem + pl.offBhi;
+  uint8_t* sBlo = smem + pl.offBlo;
+  uint8_t* sThi = smem + pl.offThi;  // ea^T hi: element (k, slot) at (slot/4)*kTChunk + (k/8)*128 + (k%8)*16 + (slot%4)*4
+  uint8_t* sTlo = smem + pl.offTlo;
+  float* sEA = reinterpret_cast<float*>(smem + pl.offEA);
+  float* sV = reinterpret_cast<float*>(smem + pl.offV);    // node rows (window / per slot), then [d a_f | d a_s] per slot
+  int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);    // [2][src | dst][128]
+  TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);
+  auto sync_consumers = [] { asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory"); };
+  auto sync_issuer = [] { asm volatile("bar.sync 1, %0;" ::"n"(kS2) : "memory"); };
+
+  const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  int info_base = 0;
+  auto fill_infos = [&](int base) {
+    if (tid >= kThreads) return;
+    for (int k = base + tid; k < min(my_tiles, base + kInfoCap); k += kThreads) {
+      TileInfo t;
+      const int tile = blockIdx.x + k * gridDim.x;
+      t.n_lo = first_segment_at_or_after<CG_BWD_DST>(p, tile * kTile);
+      t.n_hi = (tile == p.n_tiles - 1) ? p.N : first_segment_at_or_after<CG_BWD_DST>(p, (tile + 1) * kTile);
+      if (t.n_hi < t.n_lo) t.n_hi = t.n_lo;
+      t.e_lo = __ldg(p.seg_ptr + t.n_lo);
+      t.e_hi = __ldg(p.seg_ptr + t.n_hi);
+      sInfo[k - base] = t;
+    }
+  };
+  auto make_round = [&](int k, int rd) -> Round {
+    Round R{k, rd, 0, 0, true};
+    if (k < my_tiles) {
+      const TileInfo T = sInfo[k - info_base];
+      R.r_lo = T.e_lo + rd * kRows;
+      R.cnt = max(0, min(T.e_hi - R.r_lo, kRows));
+      R.last = R.r_lo + kRows >= T.e_hi;
+    }
+    return R;
+  };
+  auto valid = [&](const Round& R) { return R.k < my_tiles; };
+  auto next_round = [&](const Round& R) -> Round { return R.last ? make_round(R.k + 1, 0) : make_round(R.k, R.rd + 1); };
+
+  // ---- setup
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemCols);
+  if (tid == 32) {
+    umma::mbar_init(&bar_mma, 1);
+    umma::mbar_init(&bar_dwe, 1);
+    umma::mbar_init(&bar_ea, 1);
+    umma::fence_mbar_init();
+  }
+  fill_infos(0);
+  for (int i = tid; i < kNP * KP; i += kLaunch) {
+    const int n = i % kNP, k = i / kNP;
+    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) : 0.0f;
+    const float hi = umma::tf32_hi(w);
+    const int off = umma::tile_offset_bytes(n, k, kNP);
+    *reinterpret_cast<float*>(sBhi + off) = hi;
+    *reinterpret_cast<float*>(sBlo + off) = w - hi;
+  }
+  for (uint32_t i = tid; i < (kRows / 4) * kTChunk / 4; i += kLaunch) {  // ea^T tiles: rows k >= G stay zero
+    reinterpret_cast<float*>(sThi)[i] = 0.0f;
+    reinterpret_cast<float*>(sTlo)[i] = 0.0f;
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc_g = umma::make_idesc_tf32(kRows, kNP);  // gate recompute: M = 128 slots, N = 128
+  const uint32_t idesc_w = umma::make_idesc_tf32(kNP, kKT);    // dW_e: M = 128 gate-channels, N = 64
+  const uint32_t tmA_hi = tmem + kColOp, tmA_lo = tmA_hi + (uint32_t)KP;  // edge rows (recompute)
+  const uint32_t tmD_hi = tmem + kColOp, tmD_lo = tmD_hi + kRows;         // da^T (aliases the above)
+  uint32_t ph_mma = 0, ph_dwe = 0, ph_ea = 0;
+
+  auto ea_bulk_bytes = [&](int r_lo, int cnt) -> uint32_t {
+    if (cnt <= 0) return 0u;
+    const long long first = (long long)r_lo * G;
+    const uint32_t bytes = (uint32_t)(((int)(first & 3) + cnt * G) * 4);
+    const bool more = ((long long)p.E * G - (first + (long long)cnt * G)) >= 3;
+    return more ? ((bytes + 15u) & ~15u) : (bytes & ~15u);
+  };
+  auto issue_ea_bulk = [&](int r_lo, int cnt) {
+    const uint32_t nb = ea_bulk_bytes(r_lo, cnt);
+    if (!nb) return;
+    const long long first = (long long)r_lo * G;
+    umma::mbar_arrive_expect_tx(&bar_ea, nb);
+    umma::bulk_g2s(sEA, p.ea + (first - (first & 3)), nb, &bar_ea);
+  };
+
+  // ---- issuer warp
+  if (warp >= kWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    bool first_dwe = true;
+    for (uint32_t mb = 0; warp == kWarps; mb ^= 1) {
+      sync_issuer();
+      const int kind = sMail[mb][0], xcnt = sMail[mb][1], y_lo = sMail[mb][2], ycnt = sMail[mb][3];
+      if (kind == 2) break;
+      if (lane == 0) {
+        umma::fence_after_sync();
+        if (kind == 0) {  // gate recompute of the staged round, then the next round's edge rows
+          if (ycnt >= 0) issue_ea_bulk(y_lo, ycnt);
+          if (xcnt > 0) {
+            const uint32_t step_b = 2 * (uint32_t)kNP * 16;
+            const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+            uint32_t acc = 0;
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a = (pass == 2) ? tmA_lo : tmA_hi;
+              const uint32_t b = (pass == 1) ? b_lo : b_hi;
+              for (int kk = 0; kk < (KP >> 3); ++kk) {
+                umma::mma_tf32_ts(tmem + kColAcc, a + kk * 8, umma::make_desc(b + kk * step_b, (uint32_t)kNP * 16, 128),
+                                  idesc_g, acc);
+                acc = 1;
+              }
+            }
+            umma::mma_commit(&bar_mma);
+          }
+        } else if (xcnt > 0) {  // dW_e of the round: contraction over its 128 slots (columns of da^T, k-chunks of ea^T)
+          const uint32_t t_hi = umma::smem_u32(sThi), t_lo = umma::smem_u32(sTlo);
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? tmD_lo : tmD_hi;
+            const uint32_t b = (pass == 1) ? t_lo : t_hi;
+            for (int kk = 0; kk < kRows / 8; ++kk) {
+              umma::mma_tf32_ts(tmem + kColDwe, a + kk * 8, umma::make_desc(b + kk * 2 * kTChunk, kTChunk, 128), idesc_w,
+                                first_dwe ? 0u : 1u);
+              first_dwe = false;
+            }
+          }
+          umma::mma_commit(&bar_dwe);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+
+  const int q = warp & 3, part = warp >> 2;
+  const int c_begin = part * 16;
+  Round cur = make_round(0, 0);
+  int buf = 0;
+  uint32_t mb = 0;  // mailbox slot of the next hand-off
+  auto post = [&](int kind, int cnt_, int y_lo, int y_cnt) {  // tid 0, before the issuer barrier
+    sMail[mb][0] = kind; sMail[mb][1] = cnt_; sMail[mb][2] = y_lo; sMail[mb][3] = y_cnt;
+  };
+  long long t_prev = PROFILE ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (PROFILE && pl.prof && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
+      t_prev = now;
+    }
+  };
+  bool dwe_pending = false;  // a dW_e batch has been handed to the issuer and not waited for yet
+  bool dwe_ever = false;     // the dW_e accumulator has been written at all (else the partial is zero)
+  if (valid(cur)) {
+    if (tid == 0) issue_ea_bulk(cur.r_lo, cur.cnt);
+    if (tid < 2 * kRows) {
+      const int e = tid & (kRows - 1);
+      if (e < cur.cnt) sIdx[tid] = __ldg((tid < kRows ? p.dst_src : p.dst_dst) + cur.r_lo + e);
+    }
+  }
+
+  while (valid(cur)) {
+    if (cur.k + 2 >= info_base + kInfoCap && info_base + kInfoCap < my_tiles) {
+      sync_consumers();
+      info_base = cur.k;
+      fill_infos(info_base);
+      sync_consumers();
+    }
+    const Round nxt = next_round(cur);
+    const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
+    const int n_lo = sInfo[cur.k - info_base].n_lo, n_hi = sInfo[cur.k - info_base].n_hi;
+    const int* bSrc = sIdx + buf * 2 * kRows;
+    const int* bDst = bSrc + kRows;
+    mark(0);
+    sync_consumers();  // [S1] value tile free; this round's indices visible
+    mark(1);
+
+    // ---- next indices, window decision, node rows -> registers (as cgconv_fwd.cu)
+    int nidx = 0;
+    if (valid(nxt) && tid < 2 * kRows) {
+      const int e = tid & (kRows - 1);
+      if (e < nxt.cnt) nidx = __ldg((tid < kRows ? p.dst_src : p.dst_dst) + nxt.r_lo + e);
+    }
+    bool win = false;
+    int w_smin = 0, w_dmin = 0, w_nq = 0, nrows = 0;
+    if (cnt > 0) {
+      int s_lo = 0x7fffffff, s_hi = -1;
+      const int4 sv = *reinterpret_cast<const int4*>(bSrc + 4 * lane);
+      const int e0 = 4 * lane;
+      if (e0 + 0 < cnt) { s_lo = min(s_lo, sv.x); s_hi = max(s_hi, sv.x); }
+      if (e0 + 1 < cnt) { s_lo = min(s_lo, sv.y); s_hi = max(s_hi, sv.y); }
+      if (e0 + 2 < cnt) { s_lo = min(s_lo, sv.z); s_hi = max(s_hi, sv.z); }
+      if (e0 + 3 < cnt) { s_lo = min(s_lo, sv.w); s_hi = max(s_hi, sv.w); }
+      s_lo = __reduce_min_sync(0xffffffffu, s_lo);
+      s_hi = __reduce_max_sync(0xffffffffu, s_hi);
+      const int d_lo = bDst[0], d_hi = bDst[cnt - 1];
+      const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
+      win = pl.window && nq + np_ <= kRows;
+      w_smin = s_lo; w_dmin = d_lo; w_nq = nq;
+      nrows = win ? nq + np_ : cnt;
+    }
+    auto row_src = [&](int r) -> const float4* {
+      const float* g;
+      if (win) g = (r < w_nq) ? p.PQ + (size_t)(w_smin + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(w_dmin + r - w_nq) * (4 * kC);
+      else g = p.PQ + (size_t)bSrc[r] * (4 * kC) + 2 * kC;
+      return reinterpret_cast<const float4*>(g);
+    };
+    float4 rr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + kThreads * i, r = c >> 5, col = c & 31;
+      if (r < nrows) rr[i] = __ldg(row_src(r) + col);
+    }
+    const int n0 = n_lo + warp;
+    int seg_a = 0, seg_b = 0;
+    if (n0 < n_hi) { seg_a = __ldg(p.seg_ptr + n0); seg_b = __ldg(p.seg_ptr + n0 + 1); }
+    mark(2);
+
+    // ---- the last round's dW_e MMAs read the operand columns and the ea^T tiles: both are rewritten below
+    if (dwe_pending) {
+      umma::mbar_wait(&bar_dwe, ph_dwe);
+      ph_dwe ^= 1;
+      umma::fence_after_sync();
+      dwe_pending = false;
+    }
+    mark(3);
+    // ---- split: edge rows -> hi / lo -> (a) tensor memory, A operand of the gate recompute
+    //                                  -> (b) ea^T tiles, B operand of this round's dW_e
+    {
+      const int ea_off = (int)(((long long)r_lo * G) & 3);
+      if (ea_bulk_bytes(r_lo, cnt)) {
+        umma::mbar_wait(&bar_ea, ph_ea);
+        ph_ea ^= 1;
+      }
+      const int e = tid & (kRows - 1);
+      const float* row = sEA + ea_off + e * G;
+      const int landed = (int)(ea_bulk_bytes(r_lo, cnt) >> 2);
+      const bool patch = e < cnt && landed < ea_off + (e + 1) * G;
+      const uint32_t t_off = (uint32_t)(e >> 2) * kTChunk + (uint32_t)(e & 3) * 4;
+      for (int ch = (tid >> 7); ch < (KP >> 3); ch += kThreads / kRows) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+        if (e < cnt) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (8 * ch + t < G) v[t] = row[8 * ch + t];
+          if (patch) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int k = 8 * ch + t;
+              if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)r_lo + e) * G + k);
+            }
+          }
+        }
+        float hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+        umma::tmem_st8(umma::tmem_addr(tmA_hi, warp, 8 * ch), hi);
+        umma::tmem_st8(umma::tmem_addr(tmA_lo, warp, 8 * ch), lo);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {  // k = 8 ch + t: core-matrix row t of k-group ch; lanes = slots -> distinct banks
+          const uint32_t o = t_off + (uint32_t)ch * 128 + (uint32_t)t * 16;
+          *reinterpret_cast<float*>(sThi + o) = hi[t];
+          *reinterpret_cast<float*>(sTlo + o) = lo[t];
+        }
+      }
+      umma::tmem_st_wait();
+    }
+    mark(4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + kThreads * i, r = c >> 5, col = c & 31;
+      if (r < nrows) *(reinterpret_cast<float4*>(sV + r * kVW) + col) = rr[i];
+    }
+    for (int c = tid + kThreads * 4; c < nrows * 32; c += kThreads)
+      *(reinterpret_cast<float4*>(sV + (c >> 5) * kVW) + (c & 31)) = __ldg(row_src(c >> 5) + (c & 31));
+    if (valid(nxt) && tid < 2 * kRows) sIdx[(buf ^ 1) * 2 * kRows + tid] = nidx;
+    if (tid == 0) post(0, cnt, nxt.r_lo, valid(nxt) ? nxt.cnt : -1);
+    umma::fence_proxy_async_smem();
+    umma::fence_before_sync();
+    mark(5);
+    sync_issuer();  // [S2] -> issuer: next edge rows, gate recompute
+    mb ^= 1;
+    mark(6);
+
+    // ---- epilogue, part 1: a = accumulator + P[dst] + Q[src]
+    float f[16], sacc[16];
+    const int e_ep = 32 * q + lane;
+    const bool live = e_ep < cnt;
+    int sd = 0;
+    // grad_out row of this slot's destination (pre-divided by the degree): requested before the wait on the
+    // contraction, consumed in part 2 (slots are destination-sorted: a warp touches a few distinct rows)
+    float4 gq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      sd = bDst[e_ep];
+      const float4* gp = reinterpret_cast<const float4*>(p.gout + (size_t)sd * kC + c_begin);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gq[j] = __ldg(gp + j);
+    }
+    if (cnt > 0) {
+      umma::mbar_wait(&bar_mma, ph_mma);
+      ph_mma ^= 1;
+      umma::fence_after_sync();
+      mark(7);
+      umma::tmem_ld16(umma::tmem_addr(tmem, q, kColAcc + c_begin), f);
+      umma::tmem_ld16(umma::tmem_addr(tmem, q, kColAcc + kC + c_begin), sacc);
+      umma::tmem_ld_wait();
+      if (live) {
+        const int ss = bSrc[e_ep];
+        const float* r0 = win ? sV + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
+        const float* r1 = win ? sV + (ss - w_smin) * kVW + c_begin : sV + e_ep * kVW + c_begin;
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 pf = win ? *reinterpret_cast<const float4*>(r0 + j4) : __ldg(reinterpret_cast<const float4*>(r0 + j4));
+          const float4 ps = win ? *reinterpret_cast<const float4*>(r0 + kC + j4)
+                                : __ldg(reinterpret_cast<const float4*>(r0 + kC + j4));
+          const float4 qf = *reinterpret_cast<const float4*>(r1 + j4);
+          const float4 qs = *reinterpret_cast<const float4*>(r1 + kC + j4);
+          f[j4] += pf.x + qf.x; f[j4 + 1] += pf.y + qf.y; f[j4 + 2] += pf.z + qf.z; f[j4 + 3] += pf.w + qf.w;
+          sacc[j4] += ps.x + qs.x; sacc[j4 + 1] += ps.y + qs.y; sacc[j4 + 2] += ps.z + qs.z; sacc[j4 + 3] += ps.w + qs.w;
+        }
+      }
+    }
+    mark(8);
+    umma::fence_before_sync();
+    sync_consumers();  // [S2d] node rows read: the value tile may be overwritten
+    mark(9);
+    // ---- part 2: d m / d a_f, d m / d a_s times grad_out[dst] (pre-divided by the degree) -> value tile
+    if (live) {
+      float* rowv = sV + e_ep * kVW;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        float r0[4], r1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float sg = sigmoid_mixed(f[j4 + j]);
+          float sp, sgs;
+          softplus_sigmoid_mufu(sacc[j4 + j], sp, sgs);
+          const float4 gv = gq[j4 >> 2];
+          const float g = j == 0 ? gv.x : j == 1 ? gv.y : j == 2 ? gv.z : gv.w;
+          r0[j] = g * sp * sg * (1.0f - sg);
+          r1[j] = g * sg * sgs;
+        }
+        *reinterpret_cast<float4*>(rowv + c_begin + j4) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+        *reinterpret_cast<float4*>(rowv + kC + c_begin + j4) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+      }
+    }
+    mark(10);
+    sync_consumers();  // [S3] value tile = da of the round
+    mark(11);
+
+    // ---- da^T -> tensor memory: thread = gate-channel m (TMEM lane), its quarter of the slots; rows >= cnt are zero
+    if (cnt > 0) {
+      const int m = tid & (kNP - 1);
+      for (int s8 = 4 * part; s8 < 4 * part + 4; ++s8) {  // 8-slot groups 4*part .. 4*part+3
+        float hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int s = 8 * s8 + t;
+          const float v = s < cnt ? sV[s * kVW + m] : 0.0f;  // bank = 4 s + m: lanes = consecutive m
+          hi[t] = umma::tf32_hi(v);
+          lo[t] = v - hi[t];
+        }
+        umma::tmem_st8(umma::tmem_addr(tmD_hi, warp, 8 * s8), hi);
+        umma::tmem_st8(umma::tmem_addr(tmD_lo, warp, 8 * s8), lo);
+      }
+      umma::tmem_st_wait();
+    }
+    if (tid == 0) post(1, cnt, 0, -1);
+    umma::fence_before_sync();
+    mark(12);
+    sync_issuer();  // [S4] -> issuer: dW_e MMAs of this round (they run under the atomics and sums below)
+    mb ^= 1;
+    mark(13);
+    dwe_pending = cnt > 0;
+    dwe_ever |= cnt > 0;
+
+    // ---- dQ[src] += da, one 512-byte row per warp instruction
+    {
+      const int row0 = warp * (kRows / kWarps);
+#pragma unroll
+      for (int i = 0; i < kRows / kWarps; ++i) {
+        const int e = row0 + i;
+        if (e < cnt) {
+          const float4 v = *(reinterpret_cast<const float4*>(sV + e * kVW) + lane);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + (size_t)bSrc[e] * (4 * kC) + 2 * kC + 4 * lane),
+                       "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                       : "memory");
+        }
+      }
+    }
+    mark(14);
+    // ---- dP[i] = sum over the segment's slots, slot order
+    for (int n = n0; n < n_hi; n += kWarps) {
+      int a, b;
+      if (n == n0) { a = seg_a; b = seg_b; }
+      else { a = __ldg(p.seg_ptr + n); b = __ldg(p.seg_ptr + n + 1); }
+      const int lo = max(a, r_lo), hi = min(b, r_hi);
+      const bool empty_seg = (a == b);
+      if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
+      const bool first = empty_seg || (a >= r_lo);
+      float* o = p.out + (size_t)n * (4 * kC);
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = first ? 0.0f : o[32 * u + lane];
+      for (int s = lo; s < hi; ++s) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += sV[(s - r_lo) * kVW + 32 * u + lane];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) o[32 * u + lane] = acc[u];
+    }
+    mark(15);
+    if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
+    cur = nxt; buf ^= 1;
+  }
+
+  // ---- the CTA's dW_e^T partial: accumulator lane = gate-channel m, column = k
+  if (dwe_pending) {
+    umma::mbar_wait(&bar_dwe, ph_dwe);
+    umma::fence_after_sync();
+  }
+  if (my_tiles > 0) {
+    float* part_out = p.dW_part + (size_t)blockIdx.x * G * kNP;
+    const int m = 32 * q + lane;
+    float d[16];
+    umma::tmem_ld16(umma::tmem_addr(tmem, q, kColDwe + c_begin), d);  // columns k = c_begin .. c_begin + 15
+    umma::tmem_ld_wait();
+    if (!dwe_ever) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c_begin + j < G) part_out[(size_t)(c_begin + j) * kNP + m] = d[j];
+  }
+  if (tid == 0) post(2, 0, 0, -1);
+  umma::fence_before_sync();
+  sync_issuer();  // the issuer warp leaves
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int PROFILE>
+int bwd_launch_t(const CgParams& p, const Plan& pl, int grid, cudaStream_t st) {
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_acquire)) {
+    MDL_CUDA(cudaFuncSetAttribute(k_cgconv_bwd_pipe<PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    configured.store(1, std::memory_order_release);
+  }
+  k_cgconv_bwd_pipe<PROFILE><<<grid, kLaunch, pl.total, st>>>(p, pl);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+}  // namespace
+
+void cgbwd_set_phase_buffer(unsigned long long* dev_ptr) { g_bwd_phase_buf = dev_ptr; }
+
+// C = 64, G <= 64, 16-byte aligned ea / PQ / gout / dPQ (bulk copy, vector loads, vector atomics)
+bool cgbwd_supported(const CgParams& p) {
+  Plan pl;
+  return plan(p.C, p.G, &pl) && (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.PQ) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.gout) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (int64_t)p.N * 4 * p.C < (int64_t)1 << 31;
+}
+
+// dP (by destination, deterministic) + dQ (vector atomics: the caller zeroes the dQ half first) + per-CTA dW_e^T
+// partials in p.dW_part ([grid][G][2C]); *grid_out = number of partials
+int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out) {
+  Plan pl;
+  MDL_REQUIRE(plan(p.C, p.G, &pl), "cgconv_bwd: unsupported shape C=%d G=%d", p.C, p.G);
+  const char* wenv = getenv("MDL_CGCONV_WINDOW");
+  pl.window = !(wenv && wenv[0] == '0');
+  p.c_off = 0; p.CC = p.C; p.cap = kRows; p.te = kTile;
+  p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTile));
+  const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+  if (grid_out) *grid_out = grid;
+  return pl.prof ? bwd_launch_t<1>(p, pl, grid, st) : bwd_launch_t<0>(p, pl, grid, st);
+}
+
+}  // namespace mdl

@@ -55,11 +55,17 @@ def bwd():
 PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue",
               6: "wait MMA(r)", 2: "wait ea(r+1)", 3: "split(r+1) -> TMEM", 4: "row+idx STS, fences, S2",
               7: "TMEM ld", 10: "node terms + gate math", 11: "S3 barrier", 12: "reduce"}
+BWD_PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 2: "next idx, window, row/seg loads issue", 3: "wait dW_e(r-1)",
+                  4: "wait ea + split -> TMEM + ea^T tiles", 5: "row/idx STS, fences", 6: "S2 (issuer hand-off)",
+                  7: "grad loads + wait recompute MMA", 8: "TMEM ld + node terms", 9: "S2d barrier", 10: "gate math",
+                  11: "S3 barrier", 12: "da^T -> TMEM", 13: "S4 (issuer hand-off)", 14: "dQ atomics", 15: "dP sums"}
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if os.environ.get("ONLY", name) != name:
         continue
     if name == "fwd" and os.environ.get("MDL_CGCONV_IMPL", "pipe") == "pipe":
         NAMES_ = PIPE_NAMES
+    elif name == "bwd" and os.environ.get("MDL_CGCONV_BWD", "pipe") != "tc":
+        NAMES_ = BWD_PIPE_NAMES
     else:
         NAMES_ = NAMES
     fn(); torch.cuda.synchronize()
@@ -98,9 +104,9 @@ def timed(fn, n=10):
 
 
 bytes_fwd = 8 * N * C + 8 * E + 4 * E * G
-for impl, win, gate, ea_mode in (("pipe", "1", "mixed", "bulk"), ("pipe", "0", "mixed", "bulk"), ("tc", "1", "mixed", "bulk"),
-                                 ("tc", "0", "mixed", "bulk"), ("tc", "1", "mufu", "bulk"), ("tc", "1", "mixed", "rows")):
+for impl, win, gate, ea_mode in (("pipe", "1", "mixed", "bulk"), ("pipe", "0", "mixed", "bulk"), ("tc", "1", "mixed", "bulk")):
     os.environ["MDL_CGCONV_IMPL"] = impl
+    os.environ["MDL_CGCONV_BWD"] = impl
     os.environ["MDL_CGCONV_WINDOW"] = win
     os.environ["MDL_CGCONV_GATE"] = gate
     os.environ["MDL_CGCONV_EA"] = ea_mode

@@ -29,7 +29,8 @@ def _maxerr(a, b):
     return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item()
 
 
-def _check_model(name, kind, graphs, cfg, edge_length=50, seed=7, out_tol=1e-4, g_rel=1e-4, g_abs=1e-5):
+def _check_model(name, kind, graphs, cfg, edge_length=50, seed=7, out_tol=1e-4, g_rel=1e-4, g_abs=1e-5,
+                 fp32_yardstick=False):
     from matdeeplearn_b200 import models as M, process as pr
     from oracle import models as OM
     ds = pr.synthetic_dataset(kind, graphs, seed=seed, edge_length=edge_length)
@@ -39,6 +40,10 @@ def _check_model(name, kind, graphs, cfg, edge_length=50, seed=7, out_tol=1e-4, 
     ref_model = getattr(OM, name)(ds, **cfg)
     model = getattr(M, name)(ds, **cfg)
     model.load_state_dict(ref_model.state_dict())
+    o32 = None
+    if fp32_yardstick:   # the same oracle in fp32 on the CPU: how far plain fp32 arithmetic sits from the fp64 truth
+        import copy
+        o32 = copy.deepcopy(ref_model).train()
     ref_model = ref_model.double().train()
     model = model.to(DEV).train()
     gb = b.to(DEV)
@@ -55,6 +60,10 @@ def _check_model(name, kind, graphs, cfg, edge_length=50, seed=7, out_tol=1e-4, 
     assert e <= out_tol * scale, (name, "forward", e, scale)
     ref_grads = {k: p.grad for k, p in ref_model.named_parameters()}
     gscale = max(g.abs().max().item() for g in ref_grads.values() if g is not None and g.numel())
+    o32_grads = {}
+    if o32 is not None:
+        torch.nn.functional.l1_loss(o32(b), b.y).backward()
+        o32_grads = {k: p.grad for k, p in o32.named_parameters()}
     worst = (0.0, None)
     for k, p in model.named_parameters():
         r = ref_grads[k]
@@ -63,6 +72,8 @@ def _check_model(name, kind, graphs, cfg, edge_length=50, seed=7, out_tol=1e-4, 
             continue
         e = _maxerr(p.grad, r)
         tol = g_rel * r.abs().max().item() + g_abs * gscale
+        if o32_grads.get(k) is not None:
+            tol = max(tol, _maxerr(o32_grads[k], r))   # never looser than the fp32 CPU oracle's own deviation
         _log(f"{name} {kind}x{graphs} G={edge_length} grad {k}", e, r.abs().max().item())
         if e / tol > worst[0]:
             worst = (e / tol, k)
@@ -80,8 +91,14 @@ def test_schnet_config2_shape():
 
 
 def test_megnet_config3_shape():
+    """The reference feeds u = zeros[B,3] (process.py:330-332): every row of the first block's global-state
+    MLP is identical, its BatchNorm sees zero variance and amplifies rounding by 1/sqrt(eps) -- the fp32 CPU
+    oracle's own gradients sit ~1e-1 (relative) from the fp64 ones on this config.  Output: 1e-4 of scale as
+    everywhere; gradients: the usual bound, or the fp32 oracle's own distance from fp64 where that is larger
+    (the engine must be at least as close to the truth as fp32 PyTorch on the CPU is)."""
     _check_model("MEGNet", "mof", 64,
-                 dict(dim1=128, dim2=128, dim3=128, pre_fc_count=1, gc_count=3, gc_fc_count=2, post_fc_count=1))
+                 dict(dim1=128, dim2=128, dim3=128, pre_fc_count=1, gc_count=3, gc_fc_count=2, post_fc_count=1),
+                 fp32_yardstick=True)
 
 
 @pytest.mark.parametrize("G", [100, 200])

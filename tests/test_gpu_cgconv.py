@@ -92,7 +92,6 @@ def impl(request, monkeypatch):
     """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
     atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
     tensor-core kernels in deterministic two-pass mode, and with the SIMT kernels forced."""
-    # "tt": transposed-tile forward kernel (cgconv_tt.cu); the backward stays on the tc kernels
     # "tc_nowin": tensor-core kernels with the shared-memory node-row window off (per-slot rows only)
     # "tc_rows": edge rows by per-row cp.async instead of one bulk (TMA) copy per round
     monkeypatch.setenv("MDL_CGCONV_WINDOW", "0" if request.param.endswith("_nowin") else "1")
@@ -101,6 +100,8 @@ def impl(request, monkeypatch):
     monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt",) else
                        ("pipe" if request.param.startswith("pipe") else "tc"))
     monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
+    # backward: "pipe*" = default single-pass kernel with dW_e on tcgen05 (cgconv_bwd.cu); "tc*" = the mma.sync one
+    monkeypatch.setenv("MDL_CGCONV_BWD", "tc" if request.param.startswith("tc") else "pipe")
     return request.param
 
 
