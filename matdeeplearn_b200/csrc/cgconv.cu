@@ -394,10 +394,13 @@ extern "C" int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, 
   p.dst_dst = dst_dst; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg_dst : nullptr;
   p.out = out; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
   if (use_tc(CG_FWD, C, G)) {
-    // default: the software-pipelined forward kernel (cgconv_fwd.cu); MDL_CGCONV_IMPL=tc keeps the
-    // round-serial tensor-core kernel (A/B, and the shapes / alignments the pipelined one declines)
+    // default: the warp-specialised forward kernel (cgconv_fwd_ws.cu); MDL_CGCONV_IMPL=pipe selects the
+    // software-pipelined one (cgconv_fwd.cu), =tc the round-serial tensor-core kernel (A/B, and the shapes /
+    // alignments the others decline)
     const char* env = getenv("MDL_CGCONV_IMPL");
-    if (!(env && strcmp(env, "tc") == 0) && cgfwd_supported(p)) return cgfwd_launch(p, as_stream(stream));
+    const bool want_tc = env && strcmp(env, "tc") == 0, want_pipe = env && strcmp(env, "pipe") == 0;
+    if (!want_tc && !want_pipe && cgws_supported(p)) return cgws_launch(p, as_stream(stream));
+    if (!want_tc && cgfwd_supported(p)) return cgfwd_launch(p, as_stream(stream));
     return cgtc_launch(CG_FWD, p, as_stream(stream), nullptr);
   }
   p.cap = plan.cap; p.te = plan.te;
@@ -533,5 +536,6 @@ extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
   cgtc_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgfwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgbwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
+  cgws_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   return MDL_OK;
 }

@@ -62,6 +62,10 @@ void cgtc_set_phase_buffer(unsigned long long* dev_ptr);
 bool cgfwd_supported(const CgParams& p);
 int cgfwd_launch(CgParams p, cudaStream_t st);
 void cgfwd_set_phase_buffer(unsigned long long* dev_ptr);
+// warp-specialised forward kernel (cgconv_fwd_ws.cu): staging, MMA issue and epilogue on separate warps
+bool cgws_supported(const CgParams& p);
+int cgws_launch(CgParams p, cudaStream_t st);
+void cgws_set_phase_buffer(unsigned long long* dev_ptr);
 // single-pass backward with dW_e on tcgen05 (cgconv_bwd.cu)
 bool cgbwd_supported(const CgParams& p);
 int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out);

@@ -55,6 +55,8 @@ def bwd():
 PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue",
               6: "wait MMA(r)", 2: "wait ea(r+1)", 3: "split(r+1) -> TMEM", 4: "row+idx STS, fences, S2",
               7: "TMEM ld", 10: "node terms + gate math", 11: "S3 barrier", 12: "reduce"}
+WS_NAMES = {0: "loop top + seg loads issue", 1: "wait indices / node rows", 2: "wait MMA", 3: "TMEM ld + release",
+            4: "node terms + gate math", 5: "S3 barrier", 6: "reduce", 7: "S1 barrier"}
 BWD_PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 2: "next idx, window, row/seg loads issue", 3: "wait dW_e(r-1)",
                   4: "wait ea + split -> TMEM + ea^T tiles", 5: "row/idx STS, fences", 6: "S2 (issuer hand-off)",
                   7: "grad loads + wait recompute MMA", 8: "TMEM ld + node terms", 9: "S2d barrier", 10: "gate math",
@@ -62,7 +64,9 @@ BWD_PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 2: "next idx, window, row/seg 
 for name, fn in (("fwd", fwd), ("bwd", bwd)):
     if os.environ.get("ONLY", name) != name:
         continue
-    if name == "fwd" and os.environ.get("MDL_CGCONV_IMPL", "pipe") == "pipe":
+    if name == "fwd" and os.environ.get("MDL_CGCONV_IMPL", "ws") == "ws":
+        NAMES_ = WS_NAMES
+    elif name == "fwd" and os.environ.get("MDL_CGCONV_IMPL", "ws") == "pipe":
         NAMES_ = PIPE_NAMES
     elif name == "bwd" and os.environ.get("MDL_CGCONV_BWD", "pipe") != "tc":
         NAMES_ = BWD_PIPE_NAMES
@@ -104,7 +108,8 @@ def timed(fn, n=10):
 
 
 bytes_fwd = 8 * N * C + 8 * E + 4 * E * G
-for impl, win, gate, ea_mode in (("pipe", "1", "mixed", "bulk"), ("pipe", "0", "mixed", "bulk"), ("tc", "1", "mixed", "bulk")):
+for impl, win, gate, ea_mode in (("ws", "1", "mixed", "bulk"), ("ws", "0", "mixed", "bulk"), ("pipe", "1", "mixed", "bulk"),
+                                 ("tc", "1", "mixed", "bulk")):
     os.environ["MDL_CGCONV_IMPL"] = impl
     os.environ["MDL_CGCONV_BWD"] = impl
     os.environ["MDL_CGCONV_WINDOW"] = win

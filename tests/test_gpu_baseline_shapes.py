@@ -103,7 +103,13 @@ def test_megnet_config3_shape():
 
 @pytest.mark.parametrize("G", [100, 200])
 def test_mpnn_config4_edge_lengths(G):
-    _check_model("MPNN", "bulk", 32, dict(dim1=64, dim2=64, dim3=64, pre_fc_count=1, gc_count=3, post_fc_count=1),
+    """act="softplus" between the layers: with ReLU everywhere the comparison with fp64 is decided by which side
+    of a kink a rounding-sized pre-activation falls on -- measured on this batch (profiles/debug_mpnn_parity2.py):
+    one of the 2048 post-FC pre-activations is 5.7e-8, the fp32 engine (error 1.7e-6 there, like the fp32 oracle on
+    the GPU) lands on the other side, one ReLU mask flips and every gradient upstream moves by ~1e-2 although
+    forward, kernels and autograd all agree to 1e-6.  The NNConv edge network keeps its ReLU (reference mpnn.py:83-85)."""
+    _check_model("MPNN", "bulk", 32, dict(dim1=64, dim2=64, dim3=64, pre_fc_count=1, gc_count=3, post_fc_count=1,
+                                          act="softplus"),
                  edge_length=G)
 
 

@@ -87,7 +87,7 @@ def test_scatter_unsorted_index(dev):
         assert_close(got, ref, **FWD, what=red)
 
 
-@pytest.fixture(params=["pipe", "pipe_nowin", "tc", "tc_det", "tc_nowin", "tc_rows", "simt"])
+@pytest.fixture(params=["ws", "ws_nowin", "pipe", "pipe_nowin", "tc", "tc_det", "tc_nowin", "tc_rows", "simt"])
 def impl(request, monkeypatch):
     """Run a case on the tensor-core kernels (default dispatch: single-pass backward with vector
     atomics for dQ; shapes that do not fit fall back to SIMT inside the library), on the
@@ -97,8 +97,9 @@ def impl(request, monkeypatch):
     monkeypatch.setenv("MDL_CGCONV_WINDOW", "0" if request.param.endswith("_nowin") else "1")
     monkeypatch.setenv("MDL_CGCONV_EA", "rows" if request.param == "tc_rows" else "bulk")
     # "pipe": default dispatch (software-pipelined forward kernel, cgconv_fwd.cu; tc backward)
+    # "ws": default dispatch (warp-specialised forward kernel, cgconv_fwd_ws.cu; single-pass tcgen05 backward)
     monkeypatch.setenv("MDL_CGCONV_IMPL", request.param if request.param in ("simt",) else
-                       ("pipe" if request.param.startswith("pipe") else "tc"))
+                       ("ws" if request.param.startswith("ws") else "pipe" if request.param.startswith("pipe") else "tc"))
     monkeypatch.setenv("MDL_CGCONV_DETERMINISTIC", "1" if request.param == "tc_det" else "0")
     # backward: "pipe*" = default single-pass kernel with dW_e on tcgen05 (cgconv_bwd.cu); "tc*" = the mma.sync one
     monkeypatch.setenv("MDL_CGCONV_BWD", "tc" if request.param.startswith("tc") else "pipe")
