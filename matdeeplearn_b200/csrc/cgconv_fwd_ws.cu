@@ -2,25 +2,29 @@
 //
 // Reference: PyG CGConv.forward as the reference calls it (matdeeplearn/models/cgcnn.py:80-82,136-145):
 //   out_i = x_i + mean_{j->i} sigmoid(W_f z + b_f) * softplus(W_s z + b_s),  z = [x_i | x_j | e_ij].
-// Same operator, tile ownership, 3xTF32 contraction, gate math and deterministic per-segment sums as
-// k_cgconv_fwd_pipe (cgconv_fwd.cu).  There, the 16 epilogue warps also stage everything a round needs
-// (indices, node rows, the hi/lo split of the edge rows into tensor memory) between CTA-wide barriers, and
-// that staging is ~45 % of the round.  Here every stage has its own warps and its own mbarrier hand-offs, so
-// the epilogue warps do nothing but epilogue + per-segment sums while the next rounds are staged under them:
+// Same operator, tile ownership, 3xTF32 contraction and deterministic per-segment sums as k_cgconv_fwd_pipe
+// (cgconv_fwd.cu).  There, the 16 epilogue warps also stage everything a round needs and sum the segments,
+// phase after phase between CTA-wide barriers.  Here every stage has its own warps and mbarrier hand-offs;
+// there is no CTA-wide barrier inside the loop and the gate warps do nothing but gate math:
 //
-//   warp 20 (one lane)   issuer: bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma of a round
-//   warps 16-19          splitters: thread = slot = TMEM lane; landing zone -> hi / lo -> tcgen05.st (A operand)
-//   warps 21-23          loaders: the round's indices, its node-row window decision, one bulk copy per P / Q row
-//   warps 0-15           consumers: tcgen05.ld -> + P[dst] + Q[src] -> gates -> message tile -> per-segment sums
+//   warps 21-23  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
+//   warps 16-19  splitters  thread = slot = TMEM lane: edge row (landing zone) -> hi / lo -> tcgen05.st (A operand);
+//                           node terms c * (P[dst] + Q[src]) -> tcgen05.st INTO THE ACCUMULATOR (the MMAs then
+//                           accumulate onto them: the epilogue has no node-row reads and no adds left)
+//   warp 20      issuer     bulk copy of a round's edge rows; the 21 tcgen05.mma (3xTF32) of a round
+//   warps 0-15   gates      tcgen05.ld -> sigmoid * softplus on packed f32x2 / MUFU -> message tile
+//   warps 24-27  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
 //
-//   edge rows   issuer --bar_ea_full--> splitters --bar_a_full[b]--> issuer (MMA) --bar_mma[b]--> consumers
-//               consumers --bar_acc_free[b]--> issuer     splitters wait bar_mma[b] before reusing A buffer b
-//   node rows   loaders --bar_rows_full[b]--> consumers --bar_rows_free[b]--> loaders
+//   loaders --rows_full[b]--> splitters --a_full[b]--> issuer --mma[b]--> gates --v_full[b]--> reducers
+//   splitters --ea_free--> issuer --ea_full--> splitters      gates --acc_free[b]--> splitters
+//   splitters --rows_free[b]--> loaders                       reducers --v_free[b]--> gates
 //
-// Everything per round is double-buffered (two accumulators, two A-operand buffers, two index / node-row
-// buffers), so the producers run up to two rounds ahead.  The node-row window (the P / Q rows a round needs
-// lie in two short contiguous node ranges) holds WR rows per buffer; a round whose ranges do not fit reads its
-// node terms from global memory (L2) in the epilogue.
+// Every per-round resource is double-buffered (accumulators, A-operand columns, index / node-row buffers, message
+// tiles); only the edge-row landing zone is single (its copy for round r+1 is issued as soon as round r is split).
+// Exponents are taken in base 2 with the scale folded in up front: the f-gate columns of W_e and of the node terms
+// carry -log2(e), the s-gate columns +log2(e), and the final ln(2) of the softplus rides in the per-node scale.
+// The node-row window (the P / Q rows a round needs lie in two short contiguous node ranges) holds WR rows per
+// buffer; a round whose ranges do not fit reads its node rows from global memory (L2) in the splitters.
 #include "cgconv.cuh"
 #include "umma.cuh"
 #include "edge_dev.cuh"
@@ -29,15 +33,16 @@ namespace mdl {
 
 namespace {
 
-constexpr int kCons = 512, kConsWarps = 16;       // consumer (epilogue) threads
+constexpr int kGateWarps = 16;                    // warps 0..15
 constexpr int kSplitWarp0 = 16;                   // warps 16..19: TMEM lane quadrants 0..3
 constexpr int kIssuerWarp = 20;
 constexpr int kLoadWarp0 = 21, kLoaders = 96;     // warps 21..23
-constexpr int kLaunchW = 768;
+constexpr int kRedWarp0 = 24, kRedWarps = 4;      // warps 24..27
+constexpr int kLaunchW = 896;
 constexpr int kRowsW = 128, kTileW = 112, kInfoCapW = 512;
 constexpr int kC = 64, kNP = 2 * kC;
 constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tiles (bank spread)
-constexpr int kVP = kC + 4;                       // row stride of the message tile
+constexpr int kVP = kC + 4;                       // row stride of the message tiles
 constexpr int kTmemColsW = 512;
 
 unsigned long long* g_ws_phase_buf = nullptr;
@@ -45,7 +50,7 @@ unsigned long long* g_ws_phase_buf = nullptr;
 struct WsPlan {
   unsigned long long* prof;
   int window, KP, WR;
-  uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, offIdx, offWin, offInfo, total;
+  uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, vbytes, offIdx, offWin, offInfo, total;
 };
 
 bool ws_plan(int C, int G, WsPlan* pl) {
@@ -55,15 +60,15 @@ bool ws_plan(int C, int G, WsPlan* pl) {
   const uint32_t b = (uint32_t)kNP * KP * 4;
   const uint32_t ea = (((uint32_t)kRowsW * G * 4 + 32) + 15u) & ~15u;
   const uint32_t v = (uint32_t)kRowsW * kVP * 4, idx = 2 * 2 * kRowsW * 4, win = 64, info = kInfoCapW * 16;
-  const uint32_t fixed = 2 * b + ea + v + idx + win + info;
+  const uint32_t fixed = 2 * b + ea + 2 * v + idx + win + info;
   if (fixed + 2 * 32 * kVW * 4 > (uint32_t)kMaxDynSmem) return false;
   int WR = (int)(((uint32_t)kMaxDynSmem - fixed) / (2 * kVW * 4)) & ~7;
   if (WR > kRowsW) WR = kRowsW;
   pl->prof = g_ws_phase_buf;
   pl->window = 1; pl->KP = KP; pl->WR = WR;
-  pl->wbytes = (uint32_t)WR * kVW * 4;
+  pl->wbytes = (uint32_t)WR * kVW * 4; pl->vbytes = v;
   pl->offBhi = 0; pl->offBlo = b; pl->offEA = 2 * b; pl->offW = pl->offEA + ea;
-  pl->offV = pl->offW + 2 * pl->wbytes; pl->offIdx = pl->offV + v; pl->offWin = pl->offIdx + idx;
+  pl->offV = pl->offW + 2 * pl->wbytes; pl->offIdx = pl->offV + 2 * v; pl->offWin = pl->offIdx + idx;
   pl->offInfo = pl->offWin + win; pl->total = pl->offInfo + info;
   return pl->total <= (uint32_t)kMaxDynSmem;
 }
@@ -74,10 +79,58 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }
 
+// ---- packed fp32 pairs (one FMA-pipe instruction per two values on sm_100)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// sigmoid(a_f) * softplus(a_s) / ln 2 for two channels, from yf = -log2(e) a_f and ys = +log2(e) a_s:
+//   1 / (1 + 2^yf)  *  (max(ys, 0) + log2(1 + 2^-|ys|))
+// three MUFU ops per channel (ex2, ex2, lg2); the reciprocal runs on the FMA pipe as in rcp_fma (bit-trick seed,
+// two third-order steps), on packed pairs.
+__device__ __forceinline__ f2_t gate_pair(float yf0, float yf1, float ys0, float ys1) {
+  const f2_t one = pk2(1.0f, 1.0f);
+  const f2_t u = add2(pk2(ex2_(fminf(yf0, 126.0f)), ex2_(fminf(yf1, 126.0f))), one);
+  float u0, u1;
+  upk2(u, u0, u1);
+  f2_t r = pk2(__uint_as_float(0x7EF311C7u - __float_as_uint(u0)), __uint_as_float(0x7EF311C7u - __float_as_uint(u1)));
+  const f2_t nu = pk2(-u0, -u1);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const f2_t e = fma2(nu, r, one);
+    r = fma2(r, fma2(e, e, e), r);
+  }
+  const f2_t w = add2(pk2(ex2_(-fabsf(ys0)), ex2_(-fabsf(ys1))), one);
+  float w0, w1;
+  upk2(w, w0, w1);
+  const f2_t sp = add2(pk2(lg2_(w0), lg2_(w1)), pk2(fmaxf(ys0, 0.0f), fmaxf(ys1, 0.0f)));
+  return mul2(r, sp);
+}
+
 template <int PROFILE>
 __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p, const WsPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_ea_full, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2], bar_rows_free[2];
+  __shared__ uint64_t bar_ea_full, bar_ea_free, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2],
+      bar_rows_free[2], bar_v_full[2], bar_v_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int sRed[3][2];  // loaders: per-warp (min, max) of the round's source nodes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,11 +139,11 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   uint8_t* sBhi = smem + pl.offBhi;
   uint8_t* sBlo = smem + pl.offBlo;
   float* sEA = reinterpret_cast<float*>(smem + pl.offEA);   // landing zone of a round's edge rows
-  float* sV = reinterpret_cast<float*>(smem + pl.offV);     // [128][VP] per-slot messages
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);     // [2 buffers][src | dst][128]
   int4* sWin = reinterpret_cast<int4*>(smem + pl.offWin);   // [2 buffers] {window?, src min, dst min, nq}
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);
-  auto sWbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offW + (uint32_t)b * pl.wbytes); };
+  auto sWbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offW + (uint32_t)b * pl.wbytes); };  // node rows
+  auto sVbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offV + (uint32_t)b * pl.vbytes); };  // [128][VP] messages
 
   const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   auto make_round = [&](int k, int rd) -> RoundW {
@@ -106,16 +159,30 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   auto valid = [&](const RoundW& R) { return R.k < my_tiles; };
   auto next_round = [&](const RoundW& R) -> RoundW { return R.last ? make_round(R.k + 1, 0) : make_round(R.k, R.rd + 1); };
 
-  // ---- one-time setup (all 768 threads): TMEM, barriers, the CTA's whole tile table, resident W_e split hi/lo
+  // per-role cycle accounting (instrumented build): one thread of a role adds the cycles between its marks
+  long long t_prev = PROFILE ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (PROFILE && pl.prof) {
+      const long long now = clock64();
+      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
+      t_prev = now;
+    }
+  };
+
+  // ---- one-time setup (all threads): TMEM, barriers, the CTA's whole tile table, resident W_e split hi/lo.
+  // The exponent scale rides in the weights: f-gate columns x -log2(e), s-gate columns x +log2(e).
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsW);
   if (tid == 32) {
     umma::mbar_init(&bar_ea_full, 1);
+    umma::mbar_init(&bar_ea_free, 4);                // one arrival per splitter warp
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(&bar_a_full[b], 4);            // one arrival per splitter warp
+      umma::mbar_init(&bar_a_full[b], 4);            // splitter warps: A operand + preloaded accumulator
       umma::mbar_init(&bar_mma[b], 1);               // tcgen05.commit
-      umma::mbar_init(&bar_acc_free[b], kConsWarps); // one arrival per consumer warp
+      umma::mbar_init(&bar_acc_free[b], kGateWarps); // gate warps: accumulator read
       umma::mbar_init(&bar_rows_full[b], 1);         // loader thread 0 (+ the rows' bytes)
-      umma::mbar_init(&bar_rows_free[b], kConsWarps);
+      umma::mbar_init(&bar_rows_free[b], 4);         // splitter warps
+      umma::mbar_init(&bar_v_full[b], kGateWarps);   // gate warps: message tile written
+      umma::mbar_init(&bar_v_free[b], kRedWarps);    // reducer warps: message tile summed
     }
     umma::fence_mbar_init();
   }
@@ -131,7 +198,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   }
   for (int i = tid; i < kNP * KP; i += kLaunchW) {
     const int n = i % kNP, k = i / kNP;
-    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) : 0.0f;
+    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) * (n < kC ? -kLog2e : kLog2e) : 0.0f;
     const float hi = umma::tf32_hi(w);
     const int off = umma::tile_offset_bytes(n, k, kNP);
     *reinterpret_cast<float*>(sBhi + off) = hi;
@@ -156,6 +223,76 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   };
 
   // =====================================================================================================
+  if (warp >= kRedWarp0) {
+    // ---------------- reducers: per-destination sums of a round's message tile (slot order: deterministic)
+    const int rw = warp - kRedWarp0;
+    const bool prof_me = (tid == kRedWarp0 * 32);
+    uint32_t ph_v = 0;
+    RoundW cur = make_round(0, 0);
+    for (uint32_t it = 0; valid(cur); ++it) {
+      const int b = it & 1;
+      const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
+      const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
+      const float* sV = sVbuf(b);
+      // node data of this warp's first segment: requested before the wait on the message tile
+      const int n0 = n_lo + rw;
+      int seg_a = 0, seg_b = 0;
+      float seg_sc = kLn2;
+      float2 seg_x = make_float2(0.0f, 0.0f);  // lane l owns channels 2l, 2l+1
+      if (n0 < n_hi) {
+        seg_a = __ldg(p.seg_ptr + n0);
+        seg_b = __ldg(p.seg_ptr + n0 + 1);
+        if (p.inv_deg) seg_sc = kLn2 * __ldg(p.inv_deg + n0);
+        seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
+      }
+      if (prof_me) mark(16);
+      if (cnt > 0) {
+        umma::mbar_wait(&bar_v_full[b], (ph_v >> b) & 1);
+        ph_v ^= 1u << b;
+      }
+      if (prof_me) mark(17);
+      for (int n = n0; n < n_hi; n += kRedWarps) {
+        int a, bq;
+        float sc = seg_sc;
+        float2 x = seg_x;
+        if (n == n0) { a = seg_a; bq = seg_b; }
+        else {
+          a = __ldg(p.seg_ptr + n); bq = __ldg(p.seg_ptr + n + 1);
+          sc = p.inv_deg ? kLn2 * __ldg(p.inv_deg + n) : kLn2;
+          x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
+        }
+        const int lo = max(a, r_lo), hi = min(bq, r_hi);
+        const bool empty_seg = (a == bq);
+        if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
+        const bool first = empty_seg || (a >= r_lo);
+        const bool lastp = empty_seg || (bq <= r_hi);
+        float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
+        float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
+        const float2* vp = reinterpret_cast<const float2*>(sV + (lo - r_lo) * kVP) + lane;
+        int s = lo;
+        for (; s + 4 <= hi; s += 4, vp += 4 * (kVP / 2)) {  // four loads in flight, added in slot order
+          const float2 v0 = vp[0], v1 = vp[kVP / 2], v2 = vp[2 * (kVP / 2)], v3 = vp[3 * (kVP / 2)];
+          acc.x += v0.x; acc.y += v0.y;
+          acc.x += v1.x; acc.y += v1.y;
+          acc.x += v2.x; acc.y += v2.y;
+          acc.x += v3.x; acc.y += v3.y;
+        }
+        for (; s < hi; ++s, vp += kVP / 2) {
+          const float2 v = *vp;
+          acc.x += v.x; acc.y += v.y;
+        }
+        *o = lastp ? make_float2(fmaf(acc.x, sc, x.x), fmaf(acc.y, sc, x.y)) : acc;
+      }
+      if (cnt > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_v_free[b]);
+      }
+      if (prof_me) mark(18);
+      cur = next_round(cur);
+    }
+    __syncthreads();  // teardown barrier of the CTA
+    return;
+  }
   if (warp >= kIssuerWarp) {
     if (warp == kIssuerWarp) {
       // ---------------- issuer: bulk copies of the edge rows, MMAs
@@ -170,36 +307,33 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
         const uint32_t step_b = 2 * (uint32_t)kNP * 16;
         const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
-        uint32_t ph_a = 0, ph_f = 0;  // phase parities, bit b = buffer b (plain registers: no dynamically indexed arrays)
-        uint32_t busy = 0;            // bit b: accumulator b holds a round whose epilogue has not been waited for
+        uint32_t ph_a = 0, ph_e = 0;  // phase parities, bit b = buffer b
         RoundW R = make_round(0, 0);
         if (valid(R)) issue_ea_bulk(R);
         for (uint32_t it = 0; valid(R); ++it) {
           const int b = it & 1;
           const RoundW Rn = next_round(R);
-          if (R.cnt > 0) {  // split of this round done: its A operand is staged and the landing zone is free
+          mark(20);
+          if (R.cnt > 0) {  // the splitters have read this round's edge rows: the landing zone is free
+            umma::mbar_wait(&bar_ea_free, ph_e);
+            ph_e ^= 1;
+          }
+          if (valid(Rn)) issue_ea_bulk(Rn);
+          mark(21);
+          if (R.cnt > 0) {  // A operand staged, accumulator preloaded with the node terms
             umma::mbar_wait(&bar_a_full[b], (ph_a >> b) & 1);
             ph_a ^= 1u << b;
-          }
-          if (valid(Rn)) issue_ea_bulk(Rn);  // first: the MMA issue below blocks for ~2k cycles
-          if (R.cnt > 0) {
-            if ((busy >> b) & 1) {  // the epilogue of the round that used this accumulator two rounds ago has read it
-              umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
-              ph_f ^= 1u << b;
-            }
             umma::fence_after_sync();
-            uint32_t acc = 0;
+            mark(22);
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
               const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
               const uint32_t bb = (pass == 1) ? b_lo : b_hi;
-              for (int kk = 0; kk < (KP >> 3); ++kk) {
-                umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, acc);
-                acc = 1;
-              }
+              for (int kk = 0; kk < (KP >> 3); ++kk)
+                umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, 1u);
             }
             umma::mma_commit(&bar_mma[b]);
-            busy |= 1u << b;
+            mark(23);
           }
           R = Rn;
         }
@@ -214,10 +348,12 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       for (uint32_t it = 0; valid(R); ++it) {
         const int b = it & 1;
         if (R.cnt > 0) {
-          if ((used >> b) & 1) {  // consumers have finished with this buffer (two rounds ago)
+          if (lt == 0) mark(24);
+          if ((used >> b) & 1) {  // the splitters have finished with this buffer (two rounds ago)
             umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
             ph_rf ^= 1u << b;
           }
+          if (lt == 0) mark(25);
           int* bS = sIdx + b * 2 * kRowsW;
           int s_lo = 0x7fffffff, s_hi = -1;
           for (int i = lt; i < 2 * kRowsW; i += kLoaders) {
@@ -251,6 +387,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           }
           used |= 1u << b;
           sync_loaders();  // sRed is rewritten next round
+          if (lt == 0) mark(26);
         }
         R = next_round(R);
       }
@@ -259,64 +396,114 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     return;
   }
   if (warp >= kSplitWarp0) {
-    // ---------------- splitters: thread = slot = TMEM lane; the whole edge row -> hi / lo -> tensor memory
+    // ---------------- splitters: thread = slot = TMEM lane
     const int e = tid - kSplitWarp0 * 32;
-    uint32_t ph_ea = 0, ph_m = 0, used = 0;
+    const bool prof_me = (e == 0);
+    uint32_t ph_ea = 0, ph_r = 0, ph_f = 0, used = 0;
     RoundW R = make_round(0, 0);
     for (uint32_t it = 0; valid(R); ++it) {
       const int b = it & 1;
       if (R.cnt > 0) {
+        if (prof_me) mark(8);
+        if ((used >> b) & 1) {  // the gate warps have read accumulator b (so the MMAs that used A buffer b are done)
+          umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
+          ph_f ^= 1u << b;
+          umma::fence_after_sync();
+        }
+        if (prof_me) mark(9);
+        // ---- (1) the edge row -> hi / lo -> A operand columns
         const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
         if (nb) {
           umma::mbar_wait(&bar_ea_full, ph_ea);
           ph_ea ^= 1;
         }
-        if ((used >> b) & 1) {  // the MMAs that read this A buffer two rounds ago have retired
-          umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);
-          ph_m ^= 1u << b;
-          umma::fence_after_sync();
-        }
-        const int ea_off = (int)(((long long)R.r_lo * G) & 3);
-        const float* row = sEA + ea_off + e * G;
-        const int landed = (int)(nb >> 2);  // first float of the landing zone the bulk copy did NOT deliver
-        const bool patch = e < R.cnt && landed < ea_off + (e + 1) * G;
-        const uint32_t a_hi = umma::tmem_addr(tm_a_hi(b), warp, 0), a_lo = umma::tmem_addr(tm_a_lo(b), warp, 0);
-        for (int ch = 0; ch < (KP >> 3); ++ch) {
-          float v[8];
+        if (prof_me) mark(10);
+        {
+          const int ea_off = (int)(((long long)R.r_lo * G) & 3);
+          const float* row = sEA + ea_off + e * G;
+          const int landed = (int)(nb >> 2);  // first float of the landing zone the bulk copy did NOT deliver
+          const bool patch = e < R.cnt && landed < ea_off + (e + 1) * G;
+          const uint32_t a_hi = umma::tmem_addr(tm_a_hi(b), warp, 0), a_lo = umma::tmem_addr(tm_a_lo(b), warp, 0);
+          for (int ch = 0; ch < (KP >> 3); ++ch) {
+            float v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = 0.0f;
-          if (e < R.cnt) {
-            if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
+            for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+            if (e < R.cnt) {
+              if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
 #pragma unroll
-              for (int t = 0; t < 8; t += 2)
-                if (8 * ch + t < G) {
-                  const float2 a = *reinterpret_cast<const float2*>(row + 8 * ch + t);
-                  v[t] = a.x; v[t + 1] = a.y;
+                for (int t = 0; t < 8; t += 2)
+                  if (8 * ch + t < G) {
+                    const float2 a = *reinterpret_cast<const float2*>(row + 8 * ch + t);
+                    v[t] = a.x; v[t + 1] = a.y;
+                  }
+              } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                  if (8 * ch + t < G) v[t] = row[8 * ch + t];
+              }
+              if (patch) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  const int k = 8 * ch + t;
+                  if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)R.r_lo + e) * G + k);
                 }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; ++t)
-                if (8 * ch + t < G) v[t] = row[8 * ch + t];
-            }
-            if (patch) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const int k = 8 * ch + t;
-                if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)R.r_lo + e) * G + k);
               }
             }
-          }
-          float hi[8], lo[8];
+            float hi[8], lo[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
-          umma::tmem_st8(a_hi + 8 * ch, hi);
-          umma::tmem_st8(a_lo + 8 * ch, lo);
+            for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+            umma::tmem_st8(a_hi + 8 * ch, hi);
+            umma::tmem_st8(a_lo + 8 * ch, lo);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_ea_free);  // landing zone read: the next round's copy may be issued
+        if (prof_me) mark(11);
+        // ---- (2) node terms -> the accumulator: c * (P[dst] + Q[src]), c = -log2(e) (f gate) / +log2(e) (s gate)
+        umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);
+        ph_r ^= 1u << b;
+        if (prof_me) mark(12);
+        {
+          const int4 wr = sWin[b];
+          const bool win = wr.x != 0;
+          const int* bSrc = sIdx + b * 2 * kRowsW;
+          const bool live = e < R.cnt;
+          const int ss = live ? bSrc[e] : 0, sd = live ? bSrc[kRowsW + e] : 0;
+          const float* sW = sWbuf(b);
+          const float* r0 = win ? sW + (wr.w + sd - wr.z) * kVW : p.PQ + (size_t)sd * (4 * kC);
+          const float* r1 = win ? sW + (ss - wr.y) * kVW : p.PQ + (size_t)ss * (4 * kC) + 2 * kC;
+          const uint32_t acc = umma::tmem_addr(tm_acc(b), warp, 0);
+          auto run = [&](auto ld) {
+#pragma unroll 4
+            for (int c = 0; c < kNP / 8; ++c) {
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+              if (live) {
+                const float sc = (c < kC / 8) ? -kLog2e : kLog2e;
+                const f2_t sc2 = pk2(sc, sc);
+                const float4 p0 = ld(r0 + 8 * c), p1 = ld(r0 + 8 * c + 4);
+                const float4 q0 = ld(r1 + 8 * c), q1 = ld(r1 + 8 * c + 4);
+                upk2(mul2(add2(pk2(p0.x, p0.y), pk2(q0.x, q0.y)), sc2), v[0], v[1]);
+                upk2(mul2(add2(pk2(p0.z, p0.w), pk2(q0.z, q0.w)), sc2), v[2], v[3]);
+                upk2(mul2(add2(pk2(p1.x, p1.y), pk2(q1.x, q1.y)), sc2), v[4], v[5]);
+                upk2(mul2(add2(pk2(p1.z, p1.w), pk2(q1.z, q1.w)), sc2), v[6], v[7]);
+              }
+              umma::tmem_st8(acc + 8 * c, v);
+            }
+          };
+          if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
+          else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
         }
         umma::tmem_st_wait();
         umma::fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a_full[b]);
+        if (lane == 0) {
+          mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
+          mbar_arrive(&bar_a_full[b]);     // A operand + preloaded accumulator ready for the MMAs
+        }
         used |= 1u << b;
+        if (prof_me) mark(13);
       }
       R = next_round(R);
     }
@@ -324,117 +511,50 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     return;
   }
 
-  // ---------------- consumers: epilogue + per-segment sums
-  auto sync_consumers = [] { asm volatile("bar.sync 2, %0;" ::"n"(kCons) : "memory"); };
-  long long t_prev = PROFILE ? clock64() : 0;
-  auto mark = [&](int slot) {
-    if (PROFILE && pl.prof && tid == 0) {
-      const long long now = clock64();
-      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
-      t_prev = now;
-    }
-  };
+  // ---------------- gate warps: thread = slot (TMEM lane), 16 channels; no CTA-wide barrier in the loop
+  const bool prof_me = (tid == 0);
   const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
   const int c_begin = part * 16;
-  uint32_t ph_r = 0, ph_m = 0;
+  uint32_t ph_m = 0, ph_vf = 0, used_v = 0;
   RoundW cur = make_round(0, 0);
   for (uint32_t it = 0; valid(cur); ++it) {
     const int b = it & 1;
-    const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
-    const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
-    const int* bSrc = sIdx + b * 2 * kRowsW;
-    const int* bDst = bSrc + kRowsW;
-    mark(0);
-    // ---- reduce-stage node data of this warp's first segment (global loads in flight across the epilogue)
-    const int n0 = n_lo + warp;
-    int seg_a = 0, seg_b = 0;
-    float seg_sc = 1.0f;
-    float2 seg_x = make_float2(0.0f, 0.0f);  // lane l owns channels 2l, 2l+1
-    if (n0 < n_hi) {
-      seg_a = __ldg(p.seg_ptr + n0);
-      seg_b = __ldg(p.seg_ptr + n0 + 1);
-      if (p.inv_deg) seg_sc = __ldg(p.inv_deg + n0);
-      seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
-    }
+    const int cnt = cur.cnt;
+    if (prof_me) mark(0);
     if (cnt > 0) {
-      umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);  // indices, window record, node rows of this round
-      ph_r ^= 1u << b;
-      mark(1);
-      const int4 wr = sWin[b];
-      const bool win = wr.x != 0;
-      const int w_smin = wr.y, w_dmin = wr.z, w_nq = wr.w;
-      const float* sW = sWbuf(b);
-      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);         // this round's contraction
+      if ((used_v >> b) & 1) {  // the reducers have summed the round that used this message tile two rounds ago
+        umma::mbar_wait(&bar_v_free[b], (ph_vf >> b) & 1);
+        ph_vf ^= 1u << b;
+      }
+      if (prof_me) mark(1);
+      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);  // this round's contraction (node terms included)
       ph_m ^= 1u << b;
       umma::fence_after_sync();
-      mark(2);
+      if (prof_me) mark(2);
       float f[16], sacc[16];
       umma::tmem_ld16(umma::tmem_addr(tm_acc(b), q, c_begin), f);
       umma::tmem_ld16(umma::tmem_addr(tm_acc(b), q, kC + c_begin), sacc);
       umma::tmem_ld_wait();
       umma::fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_acc_free[b]);  // the accumulator may be overwritten (round it + 2)
-      mark(3);
-      // ---- epilogue: thread = slot (TMEM lane), 16 channels; a = accumulator + P[dst] + Q[src], gates,
-      // message parked in the message tile
+      if (lane == 0) mbar_arrive(&bar_acc_free[b]);  // the accumulator may be rewritten (round it + 2)
+      if (prof_me) mark(3);
       const int e_ep = 32 * q + lane;
       if (e_ep < cnt) {
-        const int sd = bDst[e_ep], ss = bSrc[e_ep];
-        const float* r0 = win ? sW + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
-        const float* r1 = win ? sW + (ss - w_smin) * kVW + c_begin : p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
-        float* rowv = sV + e_ep * kVP + c_begin;
-        auto run = [&](auto ld) {  // ld: how the node rows are read (shared or global memory)
+        float* rowv = sVbuf(b) + e_ep * kVP + c_begin;
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 pf = ld(r0 + j4), ps = ld(r0 + kC + j4);
-            const float4 qf = ld(r1 + j4), qs = ld(r1 + kC + j4);
-            const float af[4] = {f[j4] + (pf.x + qf.x), f[j4 + 1] + (pf.y + qf.y), f[j4 + 2] + (pf.z + qf.z),
-                                 f[j4 + 3] + (pf.w + qf.w)};
-            const float as[4] = {sacc[j4] + (ps.x + qs.x), sacc[j4 + 1] + (ps.y + qs.y), sacc[j4 + 2] + (ps.z + qs.z),
-                                 sacc[j4 + 3] + (ps.w + qs.w)};
-            float m[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) m[j] = sigmoid_mixed(af[j]) * softplus_mufu(as[j]);
-            *reinterpret_cast<float4*>(rowv + j4) = make_float4(m[0], m[1], m[2], m[3]);
-          }
-        };
-        if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
-        else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          float m0, m1, m2, m3;
+          upk2(gate_pair(f[j4], f[j4 + 1], sacc[j4], sacc[j4 + 1]), m0, m1);
+          upk2(gate_pair(f[j4 + 2], f[j4 + 3], sacc[j4 + 2], sacc[j4 + 3]), m2, m3);
+          *reinterpret_cast<float4*>(rowv + j4) = make_float4(m0, m1, m2, m3);
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
+      if (lane == 0) mbar_arrive(&bar_v_full[b]);  // this warp's part of the message tile is written
+      used_v |= 1u << b;
+      if (prof_me) mark(4);
     }
-    mark(4);
-    sync_consumers();  // [S3] message tile complete
-    mark(5);
-    // ---- segmented sum over the owned segments that have slots in this round (slot order: deterministic)
-    for (int n = n0; n < n_hi; n += kConsWarps) {
-      int a, bq;
-      if (n == n0) { a = seg_a; bq = seg_b; }
-      else { a = __ldg(p.seg_ptr + n); bq = __ldg(p.seg_ptr + n + 1); }
-      const int lo = max(a, r_lo), hi = min(bq, r_hi);
-      const bool empty_seg = (a == bq);
-      if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
-      const bool first = empty_seg || (a >= r_lo);
-      const bool lastp = empty_seg || (bq <= r_hi);
-      float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
-      float sc = seg_sc;
-      float2 x = seg_x;
-      if (n != n0) {
-        sc = p.inv_deg ? __ldg(p.inv_deg + n) : 1.0f;
-        x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
-      }
-      float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
-      for (int s = lo; s < hi; ++s) {
-        const float2 v = *(reinterpret_cast<const float2*>(sV + (s - r_lo) * kVP) + lane);
-        acc.x += v.x; acc.y += v.y;
-      }
-      *o = lastp ? make_float2(fmaf(acc.x, sc, x.x), fmaf(acc.y, sc, x.y)) : acc;
-    }
-    mark(6);
-    sync_consumers();  // [S1] message tile free for the next round's epilogue
-    mark(7);
     if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
     cur = next_round(cur);
   }
