@@ -7,17 +7,18 @@
 // phase after phase between CTA-wide barriers.  Here every stage has its own warps and mbarrier hand-offs;
 // there is no CTA-wide barrier inside the loop and the gate warps do nothing but gate math:
 //
-//   warps 21-23  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
-//   warps 16-19  splitters  thread = slot = TMEM lane: edge row (landing zone) -> hi / lo -> tcgen05.st (A operand);
-//                           node terms c * (P[dst] + Q[src]) -> tcgen05.st INTO THE ACCUMULATOR (the MMAs then
-//                           accumulate onto them: the epilogue has no node-row reads and no adds left)
-//   warp 20      issuer     bulk copy of a round's edge rows; the 21 tcgen05.mma (3xTF32) of a round
+//   warps 26-27  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
+//   warp 25      ea copy    one bulk (TMA) copy of the round's edge rows into the landing zone
+//   warps 16-19  split A    thread = slot = TMEM lane: edge row (landing zone) -> hi / lo -> tcgen05.st (A operand)
+//   warps 20-23  split B    thread = slot: node terms c * (P[dst] + Q[src]) -> tcgen05.st INTO THE ACCUMULATOR (the
+//                           MMAs then accumulate onto them: the epilogue has no node-row reads and no adds left)
+//   warp 24      mma        the 21 tcgen05.mma (3xTF32) of a round; issuing them blocks the thread for the MMAs' run time
 //   warps 0-15   gates      tcgen05.ld -> sigmoid * softplus on packed f32x2 / MUFU -> message tile
-//   warps 24-27  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
+//   warps 28-31  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
 //
-//   loaders --rows_full[b]--> splitters --a_full[b]--> issuer --mma[b]--> gates --v_full[b]--> reducers
-//   splitters --ea_free--> issuer --ea_full--> splitters      gates --acc_free[b]--> splitters
-//   splitters --rows_free[b]--> loaders                       reducers --v_free[b]--> gates
+//   ea copy --ea_full--> split A --tma_full[b]--> mma --mma[b]--> gates --v_full[b]--> reducers --v_free[b]--> gates
+//   loaders --rows_full[b]--> split B --acc_full[b]--> mma      gates --acc_free[b]--> split B
+//   split A --ea_free--> ea copy      split B --rows_free[b]--> loaders      mma[b] also frees A buffer b for split A
 //
 // Every per-round resource is double-buffered (accumulators, A-operand columns, index / node-row buffers, message
 // tiles); only the edge-row landing zone is single (its copy for round r+1 is issued as soon as round r is split).
@@ -34,11 +35,12 @@ namespace mdl {
 namespace {
 
 constexpr int kGateWarps = 16;                    // warps 0..15
-constexpr int kSplitWarp0 = 16;                   // warps 16..19: TMEM lane quadrants 0..3
-constexpr int kIssuerWarp = 20;
-constexpr int kLoadWarp0 = 21, kLoaders = 96;     // warps 21..23
-constexpr int kRedWarp0 = 24, kRedWarps = 4;      // warps 24..27
-constexpr int kLaunchW = 896;
+constexpr int kSplitAWarp0 = 16;                  // warps 16..19: TMEM lane quadrants 0..3 (edge rows)
+constexpr int kSplitBWarp0 = 20;                  // warps 20..23: TMEM lane quadrants 0..3 (node terms)
+constexpr int kMmaWarp = 24, kCopyWarp = 25;
+constexpr int kLoadWarp0 = 26, kLoaders = 64;     // warps 26..27
+constexpr int kRedWarp0 = 28, kRedWarps = 4;      // warps 28..31
+constexpr int kLaunchW = 1024;
 constexpr int kRowsW = 128, kTileW = 112, kInfoCapW = 512;
 constexpr int kC = 64, kNP = 2 * kC;
 constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tiles (bank spread)
@@ -129,10 +131,10 @@ __device__ __forceinline__ f2_t gate_pair(float yf0, float yf1, float ys0, float
 template <int PROFILE>
 __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p, const WsPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_ea_full, bar_ea_free, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2],
-      bar_rows_free[2], bar_v_full[2], bar_v_free[2];
+  __shared__ uint64_t bar_ea_full, bar_ea_free, bar_tma_full[2], bar_acc_full[2], bar_mma[2], bar_acc_free[2],
+      bar_rows_full[2], bar_rows_free[2], bar_v_full[2], bar_v_free[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int sRed[3][2];  // loaders: per-warp (min, max) of the round's source nodes
+  __shared__ int sRed[2][2];  // loaders: per-warp (min, max) of the round's source nodes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP, WR = pl.WR;
 
@@ -174,13 +176,14 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsW);
   if (tid == 32) {
     umma::mbar_init(&bar_ea_full, 1);
-    umma::mbar_init(&bar_ea_free, 4);                // one arrival per splitter warp
+    umma::mbar_init(&bar_ea_free, 4);                // one arrival per split-A warp
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(&bar_a_full[b], 4);            // splitter warps: A operand + preloaded accumulator
+      umma::mbar_init(&bar_tma_full[b], 4);          // split-A warps: A operand staged
+      umma::mbar_init(&bar_acc_full[b], 4);          // split-B warps: accumulator preloaded with the node terms
       umma::mbar_init(&bar_mma[b], 1);               // tcgen05.commit
       umma::mbar_init(&bar_acc_free[b], kGateWarps); // gate warps: accumulator read
       umma::mbar_init(&bar_rows_full[b], 1);         // loader thread 0 (+ the rows' bytes)
-      umma::mbar_init(&bar_rows_free[b], 4);         // splitter warps
+      umma::mbar_init(&bar_rows_free[b], 4);         // split-B warps
       umma::mbar_init(&bar_v_full[b], kGateWarps);   // gate warps: message tile written
       umma::mbar_init(&bar_v_free[b], kRedWarps);    // reducer warps: message tile summed
     }
@@ -228,6 +231,17 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     const int rw = warp - kRedWarp0;
     const bool prof_me = (tid == kRedWarp0 * 32);
     uint32_t ph_v = 0;
+    struct Seg { int a, b; float sc; float2 x; };
+    auto load_seg = [&](int n, int n_hi) -> Seg {  // node data of segment n (lane l owns channels 2l, 2l+1)
+      Seg s{0, 0, kLn2, make_float2(0.0f, 0.0f)};
+      if (n < n_hi) {
+        s.a = __ldg(p.seg_ptr + n);
+        s.b = __ldg(p.seg_ptr + n + 1);
+        if (p.inv_deg) s.sc = kLn2 * __ldg(p.inv_deg + n);
+        s.x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
+      }
+      return s;
+    };
     RoundW cur = make_round(0, 0);
     for (uint32_t it = 0; valid(cur); ++it) {
       const int b = it & 1;
@@ -235,37 +249,21 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
       const float* sV = sVbuf(b);
       // node data of this warp's first segment: requested before the wait on the message tile
-      const int n0 = n_lo + rw;
-      int seg_a = 0, seg_b = 0;
-      float seg_sc = kLn2;
-      float2 seg_x = make_float2(0.0f, 0.0f);  // lane l owns channels 2l, 2l+1
-      if (n0 < n_hi) {
-        seg_a = __ldg(p.seg_ptr + n0);
-        seg_b = __ldg(p.seg_ptr + n0 + 1);
-        if (p.inv_deg) seg_sc = kLn2 * __ldg(p.inv_deg + n0);
-        seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
-      }
-      if (prof_me) mark(16);
+      Seg nx = load_seg(n_lo + rw, n_hi);
+      if (prof_me) mark(21);
       if (cnt > 0) {
         umma::mbar_wait(&bar_v_full[b], (ph_v >> b) & 1);
         ph_v ^= 1u << b;
       }
-      if (prof_me) mark(17);
-      for (int n = n0; n < n_hi; n += kRedWarps) {
-        int a, bq;
-        float sc = seg_sc;
-        float2 x = seg_x;
-        if (n == n0) { a = seg_a; bq = seg_b; }
-        else {
-          a = __ldg(p.seg_ptr + n); bq = __ldg(p.seg_ptr + n + 1);
-          sc = p.inv_deg ? kLn2 * __ldg(p.inv_deg + n) : kLn2;
-          x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
-        }
-        const int lo = max(a, r_lo), hi = min(bq, r_hi);
-        const bool empty_seg = (a == bq);
+      if (prof_me) mark(22);
+      for (int n = n_lo + rw; n < n_hi; n += kRedWarps) {
+        const Seg sg = nx;
+        nx = load_seg(n + kRedWarps, n_hi);  // next segment's node data in flight under this one's sum
+        const int lo = max(sg.a, r_lo), hi = min(sg.b, r_hi);
+        const bool empty_seg = (sg.a == sg.b);
         if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
-        const bool first = empty_seg || (a >= r_lo);
-        const bool lastp = empty_seg || (bq <= r_hi);
+        const bool first = empty_seg || (sg.a >= r_lo);
+        const bool lastp = empty_seg || (sg.b <= r_hi);
         float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
         float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
         const float2* vp = reinterpret_cast<const float2*>(sV + (lo - r_lo) * kVP) + lane;
@@ -281,188 +279,170 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           const float2 v = *vp;
           acc.x += v.x; acc.y += v.y;
         }
-        *o = lastp ? make_float2(fmaf(acc.x, sc, x.x), fmaf(acc.y, sc, x.y)) : acc;
+        *o = lastp ? make_float2(fmaf(acc.x, sg.sc, sg.x.x), fmaf(acc.y, sg.sc, sg.x.y)) : acc;
       }
       if (cnt > 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_v_free[b]);
       }
-      if (prof_me) mark(18);
+      if (prof_me) mark(23);
       cur = next_round(cur);
     }
     __syncthreads();  // teardown barrier of the CTA
     return;
   }
-  if (warp >= kIssuerWarp) {
-    if (warp == kIssuerWarp) {
-      // ---------------- issuer: bulk copies of the edge rows, MMAs
-      if (lane == 0) {
-        auto issue_ea_bulk = [&](const RoundW& R) {
-          const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
-          if (!nb) return;
-          const long long first = (long long)R.r_lo * G;
-          umma::mbar_arrive_expect_tx(&bar_ea_full, nb);
-          umma::bulk_g2s(sEA, p.ea + (first - (first & 3)), nb, &bar_ea_full);
-        };
-        const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
-        const uint32_t step_b = 2 * (uint32_t)kNP * 16;
-        const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
-        uint32_t ph_a = 0, ph_e = 0;  // phase parities, bit b = buffer b
-        RoundW R = make_round(0, 0);
-        if (valid(R)) issue_ea_bulk(R);
-        for (uint32_t it = 0; valid(R); ++it) {
-          const int b = it & 1;
-          const RoundW Rn = next_round(R);
-          mark(20);
-          if (R.cnt > 0) {  // the splitters have read this round's edge rows: the landing zone is free
-            umma::mbar_wait(&bar_ea_free, ph_e);
-            ph_e ^= 1;
-          }
-          if (valid(Rn)) issue_ea_bulk(Rn);
-          mark(21);
-          if (R.cnt > 0) {  // A operand staged, accumulator preloaded with the node terms
-            umma::mbar_wait(&bar_a_full[b], (ph_a >> b) & 1);
-            ph_a ^= 1u << b;
-            umma::fence_after_sync();
-            mark(22);
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
-              const uint32_t bb = (pass == 1) ? b_lo : b_hi;
-              for (int kk = 0; kk < (KP >> 3); ++kk)
-                umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, 1u);
-            }
-            umma::mma_commit(&bar_mma[b]);
-            mark(23);
-          }
-          R = Rn;
-        }
+  if (warp >= kLoadWarp0) {
+    // ---------------- loaders: indices, window decision, node rows of a round.  The indices of round r+1 are
+    // requested (into registers) before round r is processed: their HBM latency runs under this round's work.
+    const int lt = tid - kLoadWarp0 * 32, lw = warp - kLoadWarp0;
+    auto sync_loaders = [] { asm volatile("bar.sync 3, %0;" ::"n"(kLoaders) : "memory"); };
+    constexpr int kPer = 2 * kRowsW / kLoaders;  // index entries per loader thread (4)
+    auto fetch = [&](const RoundW& R, int (&v)[kPer]) {
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = lt + j * kLoaders, e = i & (kRowsW - 1);
+        v[j] = 0;
+        if (valid(R) && e < R.cnt) v[j] = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
       }
-      __syncwarp();
-    } else {
-      // ---------------- loaders: indices, window decision, node rows of a round
-      const int lt = tid - kLoadWarp0 * 32, lw = warp - kLoadWarp0;
-      auto sync_loaders = [] { asm volatile("bar.sync 3, %0;" ::"n"(kLoaders) : "memory"); };
-      uint32_t ph_rf = 0, used = 0;
-      RoundW R = make_round(0, 0);
-      for (uint32_t it = 0; valid(R); ++it) {
-        const int b = it & 1;
-        if (R.cnt > 0) {
-          if (lt == 0) mark(24);
-          if ((used >> b) & 1) {  // the splitters have finished with this buffer (two rounds ago)
-            umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
-            ph_rf ^= 1u << b;
-          }
-          if (lt == 0) mark(25);
-          int* bS = sIdx + b * 2 * kRowsW;
-          int s_lo = 0x7fffffff, s_hi = -1;
-          for (int i = lt; i < 2 * kRowsW; i += kLoaders) {
-            const int e = i & (kRowsW - 1);
-            int v = 0;
-            if (e < R.cnt) {
-              v = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
-              if (i < kRowsW) { s_lo = min(s_lo, v); s_hi = max(s_hi, v); }
-            }
-            bS[i] = v;
-          }
-          s_lo = __reduce_min_sync(0xffffffffu, s_lo);
-          s_hi = __reduce_max_sync(0xffffffffu, s_hi);
-          if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
-          sync_loaders();  // indices and per-warp ranges visible to all loaders
-          s_lo = min(sRed[0][0], min(sRed[1][0], sRed[2][0]));
-          s_hi = max(sRed[0][1], max(sRed[1][1], sRed[2][1]));
-          const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
-          const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
-          const bool win = pl.window && nq + np_ <= WR;
-          const int nrows = win ? nq + np_ : 0;
-          if (lt == 0) {
-            sWin[b] = make_int4(win ? 1 : 0, s_lo, d_lo, nq);
-            if (nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)nrows * (uint32_t)(2 * kC * 4));
-            else mbar_arrive(&bar_rows_full[b]);
-          }
-          float* W = sWbuf(b);
-          for (int r = lt; r < nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
-            const float* g = (r < nq) ? p.PQ + (size_t)(s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(d_lo + r - nq) * (4 * kC);
-            umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
-          }
-          used |= 1u << b;
-          sync_loaders();  // sRed is rewritten next round
-          if (lt == 0) mark(26);
+    };
+    uint32_t ph_rf = 0, used = 0;
+    RoundW R = make_round(0, 0);
+    int vcur[kPer], vnext[kPer];
+    fetch(R, vcur);
+    for (uint32_t it = 0; valid(R); ++it) {
+      const int b = it & 1;
+      const RoundW Rn = next_round(R);
+      fetch(Rn, vnext);
+      if (R.cnt > 0) {
+        if (lt == 0) mark(18);
+        if ((used >> b) & 1) {  // split B has finished with this buffer (two rounds ago)
+          umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
+          ph_rf ^= 1u << b;
         }
-        R = next_round(R);
+        if (lt == 0) mark(19);
+        int* bS = sIdx + b * 2 * kRowsW;
+        int s_lo = 0x7fffffff, s_hi = -1;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          const int i = lt + j * kLoaders, e = i & (kRowsW - 1);
+          bS[i] = vcur[j];
+          if (i < kRowsW && e < R.cnt) { s_lo = min(s_lo, vcur[j]); s_hi = max(s_hi, vcur[j]); }
+        }
+        s_lo = __reduce_min_sync(0xffffffffu, s_lo);
+        s_hi = __reduce_max_sync(0xffffffffu, s_hi);
+        if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
+        sync_loaders();  // indices and per-warp ranges visible to all loaders
+        s_lo = min(sRed[0][0], sRed[1][0]);
+        s_hi = max(sRed[0][1], sRed[1][1]);
+        const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
+        const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
+        const bool win = pl.window && nq + np_ <= WR;
+        const int nrows = win ? nq + np_ : 0;
+        if (lt == 0) {
+          sWin[b] = make_int4(win ? 1 : 0, s_lo, d_lo, nq);
+          if (nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)nrows * (uint32_t)(2 * kC * 4));
+          else mbar_arrive(&bar_rows_full[b]);
+        }
+        float* W = sWbuf(b);
+        for (int r = lt; r < nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
+          const float* g = (r < nq) ? p.PQ + (size_t)(s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(d_lo + r - nq) * (4 * kC);
+          umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
+        }
+        used |= 1u << b;
+        sync_loaders();  // sRed is rewritten next round
+        if (lt == 0) mark(20);
       }
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) vcur[j] = vnext[j];
+      R = Rn;
     }
     __syncthreads();  // teardown barrier of the CTA
     return;
   }
-  if (warp >= kSplitWarp0) {
-    // ---------------- splitters: thread = slot = TMEM lane
-    const int e = tid - kSplitWarp0 * 32;
+  if (warp == kCopyWarp) {
+    // ---------------- ea copy: one bulk copy of a round's edge rows, issued as soon as the landing zone is free
+    if (lane == 0) {
+      auto issue_ea_bulk = [&](const RoundW& R) {
+        const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
+        if (!nb) return;
+        const long long first = (long long)R.r_lo * G;
+        umma::mbar_arrive_expect_tx(&bar_ea_full, nb);
+        umma::bulk_g2s(sEA, p.ea + (first - (first & 3)), nb, &bar_ea_full);
+      };
+      uint32_t ph_e = 0;
+      RoundW R = make_round(0, 0);
+      if (valid(R)) issue_ea_bulk(R);
+      while (valid(R)) {
+        const RoundW Rn = next_round(R);
+        mark(16);
+        if (R.cnt > 0) {  // split A has read this round's edge rows: the landing zone is free
+          umma::mbar_wait(&bar_ea_free, ph_e);
+          ph_e ^= 1;
+        }
+        if (valid(Rn)) issue_ea_bulk(Rn);
+        mark(17);
+        R = Rn;
+      }
+    }
+    __syncwarp();
+    __syncthreads();  // teardown barrier of the CTA
+    return;
+  }
+  if (warp == kMmaWarp) {
+    // ---------------- mma: the round's contraction, accumulated onto the preloaded node terms
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
+      const uint32_t step_b = 2 * (uint32_t)kNP * 16;
+      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+      uint32_t ph_a = 0, ph_c = 0;  // phase parities, bit b = buffer b
+      RoundW R = make_round(0, 0);
+      for (uint32_t it = 0; valid(R); ++it) {
+        const int b = it & 1;
+        mark(13);
+        if (R.cnt > 0) {
+          umma::mbar_wait(&bar_tma_full[b], (ph_a >> b) & 1);  // A operand staged
+          ph_a ^= 1u << b;
+          umma::mbar_wait(&bar_acc_full[b], (ph_c >> b) & 1);  // accumulator preloaded with the node terms
+          ph_c ^= 1u << b;
+          umma::fence_after_sync();
+          mark(14);
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
+            const uint32_t bb = (pass == 1) ? b_lo : b_hi;
+            for (int kk = 0; kk < (KP >> 3); ++kk)
+              umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, 1u);
+          }
+          umma::mma_commit(&bar_mma[b]);
+          mark(15);
+        }
+        R = next_round(R);
+      }
+    }
+    __syncwarp();
+    __syncthreads();  // teardown barrier of the CTA
+    return;
+  }
+  if (warp >= kSplitBWarp0) {
+    // ---------------- split B: thread = slot = TMEM lane; node terms -> the accumulator:
+    // c * (P[dst] + Q[src]), c = -log2(e) (f gate) / +log2(e) (s gate), 16 columns per tcgen05.st
+    const int e = tid - kSplitBWarp0 * 32;
     const bool prof_me = (e == 0);
-    uint32_t ph_ea = 0, ph_r = 0, ph_f = 0, used = 0;
+    uint32_t ph_r = 0, ph_f = 0, used = 0;
     RoundW R = make_round(0, 0);
     for (uint32_t it = 0; valid(R); ++it) {
       const int b = it & 1;
       if (R.cnt > 0) {
-        if (prof_me) mark(8);
-        if ((used >> b) & 1) {  // the gate warps have read accumulator b (so the MMAs that used A buffer b are done)
+        if (prof_me) mark(9);
+        if ((used >> b) & 1) {  // the gate warps have read accumulator b (round it - 2)
           umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
           ph_f ^= 1u << b;
           umma::fence_after_sync();
         }
-        if (prof_me) mark(9);
-        // ---- (1) the edge row -> hi / lo -> A operand columns
-        const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
-        if (nb) {
-          umma::mbar_wait(&bar_ea_full, ph_ea);
-          ph_ea ^= 1;
-        }
         if (prof_me) mark(10);
-        {
-          const int ea_off = (int)(((long long)R.r_lo * G) & 3);
-          const float* row = sEA + ea_off + e * G;
-          const int landed = (int)(nb >> 2);  // first float of the landing zone the bulk copy did NOT deliver
-          const bool patch = e < R.cnt && landed < ea_off + (e + 1) * G;
-          const uint32_t a_hi = umma::tmem_addr(tm_a_hi(b), warp, 0), a_lo = umma::tmem_addr(tm_a_lo(b), warp, 0);
-          for (int ch = 0; ch < (KP >> 3); ++ch) {
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = 0.0f;
-            if (e < R.cnt) {
-              if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
-#pragma unroll
-                for (int t = 0; t < 8; t += 2)
-                  if (8 * ch + t < G) {
-                    const float2 a = *reinterpret_cast<const float2*>(row + 8 * ch + t);
-                    v[t] = a.x; v[t + 1] = a.y;
-                  }
-              } else {
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                  if (8 * ch + t < G) v[t] = row[8 * ch + t];
-              }
-              if (patch) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  const int k = 8 * ch + t;
-                  if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)R.r_lo + e) * G + k);
-                }
-              }
-            }
-            float hi[8], lo[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
-            umma::tmem_st8(a_hi + 8 * ch, hi);
-            umma::tmem_st8(a_lo + 8 * ch, lo);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_ea_free);  // landing zone read: the next round's copy may be issued
-        if (prof_me) mark(11);
-        // ---- (2) node terms -> the accumulator: c * (P[dst] + Q[src]), c = -log2(e) (f gate) / +log2(e) (s gate)
         umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);
         ph_r ^= 1u << b;
-        if (prof_me) mark(12);
+        if (prof_me) mark(11);
         {
           const int4 wr = sWin[b];
           const bool win = wr.x != 0;
@@ -474,36 +454,119 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           const float* r1 = win ? sW + (ss - wr.y) * kVW : p.PQ + (size_t)ss * (4 * kC) + 2 * kC;
           const uint32_t acc = umma::tmem_addr(tm_acc(b), warp, 0);
           auto run = [&](auto ld) {
-#pragma unroll 4
-            for (int c = 0; c < kNP / 8; ++c) {
-              float v[8];
+#pragma unroll 2
+            for (int c = 0; c < kNP / 16; ++c) {
+              float v[16];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+              for (int t = 0; t < 16; ++t) v[t] = 0.0f;
               if (live) {
-                const float sc = (c < kC / 8) ? -kLog2e : kLog2e;
+                const float sc = (c < kC / 16) ? -kLog2e : kLog2e;
                 const f2_t sc2 = pk2(sc, sc);
-                const float4 p0 = ld(r0 + 8 * c), p1 = ld(r0 + 8 * c + 4);
-                const float4 q0 = ld(r1 + 8 * c), q1 = ld(r1 + 8 * c + 4);
-                upk2(mul2(add2(pk2(p0.x, p0.y), pk2(q0.x, q0.y)), sc2), v[0], v[1]);
-                upk2(mul2(add2(pk2(p0.z, p0.w), pk2(q0.z, q0.w)), sc2), v[2], v[3]);
-                upk2(mul2(add2(pk2(p1.x, p1.y), pk2(q1.x, q1.y)), sc2), v[4], v[5]);
-                upk2(mul2(add2(pk2(p1.z, p1.w), pk2(q1.z, q1.w)), sc2), v[6], v[7]);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const float4 pp = ld(r0 + 16 * c + 4 * h), qq = ld(r1 + 16 * c + 4 * h);
+                  upk2(mul2(add2(pk2(pp.x, pp.y), pk2(qq.x, qq.y)), sc2), v[4 * h], v[4 * h + 1]);
+                  upk2(mul2(add2(pk2(pp.z, pp.w), pk2(qq.z, qq.w)), sc2), v[4 * h + 2], v[4 * h + 3]);
+                }
               }
-              umma::tmem_st8(acc + 8 * c, v);
+              umma::tmem_st16(acc + 16 * c, v);
             }
           };
           if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
           else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
         umma::tmem_st_wait();
         umma::fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
-          mbar_arrive(&bar_a_full[b]);     // A operand + preloaded accumulator ready for the MMAs
-        }
+        if (lane == 0) mbar_arrive(&bar_acc_full[b]);   // accumulator ready for the MMAs
         used |= 1u << b;
-        if (prof_me) mark(13);
+        if (prof_me) mark(12);
+      }
+      R = next_round(R);
+    }
+    __syncthreads();  // teardown barrier of the CTA
+    return;
+  }
+  if (warp >= kSplitAWarp0) {
+    // ---------------- split A: thread = slot = TMEM lane; the edge row -> hi / lo -> A operand columns
+    const int e = tid - kSplitAWarp0 * 32;
+    const bool prof_me = (e == 0);
+    uint32_t ph_ea = 0, ph_m = 0, used = 0;
+    RoundW R = make_round(0, 0);
+    for (uint32_t it = 0; valid(R); ++it) {
+      const int b = it & 1;
+      if (R.cnt > 0) {
+        if (prof_me) mark(5);
+        if ((used >> b) & 1) {  // the MMAs that read this A buffer two rounds ago have retired
+          umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);
+          ph_m ^= 1u << b;
+          umma::fence_after_sync();
+        }
+        if (prof_me) mark(6);
+        const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
+        if (nb) {
+          umma::mbar_wait(&bar_ea_full, ph_ea);
+          ph_ea ^= 1;
+        }
+        if (prof_me) mark(7);
+        const int ea_off = (int)(((long long)R.r_lo * G) & 3);
+        const float* row = sEA + ea_off + e * G;
+        const int landed = (int)(nb >> 2);  // first float of the landing zone the bulk copy did NOT deliver
+        const bool patch = e < R.cnt && landed < ea_off + (e + 1) * G;
+        const uint32_t a_hi = umma::tmem_addr(tm_a_hi(b), warp, 0), a_lo = umma::tmem_addr(tm_a_lo(b), warp, 0);
+        auto load8 = [&](int k0, float* v) {  // row[k0 .. k0+8) (zero beyond G / beyond the round)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+          if (e < R.cnt) {
+            if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
+#pragma unroll
+              for (int t = 0; t < 8; t += 2)
+                if (k0 + t < G) {
+                  const float2 a = *reinterpret_cast<const float2*>(row + k0 + t);
+                  v[t] = a.x; v[t + 1] = a.y;
+                }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (k0 + t < G) v[t] = row[k0 + t];
+            }
+            if (patch) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int k = k0 + t;
+                if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)R.r_lo + e) * G + k);
+              }
+            }
+          }
+        };
+        int k0 = 0;
+        for (; k0 + 16 <= KP; k0 += 16) {  // 16 columns per tcgen05.st
+          float v[16], hi[16], lo[16];
+          load8(k0, v);
+          load8(k0 + 8, v + 8);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+          umma::tmem_st16(a_hi + k0, hi);
+          umma::tmem_st16(a_lo + k0, lo);
+        }
+        if (k0 < KP) {  // KP is a multiple of 8: one 8-column remainder
+          float v[8], hi[8], lo[8];
+          load8(k0, v);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+          umma::tmem_st8(a_hi + k0, hi);
+          umma::tmem_st8(a_lo + k0, lo);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_ea_free);  // landing zone read: the next round's copy may be issued
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tma_full[b]);
+        used |= 1u << b;
+        if (prof_me) mark(8);
       }
       R = next_round(R);
     }

@@ -56,12 +56,12 @@ PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14:
               6: "wait MMA(r)", 2: "wait ea(r+1)", 3: "split(r+1) -> TMEM", 4: "row+idx STS, fences, S2",
               7: "TMEM ld", 10: "node terms + gate math", 11: "S3 barrier", 12: "reduce"}
 WS_NAMES = {0: "gates: loop top", 1: "gates: wait message tile free", 2: "gates: wait MMA", 3: "gates: TMEM ld + release",
-            4: "gates: gate math + STS", 8: "(splitters: loop top)", 9: "(splitters: wait accumulator free)",
-            10: "(splitters: wait edge rows)", 11: "(splitters: split -> TMEM)", 12: "(splitters: wait indices / node rows)",
-            13: "(splitters: node terms -> accumulator)", 16: "(reducers: loop top + seg loads)", 17: "(reducers: wait message tile)",
-            18: "(reducers: sums)", 20: "(issuer: loop top)", 21: "(issuer: wait landing zone free + bulk issue)",
-            22: "(issuer: wait A operand)", 23: "(issuer: MMA issue)", 24: "(loaders: loop top)", 25: "(loaders: wait buffer free)",
-            26: "(loaders: indices + window + row copies)"}
+            4: "gates: gate math + STS", 5: "(split A: loop top)", 6: "(split A: wait A buffer free)", 7: "(split A: wait edge rows)",
+            8: "(split A: split -> TMEM)", 9: "(split B: loop top)", 10: "(split B: wait accumulator free)",
+            11: "(split B: wait indices / node rows)", 12: "(split B: node terms -> accumulator)", 13: "(mma: loop top)",
+            14: "(mma: wait operands)", 15: "(mma: issue)", 16: "(ea copy: loop top)", 17: "(ea copy: wait landing zone + issue)",
+            18: "(loaders: loop top)", 19: "(loaders: wait buffer free)", 20: "(loaders: indices + window + row copies)",
+            21: "(reducers: loop top + seg loads)", 22: "(reducers: wait message tile)", 23: "(reducers: sums)"}
 BWD_PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 2: "next idx, window, row/seg loads issue", 3: "wait dW_e(r-1)",
                   4: "wait ea + split -> TMEM + ea^T tiles", 5: "row/idx STS, fences", 6: "S2 (issuer hand-off)",
                   7: "grad loads + wait recompute MMA", 8: "TMEM ld + node terms", 9: "S2d barrier", 10: "gate math",
@@ -85,7 +85,7 @@ for name, fn in (("fwd", fwd), ("bwd", bwd)):
     lib.mdl_debug_set_phase_buffer(None)
     v = prof.cpu().tolist()
     rounds = max(v[31], 1)
-    if v[25]:
+    if v[25] and NAMES_ is NAMES:
         print(f"!! wait timed out: barrier id {v[26]} (1 ea, 2 node rows, 3 mma), CTA {v[27]}, round {v[28]}, "
               f"thread {v[29]}, parity {v[30]}")
     tot = max(sum(v[i] for i, nm in NAMES_.items() if not nm.startswith("(")), 1)
