@@ -7,18 +7,19 @@
 // phase after phase between CTA-wide barriers.  Here every stage has its own warps and mbarrier hand-offs;
 // there is no CTA-wide barrier inside the loop and the gate warps do nothing but gate math:
 //
-//   warps 26-27  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
-//   warp 25      ea copy    one bulk (TMA) copy of the round's edge rows into the landing zone
-//   warps 16-19  split A    thread = slot = TMEM lane: edge row (landing zone) -> hi / lo -> tcgen05.st (A operand)
-//   warps 20-23  split B    thread = slot: node terms c * (P[dst] + Q[src]) -> tcgen05.st INTO THE ACCUMULATOR (the
-//                           MMAs then accumulate onto them: the epilogue has no node-row reads and no adds left)
-//   warp 24      mma        the 21 tcgen05.mma (3xTF32) of a round; issuing them blocks the thread for the MMAs' run time
-//   warps 0-15   gates      tcgen05.ld -> sigmoid * softplus on packed f32x2 / MUFU -> message tile
-//   warps 28-31  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
+//   warps 21-23  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
+//   warps 16-19  splitters  thread = slot = TMEM lane: edge row (landing zone) -> hi / lo -> tcgen05.st (A operand)
+//   warp 20      issuer     bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma (3xTF32) of a round
+//   warps 0-15   gates      tcgen05.ld -> + c (P[dst] + Q[src]) -> sigmoid * softplus on packed f32x2 / MUFU -> message tile
+//   warps 24-27  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
 //
-//   ea copy --ea_full--> split A --tma_full[b]--> mma --mma[b]--> gates --v_full[b]--> reducers --v_free[b]--> gates
-//   loaders --rows_full[b]--> split B --acc_full[b]--> mma      gates --acc_free[b]--> split B
-//   split A --ea_free--> ea copy      split B --rows_free[b]--> loaders      mma[b] also frees A buffer b for split A
+//   issuer --ea_full--> splitters --a_full[b]--> issuer (MMA) --mma[b]--> gates --v_full[b]--> reducers --v_free[b]--> gates
+//   loaders --rows_full[b]--> gates --rows_free[b]--> loaders      gates --acc_free[b]--> issuer
+//   mma[b] also frees A buffer b for the splitters
+//
+// (Measured dead end, profiles/r2_phase_profile_ws_v3.txt: preloading the node terms into the accumulator with
+// tcgen05.st from extra splitter warps -- tensor-memory stores queue behind the running MMAs, the splitters became the
+// bottleneck at ~5k cycles per round.  The node terms are added by the gate warps from shared memory.)
 //
 // Every per-round resource is double-buffered (accumulators, A-operand columns, index / node-row buffers, message
 // tiles); only the edge-row landing zone is single (its copy for round r+1 is issued as soon as round r is split).
@@ -35,12 +36,11 @@ namespace mdl {
 namespace {
 
 constexpr int kGateWarps = 16;                    // warps 0..15
-constexpr int kSplitAWarp0 = 16;                  // warps 16..19: TMEM lane quadrants 0..3 (edge rows)
-constexpr int kSplitBWarp0 = 20;                  // warps 20..23: TMEM lane quadrants 0..3 (node terms)
-constexpr int kMmaWarp = 24, kCopyWarp = 25;
-constexpr int kLoadWarp0 = 26, kLoaders = 64;     // warps 26..27
-constexpr int kRedWarp0 = 28, kRedWarps = 4;      // warps 28..31
-constexpr int kLaunchW = 1024;
+constexpr int kSplitWarp0 = 16;                   // warps 16..19: TMEM lane quadrants 0..3
+constexpr int kIssuerWarp = 20;
+constexpr int kLoadWarp0 = 21, kLoaders = 96;     // warps 21..23
+constexpr int kRedWarp0 = 24, kRedWarps = 4;      // warps 24..27
+constexpr int kLaunchW = 896;
 constexpr int kRowsW = 128, kTileW = 112, kInfoCapW = 512;
 constexpr int kC = 64, kNP = 2 * kC;
 constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tiles (bank spread)
@@ -131,10 +131,10 @@ __device__ __forceinline__ f2_t gate_pair(float yf0, float yf1, float ys0, float
 template <int PROFILE>
 __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p, const WsPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_ea_full, bar_ea_free, bar_tma_full[2], bar_acc_full[2], bar_mma[2], bar_acc_free[2],
-      bar_rows_full[2], bar_rows_free[2], bar_v_full[2], bar_v_free[2];
+  __shared__ uint64_t bar_ea_full, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2], bar_rows_free[2],
+      bar_v_full[2], bar_v_free[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int sRed[2][2];  // loaders: per-warp (min, max) of the round's source nodes
+  __shared__ int sRed[3][2];  // loaders: per-warp (min, max) of the round's source nodes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP, WR = pl.WR;
 
@@ -176,16 +176,14 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsW);
   if (tid == 32) {
     umma::mbar_init(&bar_ea_full, 1);
-    umma::mbar_init(&bar_ea_free, 4);                // one arrival per split-A warp
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(&bar_tma_full[b], 4);          // split-A warps: A operand staged
-      umma::mbar_init(&bar_acc_full[b], 4);          // split-B warps: accumulator preloaded with the node terms
-      umma::mbar_init(&bar_mma[b], 1);               // tcgen05.commit
-      umma::mbar_init(&bar_acc_free[b], kGateWarps); // gate warps: accumulator read
-      umma::mbar_init(&bar_rows_full[b], 1);         // loader thread 0 (+ the rows' bytes)
-      umma::mbar_init(&bar_rows_free[b], 4);         // split-B warps
-      umma::mbar_init(&bar_v_full[b], kGateWarps);   // gate warps: message tile written
-      umma::mbar_init(&bar_v_free[b], kRedWarps);    // reducer warps: message tile summed
+      umma::mbar_init(&bar_a_full[b], 4);              // splitter warps: A operand staged (and the landing zone read)
+      umma::mbar_init(&bar_mma[b], 1);                 // tcgen05.commit
+      umma::mbar_init(&bar_acc_free[b], kGateWarps);   // gate warps: accumulator read
+      umma::mbar_init(&bar_rows_full[b], 1);           // loader thread 0 (+ the rows' bytes)
+      umma::mbar_init(&bar_rows_free[b], kGateWarps);  // gate warps: indices / node rows read
+      umma::mbar_init(&bar_v_full[b], kGateWarps);     // gate warps: message tile written
+      umma::mbar_init(&bar_v_free[b], kRedWarps);      // reducer warps: message tile summed
     }
     umma::fence_mbar_init();
   }
@@ -291,18 +289,18 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     __syncthreads();  // teardown barrier of the CTA
     return;
   }
-  if (warp >= kLoadWarp0) {
+  if (warp > kIssuerWarp) {
     // ---------------- loaders: indices, window decision, node rows of a round.  The indices of round r+1 are
     // requested (into registers) before round r is processed: their HBM latency runs under this round's work.
     const int lt = tid - kLoadWarp0 * 32, lw = warp - kLoadWarp0;
     auto sync_loaders = [] { asm volatile("bar.sync 3, %0;" ::"n"(kLoaders) : "memory"); };
-    constexpr int kPer = 2 * kRowsW / kLoaders;  // index entries per loader thread (4)
+    constexpr int kPer = (2 * kRowsW + kLoaders - 1) / kLoaders;  // index entries per loader thread (3)
     auto fetch = [&](const RoundW& R, int (&v)[kPer]) {
 #pragma unroll
       for (int j = 0; j < kPer; ++j) {
         const int i = lt + j * kLoaders, e = i & (kRowsW - 1);
         v[j] = 0;
-        if (valid(R) && e < R.cnt) v[j] = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
+        if (valid(R) && i < 2 * kRowsW && e < R.cnt) v[j] = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
       }
     };
     uint32_t ph_rf = 0, used = 0;
@@ -315,7 +313,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       fetch(Rn, vnext);
       if (R.cnt > 0) {
         if (lt == 0) mark(18);
-        if ((used >> b) & 1) {  // split B has finished with this buffer (two rounds ago)
+        if ((used >> b) & 1) {  // the gate warps have finished with this buffer (two rounds ago)
           umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
           ph_rf ^= 1u << b;
         }
@@ -325,15 +323,15 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
           const int i = lt + j * kLoaders, e = i & (kRowsW - 1);
-          bS[i] = vcur[j];
+          if (i < 2 * kRowsW) bS[i] = vcur[j];
           if (i < kRowsW && e < R.cnt) { s_lo = min(s_lo, vcur[j]); s_hi = max(s_hi, vcur[j]); }
         }
         s_lo = __reduce_min_sync(0xffffffffu, s_lo);
         s_hi = __reduce_max_sync(0xffffffffu, s_hi);
         if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
         sync_loaders();  // indices and per-warp ranges visible to all loaders
-        s_lo = min(sRed[0][0], sRed[1][0]);
-        s_hi = max(sRed[0][1], sRed[1][1]);
+        s_lo = min(sRed[0][0], min(sRed[1][0], sRed[2][0]));
+        s_hi = max(sRed[0][1], max(sRed[1][1], sRed[2][1]));
         const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
         const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
         const bool win = pl.window && nq + np_ <= WR;
@@ -359,8 +357,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     __syncthreads();  // teardown barrier of the CTA
     return;
   }
-  if (warp == kCopyWarp) {
-    // ---------------- ea copy: one bulk copy of a round's edge rows, issued as soon as the landing zone is free
+  if (warp == kIssuerWarp) {
+    // ---------------- issuer: bulk copies of the edge rows, MMAs
     if (lane == 0) {
       auto issue_ea_bulk = [&](const RoundW& R) {
         const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
@@ -369,18 +367,43 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         umma::mbar_arrive_expect_tx(&bar_ea_full, nb);
         umma::bulk_g2s(sEA, p.ea + (first - (first & 3)), nb, &bar_ea_full);
       };
-      uint32_t ph_e = 0;
+      const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
+      const uint32_t step_b = 2 * (uint32_t)kNP * 16;
+      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+      uint32_t ph_a = 0, ph_f = 0;  // phase parities, bit b = buffer b
+      uint32_t busy = 0;            // bit b: accumulator b holds a round whose epilogue has not been waited for
       RoundW R = make_round(0, 0);
       if (valid(R)) issue_ea_bulk(R);
-      while (valid(R)) {
+      for (uint32_t it = 0; valid(R); ++it) {
+        const int b = it & 1;
         const RoundW Rn = next_round(R);
-        mark(16);
-        if (R.cnt > 0) {  // split A has read this round's edge rows: the landing zone is free
-          umma::mbar_wait(&bar_ea_free, ph_e);
-          ph_e ^= 1;
+        mark(13);
+        if (R.cnt > 0) {  // split of this round done: its A operand is staged and the landing zone is free
+          umma::mbar_wait(&bar_a_full[b], (ph_a >> b) & 1);
+          ph_a ^= 1u << b;
         }
-        if (valid(Rn)) issue_ea_bulk(Rn);
-        mark(17);
+        if (valid(Rn)) issue_ea_bulk(Rn);  // first: the MMA issue below blocks for the MMAs' run time
+        if (R.cnt > 0) {
+          if ((busy >> b) & 1) {  // the gate warps have read the round that used this accumulator two rounds ago
+            umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
+            ph_f ^= 1u << b;
+          }
+          umma::fence_after_sync();
+          mark(14);
+          uint32_t acc = 0;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
+            const uint32_t bb = (pass == 1) ? b_lo : b_hi;
+            for (int kk = 0; kk < (KP >> 3); ++kk) {
+              umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, acc);
+              acc = 1;
+            }
+          }
+          umma::mma_commit(&bar_mma[b]);
+          busy |= 1u << b;
+          mark(15);
+        }
         R = Rn;
       }
     }
@@ -388,110 +411,9 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     __syncthreads();  // teardown barrier of the CTA
     return;
   }
-  if (warp == kMmaWarp) {
-    // ---------------- mma: the round's contraction, accumulated onto the preloaded node terms
-    if (lane == 0) {
-      const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
-      const uint32_t step_b = 2 * (uint32_t)kNP * 16;
-      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
-      uint32_t ph_a = 0, ph_c = 0;  // phase parities, bit b = buffer b
-      RoundW R = make_round(0, 0);
-      for (uint32_t it = 0; valid(R); ++it) {
-        const int b = it & 1;
-        mark(13);
-        if (R.cnt > 0) {
-          umma::mbar_wait(&bar_tma_full[b], (ph_a >> b) & 1);  // A operand staged
-          ph_a ^= 1u << b;
-          umma::mbar_wait(&bar_acc_full[b], (ph_c >> b) & 1);  // accumulator preloaded with the node terms
-          ph_c ^= 1u << b;
-          umma::fence_after_sync();
-          mark(14);
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
-            const uint32_t bb = (pass == 1) ? b_lo : b_hi;
-            for (int kk = 0; kk < (KP >> 3); ++kk)
-              umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, 1u);
-          }
-          umma::mma_commit(&bar_mma[b]);
-          mark(15);
-        }
-        R = next_round(R);
-      }
-    }
-    __syncwarp();
-    __syncthreads();  // teardown barrier of the CTA
-    return;
-  }
-  if (warp >= kSplitBWarp0) {
-    // ---------------- split B: thread = slot = TMEM lane; node terms -> the accumulator:
-    // c * (P[dst] + Q[src]), c = -log2(e) (f gate) / +log2(e) (s gate), 16 columns per tcgen05.st
-    const int e = tid - kSplitBWarp0 * 32;
-    const bool prof_me = (e == 0);
-    uint32_t ph_r = 0, ph_f = 0, used = 0;
-    RoundW R = make_round(0, 0);
-    for (uint32_t it = 0; valid(R); ++it) {
-      const int b = it & 1;
-      if (R.cnt > 0) {
-        if (prof_me) mark(9);
-        if ((used >> b) & 1) {  // the gate warps have read accumulator b (round it - 2)
-          umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
-          ph_f ^= 1u << b;
-          umma::fence_after_sync();
-        }
-        if (prof_me) mark(10);
-        umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);
-        ph_r ^= 1u << b;
-        if (prof_me) mark(11);
-        {
-          const int4 wr = sWin[b];
-          const bool win = wr.x != 0;
-          const int* bSrc = sIdx + b * 2 * kRowsW;
-          const bool live = e < R.cnt;
-          const int ss = live ? bSrc[e] : 0, sd = live ? bSrc[kRowsW + e] : 0;
-          const float* sW = sWbuf(b);
-          const float* r0 = win ? sW + (wr.w + sd - wr.z) * kVW : p.PQ + (size_t)sd * (4 * kC);
-          const float* r1 = win ? sW + (ss - wr.y) * kVW : p.PQ + (size_t)ss * (4 * kC) + 2 * kC;
-          const uint32_t acc = umma::tmem_addr(tm_acc(b), warp, 0);
-          auto run = [&](auto ld) {
-#pragma unroll 2
-            for (int c = 0; c < kNP / 16; ++c) {
-              float v[16];
-#pragma unroll
-              for (int t = 0; t < 16; ++t) v[t] = 0.0f;
-              if (live) {
-                const float sc = (c < kC / 16) ? -kLog2e : kLog2e;
-                const f2_t sc2 = pk2(sc, sc);
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  const float4 pp = ld(r0 + 16 * c + 4 * h), qq = ld(r1 + 16 * c + 4 * h);
-                  upk2(mul2(add2(pk2(pp.x, pp.y), pk2(qq.x, qq.y)), sc2), v[4 * h], v[4 * h + 1]);
-                  upk2(mul2(add2(pk2(pp.z, pp.w), pk2(qq.z, qq.w)), sc2), v[4 * h + 2], v[4 * h + 3]);
-                }
-              }
-              umma::tmem_st16(acc + 16 * c, v);
-            }
-          };
-          if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
-          else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
-        umma::tmem_st_wait();
-        umma::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_acc_full[b]);   // accumulator ready for the MMAs
-        used |= 1u << b;
-        if (prof_me) mark(12);
-      }
-      R = next_round(R);
-    }
-    __syncthreads();  // teardown barrier of the CTA
-    return;
-  }
-  if (warp >= kSplitAWarp0) {
-    // ---------------- split A: thread = slot = TMEM lane; the edge row -> hi / lo -> A operand columns
-    const int e = tid - kSplitAWarp0 * 32;
+  if (warp >= kSplitWarp0) {
+    // ---------------- splitters: thread = slot = TMEM lane; the edge row -> hi / lo -> A operand columns
+    const int e = tid - kSplitWarp0 * 32;
     const bool prof_me = (e == 0);
     uint32_t ph_ea = 0, ph_m = 0, used = 0;
     RoundW R = make_round(0, 0);
@@ -559,12 +481,10 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           umma::tmem_st8(a_hi + k0, hi);
           umma::tmem_st8(a_lo + k0, lo);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_ea_free);  // landing zone read: the next round's copy may be issued
         umma::tmem_st_wait();
         umma::fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tma_full[b]);
+        if (lane == 0) mbar_arrive(&bar_a_full[b]);  // A operand staged; the landing zone has been read
         used |= 1u << b;
         if (prof_me) mark(8);
       }
@@ -578,19 +498,31 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   const bool prof_me = (tid == 0);
   const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
   const int c_begin = part * 16;
-  uint32_t ph_m = 0, ph_vf = 0, used_v = 0;
+  uint32_t ph_m = 0, ph_vf = 0, ph_r = 0, used_v = 0;
   RoundW cur = make_round(0, 0);
   for (uint32_t it = 0; valid(cur); ++it) {
     const int b = it & 1;
     const int cnt = cur.cnt;
     if (prof_me) mark(0);
     if (cnt > 0) {
+      umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);  // indices, window record, node rows of this round
+      ph_r ^= 1u << b;
       if ((used_v >> b) & 1) {  // the reducers have summed the round that used this message tile two rounds ago
         umma::mbar_wait(&bar_v_free[b], (ph_vf >> b) & 1);
         ph_vf ^= 1u << b;
       }
       if (prof_me) mark(1);
-      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);  // this round's contraction (node terms included)
+      // node rows of this slot: requested from shared memory (window) or L2 before the wait on the contraction
+      const int e_ep = 32 * q + lane;
+      const bool live = e_ep < cnt;
+      const int4 wr = sWin[b];
+      const bool win = wr.x != 0;
+      const int* bSrc = sIdx + b * 2 * kRowsW;
+      const int ss = live ? bSrc[e_ep] : 0, sd = live ? bSrc[kRowsW + e_ep] : 0;
+      const float* sW = sWbuf(b);
+      const float* r0 = win ? sW + (wr.w + sd - wr.z) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
+      const float* r1 = win ? sW + (ss - wr.y) * kVW + c_begin : p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
+      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);  // this round's contraction
       ph_m ^= 1u << b;
       umma::fence_after_sync();
       if (prof_me) mark(2);
@@ -602,19 +534,34 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_free[b]);  // the accumulator may be rewritten (round it + 2)
       if (prof_me) mark(3);
-      const int e_ep = 32 * q + lane;
-      if (e_ep < cnt) {
+      if (live) {
         float* rowv = sVbuf(b) + e_ep * kVP + c_begin;
+        const f2_t cf = pk2(-kLog2e, -kLog2e), cs = pk2(kLog2e, kLog2e);
+        auto run = [&](auto ld) {  // ld: how the node rows are read (shared or global memory)
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          float m0, m1, m2, m3;
-          upk2(gate_pair(f[j4], f[j4 + 1], sacc[j4], sacc[j4 + 1]), m0, m1);
-          upk2(gate_pair(f[j4 + 2], f[j4 + 3], sacc[j4 + 2], sacc[j4 + 3]), m2, m3);
-          *reinterpret_cast<float4*>(rowv + j4) = make_float4(m0, m1, m2, m3);
-        }
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 pf = ld(r0 + j4), ps = ld(r0 + kC + j4);
+            const float4 qf = ld(r1 + j4), qs = ld(r1 + kC + j4);
+            // y = accumulator (already in base-2 units: W_e is pre-scaled) + c (P + Q)
+            float yf0, yf1, yf2, yf3, ys0, ys1, ys2, ys3;
+            upk2(fma2(cf, add2(pk2(pf.x, pf.y), pk2(qf.x, qf.y)), pk2(f[j4], f[j4 + 1])), yf0, yf1);
+            upk2(fma2(cf, add2(pk2(pf.z, pf.w), pk2(qf.z, qf.w)), pk2(f[j4 + 2], f[j4 + 3])), yf2, yf3);
+            upk2(fma2(cs, add2(pk2(ps.x, ps.y), pk2(qs.x, qs.y)), pk2(sacc[j4], sacc[j4 + 1])), ys0, ys1);
+            upk2(fma2(cs, add2(pk2(ps.z, ps.w), pk2(qs.z, qs.w)), pk2(sacc[j4 + 2], sacc[j4 + 3])), ys2, ys3);
+            float m0, m1, m2, m3;
+            upk2(gate_pair(yf0, yf1, ys0, ys1), m0, m1);
+            upk2(gate_pair(yf2, yf3, ys2, ys3), m2, m3);
+            *reinterpret_cast<float4*>(rowv + j4) = make_float4(m0, m1, m2, m3);
+          }
+        };
+        if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
+        else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_v_full[b]);  // this warp's part of the message tile is written
+      if (lane == 0) {
+        mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
+        mbar_arrive(&bar_v_full[b]);     // this warp's part of the message tile is written
+      }
       used_v |= 1u << b;
       if (prof_me) mark(4);
     }

@@ -12,6 +12,8 @@
 // gradient lives (e.g. the column blocks of CGConv's lin_f.weight / lin_s.weight inside the flat
 // gradient buffer): no concatenation, no separate bias reduction.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace mdl {
 
@@ -176,6 +178,17 @@ __global__ void k_copy_mapped(const float* __restrict__ src, int I, int O, int t
   }
 }
 
+// shared with wgrad_tc.cu: sum `nparts` partials ([O*I | O] each) in order and deliver through the block map
+int wgrad_reduce_launch(const float* part, int nparts, int I, int O, const mdl_wgrad_out& m, cudaStream_t st) {
+  const int64_t len = (int64_t)O * I + O;
+  k_wgrad_reduce<<<(int)ceil_div<int64_t>(len, 32), 256, 0, st>>>(part, nparts, I, O, m);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+bool wgrad_tc_supported(int64_t R, int I, int O);
+int wgrad_tc_launch(const float* X, const float* G, int64_t R, int I, int O, const mdl_wgrad_out& out, float* part,
+                    cudaStream_t st);
+
 static size_t wg_ws_bytes(int64_t N, int I, int O) {
   return (size_t)wg_grid(N) * ((size_t)O * I + O) * sizeof(float);
 }
@@ -203,6 +216,11 @@ extern "C" int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32
   if (int rc = wg_check_map(out, O, "linear_wgrad")) return rc;
   MDL_REQUIRE(X && G && workspace, "linear_wgrad: null pointer");
   MDL_REQUIRE(workspace_bytes >= wg_ws_bytes(N, I, O), "linear_wgrad: workspace too small");
+  {  // long batches (edge-level layers): the tcgen05 kernel (wgrad_tc.cu); MDL_WGRAD=simt keeps the SIMT one (A/B)
+    const char* env = getenv("MDL_WGRAD");
+    if (!(env && strcmp(env, "simt") == 0) && wgrad_tc_supported(N, I, O))
+      return wgrad_tc_launch(X, G, N, I, O, *out, reinterpret_cast<float*>(workspace), as_stream(stream));
+  }
   const size_t smem = (size_t)2 * kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
   // two stages of 32 rows of X and G: I + O <= ~780 floats per row pair (one CTA per SM above ~100 KB)
   MDL_REQUIRE(smem <= 200 * 1024, "linear_wgrad: layer too wide (needs %zu bytes of shared memory, I + O <= ~780)", smem);

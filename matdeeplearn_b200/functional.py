@@ -57,9 +57,14 @@ def linear_wgrad_into(x, g, wmap):
     _lib.check(rc, "mdl_linear_wgrad")
 
 
+# rows from which the tcgen05 weight-gradient kernel (csrc/wgrad_tc.cu) takes over from the library GEMM + column sum
+_WGRAD_TC_MIN_ROWS = 2048
+
+
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b: library GEMMs for y and dx; with direct delivery, dW and db come from
-    mdl_linear_wgrad and land in the flat gradient buffer."""
+    """y = x W^T + b: library GEMMs for y and dx; dW and db come from mdl_linear_wgrad -- delivered straight into
+    the flat gradient buffer when the engine owns one (direct delivery), and for long batches (edge-level MLPs:
+    a K = E contraction + a column sum on the reference's path) also without one."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -75,22 +80,37 @@ class LinearFn(torch.autograd.Function):
         dx = g.mm(weight) if ctx.needs_input_grad[0] else None
         wd = _grad_dest(wparam)
         bd = _grad_dest(bparam) if bparam is not None else None
+        O, I = weight.shape
         if wd is not None and (bparam is None or bd is not None) and x.shape[0] > 0:
-            O, I = weight.shape
             linear_wgrad_into(x, g, _wgrad_map(O, I, [_ptr_off(wd)], [_ptr_off(bd)]))
             wparam._mdl_written = True
             if bparam is not None:
                 bparam._mdl_written = True
             return dx, None, None
+        if x.shape[0] >= _WGRAD_TC_MIN_ROWS and I <= 256 and I >= 8 and O >= 8:
+            dW = torch.empty_like(weight)
+            db = torch.empty(O, dtype=weight.dtype, device=weight.device) if bparam is not None else None
+            linear_wgrad_into(x, g, _wgrad_map(O, I, [_ptr_off(dW)], [_ptr_off(db)]))
+            return dx, dW, db
         return dx, g.t().mm(x), (g.sum(0) if bparam is not None else None)
 
 
 def linear(x, weight, bias=None):
-    """torch.nn.functional.linear; routed through LinearFn when the engine delivers gradients directly."""
-    if (x.dim() == 2 and x.is_cuda and torch.is_grad_enabled() and weight.requires_grad
-            and getattr(weight, "_mdl_grad_dest", None) is not None):
+    """torch.nn.functional.linear; routed through LinearFn when the engine delivers gradients directly or the
+    batch is long enough for the tensor-core weight-gradient kernel."""
+    if (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and weight.requires_grad
+            and (getattr(weight, "_mdl_grad_dest", None) is not None or x.shape[0] >= _WGRAD_TC_MIN_ROWS)):
         return LinearFn.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)
+
+
+def apply_mlp(seq, x):
+    """Run an nn.Sequential (or a single module) with every nn.Linear going through `linear` above; other
+    layers (activations, BatchNorm) are called as they are."""
+    mods = list(seq) if isinstance(seq, torch.nn.Sequential) else [seq]
+    for m in mods:
+        x = linear(x, m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m(x)
+    return x
 
 
 class SegmentReduceFn(torch.autograd.Function):

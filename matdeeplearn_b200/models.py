@@ -223,7 +223,7 @@ class _MegnetStack(tnn.Module):
         layers = getattr(self, self._name)
         for i, lin in enumerate(layers):
             if not (i == 0 and first_done):
-                h = getattr(F, self.act)(lin(h))
+                h = getattr(F, self.act)(MF.linear(h, lin.weight, lin.bias))
             if self.batch_norm == "True":
                 h = self.bn_list[i](h)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
@@ -247,7 +247,7 @@ class Megnet_EdgeModel(_MegnetStack):
         W = lin.weight
         A = x @ W[:, :D].t()
         B = x @ W[:, D:2 * D].t()
-        base = edge_attr @ W[:, 2 * D:3 * D].t()
+        base = MF.linear(edge_attr, W[:, 2 * D:3 * D].contiguous())     # the edge-level GEMM of the block
         U = u @ W[:, 3 * D:].t()
         csr = csr_for(edge_index, batch, num_nodes=x.shape[0], num_graphs=u.shape[0])
         relu = self.act == "relu"
@@ -326,7 +326,8 @@ class MEGNet(tnn.Module):
             h = act(lin(h))
         x, e, u = h, data.edge_attr, data.u
         for i, block in enumerate(self.conv_list):
-            e_t, x_t, u_t = self.e_embed_list[i](e), self.x_embed_list[i](x), self.u_embed_list[i](u)
+            e_t = MF.apply_mlp(self.e_embed_list[i], e)     # edge-level: long batch -> tensor-core weight gradients
+            x_t, u_t = MF.apply_mlp(self.x_embed_list[i], x), self.u_embed_list[i](u)
             x_o, e_o, u_o = block(x_t, data.edge_index, e_t, u_t, data.batch)
             if i == 0:   # first block: residual onto the embedded inputs (megnet.py:313-315)
                 x, e, u = x_o + x_t, e_o + e_t, u_o + u_t

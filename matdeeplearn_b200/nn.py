@@ -238,10 +238,10 @@ class CFConv(nn.Module):
         if csr is None:
             csr = csr_for(edge_index, num_nodes=x.shape[0])
         C = 0.5 * (torch.cos(edge_weight * math.pi / self.cutoff) + 1.0)
-        W = self.nn(edge_attr) * C.view(-1, 1)          # [E, F], reference edge order
-        h = self.lin1(x)
+        W = MF.apply_mlp(self.nn, edge_attr) * C.view(-1, 1)          # [E, F], reference edge order
+        h = MF.linear(x, self.lin1.weight, None)
         agg = MF.cfconv_aggregate(h, W, csr)
-        return self.lin2(agg)
+        return MF.linear(agg, self.lin2.weight, self.lin2.bias)
 
 
 class InteractionBlock(nn.Module):
@@ -270,7 +270,7 @@ class InteractionBlock(nn.Module):
 
     def forward(self, x, edge_index, edge_weight, edge_attr, csr: GraphCSR | None = None):
         x = self.conv(x, edge_index, edge_weight, edge_attr, csr=csr)
-        return self.lin(self.act(x))
+        return MF.linear(self.act(x), self.lin.weight, self.lin.bias)
 
 
 # ----------------------------------------------------------------------------
@@ -306,7 +306,7 @@ class NNConv(nn.Module):
             raise NotImplementedError("NNConv: edge network must end in a Linear (as the reference's does)")
         hid = edge_attr
         for layer in list(self.nn)[:-1]:
-            hid = layer(hid)                                   # [E, K] dense edge-level GEMM + act
+            hid = MF.apply_mlp(layer, hid)                     # [E, K] dense edge-level GEMM + act
         K = hid.shape[1]
         # last.weight [Ci*Co, K]: Theta_e[i,o] = sum_k W[i*Co+o, k] hid[k] + b[i*Co+o]
         Tm = last.weight.view(Ci, Co, K).permute(0, 2, 1).reshape(Ci, K * Co)   # x . Tm -> [N, K*Co]

@@ -55,11 +55,10 @@ def bwd():
 PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue",
               6: "wait MMA(r)", 2: "wait ea(r+1)", 3: "split(r+1) -> TMEM", 4: "row+idx STS, fences, S2",
               7: "TMEM ld", 10: "node terms + gate math", 11: "S3 barrier", 12: "reduce"}
-WS_NAMES = {0: "gates: loop top", 1: "gates: wait message tile free", 2: "gates: wait MMA", 3: "gates: TMEM ld + release",
-            4: "gates: gate math + STS", 5: "(split A: loop top)", 6: "(split A: wait A buffer free)", 7: "(split A: wait edge rows)",
-            8: "(split A: split -> TMEM)", 9: "(split B: loop top)", 10: "(split B: wait accumulator free)",
-            11: "(split B: wait indices / node rows)", 12: "(split B: node terms -> accumulator)", 13: "(mma: loop top)",
-            14: "(mma: wait operands)", 15: "(mma: issue)", 16: "(ea copy: loop top)", 17: "(ea copy: wait landing zone + issue)",
+WS_NAMES = {0: "gates: loop top", 1: "gates: wait node rows / message tile free", 2: "gates: wait MMA", 3: "gates: TMEM ld + release",
+            4: "gates: node terms + gate math + STS", 5: "(splitters: loop top)", 6: "(splitters: wait A buffer free)",
+            7: "(splitters: wait edge rows)", 8: "(splitters: split -> TMEM)", 13: "(issuer: loop top)",
+            14: "(issuer: wait A operand, bulk issue, wait accumulator free)", 15: "(issuer: MMA issue)",
             18: "(loaders: loop top)", 19: "(loaders: wait buffer free)", 20: "(loaders: indices + window + row copies)",
             21: "(reducers: loop top + seg loads)", 22: "(reducers: wait message tile)", 23: "(reducers: sums)"}
 BWD_PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 2: "next idx, window, row/seg loads issue", 3: "wait dW_e(r-1)",
