@@ -362,9 +362,7 @@ int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, flo
 static bool use_tc(int mode, int C, int G) {
   const char* env = getenv("MDL_CGCONV_IMPL");
   if (env && strcmp(env, "simt") == 0) return false;
-  // The tensor-core kernels' edge-row staging has a separate code path for odd G (4-byte granules); the GPU
-  // parity suite covers them with even G only (G = 50), so odd widths stay on the SIMT kernels, which it covers.
-  if (G & 1) return false;
+  // odd G takes the 4-byte-granule staging paths of the tensor-core kernels (tests: test_cgconv_odd_edge_width_c64)
   return cgtc_supported(mode, C, G);
 }
 

@@ -7,11 +7,13 @@
 // phase after phase between CTA-wide barriers.  Here every stage has its own warps and mbarrier hand-offs;
 // there is no CTA-wide barrier inside the loop and the gate warps do nothing but gate math:
 //
-//   warps 21-23  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
-//   warps 16-19  splitters  thread = slot = TMEM lane: edge row (landing zone) -> hi / lo -> tcgen05.st (A operand)
-//   warp 20      issuer     bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma (3xTF32) of a round
+//   warps 25-27  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
+//   warps 16-23  splitters  thread = slot = TMEM lane: edge row (landing zone) -> hi (warps 16-19) / lo (warps 20-23)
+//                           -> tcgen05.st, 32 columns per instruction (a tensor-memory store costs its warp ~600
+//                           cycles whatever its width, so few wide stores on many warps)
+//   warp 24      issuer     bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma (3xTF32) of a round
 //   warps 0-15   gates      tcgen05.ld -> + c (P[dst] + Q[src]) -> sigmoid * softplus on packed f32x2 / MUFU -> message tile
-//   warps 24-27  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
+//   warps 28-31  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
 //
 //   issuer --ea_full--> splitters --a_full[b]--> issuer (MMA) --mma[b]--> gates --v_full[b]--> reducers --v_free[b]--> gates
 //   loaders --rows_full[b]--> gates --rows_free[b]--> loaders      gates --acc_free[b]--> issuer
@@ -36,11 +38,12 @@ namespace mdl {
 namespace {
 
 constexpr int kGateWarps = 16;                    // warps 0..15
-constexpr int kSplitWarp0 = 16;                   // warps 16..19: TMEM lane quadrants 0..3
-constexpr int kIssuerWarp = 20;
-constexpr int kLoadWarp0 = 21, kLoaders = 96;     // warps 21..23
-constexpr int kRedWarp0 = 24, kRedWarps = 4;      // warps 24..27
-constexpr int kLaunchW = 896;
+constexpr int kSplitWarp0 = 16, kSplitWarps = 8;  // warps 16..19: hi halves, 20..23: lo halves (TMEM lane quadrants 0..3)
+constexpr int kIssuerWarp = 24;
+constexpr int kLoadWarp0 = 25, kLoaders = 96;     // warps 25..27
+constexpr int kRedWarp0 = 28, kRedWarps = 4;      // warps 28..31
+constexpr int kLaunchW = 1024;
+constexpr int kAW = 64;                           // columns of one A-operand half (hi or lo) in tensor memory
 constexpr int kRowsW = 128, kTileW = 112, kInfoCapW = 512;
 constexpr int kC = 64, kNP = 2 * kC;
 constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tiles (bank spread)
@@ -58,7 +61,7 @@ struct WsPlan {
 bool ws_plan(int C, int G, WsPlan* pl) {
   if (C != kC || G < 1) return false;
   const int KP = (G + 7) & ~7;
-  if (2 * kNP + 4 * KP > kTmemColsW) return false;  // two accumulators + two hi/lo A-operand buffers
+  if (KP > kAW) return false;  // tensor memory: two accumulators (2 x 128) + two hi / lo A-operand buffers (4 x 64)
   const uint32_t b = (uint32_t)kNP * KP * 4;
   const uint32_t ea = (((uint32_t)kRowsW * G * 4 + 32) + 15u) & ~15u;
   const uint32_t v = (uint32_t)kRowsW * kVP * 4, idx = 2 * 2 * kRowsW * 4, win = 64, info = kInfoCapW * 16;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   if (tid == 32) {
     umma::mbar_init(&bar_ea_full, 1);
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(&bar_a_full[b], 4);              // splitter warps: A operand staged (and the landing zone read)
+      umma::mbar_init(&bar_a_full[b], kSplitWarps);    // splitter warps: A operand staged (and the landing zone read)
       umma::mbar_init(&bar_mma[b], 1);                 // tcgen05.commit
       umma::mbar_init(&bar_acc_free[b], kGateWarps);   // gate warps: accumulator read
       umma::mbar_init(&bar_rows_full[b], 1);           // loader thread 0 (+ the rows' bytes)
@@ -211,8 +214,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   auto tm_acc = [&](int b) { return tmem + (uint32_t)b * kNP; };
-  auto tm_a_hi = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * KP; };
-  auto tm_a_lo = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * KP + (uint32_t)KP; };
+  auto tm_a_hi = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * kAW; };
+  auto tm_a_lo = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * kAW + (uint32_t)kAW; };
 
   // ---- edge rows of a round: one bulk copy from the 16-byte boundary below the block (see cgconv_tc.cu)
   auto ea_bulk_bytes = [&](int r_lo, int cnt) -> uint32_t {
@@ -225,10 +228,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
 
   // =====================================================================================================
   if (warp >= kRedWarp0) {
-    // ---------------- reducers: per-destination sums of a round's message tile (slot order: deterministic)
+    // ---------------- reducers: per-destination sums of a round's message tile (slot order: deterministic).
+    // The node data (segment bounds, 1/deg, x row) of a warp's first kPre segments of a round are requested one
+    // whole round ahead: they stream from HBM, and a segment's sum is far shorter than that latency.
     const int rw = warp - kRedWarp0;
     const bool prof_me = (tid == kRedWarp0 * 32);
     uint32_t ph_v = 0;
+    constexpr int kPre = 4;
     struct Seg { int a, b; float sc; float2 x; };
     auto load_seg = [&](int n, int n_hi) -> Seg {  // node data of segment n (lane l owns channels 2l, 2l+1)
       Seg s{0, 0, kLn2, make_float2(0.0f, 0.0f)};
@@ -240,26 +246,32 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       }
       return s;
     };
+    auto load_round = [&](const RoundW& R, Seg (&sg)[kPre]) {
+      if (!valid(R)) return;
+      const int n_lo = sInfo[R.k].n_lo, n_hi = sInfo[R.k].n_hi;
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) sg[j] = load_seg(n_lo + rw + j * kRedWarps, n_hi);
+    };
     RoundW cur = make_round(0, 0);
+    Seg pre[kPre], nxt[kPre];
+    load_round(cur, pre);
     for (uint32_t it = 0; valid(cur); ++it) {
       const int b = it & 1;
       const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
       const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
       const float* sV = sVbuf(b);
-      // node data of this warp's first segment: requested before the wait on the message tile
-      Seg nx = load_seg(n_lo + rw, n_hi);
+      const RoundW nr = next_round(cur);
+      load_round(nr, nxt);  // in flight under this whole round
       if (prof_me) mark(21);
       if (cnt > 0) {
         umma::mbar_wait(&bar_v_full[b], (ph_v >> b) & 1);
         ph_v ^= 1u << b;
       }
       if (prof_me) mark(22);
-      for (int n = n_lo + rw; n < n_hi; n += kRedWarps) {
-        const Seg sg = nx;
-        nx = load_seg(n + kRedWarps, n_hi);  // next segment's node data in flight under this one's sum
+      auto sum_seg = [&](int n, const Seg& sg) {
         const int lo = max(sg.a, r_lo), hi = min(sg.b, r_hi);
         const bool empty_seg = (sg.a == sg.b);
-        if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
+        if (empty_seg ? (cur.rd != 0) : (lo >= hi)) return;
         const bool first = empty_seg || (sg.a >= r_lo);
         const bool lastp = empty_seg || (sg.b <= r_hi);
         float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
@@ -278,13 +290,21 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           acc.x += v.x; acc.y += v.y;
         }
         *o = lastp ? make_float2(fmaf(acc.x, sg.sc, sg.x.x), fmaf(acc.y, sg.sc, sg.x.y)) : acc;
+      };
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        const int n = n_lo + rw + j * kRedWarps;
+        if (n < n_hi) sum_seg(n, pre[j]);
       }
+      for (int n = n_lo + rw + kPre * kRedWarps; n < n_hi; n += kRedWarps) sum_seg(n, load_seg(n, n_hi));  // many tiny segments
       if (cnt > 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_v_free[b]);
       }
       if (prof_me) mark(23);
-      cur = next_round(cur);
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) pre[j] = nxt[j];
+      cur = nr;
     }
     __syncthreads();  // teardown barrier of the CTA
     return;
@@ -412,9 +432,11 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     return;
   }
   if (warp >= kSplitWarp0) {
-    // ---------------- splitters: thread = slot = TMEM lane; the edge row -> hi / lo -> A operand columns
-    const int e = tid - kSplitWarp0 * 32;
-    const bool prof_me = (e == 0);
+    // ---------------- splitters: thread = slot = TMEM lane; the edge row -> its hi (warps 16..19) or lo (20..23)
+    // tf32 half -> A operand columns, two 32-column tensor-memory stores per round and warp
+    const int e = (tid - kSplitWarp0 * 32) & (kRowsW - 1);
+    const bool lo_half = warp >= kSplitWarp0 + 4;
+    const bool prof_me = (tid == kSplitWarp0 * 32);
     uint32_t ph_ea = 0, ph_m = 0, used = 0;
     RoundW R = make_round(0, 0);
     for (uint32_t it = 0; valid(R); ++it) {
@@ -437,54 +459,44 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         const float* row = sEA + ea_off + e * G;
         const int landed = (int)(nb >> 2);  // first float of the landing zone the bulk copy did NOT deliver
         const bool patch = e < R.cnt && landed < ea_off + (e + 1) * G;
-        const uint32_t a_hi = umma::tmem_addr(tm_a_hi(b), warp, 0), a_lo = umma::tmem_addr(tm_a_lo(b), warp, 0);
-        auto load8 = [&](int k0, float* v) {  // row[k0 .. k0+8) (zero beyond G / beyond the round)
+        const uint32_t dst = umma::tmem_addr(lo_half ? tm_a_lo(b) : tm_a_hi(b), warp, 0);
+#pragma unroll 1
+        for (int k0 = 0; k0 < KP; k0 += 32) {
+          float v[32];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+          for (int t = 0; t < 32; ++t) v[t] = 0.0f;
           if (e < R.cnt) {
             if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
 #pragma unroll
-              for (int t = 0; t < 8; t += 2)
+              for (int t = 0; t < 32; t += 2)
                 if (k0 + t < G) {
                   const float2 a = *reinterpret_cast<const float2*>(row + k0 + t);
                   v[t] = a.x; v[t + 1] = a.y;
                 }
             } else {
 #pragma unroll
-              for (int t = 0; t < 8; ++t)
+              for (int t = 0; t < 32; ++t)
                 if (k0 + t < G) v[t] = row[k0 + t];
             }
             if (patch) {
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
+              for (int t = 0; t < 32; ++t) {
                 const int k = k0 + t;
                 if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)R.r_lo + e) * G + k);
               }
             }
           }
-        };
-        int k0 = 0;
-        for (; k0 + 16 <= KP; k0 += 16) {  // 16 columns per tcgen05.st
-          float v[16], hi[16], lo[16];
-          load8(k0, v);
-          load8(k0 + 8, v + 8);
 #pragma unroll
-          for (int t = 0; t < 16; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
-          umma::tmem_st16(a_hi + k0, hi);
-          umma::tmem_st16(a_lo + k0, lo);
-        }
-        if (k0 < KP) {  // KP is a multiple of 8: one 8-column remainder
-          float v[8], hi[8], lo[8];
-          load8(k0, v);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
-          umma::tmem_st8(a_hi + k0, hi);
-          umma::tmem_st8(a_lo + k0, lo);
+          for (int t = 0; t < 32; ++t) {
+            const float hi = umma::tf32_hi(v[t]);
+            v[t] = lo_half ? v[t] - hi : hi;
+          }
+          umma::tmem_st32(dst + k0, v);
         }
         umma::tmem_st_wait();
         umma::fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a_full[b]);  // A operand staged; the landing zone has been read
+        if (lane == 0) mbar_arrive(&bar_a_full[b]);  // A operand half staged; the landing zone has been read
         used |= 1u << b;
         if (prof_me) mark(8);
       }

@@ -167,6 +167,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
 }
+// 32 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+#define MDL_U(i) "r"(__float_as_uint(v[i]))
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      MDL_U(0), MDL_U(1), MDL_U(2), MDL_U(3), MDL_U(4), MDL_U(5), MDL_U(6), MDL_U(7), MDL_U(8), MDL_U(9), MDL_U(10),
+      MDL_U(11), MDL_U(12), MDL_U(13), MDL_U(14), MDL_U(15), MDL_U(16), MDL_U(17), MDL_U(18), MDL_U(19), MDL_U(20),
+      MDL_U(21), MDL_U(22), MDL_U(23), MDL_U(24), MDL_U(25), MDL_U(26), MDL_U(27), MDL_U(28), MDL_U(29), MDL_U(30),
+      MDL_U(31)
+      : "memory");
+#undef MDL_U
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }

@@ -155,6 +155,13 @@ def test_cgconv_odd_edge_width(dev, impl):
     _cgconv_case(dev, n=150, e=1200, C=32, G=37, aggr="mean", tag=impl)
 
 
+@pytest.mark.parametrize("G", [37, 51, 1, 63])
+def test_cgconv_odd_edge_width_c64(dev, impl, G):
+    """odd edge widths on the C = 64 tensor-core kernels: edge rows start at any 4-byte offset of the landing
+    zone (4-byte loads in the split), the last k-chunk is partly padding, the tail of ea is patched from global"""
+    _cgconv_case(dev, n=300, e=2500, C=64, G=G, aggr="mean", tag=impl + " oddG")
+
+
 def test_cgconv_add_aggr(dev, impl):
     _cgconv_case(dev, n=200, e=1500, C=64, G=50, aggr="add", tag=impl)
 
@@ -172,7 +179,7 @@ def test_cgconv_crystal_batches(dev, impl, sizes, k):
     per-slot rows: blocks above the 128-row capacity, rounds that straddle several blocks)."""
     ei = block_diagonal_graph(sizes, k, seed=len(sizes))
     got = _cgconv_case(dev, n=sum(sizes), e=0, C=64, G=50, aggr="mean", seed=3, tag=impl, ei=ei)
-    if impl in ("tc", "tc_nowin", "pipe", "pipe_nowin"):
+    if impl in ("tc", "tc_nowin", "pipe", "pipe_nowin", "ws", "ws_nowin"):
         import os
         os.environ["MDL_CGCONV_WINDOW"] = "1" if impl.endswith("_nowin") else "0"
         other = _cgconv_case(dev, n=sum(sizes), e=0, C=64, G=50, aggr="mean", seed=3, ei=ei)
