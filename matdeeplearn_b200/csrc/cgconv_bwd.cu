@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   const uint32_t tmem = tmem_base_s;
   const uint32_t idesc_g = umma::make_idesc_tf32(kRows, kNP);  // gate recompute: M = 128 slots, N = 128
   const uint32_t idesc_w = umma::make_idesc_tf32(kNP, kKT);    // dW_e: M = 128 gate-channels, N = 64
-  const uint32_t tmA_hi = tmem + kColOp, tmA_lo = tmA_hi + (uint32_t)KP;  // edge rows (recompute)
+  const uint32_t tmA_hi = tmem + kColOp, tmA_lo = tmA_hi + 64;            // edge rows (recompute), 64 columns per half
   const uint32_t tmD_hi = tmem + kColOp, tmD_lo = tmD_hi + kRows;         // da^T (aliases the above)
   uint32_t ph_mma = 0, ph_dwe = 0, ph_ea = 0;
 
@@ -301,32 +301,46 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
       const int landed = (int)(ea_bulk_bytes(r_lo, cnt) >> 2);
       const bool patch = e < cnt && landed < ea_off + (e + 1) * G;
       const uint32_t t_off = (uint32_t)(e >> 2) * kTChunk + (uint32_t)(e & 3) * 4;
-      for (int ch = (tid >> 7); ch < (KP >> 3); ch += kThreads / kRows) {
-        float v[8];
+      // thread = (slot e, 16-column group): ONE 16-column tensor-memory store per half and warp (a tcgen05.st costs
+      // its warp several hundred cycles whatever its width: few wide stores spread over all 16 warps)
+      const int k0 = 16 * (tid >> 7);
+      if (k0 < KP) {
+        float v[16];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = 0.0f;
+        for (int t = 0; t < 16; ++t) v[t] = 0.0f;
         if (e < cnt) {
+          if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
 #pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (8 * ch + t < G) v[t] = row[8 * ch + t];
+            for (int t = 0; t < 16; t += 2)
+              if (k0 + t < G) {
+                const float2 a = *reinterpret_cast<const float2*>(row + k0 + t);
+                v[t] = a.x; v[t + 1] = a.y;
+              }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+              if (k0 + t < G) v[t] = row[k0 + t];
+          }
           if (patch) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int k = 8 * ch + t;
+            for (int t = 0; t < 16; ++t) {
+              const int k = k0 + t;
               if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)r_lo + e) * G + k);
             }
           }
         }
-        float hi[8], lo[8];
+        float hi[16], lo[16];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
-        umma::tmem_st8(umma::tmem_addr(tmA_hi, warp, 8 * ch), hi);
-        umma::tmem_st8(umma::tmem_addr(tmA_lo, warp, 8 * ch), lo);
+        for (int t = 0; t < 16; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+        umma::tmem_st16(umma::tmem_addr(tmA_hi, warp, k0), hi);
+        umma::tmem_st16(umma::tmem_addr(tmA_lo, warp, k0), lo);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {  // k = 8 ch + t: core-matrix row t of k-group ch; lanes = slots -> distinct banks
-          const uint32_t o = t_off + (uint32_t)ch * 128 + (uint32_t)t * 16;
-          *reinterpret_cast<float*>(sThi + o) = hi[t];
-          *reinterpret_cast<float*>(sTlo + o) = lo[t];
+        for (int t = 0; t < 16; ++t) {  // k = k0 + t: core-matrix row k % 8 of k-group k / 8; lanes = slots -> distinct banks
+          if (k0 + t < kKT) {
+            const uint32_t o = t_off + (uint32_t)((k0 + t) >> 3) * 128 + (uint32_t)((k0 + t) & 7) * 16;
+            *reinterpret_cast<float*>(sThi + o) = hi[t];
+            *reinterpret_cast<float*>(sTlo + o) = lo[t];
+          }
         }
       }
       umma::tmem_st_wait();
@@ -419,17 +433,20 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
     // ---- da^T -> tensor memory: thread = gate-channel m (TMEM lane), its quarter of the slots; rows >= cnt are zero
     if (cnt > 0) {
       const int m = tid & (kNP - 1);
-      for (int s8 = 4 * part; s8 < 4 * part + 4; ++s8) {  // 8-slot groups 4*part .. 4*part+3
-        float hi[8], lo[8];
+      float v[32];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int s = 8 * s8 + t;
-          const float v = s < cnt ? sV[s * kVW + m] : 0.0f;  // bank = 4 s + m: lanes = consecutive m
-          hi[t] = umma::tf32_hi(v);
-          lo[t] = v - hi[t];
-        }
-        umma::tmem_st8(umma::tmem_addr(tmD_hi, warp, 8 * s8), hi);
-        umma::tmem_st8(umma::tmem_addr(tmD_lo, warp, 8 * s8), lo);
+      for (int t = 0; t < 32; ++t) {
+        const int s = 32 * part + t;
+        v[t] = s < cnt ? sV[s * kVW + m] : 0.0f;  // bank = 4 s + m: lanes = consecutive m
+      }
+      {
+        float hi[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) hi[t] = umma::tf32_hi(v[t]);
+        umma::tmem_st32(umma::tmem_addr(tmD_hi, warp, 32 * part), hi);   // one 32-column store per half and warp
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] -= hi[t];
+        umma::tmem_st32(umma::tmem_addr(tmD_lo, warp, 32 * part), v);
       }
       umma::tmem_st_wait();
     }

@@ -2,33 +2,34 @@
 //
 // Reference: PyG CGConv.forward as the reference calls it (matdeeplearn/models/cgcnn.py:80-82,136-145):
 //   out_i = x_i + mean_{j->i} sigmoid(W_f z + b_f) * softplus(W_s z + b_s),  z = [x_i | x_j | e_ij].
-// Same operator, tile ownership, 3xTF32 contraction and deterministic per-segment sums as k_cgconv_fwd_pipe
-// (cgconv_fwd.cu).  There, the 16 epilogue warps also stage everything a round needs and sum the segments,
-// phase after phase between CTA-wide barriers.  Here every stage has its own warps and mbarrier hand-offs;
-// there is no CTA-wide barrier inside the loop and the gate warps do nothing but gate math:
+// Same operator, tile ownership, 3xTF32 contraction, gate math and deterministic per-segment sums as
+// k_cgconv_fwd_pipe (cgconv_fwd.cu).  There, the 16 epilogue warps also stage everything a round needs
+// (indices, node rows, the hi/lo split of the edge rows into tensor memory) between CTA-wide barriers, and
+// that staging is ~45 % of the round.  Here every stage has its own warps and its own mbarrier hand-offs, so
+// the epilogue warps do nothing but epilogue + per-segment sums while the next rounds are staged under them:
 //
-//   warps 25-27  loaders    the round's indices, its node-row window decision, one bulk (TMA) copy per P / Q row
-//   warps 16-23  splitters  thread = slot = TMEM lane: edge row (landing zone) -> hi (warps 16-19) / lo (warps 20-23)
-//                           -> tcgen05.st, 32 columns per instruction (a tensor-memory store costs its warp ~600
-//                           cycles whatever its width, so few wide stores on many warps)
-//   warp 24      issuer     bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma (3xTF32) of a round
-//   warps 0-15   gates      tcgen05.ld -> + c (P[dst] + Q[src]) -> sigmoid * softplus on packed f32x2 / MUFU -> message tile
-//   warps 28-31  reducers   per-destination sums of a round's message tile in slot order -> out (+ x, * 1/deg)
+//   warp 20 (one lane)   issuer: bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma of a round
+//   warps 16-19          splitters: thread = slot = TMEM lane; landing zone -> hi / lo -> tcgen05.st (A operand)
+//   warps 21-23          loaders: the round's indices, its node-row window decision, one bulk copy per P / Q row
+//   warps 0-15           consumers: tcgen05.ld -> + P[dst] + Q[src] -> gates -> message tile -> per-segment sums
 //
-//   issuer --ea_full--> splitters --a_full[b]--> issuer (MMA) --mma[b]--> gates --v_full[b]--> reducers --v_free[b]--> gates
-//   loaders --rows_full[b]--> gates --rows_free[b]--> loaders      gates --acc_free[b]--> issuer
-//   mma[b] also frees A buffer b for the splitters
+//   edge rows   issuer --bar_ea_full--> splitters --bar_a_full[b]--> issuer (MMA) --bar_mma[b]--> consumers
+//               consumers --bar_acc_free[b]--> issuer     splitters wait bar_mma[b] before reusing A buffer b
+//   node rows   loaders --bar_rows_full[b]--> consumers --bar_rows_free[b]--> loaders
 //
-// (Measured dead end, profiles/r2_phase_profile_ws_v3.txt: preloading the node terms into the accumulator with
-// tcgen05.st from extra splitter warps -- tensor-memory stores queue behind the running MMAs, the splitters became the
-// bottleneck at ~5k cycles per round.  The node terms are added by the gate warps from shared memory.)
+// Measured dead ends (profiles/r2_phase_profile_ws_v3.txt, _v4, _v5; profiles/experiments/cgconv_fwd_ws_v5_reducers.cu):
+// node terms preloaded into the accumulator by extra splitter warps, separate reducer warps with double-buffered
+// message tiles, 8 splitter warps with 32-column stores -- tensor-memory stores queue behind the running MMAs and the
+// extra warps starve each other (1.30 - 2.08 ms against 1.20 ms for this layout).
 //
-// Every per-round resource is double-buffered (accumulators, A-operand columns, index / node-row buffers, message
-// tiles); only the edge-row landing zone is single (its copy for round r+1 is issued as soon as round r is split).
-// Exponents are taken in base 2 with the scale folded in up front: the f-gate columns of W_e and of the node terms
-// carry -log2(e), the s-gate columns +log2(e), and the final ln(2) of the softplus rides in the per-node scale.
-// The node-row window (the P / Q rows a round needs lie in two short contiguous node ranges) holds WR rows per
-// buffer; a round whose ranges do not fit reads its node rows from global memory (L2) in the splitters.
+// Exponents are taken in base 2 with the scale folded in up front: the f-gate columns of W_e carry -log2(e), the
+// s-gate columns +log2(e), the node terms enter as c * (P + Q) by one packed fma, and the final ln(2) of the softplus
+// rides in the per-node scale.  Gate math runs on packed f32x2 (FFMA2 / FADD2 / FMUL2) and the MUFU pipe.
+//
+// Everything per round is double-buffered (two accumulators, two A-operand buffers, two index / node-row
+// buffers), so the producers run up to two rounds ahead.  The node-row window (the P / Q rows a round needs
+// lie in two short contiguous node ranges) holds WR rows per buffer; a round whose ranges do not fit reads its
+// node terms from global memory (L2) in the epilogue.
 #include "cgconv.cuh"
 #include "umma.cuh"
 #include "edge_dev.cuh"
@@ -37,17 +38,15 @@ namespace mdl {
 
 namespace {
 
-constexpr int kGateWarps = 16;                    // warps 0..15
-constexpr int kSplitWarp0 = 16, kSplitWarps = 8;  // warps 16..19: hi halves, 20..23: lo halves (TMEM lane quadrants 0..3)
-constexpr int kIssuerWarp = 24;
-constexpr int kLoadWarp0 = 25, kLoaders = 96;     // warps 25..27
-constexpr int kRedWarp0 = 28, kRedWarps = 4;      // warps 28..31
-constexpr int kLaunchW = 1024;
-constexpr int kAW = 64;                           // columns of one A-operand half (hi or lo) in tensor memory
+constexpr int kCons = 512, kConsWarps = 16;       // consumer (epilogue) threads
+constexpr int kSplitWarp0 = 16;                   // warps 16..19: TMEM lane quadrants 0..3
+constexpr int kIssuerWarp = 20;
+constexpr int kLoadWarp0 = 21, kLoaders = 96;     // warps 21..23
+constexpr int kLaunchW = 768;
 constexpr int kRowsW = 128, kTileW = 112, kInfoCapW = 512;
 constexpr int kC = 64, kNP = 2 * kC;
 constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tiles (bank spread)
-constexpr int kVP = kC + 4;                       // row stride of the message tiles
+constexpr int kVP = kC + 4;                       // row stride of the message tile
 constexpr int kTmemColsW = 512;
 
 unsigned long long* g_ws_phase_buf = nullptr;
@@ -55,25 +54,25 @@ unsigned long long* g_ws_phase_buf = nullptr;
 struct WsPlan {
   unsigned long long* prof;
   int window, KP, WR;
-  uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, vbytes, offIdx, offWin, offInfo, total;
+  uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, offIdx, offWin, offInfo, total;
 };
 
 bool ws_plan(int C, int G, WsPlan* pl) {
   if (C != kC || G < 1) return false;
   const int KP = (G + 7) & ~7;
-  if (KP > kAW) return false;  // tensor memory: two accumulators (2 x 128) + two hi / lo A-operand buffers (4 x 64)
+  if (2 * kNP + 4 * KP > kTmemColsW) return false;  // two accumulators + two hi/lo A-operand buffers
   const uint32_t b = (uint32_t)kNP * KP * 4;
   const uint32_t ea = (((uint32_t)kRowsW * G * 4 + 32) + 15u) & ~15u;
   const uint32_t v = (uint32_t)kRowsW * kVP * 4, idx = 2 * 2 * kRowsW * 4, win = 64, info = kInfoCapW * 16;
-  const uint32_t fixed = 2 * b + ea + 2 * v + idx + win + info;
+  const uint32_t fixed = 2 * b + ea + v + idx + win + info;
   if (fixed + 2 * 32 * kVW * 4 > (uint32_t)kMaxDynSmem) return false;
   int WR = (int)(((uint32_t)kMaxDynSmem - fixed) / (2 * kVW * 4)) & ~7;
   if (WR > kRowsW) WR = kRowsW;
   pl->prof = g_ws_phase_buf;
   pl->window = 1; pl->KP = KP; pl->WR = WR;
-  pl->wbytes = (uint32_t)WR * kVW * 4; pl->vbytes = v;
+  pl->wbytes = (uint32_t)WR * kVW * 4;
   pl->offBhi = 0; pl->offBlo = b; pl->offEA = 2 * b; pl->offW = pl->offEA + ea;
-  pl->offV = pl->offW + 2 * pl->wbytes; pl->offIdx = pl->offV + 2 * v; pl->offWin = pl->offIdx + idx;
+  pl->offV = pl->offW + 2 * pl->wbytes; pl->offIdx = pl->offV + v; pl->offWin = pl->offIdx + idx;
   pl->offInfo = pl->offWin + win; pl->total = pl->offInfo + info;
   return pl->total <= (uint32_t)kMaxDynSmem;
 }
@@ -83,6 +82,7 @@ struct RoundW { int k, rd, r_lo, cnt; bool last; };
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }
+
 
 // ---- packed fp32 pairs (one FMA-pipe instruction per two values on sm_100)
 typedef unsigned long long f2_t;
@@ -134,8 +134,7 @@ __device__ __forceinline__ f2_t gate_pair(float yf0, float yf1, float ys0, float
 template <int PROFILE>
 __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p, const WsPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_ea_full, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2], bar_rows_free[2],
-      bar_v_full[2], bar_v_free[2];
+  __shared__ uint64_t bar_ea_full, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2], bar_rows_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int sRed[3][2];  // loaders: per-warp (min, max) of the round's source nodes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -144,11 +143,11 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   uint8_t* sBhi = smem + pl.offBhi;
   uint8_t* sBlo = smem + pl.offBlo;
   float* sEA = reinterpret_cast<float*>(smem + pl.offEA);   // landing zone of a round's edge rows
+  float* sV = reinterpret_cast<float*>(smem + pl.offV);     // [128][VP] per-slot messages
   int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);     // [2 buffers][src | dst][128]
   int4* sWin = reinterpret_cast<int4*>(smem + pl.offWin);   // [2 buffers] {window?, src min, dst min, nq}
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);
-  auto sWbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offW + (uint32_t)b * pl.wbytes); };  // node rows
-  auto sVbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offV + (uint32_t)b * pl.vbytes); };  // [128][VP] messages
+  auto sWbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offW + (uint32_t)b * pl.wbytes); };
 
   const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   auto make_round = [&](int k, int rd) -> RoundW {
@@ -164,29 +163,16 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   auto valid = [&](const RoundW& R) { return R.k < my_tiles; };
   auto next_round = [&](const RoundW& R) -> RoundW { return R.last ? make_round(R.k + 1, 0) : make_round(R.k, R.rd + 1); };
 
-  // per-role cycle accounting (instrumented build): one thread of a role adds the cycles between its marks
-  long long t_prev = PROFILE ? clock64() : 0;
-  auto mark = [&](int slot) {
-    if (PROFILE && pl.prof) {
-      const long long now = clock64();
-      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
-      t_prev = now;
-    }
-  };
-
-  // ---- one-time setup (all threads): TMEM, barriers, the CTA's whole tile table, resident W_e split hi/lo.
-  // The exponent scale rides in the weights: f-gate columns x -log2(e), s-gate columns x +log2(e).
+  // ---- one-time setup (all 768 threads): TMEM, barriers, the CTA's whole tile table, resident W_e split hi/lo
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, kTmemColsW);
   if (tid == 32) {
     umma::mbar_init(&bar_ea_full, 1);
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(&bar_a_full[b], kSplitWarps);    // splitter warps: A operand staged (and the landing zone read)
-      umma::mbar_init(&bar_mma[b], 1);                 // tcgen05.commit
-      umma::mbar_init(&bar_acc_free[b], kGateWarps);   // gate warps: accumulator read
-      umma::mbar_init(&bar_rows_full[b], 1);           // loader thread 0 (+ the rows' bytes)
-      umma::mbar_init(&bar_rows_free[b], kGateWarps);  // gate warps: indices / node rows read
-      umma::mbar_init(&bar_v_full[b], kGateWarps);     // gate warps: message tile written
-      umma::mbar_init(&bar_v_free[b], kRedWarps);      // reducer warps: message tile summed
+      umma::mbar_init(&bar_a_full[b], 4);            // one arrival per splitter warp
+      umma::mbar_init(&bar_mma[b], 1);               // tcgen05.commit
+      umma::mbar_init(&bar_acc_free[b], kConsWarps); // one arrival per consumer warp
+      umma::mbar_init(&bar_rows_full[b], 1);         // loader thread 0 (+ the rows' bytes)
+      umma::mbar_init(&bar_rows_free[b], kConsWarps);
     }
     umma::fence_mbar_init();
   }
@@ -214,8 +200,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   auto tm_acc = [&](int b) { return tmem + (uint32_t)b * kNP; };
-  auto tm_a_hi = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * kAW; };
-  auto tm_a_lo = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * kAW + (uint32_t)kAW; };
+  auto tm_a_hi = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * KP; };
+  auto tm_a_lo = [&](int b) { return tmem + 2 * kNP + (uint32_t)b * 2 * KP + (uint32_t)KP; };
 
   // ---- edge rows of a round: one bulk copy from the 16-byte boundary below the block (see cgconv_tc.cu)
   auto ea_bulk_bytes = [&](int r_lo, int cnt) -> uint32_t {
@@ -227,278 +213,167 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   };
 
   // =====================================================================================================
-  if (warp >= kRedWarp0) {
-    // ---------------- reducers: per-destination sums of a round's message tile (slot order: deterministic).
-    // The node data (segment bounds, 1/deg, x row) of a warp's first kPre segments of a round are requested one
-    // whole round ahead: they stream from HBM, and a segment's sum is far shorter than that latency.
-    const int rw = warp - kRedWarp0;
-    const bool prof_me = (tid == kRedWarp0 * 32);
-    uint32_t ph_v = 0;
-    constexpr int kPre = 4;
-    struct Seg { int a, b; float sc; float2 x; };
-    auto load_seg = [&](int n, int n_hi) -> Seg {  // node data of segment n (lane l owns channels 2l, 2l+1)
-      Seg s{0, 0, kLn2, make_float2(0.0f, 0.0f)};
-      if (n < n_hi) {
-        s.a = __ldg(p.seg_ptr + n);
-        s.b = __ldg(p.seg_ptr + n + 1);
-        if (p.inv_deg) s.sc = kLn2 * __ldg(p.inv_deg + n);
-        s.x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
-      }
-      return s;
-    };
-    auto load_round = [&](const RoundW& R, Seg (&sg)[kPre]) {
-      if (!valid(R)) return;
-      const int n_lo = sInfo[R.k].n_lo, n_hi = sInfo[R.k].n_hi;
-#pragma unroll
-      for (int j = 0; j < kPre; ++j) sg[j] = load_seg(n_lo + rw + j * kRedWarps, n_hi);
-    };
-    RoundW cur = make_round(0, 0);
-    Seg pre[kPre], nxt[kPre];
-    load_round(cur, pre);
-    for (uint32_t it = 0; valid(cur); ++it) {
-      const int b = it & 1;
-      const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
-      const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
-      const float* sV = sVbuf(b);
-      const RoundW nr = next_round(cur);
-      load_round(nr, nxt);  // in flight under this whole round
-      if (prof_me) mark(21);
-      if (cnt > 0) {
-        umma::mbar_wait(&bar_v_full[b], (ph_v >> b) & 1);
-        ph_v ^= 1u << b;
-      }
-      if (prof_me) mark(22);
-      auto sum_seg = [&](int n, const Seg& sg) {
-        const int lo = max(sg.a, r_lo), hi = min(sg.b, r_hi);
-        const bool empty_seg = (sg.a == sg.b);
-        if (empty_seg ? (cur.rd != 0) : (lo >= hi)) return;
-        const bool first = empty_seg || (sg.a >= r_lo);
-        const bool lastp = empty_seg || (sg.b <= r_hi);
-        float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
-        float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
-        const float2* vp = reinterpret_cast<const float2*>(sV + (lo - r_lo) * kVP) + lane;
-        int s = lo;
-        for (; s + 4 <= hi; s += 4, vp += 4 * (kVP / 2)) {  // four loads in flight, added in slot order
-          const float2 v0 = vp[0], v1 = vp[kVP / 2], v2 = vp[2 * (kVP / 2)], v3 = vp[3 * (kVP / 2)];
-          acc.x += v0.x; acc.y += v0.y;
-          acc.x += v1.x; acc.y += v1.y;
-          acc.x += v2.x; acc.y += v2.y;
-          acc.x += v3.x; acc.y += v3.y;
+  if (warp >= kIssuerWarp) {
+    if (warp == kIssuerWarp) {
+      // ---------------- issuer: bulk copies of the edge rows, MMAs
+      if (lane == 0) {
+        auto issue_ea_bulk = [&](const RoundW& R) {
+          const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
+          if (!nb) return;
+          const long long first = (long long)R.r_lo * G;
+          umma::mbar_arrive_expect_tx(&bar_ea_full, nb);
+          umma::bulk_g2s(sEA, p.ea + (first - (first & 3)), nb, &bar_ea_full);
+        };
+        const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
+        const uint32_t step_b = 2 * (uint32_t)kNP * 16;
+        const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+        uint32_t ph_a = 0, ph_f = 0;  // phase parities, bit b = buffer b (plain registers: no dynamically indexed arrays)
+        uint32_t busy = 0;            // bit b: accumulator b holds a round whose epilogue has not been waited for
+        RoundW R = make_round(0, 0);
+        if (valid(R)) issue_ea_bulk(R);
+        for (uint32_t it = 0; valid(R); ++it) {
+          const int b = it & 1;
+          const RoundW Rn = next_round(R);
+          if (R.cnt > 0) {  // split of this round done: its A operand is staged and the landing zone is free
+            umma::mbar_wait(&bar_a_full[b], (ph_a >> b) & 1);
+            ph_a ^= 1u << b;
+          }
+          if (valid(Rn)) issue_ea_bulk(Rn);  // first: the MMA issue below blocks for ~2k cycles
+          if (R.cnt > 0) {
+            if ((busy >> b) & 1) {  // the epilogue of the round that used this accumulator two rounds ago has read it
+              umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
+              ph_f ^= 1u << b;
+            }
+            umma::fence_after_sync();
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
+              const uint32_t bb = (pass == 1) ? b_lo : b_hi;
+              for (int kk = 0; kk < (KP >> 3); ++kk) {
+                umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, acc);
+                acc = 1;
+              }
+            }
+            umma::mma_commit(&bar_mma[b]);
+            busy |= 1u << b;
+          }
+          R = Rn;
         }
-        for (; s < hi; ++s, vp += kVP / 2) {
-          const float2 v = *vp;
-          acc.x += v.x; acc.y += v.y;
-        }
-        *o = lastp ? make_float2(fmaf(acc.x, sg.sc, sg.x.x), fmaf(acc.y, sg.sc, sg.x.y)) : acc;
-      };
-#pragma unroll
-      for (int j = 0; j < kPre; ++j) {
-        const int n = n_lo + rw + j * kRedWarps;
-        if (n < n_hi) sum_seg(n, pre[j]);
       }
-      for (int n = n_lo + rw + kPre * kRedWarps; n < n_hi; n += kRedWarps) sum_seg(n, load_seg(n, n_hi));  // many tiny segments
-      if (cnt > 0) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_v_free[b]);
-      }
-      if (prof_me) mark(23);
-#pragma unroll
-      for (int j = 0; j < kPre; ++j) pre[j] = nxt[j];
-      cur = nr;
-    }
-    __syncthreads();  // teardown barrier of the CTA
-    return;
-  }
-  if (warp > kIssuerWarp) {
-    // ---------------- loaders: indices, window decision, node rows of a round.  The indices of round r+1 are
-    // requested (into registers) before round r is processed: their HBM latency runs under this round's work.
-    const int lt = tid - kLoadWarp0 * 32, lw = warp - kLoadWarp0;
-    auto sync_loaders = [] { asm volatile("bar.sync 3, %0;" ::"n"(kLoaders) : "memory"); };
-    constexpr int kPer = (2 * kRowsW + kLoaders - 1) / kLoaders;  // index entries per loader thread (3)
-    auto fetch = [&](const RoundW& R, int (&v)[kPer]) {
-#pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        const int i = lt + j * kLoaders, e = i & (kRowsW - 1);
-        v[j] = 0;
-        if (valid(R) && i < 2 * kRowsW && e < R.cnt) v[j] = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
-      }
-    };
-    uint32_t ph_rf = 0, used = 0;
-    RoundW R = make_round(0, 0);
-    int vcur[kPer], vnext[kPer];
-    fetch(R, vcur);
-    for (uint32_t it = 0; valid(R); ++it) {
-      const int b = it & 1;
-      const RoundW Rn = next_round(R);
-      fetch(Rn, vnext);
-      if (R.cnt > 0) {
-        if (lt == 0) mark(18);
-        if ((used >> b) & 1) {  // the gate warps have finished with this buffer (two rounds ago)
-          umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
-          ph_rf ^= 1u << b;
-        }
-        if (lt == 0) mark(19);
-        int* bS = sIdx + b * 2 * kRowsW;
-        int s_lo = 0x7fffffff, s_hi = -1;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int i = lt + j * kLoaders, e = i & (kRowsW - 1);
-          if (i < 2 * kRowsW) bS[i] = vcur[j];
-          if (i < kRowsW && e < R.cnt) { s_lo = min(s_lo, vcur[j]); s_hi = max(s_hi, vcur[j]); }
-        }
-        s_lo = __reduce_min_sync(0xffffffffu, s_lo);
-        s_hi = __reduce_max_sync(0xffffffffu, s_hi);
-        if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
-        sync_loaders();  // indices and per-warp ranges visible to all loaders
-        s_lo = min(sRed[0][0], min(sRed[1][0], sRed[2][0]));
-        s_hi = max(sRed[0][1], max(sRed[1][1], sRed[2][1]));
-        const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
-        const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
-        const bool win = pl.window && nq + np_ <= WR;
-        const int nrows = win ? nq + np_ : 0;
-        if (lt == 0) {
-          sWin[b] = make_int4(win ? 1 : 0, s_lo, d_lo, nq);
-          if (nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)nrows * (uint32_t)(2 * kC * 4));
-          else mbar_arrive(&bar_rows_full[b]);
-        }
-        float* W = sWbuf(b);
-        for (int r = lt; r < nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
-          const float* g = (r < nq) ? p.PQ + (size_t)(s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(d_lo + r - nq) * (4 * kC);
-          umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
-        }
-        used |= 1u << b;
-        sync_loaders();  // sRed is rewritten next round
-        if (lt == 0) mark(20);
-      }
-#pragma unroll
-      for (int j = 0; j < kPer; ++j) vcur[j] = vnext[j];
-      R = Rn;
-    }
-    __syncthreads();  // teardown barrier of the CTA
-    return;
-  }
-  if (warp == kIssuerWarp) {
-    // ---------------- issuer: bulk copies of the edge rows, MMAs
-    if (lane == 0) {
-      auto issue_ea_bulk = [&](const RoundW& R) {
-        const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
-        if (!nb) return;
-        const long long first = (long long)R.r_lo * G;
-        umma::mbar_arrive_expect_tx(&bar_ea_full, nb);
-        umma::bulk_g2s(sEA, p.ea + (first - (first & 3)), nb, &bar_ea_full);
-      };
-      const uint32_t idesc = umma::make_idesc_tf32(kRowsW, kNP);
-      const uint32_t step_b = 2 * (uint32_t)kNP * 16;
-      const uint32_t b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
-      uint32_t ph_a = 0, ph_f = 0;  // phase parities, bit b = buffer b
-      uint32_t busy = 0;            // bit b: accumulator b holds a round whose epilogue has not been waited for
+      __syncwarp();
+    } else {
+      // ---------------- loaders: indices, window decision, node rows of a round
+      const int lt = tid - kLoadWarp0 * 32, lw = warp - kLoadWarp0;
+      auto sync_loaders = [] { asm volatile("bar.sync 3, %0;" ::"n"(kLoaders) : "memory"); };
+      uint32_t ph_rf = 0, used = 0;
       RoundW R = make_round(0, 0);
-      if (valid(R)) issue_ea_bulk(R);
       for (uint32_t it = 0; valid(R); ++it) {
         const int b = it & 1;
-        const RoundW Rn = next_round(R);
-        mark(13);
-        if (R.cnt > 0) {  // split of this round done: its A operand is staged and the landing zone is free
-          umma::mbar_wait(&bar_a_full[b], (ph_a >> b) & 1);
-          ph_a ^= 1u << b;
-        }
-        if (valid(Rn)) issue_ea_bulk(Rn);  // first: the MMA issue below blocks for the MMAs' run time
         if (R.cnt > 0) {
-          if ((busy >> b) & 1) {  // the gate warps have read the round that used this accumulator two rounds ago
-            umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
-            ph_f ^= 1u << b;
+          if ((used >> b) & 1) {  // consumers have finished with this buffer (two rounds ago)
+            umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
+            ph_rf ^= 1u << b;
           }
-          umma::fence_after_sync();
-          mark(14);
-          uint32_t acc = 0;
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? tm_a_lo(b) : tm_a_hi(b);
-            const uint32_t bb = (pass == 1) ? b_lo : b_hi;
-            for (int kk = 0; kk < (KP >> 3); ++kk) {
-              umma::mma_tf32_ts(tm_acc(b), a + kk * 8, umma::make_desc(bb + kk * step_b, (uint32_t)kNP * 16, 128), idesc, acc);
-              acc = 1;
+          int* bS = sIdx + b * 2 * kRowsW;
+          int s_lo = 0x7fffffff, s_hi = -1;
+          for (int i = lt; i < 2 * kRowsW; i += kLoaders) {
+            const int e = i & (kRowsW - 1);
+            int v = 0;
+            if (e < R.cnt) {
+              v = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
+              if (i < kRowsW) { s_lo = min(s_lo, v); s_hi = max(s_hi, v); }
             }
+            bS[i] = v;
           }
-          umma::mma_commit(&bar_mma[b]);
-          busy |= 1u << b;
-          mark(15);
+          s_lo = __reduce_min_sync(0xffffffffu, s_lo);
+          s_hi = __reduce_max_sync(0xffffffffu, s_hi);
+          if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
+          sync_loaders();  // indices and per-warp ranges visible to all loaders
+          s_lo = min(sRed[0][0], min(sRed[1][0], sRed[2][0]));
+          s_hi = max(sRed[0][1], max(sRed[1][1], sRed[2][1]));
+          const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
+          const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
+          const bool win = pl.window && nq + np_ <= WR;
+          const int nrows = win ? nq + np_ : 0;
+          if (lt == 0) {
+            sWin[b] = make_int4(win ? 1 : 0, s_lo, d_lo, nq);
+            if (nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)nrows * (uint32_t)(2 * kC * 4));
+            else mbar_arrive(&bar_rows_full[b]);
+          }
+          float* W = sWbuf(b);
+          for (int r = lt; r < nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
+            const float* g = (r < nq) ? p.PQ + (size_t)(s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(d_lo + r - nq) * (4 * kC);
+            umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
+          }
+          used |= 1u << b;
+          sync_loaders();  // sRed is rewritten next round
         }
-        R = Rn;
+        R = next_round(R);
       }
     }
-    __syncwarp();
     __syncthreads();  // teardown barrier of the CTA
     return;
   }
   if (warp >= kSplitWarp0) {
-    // ---------------- splitters: thread = slot = TMEM lane; the edge row -> its hi (warps 16..19) or lo (20..23)
-    // tf32 half -> A operand columns, two 32-column tensor-memory stores per round and warp
-    const int e = (tid - kSplitWarp0 * 32) & (kRowsW - 1);
-    const bool lo_half = warp >= kSplitWarp0 + 4;
-    const bool prof_me = (tid == kSplitWarp0 * 32);
+    // ---------------- splitters: thread = slot = TMEM lane; the whole edge row -> hi / lo -> tensor memory
+    const int e = tid - kSplitWarp0 * 32;
     uint32_t ph_ea = 0, ph_m = 0, used = 0;
     RoundW R = make_round(0, 0);
     for (uint32_t it = 0; valid(R); ++it) {
       const int b = it & 1;
       if (R.cnt > 0) {
-        if (prof_me) mark(5);
-        if ((used >> b) & 1) {  // the MMAs that read this A buffer two rounds ago have retired
-          umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);
-          ph_m ^= 1u << b;
-          umma::fence_after_sync();
-        }
-        if (prof_me) mark(6);
         const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
         if (nb) {
           umma::mbar_wait(&bar_ea_full, ph_ea);
           ph_ea ^= 1;
         }
-        if (prof_me) mark(7);
+        if ((used >> b) & 1) {  // the MMAs that read this A buffer two rounds ago have retired
+          umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);
+          ph_m ^= 1u << b;
+          umma::fence_after_sync();
+        }
         const int ea_off = (int)(((long long)R.r_lo * G) & 3);
         const float* row = sEA + ea_off + e * G;
         const int landed = (int)(nb >> 2);  // first float of the landing zone the bulk copy did NOT deliver
         const bool patch = e < R.cnt && landed < ea_off + (e + 1) * G;
-        const uint32_t dst = umma::tmem_addr(lo_half ? tm_a_lo(b) : tm_a_hi(b), warp, 0);
-#pragma unroll 1
-        for (int k0 = 0; k0 < KP; k0 += 32) {
-          float v[32];
+        const uint32_t a_hi = umma::tmem_addr(tm_a_hi(b), warp, 0), a_lo = umma::tmem_addr(tm_a_lo(b), warp, 0);
+        for (int ch = 0; ch < (KP >> 3); ++ch) {
+          float v[8];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = 0.0f;
+          for (int t = 0; t < 8; ++t) v[t] = 0.0f;
           if (e < R.cnt) {
             if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
 #pragma unroll
-              for (int t = 0; t < 32; t += 2)
-                if (k0 + t < G) {
-                  const float2 a = *reinterpret_cast<const float2*>(row + k0 + t);
+              for (int t = 0; t < 8; t += 2)
+                if (8 * ch + t < G) {
+                  const float2 a = *reinterpret_cast<const float2*>(row + 8 * ch + t);
                   v[t] = a.x; v[t + 1] = a.y;
                 }
             } else {
 #pragma unroll
-              for (int t = 0; t < 32; ++t)
-                if (k0 + t < G) v[t] = row[k0 + t];
+              for (int t = 0; t < 8; ++t)
+                if (8 * ch + t < G) v[t] = row[8 * ch + t];
             }
             if (patch) {
 #pragma unroll
-              for (int t = 0; t < 32; ++t) {
-                const int k = k0 + t;
+              for (int t = 0; t < 8; ++t) {
+                const int k = 8 * ch + t;
                 if (k < G && ea_off + e * G + k >= landed) v[t] = __ldg(p.ea + ((long long)R.r_lo + e) * G + k);
               }
             }
           }
+          float hi[8], lo[8];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const float hi = umma::tf32_hi(v[t]);
-            v[t] = lo_half ? v[t] - hi : hi;
-          }
-          umma::tmem_st32(dst + k0, v);
+          for (int t = 0; t < 8; ++t) { hi[t] = umma::tf32_hi(v[t]); lo[t] = v[t] - hi[t]; }
+          umma::tmem_st8(a_hi + 8 * ch, hi);
+          umma::tmem_st8(a_lo + 8 * ch, lo);
         }
         umma::tmem_st_wait();
         umma::fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a_full[b]);  // A operand half staged; the landing zone has been read
+        if (lane == 0) mbar_arrive(&bar_a_full[b]);
         used |= 1u << b;
-        if (prof_me) mark(8);
       }
       R = next_round(R);
     }
@@ -506,48 +381,66 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     return;
   }
 
-  // ---------------- gate warps: thread = slot (TMEM lane), 16 channels; no CTA-wide barrier in the loop
-  const bool prof_me = (tid == 0);
+  // ---------------- consumers: epilogue + per-segment sums
+  auto sync_consumers = [] { asm volatile("bar.sync 2, %0;" ::"n"(kCons) : "memory"); };
+  long long t_prev = PROFILE ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (PROFILE && pl.prof && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(pl.prof + slot, (unsigned long long)(now - t_prev));
+      t_prev = now;
+    }
+  };
   const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
   const int c_begin = part * 16;
-  uint32_t ph_m = 0, ph_vf = 0, ph_r = 0, used_v = 0;
+  uint32_t ph_r = 0, ph_m = 0;
   RoundW cur = make_round(0, 0);
   for (uint32_t it = 0; valid(cur); ++it) {
     const int b = it & 1;
-    const int cnt = cur.cnt;
-    if (prof_me) mark(0);
+    const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
+    const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
+    const int* bSrc = sIdx + b * 2 * kRowsW;
+    const int* bDst = bSrc + kRowsW;
+    mark(0);
+    // ---- reduce-stage node data of this warp's first segment (global loads in flight across the epilogue)
+    const int n0 = n_lo + warp;
+    int seg_a = 0, seg_b = 0;
+    float seg_sc = kLn2;                     // the softplus' ln 2 rides in the per-node scale
+    float2 seg_x = make_float2(0.0f, 0.0f);  // lane l owns channels 2l, 2l+1
+    if (n0 < n_hi) {
+      seg_a = __ldg(p.seg_ptr + n0);
+      seg_b = __ldg(p.seg_ptr + n0 + 1);
+      if (p.inv_deg) seg_sc = kLn2 * __ldg(p.inv_deg + n0);
+      seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
+    }
     if (cnt > 0) {
       umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);  // indices, window record, node rows of this round
       ph_r ^= 1u << b;
-      if ((used_v >> b) & 1) {  // the reducers have summed the round that used this message tile two rounds ago
-        umma::mbar_wait(&bar_v_free[b], (ph_vf >> b) & 1);
-        ph_vf ^= 1u << b;
-      }
-      if (prof_me) mark(1);
-      // node rows of this slot: requested from shared memory (window) or L2 before the wait on the contraction
-      const int e_ep = 32 * q + lane;
-      const bool live = e_ep < cnt;
+      mark(1);
       const int4 wr = sWin[b];
       const bool win = wr.x != 0;
-      const int* bSrc = sIdx + b * 2 * kRowsW;
-      const int ss = live ? bSrc[e_ep] : 0, sd = live ? bSrc[kRowsW + e_ep] : 0;
+      const int w_smin = wr.y, w_dmin = wr.z, w_nq = wr.w;
       const float* sW = sWbuf(b);
-      const float* r0 = win ? sW + (wr.w + sd - wr.z) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
-      const float* r1 = win ? sW + (ss - wr.y) * kVW + c_begin : p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
-      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);  // this round's contraction
+      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);         // this round's contraction
       ph_m ^= 1u << b;
       umma::fence_after_sync();
-      if (prof_me) mark(2);
+      mark(2);
       float f[16], sacc[16];
       umma::tmem_ld16(umma::tmem_addr(tm_acc(b), q, c_begin), f);
       umma::tmem_ld16(umma::tmem_addr(tm_acc(b), q, kC + c_begin), sacc);
       umma::tmem_ld_wait();
       umma::fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_acc_free[b]);  // the accumulator may be rewritten (round it + 2)
-      if (prof_me) mark(3);
-      if (live) {
-        float* rowv = sVbuf(b) + e_ep * kVP + c_begin;
+      if (lane == 0) mbar_arrive(&bar_acc_free[b]);  // the accumulator may be overwritten (round it + 2)
+      mark(3);
+      // ---- epilogue: thread = slot (TMEM lane), 16 channels; a = accumulator + P[dst] + Q[src], gates,
+      // message parked in the message tile
+      const int e_ep = 32 * q + lane;
+      if (e_ep < cnt) {
+        const int sd = bDst[e_ep], ss = bSrc[e_ep];
+        const float* r0 = win ? sW + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
+        const float* r1 = win ? sW + (ss - w_smin) * kVW + c_begin : p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
+        float* rowv = sV + e_ep * kVP + c_begin;
         const f2_t cf = pk2(-kLog2e, -kLog2e), cs = pk2(kLog2e, kLog2e);
         auto run = [&](auto ld) {  // ld: how the node rows are read (shared or global memory)
 #pragma unroll
@@ -570,13 +463,47 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
-        mbar_arrive(&bar_v_full[b]);     // this warp's part of the message tile is written
-      }
-      used_v |= 1u << b;
-      if (prof_me) mark(4);
+      if (lane == 0) mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
     }
+    mark(4);
+    sync_consumers();  // [S3] message tile complete
+    mark(5);
+    // ---- segmented sum over the owned segments that have slots in this round (slot order: deterministic)
+    for (int n = n0; n < n_hi; n += kConsWarps) {
+      int a, bq;
+      if (n == n0) { a = seg_a; bq = seg_b; }
+      else { a = __ldg(p.seg_ptr + n); bq = __ldg(p.seg_ptr + n + 1); }
+      const int lo = max(a, r_lo), hi = min(bq, r_hi);
+      const bool empty_seg = (a == bq);
+      if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
+      const bool first = empty_seg || (a >= r_lo);
+      const bool lastp = empty_seg || (bq <= r_hi);
+      float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
+      float sc = seg_sc;
+      float2 x = seg_x;
+      if (n != n0) {
+        sc = p.inv_deg ? kLn2 * __ldg(p.inv_deg + n) : kLn2;
+        x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
+      }
+      float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
+      const float2* vp = reinterpret_cast<const float2*>(sV + (lo - r_lo) * kVP) + lane;
+      int s = lo;
+      for (; s + 4 <= hi; s += 4, vp += 4 * (kVP / 2)) {  // four loads in flight, added in slot order
+        const float2 v0 = vp[0], v1 = vp[kVP / 2], v2 = vp[2 * (kVP / 2)], v3 = vp[3 * (kVP / 2)];
+        acc.x += v0.x; acc.y += v0.y;
+        acc.x += v1.x; acc.y += v1.y;
+        acc.x += v2.x; acc.y += v2.y;
+        acc.x += v3.x; acc.y += v3.y;
+      }
+      for (; s < hi; ++s, vp += kVP / 2) {
+        const float2 v = *vp;
+        acc.x += v.x; acc.y += v.y;
+      }
+      *o = lastp ? make_float2(fmaf(acc.x, sc, x.x), fmaf(acc.y, sc, x.y)) : acc;
+    }
+    mark(6);
+    sync_consumers();  // [S1] message tile free for the next round's epilogue
+    mark(7);
     if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
     cur = next_round(cur);
   }

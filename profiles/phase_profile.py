@@ -55,12 +55,8 @@ def bwd():
 PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 13: "next idx issue + ranges", 14: "row loads issue", 5: "seg loads issue",
               6: "wait MMA(r)", 2: "wait ea(r+1)", 3: "split(r+1) -> TMEM", 4: "row+idx STS, fences, S2",
               7: "TMEM ld", 10: "node terms + gate math", 11: "S3 barrier", 12: "reduce"}
-WS_NAMES = {0: "gates: loop top", 1: "gates: wait node rows / message tile free", 2: "gates: wait MMA", 3: "gates: TMEM ld + release",
-            4: "gates: node terms + gate math + STS", 5: "(splitters: loop top)", 6: "(splitters: wait A buffer free)",
-            7: "(splitters: wait edge rows)", 8: "(splitters: split -> TMEM)", 13: "(issuer: loop top)",
-            14: "(issuer: wait A operand, bulk issue, wait accumulator free)", 15: "(issuer: MMA issue)",
-            18: "(loaders: loop top)", 19: "(loaders: wait buffer free)", 20: "(loaders: indices + window + row copies)",
-            21: "(reducers: loop top + seg loads)", 22: "(reducers: wait message tile)", 23: "(reducers: sums)"}
+WS_NAMES = {0: "loop top + seg loads issue", 1: "wait indices / node rows", 2: "wait MMA", 3: "TMEM ld + release",
+            4: "node terms + gate math", 5: "S3 barrier", 6: "reduce", 7: "S1 barrier"}
 BWD_PIPE_NAMES = {0: "loop top", 1: "S1 barrier", 2: "next idx, window, row/seg loads issue", 3: "wait dW_e(r-1)",
                   4: "wait ea + split -> TMEM + ea^T tiles", 5: "row/idx STS, fences", 6: "S2 (issuer hand-off)",
                   7: "grad loads + wait recompute MMA", 8: "TMEM ld + node terms", 9: "S2d barrier", 10: "gate math",
