@@ -336,6 +336,10 @@ MDL_API int mdl_selftest_umma_ex(const float* A, const float* B, float* D, int32
 /* same product with A staged in tensor memory (tcgen05.st) and B in shared memory */
 MDL_API int mdl_selftest_umma_ts(const float* A, const float* B, float* D, int32_t N, int32_t K,
                                  int32_t split, void* stream);
+/* microbenchmark (development aid): cycles of `nstores` tcgen05.st of `width` columns per warp, with `mma_count`
+ * 128x128x8 MMAs issued concurrently; out = 18 x int64 (per-warp cycles, [16] MMA issue, [17] MMA complete) */
+MDL_API int mdl_selftest_tmem_st_bench(long long* out, int32_t nwarps, int32_t nstores, int32_t width,
+                                       int32_t mma_count, int32_t wait_each, void* stream);
 /* layout probe: raw shared-memory images of both operand tiles + descriptor fields, nmma K=8 MMAs */
 MDL_API int mdl_selftest_umma_probe(const float* rawA, int32_t a_floats, const float* rawB, int32_t b_floats,
                                     float* D, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,

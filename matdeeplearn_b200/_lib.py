@@ -81,6 +81,7 @@ SIGNATURES = {
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "mdl_selftest_umma_ts": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
+    "mdl_selftest_tmem_st_bench": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mdl_selftest_umma_probe": (C.c_int, [_p, _i32, _p, _i32, _p] + [_i32] * 12 + [_p]),
     "mdl_selftest_umma_ex": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
 }

@@ -433,20 +433,17 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
     // ---- da^T -> tensor memory: thread = gate-channel m (TMEM lane), its quarter of the slots; rows >= cnt are zero
     if (cnt > 0) {
       const int m = tid & (kNP - 1);
-      float v[32];
+      for (int s16 = 2 * part; s16 < 2 * part + 2; ++s16) {  // 16-slot groups 2*part, 2*part+1
+        float hi[16], lo[16];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const int s = 32 * part + t;
-        v[t] = s < cnt ? sV[s * kVW + m] : 0.0f;  // bank = 4 s + m: lanes = consecutive m
-      }
-      {
-        float hi[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) hi[t] = umma::tf32_hi(v[t]);
-        umma::tmem_st32(umma::tmem_addr(tmD_hi, warp, 32 * part), hi);   // one 32-column store per half and warp
-#pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] -= hi[t];
-        umma::tmem_st32(umma::tmem_addr(tmD_lo, warp, 32 * part), v);
+        for (int t = 0; t < 16; ++t) {
+          const int s = 16 * s16 + t;
+          const float v = s < cnt ? sV[s * kVW + m] : 0.0f;  // bank = 4 s + m: lanes = consecutive m
+          hi[t] = umma::tf32_hi(v);
+          lo[t] = v - hi[t];
+        }
+        umma::tmem_st16(umma::tmem_addr(tmD_hi, warp, 16 * s16), hi);
+        umma::tmem_st16(umma::tmem_addr(tmD_lo, warp, 16 * s16), lo);
       }
       umma::tmem_st_wait();
     }

@@ -214,9 +214,74 @@ k_umma_probe(const float* __restrict__ rawA, int a_floats, const float* __restri
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
+
+// Microbenchmark (development aid): cost of tcgen05.st for a warp, alone and while another warp keeps the tensor
+// pipe busy with 128x128x8 tf32 MMAs (A from tensor memory).  out[warp] = cycles for `nstores` stores of `width`
+// columns + the final tcgen05.wait::st; out[16] = cycles the MMA issuer spent.
+__global__ void __launch_bounds__(576, 1)
+k_tmem_st_bench(long long* __restrict__ out, int nwarps, int nstores, int width, int mma_count, int wait_each) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < 128 * 64; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.001f * (i & 15);
+  umma::fence_proxy_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 17) {  // MMA issuer: D = columns [0,128), A = columns [128,192) (whatever they hold), B = sm
+    if (lane == 0 && mma_count > 0) {
+      const long long t0 = clock64();
+      const uint32_t idesc = umma::make_idesc_tf32(128, 128);
+      for (int i = 0; i < mma_count; ++i)
+        umma::mma_tf32_ts(tmem, tmem + 128 + 8 * (i & 7), umma::make_desc(umma::smem_u32(sm) + (i & 7) * 4096, 128 * 16, 128),
+                          idesc, 1u);
+      umma::mma_commit(&bar);
+      out[16] = clock64() - t0;
+      umma::mbar_wait(&bar, 0);
+      out[17] = clock64() - t0;
+    }
+  } else if (warp < nwarps) {
+    float v[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) v[t] = (float)(tid + t);
+    const uint32_t base = umma::tmem_addr(tmem + 256, warp, 0);   // columns [256, 512)
+    __syncwarp();
+    const long long t0 = clock64();
+    for (int i = 0; i < nstores; ++i) {
+      const uint32_t a = base + (uint32_t)((i * width) & 255);
+      if (width == 8) { float w[8]; for (int t = 0; t < 8; ++t) w[t] = v[t] + i; umma::tmem_st8(a, w); }
+      else if (width == 16) { float w[16]; for (int t = 0; t < 16; ++t) w[t] = v[t] + i; umma::tmem_st16(a, w); }
+      else { float w[32]; for (int t = 0; t < 32; ++t) w[t] = v[t] + i; umma::tmem_st32(a & ~31u | (base & 31u), w); }
+      if (wait_each) umma::tmem_st_wait();
+    }
+    umma::tmem_st_wait();
+    const long long t1 = clock64();
+    if (lane == 0) out[warp] = t1 - t0;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace mdl
 
 using namespace mdl;
+
+extern "C" int mdl_selftest_tmem_st_bench(long long* out, int32_t nwarps, int32_t nstores, int32_t width,
+                                          int32_t mma_count, int32_t wait_each, void* stream) {
+  MDL_REQUIRE(out && nwarps >= 1 && nwarps <= 16 && (width == 8 || width == 16 || width == 32), "tmem_st_bench: bad arguments");
+  MDL_CUDA(cudaFuncSetAttribute(k_tmem_st_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  k_tmem_st_bench<<<1, 576, 32 * 1024, as_stream(stream)>>>(out, nwarps, nstores, width, mma_count, wait_each);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
 
 extern "C" int mdl_selftest_umma_probe(const float* rawA, int32_t a_floats, const float* rawB, int32_t b_floats,
                                        float* D, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
