@@ -312,6 +312,26 @@ MDL_API int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32_t 
 MDL_API int mdl_copy_mapped(const float* src, int32_t I, int32_t O, int32_t transposed,
                             const mdl_wgrad_out* out, void* stream);
 
+/* Same, with the gradient rows scaled by rowscale[r] first (a layer whose output is multiplied per row afterwards:
+ * SchNet's filter * cosine cutoff, reference schnet.py:81 -> PyG CFConv.forward).  N >= 2048 rows, I <= 256. */
+MDL_API int mdl_linear_wgrad_rs(const float* X, const float* G, const float* rowscale, int64_t N, int32_t I, int32_t O,
+                                const mdl_wgrad_out* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused two-layer edge MLP (SchNet filter network + cosine cutoff), reference models/schnet.py:81,134-143 ->
+ * PyG InteractionBlock.mlp = Sequential(Linear(G,F), ShiftedSoftplus, Linear(F,F)) and CFConv's `W = mlp(e) * C`:
+ *   Y[e,:] = (act1(X[e,:] W1^T + b1) W2^T + b2) * rowscale[e]      X [E,G] (G <= 64), H = O = 128
+ * act1: 0 = shifted softplus, 1 = relu; act2: 0 = none, 1 = relu (applied before the row scale).
+ * T1 (optional, [E,H]) receives the hidden activations for the backward.  One pass on tcgen05 (3xTF32). ---- */
+MDL_API int mdl_edge_mlp2_supported(int32_t G, int32_t H, int32_t O);
+MDL_API int mdl_edge_mlp2_fwd(const float* X, const float* W1, const float* b1, const float* W2, const float* b2,
+                              const float* rowscale, float* Y, float* T1, int64_t E, int32_t G, int32_t H, int32_t O,
+                              int32_t act1, int32_t act2, void* stream);
+/* dPre1[e,:] = ((dY[e,:] * rowscale[e]) W2) * act1'(pre1[e,:]), act1' recovered from T1.  The weight / bias
+ * gradients are mdl_linear_wgrad_rs(T1, dY, rowscale) and mdl_linear_wgrad(X, dPre1). */
+MDL_API int mdl_edge_mlp2_bwd(const float* dY, const float* rowscale, const float* W2, const float* T1, float* dPre1,
+                              int64_t E, int32_t H, int32_t O, int32_t act1, void* stream);
+
+
 /* ---- AdamW over one flat fp32 buffer: torch.optim.AdamW semantics (the reference's optimizer,
  * config.yml "optimizer: AdamW", matdeeplearn/training/training.py:429-432, step at :49).
  * hyper = device {lr, beta1, beta2, eps, weight_decay}; step = device float step count, advanced by

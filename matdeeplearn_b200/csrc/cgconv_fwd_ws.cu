@@ -53,7 +53,7 @@ unsigned long long* g_ws_phase_buf = nullptr;
 
 struct WsPlan {
   unsigned long long* prof;
-  int window, KP, WR;
+  int window, KP, WR, sleep_ns;
   uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, offIdx, offWin, offInfo, total;
 };
 
@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   __shared__ int sRed[3][2];  // loaders: per-warp (min, max) of the round's source nodes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP, WR = pl.WR;
+  const uint32_t sleep_ns = (uint32_t)pl.sleep_ns;
+#define WAIT(bar, parity) umma::mbar_wait_sleep(bar, parity, sleep_ns)
 
   uint8_t* sBhi = smem + pl.offBhi;
   uint8_t* sBlo = smem + pl.offBlo;
@@ -235,13 +237,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           const int b = it & 1;
           const RoundW Rn = next_round(R);
           if (R.cnt > 0) {  // split of this round done: its A operand is staged and the landing zone is free
-            umma::mbar_wait(&bar_a_full[b], (ph_a >> b) & 1);
+            WAIT(&bar_a_full[b], (ph_a >> b) & 1);
             ph_a ^= 1u << b;
           }
           if (valid(Rn)) issue_ea_bulk(Rn);  // first: the MMA issue below blocks for ~2k cycles
           if (R.cnt > 0) {
             if ((busy >> b) & 1) {  // the epilogue of the round that used this accumulator two rounds ago has read it
-              umma::mbar_wait(&bar_acc_free[b], (ph_f >> b) & 1);
+              WAIT(&bar_acc_free[b], (ph_f >> b) & 1);
               ph_f ^= 1u << b;
             }
             umma::fence_after_sync();
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         const int b = it & 1;
         if (R.cnt > 0) {
           if ((used >> b) & 1) {  // consumers have finished with this buffer (two rounds ago)
-            umma::mbar_wait(&bar_rows_free[b], (ph_rf >> b) & 1);
+            WAIT(&bar_rows_free[b], (ph_rf >> b) & 1);
             ph_rf ^= 1u << b;
           }
           int* bS = sIdx + b * 2 * kRowsW;
@@ -325,11 +327,11 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       if (R.cnt > 0) {
         const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
         if (nb) {
-          umma::mbar_wait(&bar_ea_full, ph_ea);
+          WAIT(&bar_ea_full, ph_ea);
           ph_ea ^= 1;
         }
         if ((used >> b) & 1) {  // the MMAs that read this A buffer two rounds ago have retired
-          umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);
+          WAIT(&bar_mma[b], (ph_m >> b) & 1);
           ph_m ^= 1u << b;
           umma::fence_after_sync();
         }
@@ -414,14 +416,14 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
     }
     if (cnt > 0) {
-      umma::mbar_wait(&bar_rows_full[b], (ph_r >> b) & 1);  // indices, window record, node rows of this round
+      WAIT(&bar_rows_full[b], (ph_r >> b) & 1);  // indices, window record, node rows of this round
       ph_r ^= 1u << b;
       mark(1);
       const int4 wr = sWin[b];
       const bool win = wr.x != 0;
       const int w_smin = wr.y, w_dmin = wr.z, w_nq = wr.w;
       const float* sW = sWbuf(b);
-      umma::mbar_wait(&bar_mma[b], (ph_m >> b) & 1);         // this round's contraction
+      WAIT(&bar_mma[b], (ph_m >> b) & 1);         // this round's contraction
       ph_m ^= 1u << b;
       umma::fence_after_sync();
       mark(2);
@@ -512,6 +514,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsW);
 }
 
+#undef WAIT
+
 template <int PROFILE>
 int ws_launch_t(const CgParams& p, const WsPlan& pl, int grid, cudaStream_t st) {
   static std::atomic<int> configured{0};
@@ -544,6 +548,8 @@ int cgws_launch(CgParams p, cudaStream_t st) {
   MDL_REQUIRE(ws_plan(p.C, p.G, &pl), "cgconv_fwd_ws: unsupported shape C=%d G=%d", p.C, p.G);
   const char* wenv = getenv("MDL_CGCONV_WINDOW");  // "0": node terms from global memory only (A/B and test switch)
   pl.window = !(wenv && wenv[0] == '0');
+  const char* senv = getenv("MDL_WS_SLEEP");  // ns slept between mbarrier polls (A/B switch)
+  pl.sleep_ns = senv ? atoi(senv) : 0;
   p.c_off = 0; p.CC = p.C; p.cap = kRowsW; p.te = kTileW;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTileW));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;

@@ -78,6 +78,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same wait with a short sleep between polls: for the warp-specialised kernels, where many warps wait at
+// once and their polling would otherwise compete with the working warps for issue slots (MDL_WS_SLEEP A/B).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (ns) __nanosleep(ns);
+    if (spin > (1u << 22)) __trap();
+  }
+}
+
 // ---- bulk async copies (TMA, 1-D): global -> shared, completion counted in bytes on an mbarrier ----
 // one arrival + `bytes` expected on the barrier's current phase (the issuing thread)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {

@@ -186,8 +186,8 @@ int wgrad_reduce_launch(const float* part, int nparts, int I, int O, const mdl_w
   return MDL_OK;
 }
 bool wgrad_tc_supported(int64_t R, int I, int O);
-int wgrad_tc_launch(const float* X, const float* G, int64_t R, int I, int O, const mdl_wgrad_out& out, float* part,
-                    cudaStream_t st);
+int wgrad_tc_launch(const float* X, const float* G, const float* rs, int64_t R, int I, int O, const mdl_wgrad_out& out,
+                    float* part, cudaStream_t st);
 
 static size_t wg_ws_bytes(int64_t N, int I, int O) {
   return (size_t)wg_grid(N) * ((size_t)O * I + O) * sizeof(float);
@@ -219,7 +219,7 @@ extern "C" int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32
   {  // long batches (edge-level layers): the tcgen05 kernel (wgrad_tc.cu); MDL_WGRAD=simt keeps the SIMT one (A/B)
     const char* env = getenv("MDL_WGRAD");
     if (!(env && strcmp(env, "simt") == 0) && wgrad_tc_supported(N, I, O))
-      return wgrad_tc_launch(X, G, N, I, O, *out, reinterpret_cast<float*>(workspace), as_stream(stream));
+      return wgrad_tc_launch(X, G, nullptr, N, I, O, *out, reinterpret_cast<float*>(workspace), as_stream(stream));
   }
   const size_t smem = (size_t)2 * kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
   // two stages of 32 rows of X and G: I + O <= ~780 floats per row pair (one CTA per SM above ~100 KB)
@@ -253,4 +253,17 @@ extern "C" int mdl_copy_mapped(const float* src, int32_t I, int32_t O, int32_t t
                   as_stream(stream)>>>(src, I, O, transposed, *out);
   MDL_LAUNCHED();
   return MDL_OK;
+}
+
+// dW = (diag(rowscale) G)^T X, db = sum_r rowscale[r] G[r]: the weight gradient of a layer whose output is scaled per
+// row afterwards (SchNet: filter * cosine cutoff, reference schnet.py:81 / PyG CFConv.forward).  Long batches only
+// (the tcgen05 kernel, wgrad_tc.cu).
+extern "C" int mdl_linear_wgrad_rs(const float* X, const float* G, const float* rowscale, int64_t N, int32_t I, int32_t O,
+                                   const mdl_wgrad_out* out, void* workspace, size_t workspace_bytes, void* stream) {
+  MDL_REQUIRE(N > 0 && I > 0 && O > 0, "linear_wgrad_rs: bad shape");
+  if (int rc = wg_check_map(out, O, "linear_wgrad_rs")) return rc;
+  MDL_REQUIRE(X && G && workspace, "linear_wgrad_rs: null pointer");
+  MDL_REQUIRE(workspace_bytes >= wg_ws_bytes(N, I, O), "linear_wgrad_rs: workspace too small");
+  MDL_REQUIRE(wgrad_tc_supported(N, I, O), "linear_wgrad_rs: needs N >= 2048 rows and I <= 256 (got N=%lld I=%d)", (long long)N, I);
+  return wgrad_tc_launch(X, G, rowscale, N, I, O, *out, reinterpret_cast<float*>(workspace), as_stream(stream));
 }

@@ -34,8 +34,8 @@ constexpr int kWtM = 128;         // output channels per CTA (TMEM lanes)
 __host__ __device__ inline uint32_t wt_lbo(int NI) { return (uint32_t)NI * 16 + 16; }  // k-chunk stride of the X^T tiles
 
 __global__ void __launch_bounds__(kWtThreads, 2)
-k_wgrad_tc(const float* __restrict__ X, const float* __restrict__ G, int64_t R, int I, int O, int NI, int tmem_cols,
-           float* __restrict__ part) {
+k_wgrad_tc(const float* __restrict__ X, const float* __restrict__ G, const float* __restrict__ rs, int64_t R, int I, int O,
+           int NI, int tmem_cols, float* __restrict__ part) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -79,7 +79,7 @@ k_wgrad_tc(const float* __restrict__ X, const float* __restrict__ G, int64_t R, 
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int64_t r = r0 + rg * 16 + j;
-      ga[j] = (o_ok && r < R) ? __ldg(G + r * O + o_base + o) : 0.0f;
+      ga[j] = (o_ok && r < R) ? __ldg(G + r * O + o_base + o) * (rs ? __ldg(rs + r) : 1.0f) : 0.0f;  // optional row scale
     }
     // the previous chunk's MMAs read the A columns and the X^T tiles: wait before overwriting them
     if (any) {
@@ -183,8 +183,8 @@ int wgrad_tc_grid(int64_t R) {
   return (int)std::min<int64_t>(chunks, 2 * kNumSMs);
 }
 
-int wgrad_tc_launch(const float* X, const float* G, int64_t R, int I, int O, const mdl_wgrad_out& out, float* part,
-                    cudaStream_t st) {
+int wgrad_tc_launch(const float* X, const float* G, const float* rs, int64_t R, int I, int O, const mdl_wgrad_out& out,
+                    float* part, cudaStream_t st) {
   const int NI = (I + 15) & ~15;
   const int tmem_cols = (NI + 2 * kWtRows <= 256) ? 256 : 512;
   size_t smem = (size_t)2 * (kWtRows / 4) * wt_lbo(NI);
@@ -196,7 +196,7 @@ int wgrad_tc_launch(const float* X, const float* G, int64_t R, int I, int O, con
   }
   const int grid = wgrad_tc_grid(R);
   dim3 g(grid, (O + kWtM - 1) / kWtM);
-  k_wgrad_tc<<<g, kWtThreads, smem, st>>>(X, G, R, I, O, NI, tmem_cols, part);
+  k_wgrad_tc<<<g, kWtThreads, smem, st>>>(X, G, rs, R, I, O, NI, tmem_cols, part);
   MDL_LAUNCHED();
   return wgrad_reduce_launch(part, grid, I, O, out, st);
 }

@@ -104,6 +104,90 @@ def linear(x, weight, bias=None):
     return torch.nn.functional.linear(x, weight, bias)
 
 
+def linear_wgrad_rs_into(x, g, rowscale, wmap):
+    """dW = (diag(rowscale) g)^T x, db = sum_r rowscale[r] g[r] through the block map (mdl_linear_wgrad_rs)."""
+    import ctypes
+    lib = _lib.load()
+    x, g = x.contiguous(), g.contiguous()
+    N, I = x.shape
+    O = g.shape[1]
+    need = int(lib.mdl_linear_wgrad_workspace_bytes(N, I, O))
+    ws = torch.empty(max(need, 4), dtype=torch.uint8, device=x.device)
+    rc = lib.mdl_linear_wgrad_rs(_lib.ptr(x), _lib.ptr(g), _lib.ptr(rowscale), N, I, O, ctypes.byref(wmap), _lib.ptr(ws),
+                                 ws.numel(), _lib.stream())
+    _lib.check(rc, "mdl_linear_wgrad_rs")
+
+
+class EdgeMLP2Fn(torch.autograd.Function):
+    """Y = (act1(X W1^T + b1) W2^T + b2) * rowscale[:, None] on the fused tcgen05 kernel (mdl_edge_mlp2_fwd / _bwd);
+    X (edge_attr) and rowscale (the cosine cutoff) are data: no gradient flows into them."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, rowscale, act1):
+        lib = _lib.load()
+        x = x.contiguous()
+        E, G = x.shape
+        H, O = w1.shape[0], w2.shape[0]
+        y = torch.empty((E, O), dtype=torch.float32, device=x.device)
+        need_bwd = any(ctx.needs_input_grad[1:5])
+        t1 = torch.empty((E, H), dtype=torch.float32, device=x.device) if need_bwd else None
+        rs = rowscale.contiguous() if rowscale is not None else None
+        rc = lib.mdl_edge_mlp2_fwd(_lib.ptr(x), _lib.ptr(w1.contiguous()), _lib.ptr(b1), _lib.ptr(w2.contiguous()),
+                                   _lib.ptr(b2), _lib.ptr(rs), _lib.ptr(y), _lib.ptr(t1), E, G, H, O, act1, 0, _lib.stream())
+        _lib.check(rc, "mdl_edge_mlp2_fwd")
+        ctx.save_for_backward(x, t1, rs, w2)
+        ctx.act1 = act1
+        ctx.params = (w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, t1, rs, w2 = ctx.saved_tensors
+        w1p, b1p, w2p, b2p = ctx.params
+        g = g.contiguous()
+        E, H = t1.shape
+        O = g.shape[1]
+        G = x.shape[1]
+        dp1 = torch.empty_like(t1)
+        rc = lib.mdl_edge_mlp2_bwd(_lib.ptr(g), _lib.ptr(rs), _lib.ptr(w2.contiguous()), _lib.ptr(t1), _lib.ptr(dp1), E, H, O,
+                                   ctx.act1, _lib.stream())
+        _lib.check(rc, "mdl_edge_mlp2_bwd")
+
+        def deliver(xin, gin, scale, wparam, bparam, rows_out, rows_in):
+            wd = _grad_dest(wparam)
+            bd = _grad_dest(bparam) if bparam is not None else None
+            direct = wd is not None and (bparam is None or bd is not None)
+            dW = None if direct else torch.empty((rows_out, rows_in), dtype=torch.float32, device=g.device)
+            db = None if (direct or bparam is None) else torch.empty(rows_out, dtype=torch.float32, device=g.device)
+            wmap = _wgrad_map(rows_out, rows_in, [_ptr_off(wd if direct else dW)], [_ptr_off(bd if direct else db)])
+            if scale is not None:
+                linear_wgrad_rs_into(xin, gin, scale, wmap)
+            else:
+                linear_wgrad_into(xin, gin, wmap)
+            if direct:
+                wparam._mdl_written = True
+                if bparam is not None:
+                    bparam._mdl_written = True
+            return dW, db
+
+        dW2, db2 = deliver(t1, g, rs, w2p, b2p, O, H)      # dW2 = (g * rs)^T T1
+        dW1, db1 = deliver(x, dp1, None, w1p, b1p, H, G)   # dW1 = dPre1^T X
+        return None, dW1, db1, dW2, db2, None, None
+
+
+def edge_mlp2_supported(x, w1, w2):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] >= _WGRAD_TC_MIN_ROWS
+            and not x.requires_grad
+            and bool(_lib.load().mdl_edge_mlp2_supported(int(x.shape[1]), int(w1.shape[0]), int(w2.shape[0])))
+            and w2.shape[1] == w1.shape[0])
+
+
+def edge_mlp2(x, w1, b1, w2, b2, rowscale, act1="ssp"):
+    """(act1(x W1^T + b1) W2^T + b2) * rowscale[:, None]; act1 in {"ssp" (shifted softplus), "relu"}."""
+    return EdgeMLP2Fn.apply(x, w1, b1, w2, b2, rowscale, {"ssp": 0, "relu": 1}[act1])
+
+
 def apply_mlp(seq, x):
     """Run an nn.Sequential (or a single module) with every nn.Linear going through `linear` above; other
     layers (activations, BatchNorm) are called as they are."""

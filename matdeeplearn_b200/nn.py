@@ -238,7 +238,14 @@ class CFConv(nn.Module):
         if csr is None:
             csr = csr_for(edge_index, num_nodes=x.shape[0])
         C = 0.5 * (torch.cos(edge_weight * math.pi / self.cutoff) + 1.0)
-        W = MF.apply_mlp(self.nn, edge_attr) * C.view(-1, 1)          # [E, F], reference edge order
+        mlp = self.nn
+        if (isinstance(mlp, nn.Sequential) and len(mlp) == 3 and isinstance(mlp[0], nn.Linear)
+                and isinstance(mlp[1], ShiftedSoftplus) and isinstance(mlp[2], nn.Linear)
+                and MF.edge_mlp2_supported(edge_attr, mlp[0].weight, mlp[2].weight)):
+            # the filter network and the cutoff in ONE pass on tcgen05: no [E, F] hidden tensor in the forward
+            W = MF.edge_mlp2(edge_attr, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, C, "ssp")
+        else:
+            W = MF.apply_mlp(mlp, edge_attr) * C.view(-1, 1)          # [E, F], reference edge order
         h = MF.linear(x, self.lin1.weight, None)
         agg = MF.cfconv_aggregate(h, W, csr)
         return MF.linear(agg, self.lin2.weight, self.lin2.bias)

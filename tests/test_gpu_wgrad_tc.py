@@ -42,3 +42,29 @@ def test_linear_fn_long_batch_uses_the_kernel_and_matches_autograd():
     (torch.nn.functional.linear(x, lin.weight, lin.bias) * w).sum().backward()
     for a, b in zip(got, (lin.weight.grad, lin.bias.grad, x.grad)):
         assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("E,G", [(102086, 50), (5000, 37), (2048, 64), (3001, 8)])
+@pytest.mark.parametrize("act1", ["ssp", "relu"])
+def test_edge_mlp2_fused_matches_fp64(E, G, act1):
+    """The fused SchNet filter network + cutoff (csrc/edge_mlp.cu) against the same arithmetic in fp64:
+    forward, and the four weight / bias gradients (reference schnet.py:81 -> PyG InteractionBlock.mlp, CFConv)."""
+    from matdeeplearn_b200 import functional as MF
+    from tests.util import assert_close
+    torch.manual_seed(E + G)
+    H = 128
+    x = torch.rand(E, G, dtype=torch.float64)
+    rs = torch.rand(E, dtype=torch.float64)
+    lin1, lin2 = torch.nn.Linear(G, H).double(), torch.nn.Linear(H, H).double()
+    act = (lambda t: torch.nn.functional.softplus(t) - 0.6931471805599453) if act1 == "ssp" else torch.relu
+    ref = lin2(act(lin1(x))) * rs[:, None]
+    w = torch.randn_like(ref)
+    ref.backward(w)
+    p32 = [t.detach().float().to(DEV).requires_grad_(True) for t in (lin1.weight, lin1.bias, lin2.weight, lin2.bias)]
+    xg, rsg = x.float().to(DEV), rs.float().to(DEV)
+    assert MF.edge_mlp2_supported(xg, p32[0], p32[2])
+    got = MF.edge_mlp2(xg, p32[0], p32[1], p32[2], p32[3], rsg, act1)
+    assert_close(got, ref, rtol=1e-5, atol_rel=5e-6, what="edge_mlp2 fwd")
+    got.backward(w.float().to(DEV))
+    for g, r, name in zip(p32, (lin1.weight, lin1.bias, lin2.weight, lin2.bias), ("dW1", "db1", "dW2", "db2")):
+        assert_close(g.grad, r.grad, rtol=1e-4, atol_rel=2e-5, what=f"edge_mlp2 {name}")
