@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   fill_infos(0);
   for (int i = tid; i < kNP * KP; i += kLaunch) {
     const int n = i % kNP, k = i / kNP;
-    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) : 0.0f;
+    // exponents in base 2: the f-gate columns carry -log2(e), the s-gate columns +log2(e) (as cgconv_fwd_ws.cu)
+    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) * (n < kC ? -kLog2e : kLog2e) : 0.0f;
     const float hi = umma::tf32_hi(w);
     const int off = umma::tile_offset_bytes(n, k, kNP);
     *reinterpret_cast<float*>(sBhi + off) = hi;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
         const int ss = bSrc[e_ep];
         const float* r0 = win ? sV + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
         const float* r1 = win ? sV + (ss - w_smin) * kVW + c_begin : sV + e_ep * kVW + c_begin;
+        const f2_t cf = pk2(-kLog2e, -kLog2e), cs = pk2(kLog2e, kLog2e);
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
           const float4 pf = win ? *reinterpret_cast<const float4*>(r0 + j4) : __ldg(reinterpret_cast<const float4*>(r0 + j4));
@@ -397,8 +399,11 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
                                 : __ldg(reinterpret_cast<const float4*>(r0 + kC + j4));
           const float4 qf = *reinterpret_cast<const float4*>(r1 + j4);
           const float4 qs = *reinterpret_cast<const float4*>(r1 + kC + j4);
-          f[j4] += pf.x + qf.x; f[j4 + 1] += pf.y + qf.y; f[j4 + 2] += pf.z + qf.z; f[j4 + 3] += pf.w + qf.w;
-          sacc[j4] += ps.x + qs.x; sacc[j4 + 1] += ps.y + qs.y; sacc[j4 + 2] += ps.z + qs.z; sacc[j4 + 3] += ps.w + qs.w;
+          // y = accumulator (base-2 units: W_e is pre-scaled) + c (P + Q), one packed fma per pair
+          upk2(fma2(cf, add2(pk2(pf.x, pf.y), pk2(qf.x, qf.y)), pk2(f[j4], f[j4 + 1])), f[j4], f[j4 + 1]);
+          upk2(fma2(cf, add2(pk2(pf.z, pf.w), pk2(qf.z, qf.w)), pk2(f[j4 + 2], f[j4 + 3])), f[j4 + 2], f[j4 + 3]);
+          upk2(fma2(cs, add2(pk2(ps.x, ps.y), pk2(qs.x, qs.y)), pk2(sacc[j4], sacc[j4 + 1])), sacc[j4], sacc[j4 + 1]);
+          upk2(fma2(cs, add2(pk2(ps.z, ps.w), pk2(qs.z, qs.w)), pk2(sacc[j4 + 2], sacc[j4 + 3])), sacc[j4 + 2], sacc[j4 + 3]);
         }
       }
     }
@@ -411,19 +416,15 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
       float* rowv = sV + e_ep * kVW;
 #pragma unroll
       for (int j4 = 0; j4 < 16; j4 += 4) {
-        float r0[4], r1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float sg = sigmoid_mixed(f[j4 + j]);
-          float sp, sgs;
-          softplus_sigmoid_mufu(sacc[j4 + j], sp, sgs);
-          const float4 gv = gq[j4 >> 2];
-          const float g = j == 0 ? gv.x : j == 1 ? gv.y : j == 2 ? gv.z : gv.w;
-          r0[j] = g * sp * sg * (1.0f - sg);
-          r1[j] = g * sg * sgs;
-        }
-        *reinterpret_cast<float4*>(rowv + c_begin + j4) = make_float4(r0[0], r0[1], r0[2], r0[3]);
-        *reinterpret_cast<float4*>(rowv + kC + c_begin + j4) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+        const float4 gv = gq[j4 >> 2];
+        f2_t a0, a1, b0, b1;
+        gate_pair_bwd(f[j4], f[j4 + 1], sacc[j4], sacc[j4 + 1], gv.x, gv.y, a0, a1);
+        gate_pair_bwd(f[j4 + 2], f[j4 + 3], sacc[j4 + 2], sacc[j4 + 3], gv.z, gv.w, b0, b1);
+        float4 o0, o1;
+        upk2(a0, o0.x, o0.y); upk2(b0, o0.z, o0.w);
+        upk2(a1, o1.x, o1.y); upk2(b1, o1.z, o1.w);
+        *reinterpret_cast<float4*>(rowv + c_begin + j4) = o0;
+        *reinterpret_cast<float4*>(rowv + kC + c_begin + j4) = o1;
       }
     }
     mark(10);

@@ -84,53 +84,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 
-// ---- packed fp32 pairs (one FMA-pipe instruction per two values on sm_100)
-typedef unsigned long long f2_t;
-__device__ __forceinline__ f2_t pk2(float a, float b) {
-  f2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
-  f2_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
-  f2_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
-  f2_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
-// sigmoid(a_f) * softplus(a_s) / ln 2 for two channels, from yf = -log2(e) a_f and ys = +log2(e) a_s:
-//   1 / (1 + 2^yf)  *  (max(ys, 0) + log2(1 + 2^-|ys|))
-// three MUFU ops per channel (ex2, ex2, lg2); the reciprocal runs on the FMA pipe as in rcp_fma (bit-trick seed,
-// two third-order steps), on packed pairs.
-__device__ __forceinline__ f2_t gate_pair(float yf0, float yf1, float ys0, float ys1) {
-  const f2_t one = pk2(1.0f, 1.0f);
-  const f2_t u = add2(pk2(ex2_(fminf(yf0, 126.0f)), ex2_(fminf(yf1, 126.0f))), one);
-  float u0, u1;
-  upk2(u, u0, u1);
-  f2_t r = pk2(__uint_as_float(0x7EF311C7u - __float_as_uint(u0)), __uint_as_float(0x7EF311C7u - __float_as_uint(u1)));
-  const f2_t nu = pk2(-u0, -u1);
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const f2_t e = fma2(nu, r, one);
-    r = fma2(r, fma2(e, e, e), r);
-  }
-  const f2_t w = add2(pk2(ex2_(-fabsf(ys0)), ex2_(-fabsf(ys1))), one);
-  float w0, w1;
-  upk2(w, w0, w1);
-  const f2_t sp = add2(pk2(lg2_(w0), lg2_(w1)), pk2(fmaxf(ys0, 0.0f), fmaxf(ys1, 0.0f)));
-  return mul2(r, sp);
-}
-
 template <int PROFILE>
 __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p, const WsPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
