@@ -317,6 +317,14 @@ MDL_API int mdl_copy_mapped(const float* src, int32_t I, int32_t O, int32_t tran
 MDL_API int mdl_linear_wgrad_rs(const float* X, const float* G, const float* rowscale, int64_t N, int32_t I, int32_t O,
                                 const mdl_wgrad_out* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- dense layer over a long batch on tcgen05 (3xTF32): Y[r,:] = act(X[r,:] . B^T + bias), X [R,K] (K <= 128),
+ * B[n][k] = W[n*ldn + k*ldk] (N <= 128).  Forward y = x W^T with W [O,I]: ldn = I, ldk = 1; input gradient
+ * dx = g W: ldn = 1, ldk = I.  act: 0 none, 1 relu, 2 shifted softplus.  Replaces the cuBLAS SGEMMs over E rows of
+ * the reference's edge-level Linear layers (megnet.py:28-56,222-247; mpnn.py:83-85) and of their backward. ---- */
+MDL_API int mdl_linear_tc_supported(int64_t R, int32_t K, int32_t N);
+MDL_API int mdl_linear_tc(const float* X, const float* W, int64_t ldn, int64_t ldk, const float* bias, float* Y,
+                          int64_t R, int32_t K, int32_t N, int32_t act, void* stream);
+
 /* ---- fused two-layer edge MLP (SchNet filter network + cosine cutoff), reference models/schnet.py:81,134-143 ->
  * PyG InteractionBlock.mlp = Sequential(Linear(G,F), ShiftedSoftplus, Linear(F,F)) and CFConv's `W = mlp(e) * C`:
  *   Y[e,:] = (act1(X[e,:] W1^T + b1) W2^T + b2) * rowscale[e]      X [E,G] (G <= 64), H = O = 128

@@ -81,6 +81,8 @@ SIGNATURES = {
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
     "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "mdl_selftest_umma_ts": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
+    "mdl_linear_tc_supported": (C.c_int, [_i64, _i32, _i32]),
+    "mdl_linear_tc": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "mdl_linear_wgrad_rs": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "mdl_edge_mlp2_supported": (C.c_int, [_i32, _i32, _i32]),
     "mdl_edge_mlp2_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -211,9 +211,9 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_fwd(const Mlp2Params 
 #pragma unroll
       for (int j = 0; j < 32; ++j) h[j] = act_fwd(h[j] + sB[32 * part + j], p.act1);
       if (p.T1 && e < cnt) {
-        float4* dst = reinterpret_cast<float4*>(p.T1 + (r_lo + e) * kH + 32 * part);
+        float* dst = p.T1 + (r_lo + e) * kH + 32 * part;   // 128 contiguous bytes per thread: four full-sector stores
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) umma::stg256(dst + 8 * j, h + 8 * j);
       }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -242,18 +242,15 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_fwd(const Mlp2Params 
       umma::tmem_ld_wait();
       if (e < cnt) {
         const float s = p.rs ? __ldg(p.rs + r_lo + e) : 1.0f;
-        float4* dst = reinterpret_cast<float4*>(p.Y + (r_lo + e) * kH + 32 * part);
+        float* dst = p.Y + (r_lo + e) * kH + 32 * part;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float o4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float v = y[4 * j + u] + sB[kH + 32 * part + 4 * j + u];
-            if (p.act2 == 1) v = fmaxf(v, 0.0f);
-            o4[u] = v * s;
-          }
-          dst[j] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        for (int j = 0; j < 32; ++j) {
+          float v = y[j] + sB[kH + 32 * part + j];
+          if (p.act2 == 1) v = fmaxf(v, 0.0f);
+          y[j] = v * s;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::stg256(dst + 8 * j, y + 8 * j);
       }
     }
   }
@@ -340,12 +337,11 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_bwd(const Mlp2BwdPara
     for (int j = 0; j < 32; ++j) g[j] = 0.0f;
     if (live) {
       const float s = p.rs ? __ldg(p.rs + r_lo + e) : 1.0f;
-      const float4* src = reinterpret_cast<const float4*>(p.dY + (r_lo + e) * kH + 32 * part);
+      const float* src = p.dY + (r_lo + e) * kH + 32 * part;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = __ldg(src + j);
-        g[4 * j] = v.x * s; g[4 * j + 1] = v.y * s; g[4 * j + 2] = v.z * s; g[4 * j + 3] = v.w * s;
-      }
+      for (int j = 0; j < 4; ++j) umma::ldg256(src + 8 * j, g + 8 * j);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] *= s;
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -365,12 +361,9 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_bwd(const Mlp2BwdPara
 #pragma unroll
     for (int j = 0; j < 32; ++j) t1[j] = 0.0f;
     if (live) {
-      const float4* src = reinterpret_cast<const float4*>(p.T1 + (r_lo + e) * kH + 32 * part);
+      const float* src = p.T1 + (r_lo + e) * kH + 32 * part;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = __ldg(src + j);
-        t1[4 * j] = v.x; t1[4 * j + 1] = v.y; t1[4 * j + 2] = v.z; t1[4 * j + 3] = v.w;
-      }
+      for (int j = 0; j < 4; ++j) umma::ldg256(src + 8 * j, t1 + 8 * j);
     }
     umma::mbar_wait(&bar_mma, ph);
     ph ^= 1;
@@ -380,19 +373,16 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_bwd(const Mlp2BwdPara
     umma::tmem_ld16(umma::tmem_addr(tmem, q, 32 * part + 16), *reinterpret_cast<float(*)[16]>(d + 16));
     umma::tmem_ld_wait();
     if (live) {
-      float4* dst = reinterpret_cast<float4*>(p.dP1 + (r_lo + e) * kH + 32 * part);
+      float* dst = p.dP1 + (r_lo + e) * kH + 32 * part;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float o4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float tv = t1[4 * j + u];
-          // act1'(pre1) from the saved activation: relu -> [T1 > 0]; shifted softplus -> sigmoid = 1 - exp(-T1) / 2
-          const float dact = (p.act1 == 1) ? (tv > 0.0f ? 1.0f : 0.0f) : fmaf(-0.5f, ex2_(-kLog2e * tv), 1.0f);
-          o4[u] = d[4 * j + u] * dact;
-        }
-        dst[j] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      for (int j = 0; j < 32; ++j) {
+        const float tv = t1[j];
+        // act1'(pre1) from the saved activation: relu -> [T1 > 0]; shifted softplus -> sigmoid = 1 - exp(-T1) / 2
+        const float dact = (p.act1 == 1) ? (tv > 0.0f ? 1.0f : 0.0f) : fmaf(-0.5f, ex2_(-kLog2e * tv), 1.0f);
+        d[j] *= dact;
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma::stg256(dst + 8 * j, d + 8 * j);
     }
   }
   if (tid == 0) sMail[mb] = 3;
@@ -429,8 +419,8 @@ extern "C" int mdl_edge_mlp2_fwd(const float* X, const float* W1, const float* b
   MDL_REQUIRE(X && W1 && W2 && Y && E >= 0, "edge_mlp2_fwd: null pointer");
   MDL_REQUIRE(H == kH && O == kH, "edge_mlp2_fwd: hidden and output width must be 128 (got %d, %d)", H, O);
   MDL_REQUIRE((act1 == 0 || act1 == 1) && (act2 == 0 || act2 == 1), "edge_mlp2_fwd: act 0 (shifted softplus / none) or 1 (relu)");
-  MDL_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
-                  (!T1 || (reinterpret_cast<uintptr_t>(T1) & 15) == 0), "edge_mlp2_fwd: X, Y, T1 must be 16-byte aligned");
+  MDL_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 31) == 0 &&
+                  (!T1 || (reinterpret_cast<uintptr_t>(T1) & 31) == 0), "edge_mlp2_fwd: X 16-byte, Y and T1 32-byte aligned");
   Mlp2Params p{};
   MDL_REQUIRE(mlp2_plan(G, &p), "edge_mlp2_fwd: edge width %d not supported (1..64)", G);
   if (E == 0) return MDL_OK;
@@ -452,8 +442,8 @@ extern "C" int mdl_edge_mlp2_bwd(const float* dY, const float* rowscale, const f
                                  int64_t E, int32_t H, int32_t O, int32_t act1, void* stream) {
   MDL_REQUIRE(dY && W2 && T1 && dPre1 && E >= 0, "edge_mlp2_bwd: null pointer");
   MDL_REQUIRE(H == kH && O == kH, "edge_mlp2_bwd: hidden and output width must be 128");
-  MDL_REQUIRE(((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(T1) | reinterpret_cast<uintptr_t>(dPre1)) & 15) == 0,
-              "edge_mlp2_bwd: dY, T1, dPre1 must be 16-byte aligned");
+  MDL_REQUIRE(((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(T1) | reinterpret_cast<uintptr_t>(dPre1)) & 31) == 0,
+              "edge_mlp2_bwd: dY, T1, dPre1 must be 32-byte aligned");
   if (E == 0) return MDL_OK;
   Mlp2BwdParams p{dY, rowscale, W2, T1, dPre1, E, act1};
   static std::atomic<int> configured{0};

@@ -57,8 +57,23 @@ def linear_wgrad_into(x, g, wmap):
     _lib.check(rc, "mdl_linear_wgrad")
 
 
-# rows from which the tcgen05 weight-gradient kernel (csrc/wgrad_tc.cu) takes over from the library GEMM + column sum
-_WGRAD_TC_MIN_ROWS = 2048
+# rows from which the tcgen05 kernels for long batches (csrc/wgrad_tc.cu, linear_tc.cu) take over from the library
+# GEMMs: edge-level layers; node-level ones (a few thousand rows) stay where they were
+_WGRAD_TC_MIN_ROWS = 16384
+
+
+def _linear_tc(x, w, ldn, ldk, bias, K, N):
+    """x [R,K] . B^T (+ bias) with B[n][k] = w[n*ldn + k*ldk] on the tcgen05 kernel (mdl_linear_tc)."""
+    x = x.contiguous()
+    y = torch.empty((x.shape[0], N), dtype=torch.float32, device=x.device)
+    rc = _lib.load().mdl_linear_tc(_lib.ptr(x), _lib.ptr(w), ldn, ldk, _lib.ptr(bias), _lib.ptr(y), x.shape[0], K, N, 0,
+                                   _lib.stream())
+    _lib.check(rc, "mdl_linear_tc")
+    return y
+
+
+def _tc_ok(R, K, N):
+    return bool(_lib.load().mdl_linear_tc_supported(int(R), int(K), int(N)))
 
 
 class LinearFn(torch.autograd.Function):
@@ -70,6 +85,9 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.wb = (weight, bias)
+        O, I = weight.shape
+        if weight.is_contiguous() and _tc_ok(x.shape[0], I, O):
+            return _linear_tc(x, weight, I, 1, bias, I, O)          # long batch: tcgen05 (3xTF32)
         return torch.nn.functional.linear(x, weight, bias)
 
     @staticmethod
@@ -77,7 +95,13 @@ class LinearFn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         wparam, bparam = ctx.wb
         g = g.contiguous()
-        dx = g.mm(weight) if ctx.needs_input_grad[0] else None
+        O_, I_ = weight.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if weight.is_contiguous() and _tc_ok(g.shape[0], O_, I_):
+                dx = _linear_tc(g, weight, 1, I_, None, O_, I_)     # dx = g W on tcgen05
+            else:
+                dx = g.mm(weight)
         wd = _grad_dest(wparam)
         bd = _grad_dest(bparam) if bparam is not None else None
         O, I = weight.shape
@@ -87,7 +111,7 @@ class LinearFn(torch.autograd.Function):
             if bparam is not None:
                 bparam._mdl_written = True
             return dx, None, None
-        if x.shape[0] >= _WGRAD_TC_MIN_ROWS and I <= 256 and I >= 8 and O >= 8:
+        if x.shape[0] >= 2048 and I <= 256 and I >= 8 and O >= 8:
             dW = torch.empty_like(weight)
             db = torch.empty(O, dtype=weight.dtype, device=weight.device) if bparam is not None else None
             linear_wgrad_into(x, g, _wgrad_map(O, I, [_ptr_off(dW)], [_ptr_off(db)]))
@@ -146,6 +170,8 @@ class EdgeMLP2Fn(torch.autograd.Function):
         x, t1, rs, w2 = ctx.saved_tensors
         w1p, b1p, w2p, b2p = ctx.params
         g = g.contiguous()
+        if g.data_ptr() % 32:          # 256-bit loads in the kernel
+            g = g.clone()
         E, H = t1.shape
         O = g.shape[1]
         G = x.shape[1]

@@ -68,3 +68,28 @@ def test_edge_mlp2_fused_matches_fp64(E, G, act1):
     got.backward(w.float().to(DEV))
     for g, r, name in zip(p32, (lin1.weight, lin1.bias, lin2.weight, lin2.bias), ("dW1", "db1", "dW2", "db2")):
         assert_close(g.grad, r.grad, rtol=1e-4, atol_rel=2e-5, what=f"edge_mlp2 {name}")
+
+
+@pytest.mark.parametrize("R,K,N", [(102086, 128, 128), (173823, 128, 128), (20000, 50, 128), (16384, 128, 64), (17001, 100, 72)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_linear_tc_forward_and_input_gradient(R, K, N, act):
+    """mdl_linear_tc (csrc/linear_tc.cu): y = act(x W^T + b) and dx = g W against fp64."""
+    from matdeeplearn_b200 import _lib
+    from tests.util import assert_close
+    lib = _lib.load()
+    torch.manual_seed(R + K + act)
+    x = torch.randn(R, K, dtype=torch.float64)
+    w = torch.randn(N, K, dtype=torch.float64) * 0.2
+    b = torch.randn(N, dtype=torch.float64)
+    pre = x @ w.t() + b
+    ref = pre if act == 0 else torch.relu(pre) if act == 1 else torch.nn.functional.softplus(pre) - 0.6931471805599453
+    xg, wg, bg = x.float().to(DEV), w.float().to(DEV), b.float().to(DEV)
+    y = torch.full((R, N), float("nan"), device=DEV)
+    _lib.check(lib.mdl_linear_tc(_lib.ptr(xg), _lib.ptr(wg), K, 1, _lib.ptr(bg), _lib.ptr(y), R, K, N, act, _lib.stream()), "fwd")
+    assert_close(y, ref, rtol=1e-5, atol_rel=5e-6, what=f"linear_tc fwd act={act}")
+    if act == 0:
+        g = torch.randn(R, N, dtype=torch.float64)
+        gg = g.float().to(DEV)
+        dx = torch.full((R, K), float("nan"), device=DEV)
+        _lib.check(lib.mdl_linear_tc(_lib.ptr(gg), _lib.ptr(wg), 1, K, None, _lib.ptr(dx), R, N, K, 0, _lib.stream()), "dx")
+        assert_close(dx, g @ w, rtol=1e-5, atol_rel=5e-6, what="linear_tc dx")
