@@ -535,5 +535,6 @@ extern "C" MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr) {
   cgfwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgbwd_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   cgws_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
+  lin_set_phase_buffer(reinterpret_cast<unsigned long long*>(dev_ptr));
   return MDL_OK;
 }

@@ -66,6 +66,7 @@ void cgfwd_set_phase_buffer(unsigned long long* dev_ptr);
 bool cgws_supported(const CgParams& p);
 int cgws_launch(CgParams p, cudaStream_t st);
 void cgws_set_phase_buffer(unsigned long long* dev_ptr);
+void lin_set_phase_buffer(unsigned long long* dev_ptr);  // linear_tc.cu (development aid)
 // single-pass backward with dW_e on tcgen05 (cgconv_bwd.cu)
 bool cgbwd_supported(const CgParams& p);
 int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out);

@@ -327,22 +327,27 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_bwd(const Mlp2BwdPara
   const int q = warp & 3, part = warp >> 2;
   const int e = 32 * q + lane;
   uint32_t mb = 0, ph = 0;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int64_t r_lo = t * kMRows;
-    const int cnt = (int)min((int64_t)kMRows, p.E - r_lo);
-    const bool live = e < cnt;
-    // ---- (dY * rs) row piece -> hi / lo -> A operand (32 columns per thread)
-    float g[32];
+  // this thread's 32-column piece of (dY * rs) for row e of tile t (zero beyond the matrix)
+  auto load_piece = [&](int64_t t, float (&g)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) g[j] = 0.0f;
-    if (live) {
-      const float s = p.rs ? __ldg(p.rs + r_lo + e) : 1.0f;
-      const float* src = p.dY + (r_lo + e) * kH + 32 * part;
+    const int64_t r = t * kMRows + e;
+    if (t < n_tiles && r < p.E) {
+      const float s = p.rs ? __ldg(p.rs + r) : 1.0f;
+      const float* src = p.dY + r * kH + 32 * part;
 #pragma unroll
       for (int j = 0; j < 4; ++j) umma::ldg256(src + 8 * j, g + 8 * j);
 #pragma unroll
       for (int j = 0; j < 32; ++j) g[j] *= s;
     }
+  };
+  float g[32];
+  load_piece(blockIdx.x, g);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t r_lo = t * kMRows;
+    const int cnt = (int)min((int64_t)kMRows, p.E - r_lo);
+    const bool live = e < cnt;
+    // ---- (dY * rs) row piece (requested one tile ahead) -> hi / lo -> A operand (32 columns per thread)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float hi[16], lo[16];
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(kMLaunch, 1) k_edge_mlp2_bwd(const Mlp2BwdPara
 #pragma unroll
       for (int j = 0; j < 4; ++j) umma::ldg256(src + 8 * j, t1 + 8 * j);
     }
+    load_piece(t + gridDim.x, g);   // the next tile's gradient rows: in flight under this tile's MMAs and epilogue
     umma::mbar_wait(&bar_mma, ph);
     ph ^= 1;
     umma::fence_after_sync();

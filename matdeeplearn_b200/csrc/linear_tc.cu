@@ -17,7 +17,10 @@ namespace {
 
 constexpr int kLW = 512, kLWarps = 16, kLLaunch = kLW + 32, kLRows = 128;
 
+unsigned long long* g_lin_phase_buf = nullptr;
+
 struct LinParams {
+  unsigned long long* prof;
   const float* X; const float* W; const float* bias; float* Y;
   int64_t R, ldn, ldk;
   int K, N, KP, NP, act;
@@ -83,34 +86,53 @@ __global__ void __launch_bounds__(kLLaunch, 1) k_linear_tc(const LinParams p) {
     return;
   }
 
+  long long t_prev = clock64();
+  auto mark = [&](int slot) {   // development aid: per-phase cycles of thread 0 (mdl_debug_set_phase_buffer)
+    if (p.prof && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(p.prof + slot, (unsigned long long)(now - t_prev));
+      t_prev = now;
+    }
+  };
   const int q = warp & 3, part = warp >> 2;
   const int e = 32 * q + lane;
   const bool vec4 = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
   const bool vec4o = (N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0;
+  const bool vec8o = (N & 7) == 0 && (reinterpret_cast<uintptr_t>(p.Y) & 31) == 0;
   uint32_t mb = 0, ph = 0;
+  const bool vec8 = (K & 7) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 31) == 0;
+  // this thread's 32-column piece of row e of tile t (zero beyond the matrix)
+  auto load_piece = [&](int64_t t, float (&x)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+    const int64_t r = t * kLRows + e;
+    if (t < n_tiles && r < p.R && 32 * part < KP) {
+      const float* src = p.X + r * K + 32 * part;
+      if (vec8 && 32 * part + 32 <= K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::ldg256(src + 8 * j, x + 8 * j);
+      } else if (vec4 && 32 * part + 32 <= K) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src) + j);
+          x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (32 * part + j < K) x[j] = __ldg(src + j);
+      }
+    }
+  };
+  float x[32];
+  load_piece(blockIdx.x, x);
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t r_lo = t * kLRows;
     const int cnt = (int)min((int64_t)kLRows, p.R - r_lo);
     const bool live = e < cnt;
-    // ---- X row piece (32 columns per thread) -> hi / lo -> A operand
+    mark(0);
+    // ---- X row piece (32 columns per thread, requested one tile ahead) -> hi / lo -> A operand
     if (32 * part < KP) {
-      float x[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = 0.0f;
-      if (live) {
-        const float* src = p.X + (r_lo + e) * K + 32 * part;
-        if (vec4 && 32 * part + 32 <= K) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + j);
-            x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (32 * part + j < K) x[j] = __ldg(src + j);
-        }
-      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         if (32 * part + 16 * half < KP) {
@@ -122,19 +144,25 @@ __global__ void __launch_bounds__(kLLaunch, 1) k_linear_tc(const LinParams p) {
         }
       }
     }
+    mark(1);
     umma::tmem_st_wait();
+    mark(2);
     if (tid == 0) sMail[mb] = 1;
     umma::fence_before_sync();
     sync_issuer();   // also: every thread has read D of the previous tile
     mb ^= 1;
+    mark(3);
+    load_piece(t + gridDim.x, x);   // the next tile's rows: in flight under this tile's MMAs and epilogue
     umma::mbar_wait(&bar_mma, ph);
     ph ^= 1;
     umma::fence_after_sync();
+    mark(4);
     if (32 * part < NP) {
       float d[32];
       umma::tmem_ld16(umma::tmem_addr(tmem, q, 32 * part), *reinterpret_cast<float(*)[16]>(d));
       if (32 * part + 16 < NP) umma::tmem_ld16(umma::tmem_addr(tmem, q, 32 * part + 16), *reinterpret_cast<float(*)[16]>(d + 16));
       umma::tmem_ld_wait();
+      mark(5);
       if (live) {
         float* dst = p.Y + (r_lo + e) * N + 32 * part;
 #pragma unroll
@@ -144,7 +172,10 @@ __global__ void __launch_bounds__(kLLaunch, 1) k_linear_tc(const LinParams p) {
           else if (p.act == 2) v = fmaf(kLn2, lg2_(1.0f + ex2_(-kLog2e * fabsf(v))), fmaxf(v, 0.0f)) - kLn2;
           d[j] = v;
         }
-        if (vec4o && 32 * part + 32 <= N) {
+        if (vec8o && 32 * part + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma::stg256(dst + 8 * j, d + 8 * j);
+        } else if (vec4o && 32 * part + 32 <= N) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
         } else {
@@ -154,6 +185,8 @@ __global__ void __launch_bounds__(kLLaunch, 1) k_linear_tc(const LinParams p) {
         }
       }
     }
+    mark(6);
+    if (p.prof && tid == 0) atomicAdd(p.prof + 31, 1ull);
   }
   if (tid == 0) sMail[mb] = 3;
   umma::fence_before_sync();
@@ -163,6 +196,7 @@ __global__ void __launch_bounds__(kLLaunch, 1) k_linear_tc(const LinParams p) {
 }
 
 }  // namespace
+void lin_set_phase_buffer(unsigned long long* dev_ptr) { g_lin_phase_buf = dev_ptr; }
 }  // namespace mdl
 
 using namespace mdl;
@@ -178,6 +212,7 @@ extern "C" int mdl_linear_tc(const float* X, const float* W, int64_t ldn, int64_
   MDL_REQUIRE(act >= 0 && act <= 2, "linear_tc: act 0 (none), 1 (relu), 2 (shifted softplus)");
   if (R == 0) return MDL_OK;
   LinParams p{};
+  p.prof = g_lin_phase_buf;
   p.X = X; p.W = W; p.bias = bias; p.Y = Y; p.R = R; p.ldn = ldn; p.ldk = ldk;
   p.K = K; p.N = N; p.KP = (K + 7) & ~7; p.NP = (N + 15) & ~15; p.act = act;
   const int smem = 2 * p.NP * p.KP * 4;

@@ -203,7 +203,7 @@ class EdgeMLP2Fn(torch.autograd.Function):
 
 
 def edge_mlp2_supported(x, w1, w2):
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] >= _WGRAD_TC_MIN_ROWS
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] >= 2048
             and not x.requires_grad
             and bool(_lib.load().mdl_edge_mlp2_supported(int(x.shape[1]), int(w1.shape[0]), int(w2.shape[0])))
             and w2.shape[1] == w1.shape[0])

@@ -47,6 +47,10 @@ def timed(name, fn, nbytes=None, flops=None, n=10, cold=True):
 for cold in (True, False):
     timed("edge_mlp2_fwd (E x 50 -> 128 -> 128)", lambda: _lib.check(lib.mdl_edge_mlp2_fwd(P(ea), P(w1), P(b1), P(w2), P(b2), P(rs), P(Y), P(T1), E, G, F_, F_, 0, 0, st), "f"),
           nbytes=4 * E * (G + 2 * F_ + 1), flops=2.0 * E * (G * F_ + F_ * F_), cold=cold)
+    timed("edge_mlp2_fwd, no T1 store", lambda: _lib.check(lib.mdl_edge_mlp2_fwd(P(ea), P(w1), P(b1), P(w2), P(b2), P(rs), P(Y), None, E, G, F_, F_, 0, 0, st), "f"), cold=cold)
+    timed("edge_mlp2_fwd, relu (no MUFU)", lambda: _lib.check(lib.mdl_edge_mlp2_fwd(P(ea), P(w1), P(b1), P(w2), P(b2), P(rs), P(Y), P(T1), E, G, F_, F_, 1, 0, st), "f"), cold=cold)
+    timed("linear_tc  x W^T [E,128] x [128,128]", lambda: _lib.check(lib.mdl_linear_tc(P(T1), P(w2), F_, 1, P(b2), P(Y), E, F_, F_, 0, st), "l"),
+          nbytes=8 * E * F_, flops=2.0 * E * F_ * F_, cold=cold)
     timed("edge_mlp2_bwd", lambda: _lib.check(lib.mdl_edge_mlp2_bwd(P(g), P(rs), P(w2), P(T1), P(dp1), E, F_, F_, 0, st), "b"),
           nbytes=4 * E * (3 * F_ + 1), flops=2.0 * E * F_ * F_, cold=cold)
     for impl in ("tc", "simt"):
