@@ -308,16 +308,43 @@ def kernel_roofline(args, dev, flush_buf, peak, peak_src):
             ts.append(a.elapsed_time(c))
         return float(np.mean(ts)), float(np.min(ts))
 
+    # smearing-fused form: the kernels take d_hat [E] (slot order) and expand the Gaussian basis themselves
+    dh = torch.rand(E, device=dev)
+    offset = torch.linspace(0.0, 1.0, G, device=dev)
+    coeff = -0.5 / 0.2 ** 2
+
+    def fwd_fused():
+        _lib.check(lib.mdl_cgconv_smear_fwd(P(x), P(PQ), P(dh), P(offset), coeff, P(WeT), P(csr.dst_ptr), P(csr.dst_src),
+                                            P(csr.dst_dst), P(csr.inv_deg_dst), P(out), N, E, C, G, 1, st), "fwd fused")
+
+    def bwd_fused():
+        _lib.check(lib.mdl_cgconv_smear_bwd(P(gout), P(PQ), P(dh), P(offset), coeff, P(WeT), P(csr.dst_ptr), P(csr.dst_src),
+                                            P(csr.dst_dst), P(csr.inv_deg_dst), P(dPQ), P(dWeT), N, E, C, G, 1, P(ws),
+                                            ws_bytes, st), "bwd fused")
+
     f_ms, f_min = time_it(fwd)
     b_ms, b_min = time_it(bwd)
+    ff_ms, ff_min = time_it(fwd_fused)
+    bf_ms, bf_min = time_it(bwd_fused)
     bytes_fwd = 8 * N * C + 8 * E + 4 * E * G          # SURVEY.md 8d, operator-surface form
     bytes_bwd = bytes_fwd + 4 * N * C                   # whole backward (both passes)
+    bytes_fwd_fused = 8 * N * C + 12 * E                # SURVEY.md 8d, smearing-fused form (d_hat instead of edge_attr)
+    bytes_bwd_fused = bytes_fwd_fused + 4 * N * C
     res = {
         "workload": f"{base_graphs * reps} bulk graphs (N={N}, E={E}, C={C}, G={G}), cold L2",
         "fwd": {"ms": f_ms, "ms_min": f_min, "algorithmic_bytes": bytes_fwd,
                 "achieved_gbs": bytes_fwd / f_ms / 1e6, "frac": bytes_fwd / f_ms / 1e6 / peak},
         "bwd_both_passes": {"ms": b_ms, "ms_min": b_min, "algorithmic_bytes": bytes_bwd,
                             "achieved_gbs": bytes_bwd / b_ms / 1e6, "frac": bytes_bwd / b_ms / 1e6 / peak},
+        # the same operator with GaussianSmearing fused into the kernels (mdl_cgconv_smear_fwd / _bwd): the time is
+        # what a user gets; its fraction is quoted in BOTH SURVEY 8(d) accountings -- against the bytes the
+        # operator-surface form would have moved (208 B/edge) and against its own 12 B/edge
+        "fwd_smear_fused": {"ms": ff_ms, "ms_min": ff_min, "algorithmic_bytes_fused_form": bytes_fwd_fused,
+                            "frac_fused_form": bytes_fwd_fused / ff_ms / 1e6 / peak,
+                            "frac_operator_surface_form": bytes_fwd / ff_ms / 1e6 / peak},
+        "bwd_smear_fused": {"ms": bf_ms, "ms_min": bf_min, "algorithmic_bytes_fused_form": bytes_bwd_fused,
+                            "frac_fused_form": bytes_bwd_fused / bf_ms / 1e6 / peak,
+                            "frac_operator_surface_form": bytes_bwd / bf_ms / 1e6 / peak},
         "edge_flops_fwd": 2.0 * E * G * 2 * C, "fwd_tflops_fp32": 2.0 * E * G * 2 * C / f_ms / 1e9,
     }
     return res
@@ -517,12 +544,15 @@ def run_engine(args, rank, world, local_rank):
                 f, bw = r["fwd"], r["bwd_both_passes"]
                 line["roofline"] = {"bound": "hbm", "achieved": f["achieved_gbs"], "peak": peak, "unit": "GB/s",
                                     "frac": f["frac"], "traffic": None,
-                                    "kernel": "k_cgconv_fwd_pipe (fused gather -> message -> scatter_add, the kernel the "
+                                    "kernel": "k_cgconv_fwd_ws (fused gather -> message -> scatter_add, the kernel the "
                                               "north star's roofline target names)",
                                     "fwd_frac": f["frac"], "bwd_frac": bw["frac"],
                                     "bwd": {"kernel": "k_cgconv_bwd_pipe (whole CGConv backward: single pass, dP + dW_e + dQ)",
                                             "achieved": bw["achieved_gbs"], "frac": bw["frac"], "ms": bw["ms"]},
                                     "form": "operator-surface: 8NC + 8E + 4EG bytes forward, + 4NC backward (SURVEY.md 8d)",
+                                    "smear_fused": {"fwd": r["fwd_smear_fused"], "bwd": r["bwd_smear_fused"],
+                                                    "form": "kernels take d_hat [E] and expand GaussianSmearing inside: "
+                                                            "8NC + 12E bytes forward"},
                                     "traffic_note": "dram bytes per launch are in profiles/ (ncu --set full), not re-measured here",
                                     "peak_source": peak_src, "workload": r["workload"]}
                 line["roofline_detail"] = r

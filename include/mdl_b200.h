@@ -133,6 +133,27 @@ MDL_API int mdl_cgconv_bwd(const float* grad_out, const float* PQ, const float* 
                    int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
                    int32_t reduce, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- CGConv, smearing-fused form.  The reference expands every edge's normalised distance into a Gaussian basis
+ * once, at dataset build (matdeeplearn/process/process.py:500-502 calling GaussianSmearing, process.py:580-590:
+ * e[k] = exp(coeff * (d_hat - offset[k])^2), offset = linspace(start, stop, G)), and its CGConv layers then read the
+ * [E, G] tensor from memory in every layer of every step (cgcnn.py:136-145).  These entry points take d_hat [E]
+ * (slot order, i.e. permuted by dst_eid like `ea` above) plus the module's `offset` buffer [G] (device; uniform
+ * spacing, G >= 2) and `coeff`, and expand the basis inside the fused edge kernels: 4 B instead of 4 G B per edge.
+ * Same operator, outputs and gradients as mdl_cgconv_fwd / _bwd on ea = GaussianSmearing(d_hat) (basis within
+ * 2e-6 of torch.exp's).  mdl_cgconv_smear_supported: 1 if (C, G) is served by the tensor-core kernels that
+ * implement this form (C = 64, G <= 64, no MDL_CGCONV_* kernel switch in the environment); otherwise the caller
+ * materialises ea (mdl_gaussian_smear) and uses the entry points above. ---- */
+MDL_API int mdl_cgconv_smear_supported(int32_t C, int32_t G);
+MDL_API int mdl_cgconv_smear_fwd(const float* x, const float* PQ, const float* d_hat, const float* offset, float coeff,
+                   const float* We, const int32_t* dst_ptr, const int32_t* dst_src, const int32_t* dst_dst,
+                   const float* inv_deg_dst, float* out,
+                   int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G, int32_t reduce, void* stream);
+MDL_API int mdl_cgconv_smear_bwd(const float* grad_out, const float* PQ, const float* d_hat, const float* offset,
+                   float coeff, const float* We, const int32_t* dst_ptr, const int32_t* dst_src,
+                   const int32_t* dst_dst, const float* inv_deg_dst, float* dPQ, float* dWe,
+                   int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G,
+                   int32_t reduce, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- CFConv aggregate, PyG CFConv inside InteractionBlock as built at reference
  * matdeeplearn/models/schnet.py:81 and called schnet.py:134-143:
  *   out[i,:] = sum_{p in [ptr[i],ptr[i+1])} h[nbr[p],:] * w[eid[p],:]

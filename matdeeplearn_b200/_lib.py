@@ -63,6 +63,10 @@ SIGNATURES = {
     "mdl_cgconv_pack_weights": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "mdl_cgconv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "mdl_cgconv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
+    "mdl_cgconv_smear_supported": (C.c_int, [_i32, _i32]),
+    "mdl_cgconv_smear_fwd": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
+    "mdl_cgconv_smear_bwd": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p,
+                                       _sz, _p]),
     "mdl_spmm_edge": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "mdl_edge_mul": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "mdl_edge_gather_add": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_assemble(const AsmArgs a) {
         for (int j = lane; j < G; j += 32) to[j] = __ldg(from + j);
       }
     }
-  } else {
+  } else if (o.edge_attr || o.edge_attr_slots) {  // neither: the batch keeps the 4 B/edge form (fused CGConv kernels)
     for (int64_t k = warp; k < e; k += nwarps) {
       const float d_ref = o.edge_attr ? __ldg(s.d_hat + ep + k) : 0.f;
       const float d_slot = o.edge_attr_slots ? __ldg(s.d_hat + __ldg(s.dst_eid + ep + k)) : 0.f;

@@ -493,6 +493,79 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
   return MDL_OK;
 }
 
+// ---- smearing-fused form: the kernels take the normalised distance d_hat[E] (slot order) and expand the Gaussian
+// basis themselves (reference GaussianSmearing, process.py:580-590, applied at process.py:500-502) -- 4 B per edge
+// of HBM traffic per layer instead of 4 G.  Tensor-core kernels only (cgconv_fwd_ws.cu, cgconv_bwd.cu).
+namespace mdl {
+static bool smear_env_ok() {
+  const char* a = getenv("MDL_CGCONV_IMPL");
+  const char* b = getenv("MDL_CGCONV_BWD");
+  const char* d = getenv("MDL_CGCONV_DETERMINISTIC");
+  return !(a && a[0]) && !(b && b[0]) && !(d && d[0] == '1');
+}
+static CgParams smear_params(const float* PQ, const float* d_hat, const float* offset, float coeff, const float* WeT,
+                             const int32_t* dst_ptr, const int32_t* dst_src, const int32_t* dst_dst,
+                             const float* inv_deg, int reduce, int64_t N, int64_t E, int C, int G) {
+  CgParams p{};
+  p.PQ = PQ; p.dhat = d_hat; p.sm_offset = offset; p.sm_coeff = coeff; p.WeT = WeT; p.seg_ptr = dst_ptr;
+  p.dst_src = dst_src; p.dst_dst = dst_dst; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg : nullptr;
+  p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
+  return p;
+}
+}  // namespace mdl
+
+extern "C" int mdl_cgconv_smear_supported(int32_t C, int32_t G) {
+  if (!smear_env_ok() || G < 2) return 0;
+  static const float dummy = 0.0f;
+  CgParams p{};
+  p.dhat = &dummy; p.C = C; p.G = G; p.N = 1; p.E = 1;
+  return (cgws_supported(p) && cgbwd_supported(p)) ? 1 : 0;
+}
+
+extern "C" int mdl_cgconv_smear_fwd(const float* x, const float* PQ, const float* d_hat, const float* offset, float coeff,
+                                    const float* WeT, const int32_t* dst_ptr, const int32_t* dst_src,
+                                    const int32_t* dst_dst, const float* inv_deg_dst, float* out, int64_t N, int64_t E,
+                                    int32_t C, int32_t G, int32_t reduce, void* stream) {
+  if (int rc = cg_check(N, E, C, G, reduce)) return rc;
+  MDL_REQUIRE(x && PQ && WeT && dst_ptr && out && offset && (E == 0 || (d_hat && dst_src && dst_dst)),
+              "cgconv_smear_fwd: null pointer");
+  MDL_REQUIRE(reduce != MDL_REDUCE_MEAN || inv_deg_dst, "cgconv_smear_fwd: mean needs inv_deg");
+  static const float dummy = 0.0f;
+  CgParams p = smear_params(PQ, d_hat ? d_hat : &dummy, offset, coeff, WeT, dst_ptr, dst_src, dst_dst, inv_deg_dst, reduce,
+                            N, E, C, G);
+  p.x = x; p.out = out;
+  MDL_REQUIRE(smear_env_ok() && G >= 2 && cgws_supported(p),
+              "cgconv_smear_fwd: C=%d G=%d (or the kernel switches in the environment) not supported by the fused form", C, G);
+  return cgws_launch(p, as_stream(stream));
+}
+
+extern "C" int mdl_cgconv_smear_bwd(const float* gout, const float* PQ, const float* d_hat, const float* offset,
+                                    float coeff, const float* WeT, const int32_t* dst_ptr, const int32_t* dst_src,
+                                    const int32_t* dst_dst, const float* inv_deg_dst, float* dPQ, float* dWeT, int64_t N,
+                                    int64_t E, int32_t C, int32_t G, int32_t reduce, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (int rc = cg_check(N, E, C, G, reduce)) return rc;
+  MDL_REQUIRE(gout && PQ && WeT && dst_ptr && dPQ && dWeT && offset && (E == 0 || (d_hat && dst_src && dst_dst)),
+              "cgconv_smear_bwd: null pointer");
+  if (!workspace || workspace_bytes < mdl_cgconv_workspace_bytes(N, E, C, G)) {
+    set_error("cgconv_smear_bwd: workspace %zu < %zu", workspace_bytes, mdl_cgconv_workspace_bytes(N, E, C, G));
+    return MDL_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  static const float dummy = 0.0f;
+  CgParams p = smear_params(PQ, d_hat ? d_hat : &dummy, offset, coeff, WeT, dst_ptr, dst_src, dst_dst, inv_deg_dst, reduce,
+                            N, E, C, G);
+  p.gout = gout; p.out = dPQ; p.dW_part = (float*)workspace;
+  MDL_REQUIRE(smear_env_ok() && G >= 2 && cgbwd_supported(p),
+              "cgconv_smear_bwd: C=%d G=%d (or the kernel switches in the environment) not supported by the fused form", C, G);
+  // dQ[src] is accumulated with vector atomics inside the single pass: zero the Q half first (as mdl_cgconv_bwd)
+  MDL_CUDA(cudaMemset2DAsync(dPQ + 2 * C, (size_t)4 * C * 4, 0, (size_t)2 * C * 4, (size_t)N, st));
+  int grid = 0;
+  if (int rc = cgbwd_launch(p, st, &grid)) return rc;
+  const int64_t tot = (int64_t)G * 2 * C;
+  return sum_partials(p.dW_part, grid, tot, tot, dWeT, tot, nullptr, st);
+}
+
 namespace mdl {
 // lin_f / lin_s of the reference layer ([C, 2C+G] each, cat order x_i | x_j | e) -> the hoisted operands
 __global__ void k_cgconv_pack(const float* __restrict__ w_f, const float* __restrict__ b_f,

@@ -15,7 +15,10 @@ struct CgParams {
   const float* x;         // FWD  [N,C]
   const float* gout;      // BWD  [N,C]
   const float* PQ;        // [N,4C]
-  const float* ea;        // [E,G] slot order
+  const float* ea;        // [E,G] slot order (nullptr in the smearing-fused form)
+  const float* dhat;      // smearing-fused form: [E] slot order, normalised distances; the Gaussian basis
+  const float* sm_offset; //   e[k] = exp(sm_coeff (dhat - sm_offset[k])^2), sm_offset = linspace (uniform spacing), [G]
+  float sm_coeff;         //   (reference GaussianSmearing, process.py:580-590) is expanded inside the kernel
   const float* WeT;       // [G,2C] (k-major: f channels then s channels)
   const int32_t* seg_ptr; // dst_ptr (FWD, BWD_DST) or src_ptr (BWD_SRC)  [N+1]
   const int32_t* dst_src; // [E] slot -> source node

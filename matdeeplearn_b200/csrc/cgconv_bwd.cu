@@ -40,11 +40,12 @@ struct Plan {
   uint32_t offBhi, offBlo, offThi, offTlo, offEA, offV, offIdx, offInfo, total;
 };
 
-inline bool plan(int C, int G, Plan* pl) {
+inline bool plan(int C, int G, bool smear, Plan* pl) {
   if (C != kC || G < 1 || G > kKT) return false;
   const int KP = (G + 7) & ~7;
   const uint32_t b = (uint32_t)kNP * KP * 4, t = (uint32_t)(kRows / 4) * kTChunk;
-  const uint32_t ea = (((uint32_t)kRows * G * 4 + 32) + 15u) & ~15u, v = (uint32_t)kRows * kVW * 4;
+  // smearing-fused form: the edge rows are expanded from d_hat inside the split, no landing zone
+  const uint32_t ea = smear ? 0u : ((((uint32_t)kRows * G * 4 + 32) + 15u) & ~15u), v = (uint32_t)kRows * kVW * 4;
   const uint32_t idx = 4 * kRows * 4, info = kInfoCap * 16;
   pl->prof = g_bwd_phase_buf; pl->window = 1; pl->KP = KP;
   pl->offBhi = 0; pl->offBlo = b; pl->offThi = 2 * b; pl->offTlo = 2 * b + t; pl->offEA = 2 * b + 2 * t;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   __shared__ uint64_t bar_mma, bar_dwe, bar_ea;
   __shared__ uint32_t tmem_base_s;
   __shared__ int sMail[2][4];  // double-buffered {kind, cnt, next r_lo, next cnt (or -1)}: consumers -> issuer warp
+  __shared__ float sMu[64];    // smearing-fused form: the basis centres (GaussianSmearing.offset)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP;
   uint8_t* sBhi = smem + pl.offBhi;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
     reinterpret_cast<float*>(sThi)[i] = 0.0f;
     reinterpret_cast<float*>(sTlo)[i] = 0.0f;
   }
+  if (p.dhat && tid < 64) sMu[tid] = __ldg(p.sm_offset + min(tid, G - 1));
   umma::fence_proxy_async_smem();
   umma::fence_before_sync();
   __syncthreads();
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   uint32_t ph_mma = 0, ph_dwe = 0, ph_ea = 0;
 
   auto ea_bulk_bytes = [&](int r_lo, int cnt) -> uint32_t {
-    if (cnt <= 0) return 0u;
+    if (cnt <= 0 || p.dhat) return 0u;  // smearing-fused form: nothing to copy
     const long long first = (long long)r_lo * G;
     const uint32_t bytes = (uint32_t)(((int)(first & 3) + cnt * G) * 4);
     const bool more = ((long long)p.E * G - (first + (long long)cnt * G)) >= 3;
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   };
   bool dwe_pending = false;  // a dW_e batch has been handed to the issuer and not waited for yet
   bool dwe_ever = false;     // the dW_e accumulator has been written at all (else the partial is zero)
+  const SmearConst sc = p.dhat ? smear_const(sMu, G, p.sm_coeff) : SmearConst{0.0f, 0.0f, 0.0f};
   if (valid(cur)) {
     if (tid == 0) issue_ea_bulk(cur.r_lo, cur.cnt);
     if (tid < 2 * kRows) {
@@ -279,6 +283,8 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
     const int n0 = n_lo + warp;
     int seg_a = 0, seg_b = 0;
     if (n0 < n_hi) { seg_a = __ldg(p.seg_ptr + n0); seg_b = __ldg(p.seg_ptr + n0 + 1); }
+    // smearing-fused form: the normalised distance of this thread's slot (consumed by the split below)
+    const float dh = (p.dhat && (tid & (kRows - 1)) < cnt) ? __ldg(p.dhat + r_lo + (tid & (kRows - 1))) : 0.0f;
     mark(2);
 
     // ---- the last round's dW_e MMAs read the operand columns and the ea^T tiles: both are rewritten below
@@ -309,7 +315,12 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
         float v[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) v[t] = 0.0f;
-        if (e < cnt) {
+        if (p.dhat) {  // Gaussian basis of this slot, columns k0 .. k0 + 15 (reference process.py:580-590)
+          if (e < cnt) {
+            smear_chunk8(dh, sMu, k0, G, sc, *reinterpret_cast<float(*)[8]>(v));
+            smear_chunk8(dh, sMu, k0 + 8, G, sc, *reinterpret_cast<float(*)[8]>(v + 8));
+          }
+        } else if (e < cnt) {
           if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
 #pragma unroll
             for (int t = 0; t < 16; t += 2)
@@ -542,7 +553,7 @@ void cgbwd_set_phase_buffer(unsigned long long* dev_ptr) { g_bwd_phase_buf = dev
 // C = 64, G <= 64, 16-byte aligned ea / PQ / gout / dPQ (bulk copy, vector loads, vector atomics)
 bool cgbwd_supported(const CgParams& p) {
   Plan pl;
-  return plan(p.C, p.G, &pl) && (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 &&
+  return plan(p.C, p.G, p.dhat != nullptr, &pl) && (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(p.PQ) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.gout) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (int64_t)p.N * 4 * p.C < (int64_t)1 << 31;
 }
@@ -551,7 +562,7 @@ bool cgbwd_supported(const CgParams& p) {
 // partials in p.dW_part ([grid][G][2C]); *grid_out = number of partials
 int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out) {
   Plan pl;
-  MDL_REQUIRE(plan(p.C, p.G, &pl), "cgconv_bwd: unsupported shape C=%d G=%d", p.C, p.G);
+  MDL_REQUIRE(plan(p.C, p.G, p.dhat != nullptr, &pl), "cgconv_bwd: unsupported shape C=%d G=%d", p.C, p.G);
   const char* wenv = getenv("MDL_CGCONV_WINDOW");
   pl.window = !(wenv && wenv[0] == '0');
   p.c_off = 0; p.CC = p.C; p.cap = kRows; p.te = kTile;

@@ -57,12 +57,13 @@ struct WsPlan {
   uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, offIdx, offWin, offInfo, total;
 };
 
-bool ws_plan(int C, int G, WsPlan* pl) {
+// smear: the edge rows are expanded in the kernel from d_hat (no landing zone; its space goes to the node-row windows)
+bool ws_plan(int C, int G, bool smear, WsPlan* pl) {
   if (C != kC || G < 1) return false;
   const int KP = (G + 7) & ~7;
   if (2 * kNP + 4 * KP > kTmemColsW) return false;  // two accumulators + two hi/lo A-operand buffers
   const uint32_t b = (uint32_t)kNP * KP * 4;
-  const uint32_t ea = (((uint32_t)kRowsW * G * 4 + 32) + 15u) & ~15u;
+  const uint32_t ea = smear ? 0u : ((((uint32_t)kRowsW * G * 4 + 32) + 15u) & ~15u);
   const uint32_t v = (uint32_t)kRowsW * kVP * 4, idx = 2 * 2 * kRowsW * 4, win = 64, info = kInfoCapW * 16;
   const uint32_t fixed = 2 * b + ea + v + idx + win + info;
   if (fixed + 2 * 32 * kVW * 4 > (uint32_t)kMaxDynSmem) return false;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   __shared__ uint64_t bar_ea_full, bar_a_full[2], bar_mma[2], bar_acc_free[2], bar_rows_full[2], bar_rows_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int sRed[3][2];  // loaders: per-warp (min, max) of the round's source nodes
+  __shared__ float sMu[64];   // smearing-fused form: the basis centres (GaussianSmearing.offset), KP <= 64
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP, WR = pl.WR;
   const uint32_t sleep_ns = (uint32_t)pl.sleep_ns;
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     *reinterpret_cast<float*>(sBhi + off) = hi;
     *reinterpret_cast<float*>(sBlo + off) = w - hi;
   }
+  if (p.dhat && tid < 64) sMu[tid] = __ldg(p.sm_offset + min(tid, G - 1));
   umma::fence_proxy_async_smem();
   umma::fence_before_sync();
   __syncthreads();
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
 
   // ---- edge rows of a round: one bulk copy from the 16-byte boundary below the block (see cgconv_tc.cu)
   auto ea_bulk_bytes = [&](int r_lo, int cnt) -> uint32_t {
-    if (cnt <= 0) return 0u;
+    if (cnt <= 0 || p.dhat) return 0u;  // smearing-fused form: nothing to copy
     const long long first = (long long)r_lo * G;
     const uint32_t bytes = (uint32_t)(((int)(first & 3) + cnt * G) * 4);
     const bool more = ((long long)p.E * G - (first + (long long)cnt * G)) >= 3;
@@ -274,10 +277,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     // ---------------- splitters: thread = slot = TMEM lane; the whole edge row -> hi / lo -> tensor memory
     const int e = tid - kSplitWarp0 * 32;
     uint32_t ph_ea = 0, ph_m = 0, used = 0;
+    const SmearConst sc = p.dhat ? smear_const(sMu, G, p.sm_coeff) : SmearConst{0.0f, 0.0f, 0.0f};
     RoundW R = make_round(0, 0);
     for (uint32_t it = 0; valid(R); ++it) {
       const int b = it & 1;
       if (R.cnt > 0) {
+        // smearing-fused form: this slot's normalised distance (requested before the waits below)
+        const float dh = (p.dhat && e < R.cnt) ? __ldg(p.dhat + R.r_lo + e) : 0.0f;
         const uint32_t nb = ea_bulk_bytes(R.r_lo, R.cnt);
         if (nb) {
           WAIT(&bar_ea_full, ph_ea);
@@ -297,7 +303,9 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           float v[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] = 0.0f;
-          if (e < R.cnt) {
+          if (p.dhat) {  // Gaussian basis of this slot, columns 8 ch .. 8 ch + 7 (reference process.py:580-590)
+            if (e < R.cnt) smear_chunk8(dh, sMu, 8 * ch, G, sc, v);
+          } else if (e < R.cnt) {
             if ((G & 1) == 0) {  // rows start at an 8-byte offset: 8-byte loads
 #pragma unroll
               for (int t = 0; t < 8; t += 2)
@@ -490,7 +498,7 @@ bool cgws_supported(const CgParams& p) {
   WsPlan pl;
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTileW));
   const int64_t grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  return ws_plan(p.C, p.G, &pl) && ceil_div<int64_t>(n_tiles, grid) <= kInfoCapW &&
+  return ws_plan(p.C, p.G, p.dhat != nullptr, &pl) && ceil_div<int64_t>(n_tiles, grid) <= kInfoCapW &&
          (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.PQ) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0 &&
          (int64_t)p.N * 4 * p.C < (int64_t)1 << 31;
@@ -498,7 +506,7 @@ bool cgws_supported(const CgParams& p) {
 
 int cgws_launch(CgParams p, cudaStream_t st) {
   WsPlan pl;
-  MDL_REQUIRE(ws_plan(p.C, p.G, &pl), "cgconv_fwd_ws: unsupported shape C=%d G=%d", p.C, p.G);
+  MDL_REQUIRE(ws_plan(p.C, p.G, p.dhat != nullptr, &pl), "cgconv_fwd_ws: unsupported shape C=%d G=%d", p.C, p.G);
   const char* wenv = getenv("MDL_CGCONV_WINDOW");  // "0": node terms from global memory only (A/B and test switch)
   pl.window = !(wenv && wenv[0] == '0');
   const char* senv = getenv("MDL_WS_SLEEP");  // ns slept between mbarrier polls (A/B switch)

@@ -69,6 +69,31 @@ __device__ __forceinline__ void softplus_sigmoid_mufu(float x, float& sp, float&
   sg = x >= 0.0f ? r : t * r;
 }
 
+// ---- GaussianSmearing inside the edge kernels (reference process.py:580-590: exp(coeff (d - mu_k)^2), mu = linspace)
+// Eight consecutive basis values t_k .. t_{k+7} of one edge from two exponentials: with uniform spacing dmu,
+//   t_{k+1} = t_k rho_k,  rho_k = 2^(c2 dmu (dmu - 2 (d - mu_k))),  rho_{k+1} = rho_k q2,  q2 = 2^(2 c2 dmu^2)
+// (c2 = coeff log2 e).  The chunk restarts from the module's own mu_k0 (table `mu`), so position errors do not
+// accumulate beyond seven steps; measured against torch.exp(coeff * (d - mu)^2): <= 2e-6 of the basis' scale (1).
+struct SmearConst { float c2, dmu, q2; };
+__device__ __forceinline__ SmearConst smear_const(const float* mu, int G, float coeff) {
+  SmearConst s;
+  s.c2 = coeff * kLog2e;
+  s.dmu = (G > 1) ? (mu[G - 1] - mu[0]) / (float)(G - 1) : 0.0f;
+  s.q2 = ex2_(2.0f * s.c2 * s.dmu * s.dmu);
+  return s;
+}
+__device__ __forceinline__ void smear_chunk8(float d, const float* mu, int k0, int G, const SmearConst& s, float (&v)[8]) {
+  const float diff = d - mu[k0];
+  float t = ex2_(s.c2 * (diff * diff));
+  float rho = ex2_(s.c2 * s.dmu * (s.dmu - 2.0f * diff));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = (k0 + j < G) ? t : 0.0f;
+    t *= rho;
+    rho *= s.q2;
+  }
+}
+
 // ---- packed fp32 pairs (one FMA-pipe instruction per two values on sm_100)
 typedef unsigned long long f2_t;
 __device__ __forceinline__ f2_t pk2(float a, float b) {

@@ -216,12 +216,15 @@ extern "C" int mdl_linear_wgrad(const float* X, const float* G, int64_t N, int32
   if (int rc = wg_check_map(out, O, "linear_wgrad")) return rc;
   MDL_REQUIRE(X && G && workspace, "linear_wgrad: null pointer");
   MDL_REQUIRE(workspace_bytes >= wg_ws_bytes(N, I, O), "linear_wgrad: workspace too small");
-  {  // long batches (edge-level layers): the tcgen05 kernel (wgrad_tc.cu); MDL_WGRAD=simt keeps the SIMT one (A/B)
+  const size_t smem = (size_t)2 * kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
+  {  // long batches (edge-level layers, >= 16k rows) and layers too wide for the SIMT kernel's row stages: the tcgen05
+     // kernel (wgrad_tc.cu).  Node-level layers (a few thousand rows) stay on the SIMT kernel, which is faster there
+     // (profiles/r2_launches_c1_summary.txt: 24.8 vs 17.4 us).  MDL_WGRAD=simt / =tc force one or the other (A/B).
     const char* env = getenv("MDL_WGRAD");
-    if (!(env && strcmp(env, "simt") == 0) && wgrad_tc_supported(N, I, O))
+    const bool force_tc = env && strcmp(env, "tc") == 0, force_simt = env && strcmp(env, "simt") == 0;
+    if (!force_simt && wgrad_tc_supported(N, I, O) && (force_tc || N >= 16384 || smem > 200 * 1024))
       return wgrad_tc_launch(X, G, nullptr, N, I, O, *out, reinterpret_cast<float*>(workspace), as_stream(stream));
   }
-  const size_t smem = (size_t)2 * kWgRows * (wg_stride(I) + wg_stride(O)) * sizeof(float);
   // two stages of 32 rows of X and G: I + O <= ~780 floats per row pair (one CTA per SM above ~100 KB)
   MDL_REQUIRE(smem <= 200 * 1024, "linear_wgrad: layer too wide (needs %zu bytes of shared memory, I + O <= ~780)", smem);
   static std::atomic<int> attr_set{0};

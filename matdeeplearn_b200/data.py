@@ -16,6 +16,123 @@ from __future__ import annotations
 import torch
 
 
+class GaussianEdgeAttr:
+    """`edge_attr` in its 4-bytes-per-edge form: the normalised distance d_hat [E] plus the parameters of the
+    GaussianSmearing module that the reference applies once at dataset build (process/process.py:500-502,
+    580-590): edge_attr[e, k] = exp(coeff * (d_hat[e] - offset[k])^2), offset = linspace(start, stop, resolution),
+    coeff = -0.5 / ((stop - start) * width)^2.
+
+    It stands where the reference's [E, G] tensor stands (Batch.edge_attr, passed through the model files into the
+    conv layers untouched).  nn.CGConv consumes it directly -- the fused edge kernels expand the basis on the fly
+    (mdl_cgconv_smear_fwd / _bwd), so the [E, G] tensor never exists in HBM; every other consumer calls
+    `materialize()` (the GaussianSmearing kernel on CUDA, the module's formula on the host), cached per version
+    of d_hat."""
+
+    def __init__(self, d_hat, start=0.0, stop=1.0, resolution=50, width=0.2):
+        self.d_hat = d_hat
+        self.start, self.stop, self.resolution, self.width = float(start), float(stop), int(resolution), float(width)
+        self._offset = None
+        self._dense = None
+        self._slots = None
+
+    # ---- the tensor-like surface the reference's model code touches
+    @property
+    def shape(self):
+        return torch.Size((self.d_hat.shape[0], self.resolution))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 2
+
+    @property
+    def dtype(self):
+        return self.d_hat.dtype
+
+    @property
+    def device(self):
+        return self.d_hat.device
+
+    @property
+    def is_cuda(self):
+        return self.d_hat.is_cuda
+
+    @property
+    def requires_grad(self):
+        return False
+
+    @property
+    def coeff(self):
+        return -0.5 / ((self.stop - self.start) * self.width) ** 2
+
+    @property
+    def offset(self):
+        if self._offset is None or self._offset.device != self.d_hat.device or self._offset.dtype != self.d_hat.dtype:
+            self._offset = torch.linspace(self.start, self.stop, self.resolution, dtype=self.d_hat.dtype,
+                                          device=self.d_hat.device)
+        return self._offset
+
+    def params(self):
+        return dict(start=self.start, stop=self.stop, resolution=self.resolution, width=self.width)
+
+    def _like(self, d_hat):
+        return GaussianEdgeAttr(d_hat, **self.params())
+
+    def to(self, *a, **kw):
+        return self._like(self.d_hat.to(*a, **kw))
+
+    def pin_memory(self):
+        return self._like(self.d_hat.pin_memory())
+
+    def double(self):
+        return self._like(self.d_hat.double())
+
+    def fusable(self):
+        """True if the in-kernel expansion (two exponentials per 8 basis functions + a 7-step geometric
+        recurrence, csrc/edge_dev.cuh) is safe for these parameters: either no basis value of a distance within
+        one span of [start, stop] can underflow fp32 at all, or a value that underflows at the head of a chunk
+        cannot grow back to anything significant within the chunk."""
+        if self.resolution < 2 or self.d_hat.dtype != torch.float32:
+            return False
+        span = abs(self.stop - self.start)
+        c, dmu = abs(self.coeff), span / (self.resolution - 1)
+        return c * (2.0 * span) ** 2 <= 80.0 or 14.0 * c * dmu * 2.0 * span <= 50.0
+
+    def slots(self, csr):
+        """d_hat in the engine's slot (destination-major) order, memoised per (layout, version of d_hat)."""
+        hit = self._slots
+        if hit is not None and hit[0] is csr and hit[1] == self.d_hat._version:
+            return hit[2]
+        from .csr import gather_rows
+        out = gather_rows(self.d_hat.view(-1, 1), csr.dst_eid).view(-1)
+        self._slots = (csr, self.d_hat._version, out)
+        return out
+
+    def forget(self):
+        """Drop the memoised expansions (CUDA-graph capture: they must be recomputed inside the graph)."""
+        self._dense = None
+        self._slots = None
+
+    def materialize(self):
+        """The [E, G] tensor the reference stores (same formula, same offset buffer)."""
+        hit = self._dense
+        if hit is not None and hit[0] == self.d_hat._version and hit[1].device == self.d_hat.device:
+            return hit[1]
+        if self.d_hat.is_cuda and self.d_hat.dtype == torch.float32:
+            from . import functional as MF
+            dense = MF.gaussian_smear(self.d_hat, self.offset, self.coeff)
+        else:
+            dense = torch.exp(self.coeff * (self.d_hat.view(-1, 1) - self.offset.view(1, -1)) ** 2)
+        self._dense = (self.d_hat._version, dense)
+        return dense
+
+
+def dense_edge_attr(edge_attr):
+    """edge_attr as a tensor (GaussianEdgeAttr -> its [E, G] expansion)."""
+    return edge_attr.materialize() if isinstance(edge_attr, GaussianEdgeAttr) else edge_attr
+
+
 class Data:
     """One graph.  Attributes are plain tensors set by keyword."""
 
@@ -33,6 +150,10 @@ class Data:
 
     def keys(self):
         return [k for k, v in self.__dict__.items() if not k.startswith("_")]
+
+
+def _tensor_like(v):
+    return torch.is_tensor(v) or isinstance(v, GaussianEdgeAttr)
 
 
 class Batch(Data):
@@ -77,12 +198,23 @@ class Batch(Data):
         out.num_graphs = len(graphs)
         return out
 
+    def with_lazy_edge_attr(self):
+        """A shallow copy whose edge_attr is the 4 B/edge GaussianEdgeAttr(d_hat, smear parameters) instead of the
+        [E, G] tensor (batches made by process.assemble_dataset carry d_hat and `smear`)."""
+        smear = getattr(self, "smear", None)
+        if smear is None or not hasattr(self, "d_hat"):
+            raise ValueError("batch carries no d_hat / smear parameters")
+        out = Batch()
+        out.__dict__.update({k: v for k, v in self.__dict__.items() if not k.startswith("_")})
+        out.edge_attr = GaussianEdgeAttr(self.d_hat, **smear)
+        return out
+
     def to(self, device, non_blocking=False):
         out = Batch()
         for k, v in self.__dict__.items():
             if k.startswith("_"):
                 continue
-            setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+            setattr(out, k, v.to(device, non_blocking=non_blocking) if _tensor_like(v) else v)
         return out
 
     def pin_memory(self):
@@ -90,7 +222,7 @@ class Batch(Data):
         for k, v in self.__dict__.items():
             if k.startswith("_"):
                 continue
-            setattr(out, k, v.pin_memory() if torch.is_tensor(v) else v)
+            setattr(out, k, v.pin_memory() if _tensor_like(v) else v)
         return out
 
     def double(self):
@@ -98,7 +230,8 @@ class Batch(Data):
         for k, v in self.__dict__.items():
             if k.startswith("_"):
                 continue
-            setattr(out, k, v.double() if torch.is_tensor(v) and v.is_floating_point() else v)
+            setattr(out, k, v.double() if (torch.is_tensor(v) and v.is_floating_point()) or
+                    isinstance(v, GaussianEdgeAttr) else v)
         return out
 
 

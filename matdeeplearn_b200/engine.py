@@ -13,7 +13,7 @@ from collections import OrderedDict
 
 from . import _lib, dist as mdist
 from .csr import csr_for
-from .data import Batch
+from .data import Batch, GaussianEdgeAttr
 
 
 class TrainStep:
@@ -193,7 +193,9 @@ class TrainStep:
                 b.copy_(c)
 
     def _capture_store_step(self, store, B, idx):
-        static = store.static_batch(B)
+        # edge_attr in its 4 B/edge form whenever the store can provide it: CGConv expands the Gaussian basis inside
+        # its fused kernels, so no [E, G] tensor is assembled, permuted or read
+        static = store.static_batch(B, lazy=store.d_hat is not None and store.smear is not None)
         if not store.load(static, idx):
             raise RuntimeError("first batch exceeds the padded capacity; pass a typical batch first")
         distributed = mdist.is_distributed()
@@ -233,7 +235,9 @@ class TrainStep:
         from .csr import GraphCSR
         csr = GraphCSR.from_coo(static.edge_index, static.batch, num_nodes=static.x.shape[0], num_graphs=B)
         static.edge_index._mdl_csr = (static.edge_index._version, csr)  # what models' csr_for() will find
-        if hasattr(static.edge_attr, "_mdl_slots"):
+        if isinstance(static.edge_attr, GaussianEdgeAttr):
+            static.edge_attr.forget()                                     # re-expand / re-permute inside the graph
+        elif hasattr(static.edge_attr, "_mdl_slots"):
             del static.edge_attr._mdl_slots                               # re-permute inside the graph
         return csr
 
@@ -243,14 +247,10 @@ class TrainStep:
         names = list(Batch._TENSOR_KEYS)
         expand = None
         if smear is not None:
-            from . import functional as MF
+            # edge_attr stays in its 4 B/edge form: CGConv expands the basis inside its fused kernels, any other
+            # consumer materialises it (inside the graph: _layout_inside_graph drops the memoised copies)
             names = [n for n in names if n != "edge_attr"] + ["d_hat"]
-            offset = torch.linspace(smear["start"], smear["stop"], smear["resolution"], device=self.device)
-            coeff = -0.5 / ((smear["stop"] - smear["start"]) * smear["width"]) ** 2
-
-            def expand():
-                # raw-pointer write: _layout_inside_graph drops the cached slot-order copy right after
-                MF.gaussian_smear(static.d_hat, offset, coeff, out=static.edge_attr)
+            static.edge_attr = GaussianEdgeAttr(static.d_hat, **smear)
         distributed = mdist.is_distributed()
         snap = self._snapshot()      # the warm-up steps below must not count as training
         side = torch.cuda.Stream()

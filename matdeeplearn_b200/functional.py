@@ -356,14 +356,18 @@ def gaussian_smear(dist, offset, coeff, out=None):
 # CGConv
 # ----------------------------------------------------------------------------
 class CGConvFn(torch.autograd.Function):
-    """x[N,C], lin_f/lin_s weight [C, 2C+G] + bias [C], edge_attr in slot order."""
+    """x[N,C], lin_f/lin_s weight [C, 2C+G] + bias [C], edge_attr in slot order.
+
+    smear = None: ea_slots is the materialised edge_attr [E,G].  smear = (offset [G], coeff): the smearing-fused
+    form -- ea_slots is the normalised distance d_hat [E] in slot order and the kernels expand
+    exp(coeff * (d_hat - offset)^2) themselves (mdl_cgconv_smear_fwd / _bwd; reference process.py:580-590)."""
 
     @staticmethod
-    def forward(ctx, x, w_f, b_f, w_s, b_s, ea_slots, csr: GraphCSR, reduce):
+    def forward(ctx, x, w_f, b_f, w_s, b_s, ea_slots, csr: GraphCSR, reduce, smear=None):
         lib = _lib.load()
         x = x.contiguous()
         N, C = x.shape
-        G = ea_slots.shape[1]
+        G = ea_slots.shape[1] if smear is None else smear[0].shape[0]
         assert w_f.shape == (C, 2 * C + G) and w_s.shape == (C, 2 * C + G)
         # column split of lin(cat[x_i, x_j, e]) = W_i x_i + W_j x_j + W_e e + b
         Wn = torch.empty((4 * C, C), dtype=torch.float32, device=x.device)    # rows P_f | P_s | Q_f | Q_s
@@ -375,13 +379,20 @@ class CGConvFn(torch.autograd.Function):
         _lib.check(rc, "mdl_cgconv_pack_weights")
         PQ = torch.addmm(bias, x, Wn.t())                                              # [N, 4C]
         out = torch.empty_like(x)
-        rc = lib.mdl_cgconv_fwd(_lib.ptr(x), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
-                                _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src), _lib.ptr(csr.dst_dst),
-                                _lib.ptr(csr.inv_deg_dst), _lib.ptr(out), N, csr.E, C, G,
-                                _lib.REDUCE[reduce], _lib.stream())
-        _lib.check(rc, "mdl_cgconv_fwd")
+        if smear is None:
+            rc = lib.mdl_cgconv_fwd(_lib.ptr(x), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
+                                    _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src), _lib.ptr(csr.dst_dst),
+                                    _lib.ptr(csr.inv_deg_dst), _lib.ptr(out), N, csr.E, C, G,
+                                    _lib.REDUCE[reduce], _lib.stream())
+            _lib.check(rc, "mdl_cgconv_fwd")
+        else:
+            rc = lib.mdl_cgconv_smear_fwd(_lib.ptr(x), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(smear[0]),
+                                          float(smear[1]), _lib.ptr(WeT), _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src),
+                                          _lib.ptr(csr.dst_dst), _lib.ptr(csr.inv_deg_dst), _lib.ptr(out), N, csr.E,
+                                          C, G, _lib.REDUCE[reduce], _lib.stream())
+            _lib.check(rc, "mdl_cgconv_smear_fwd")
         ctx.save_for_backward(x, PQ, Wn, WeT, ea_slots)
-        ctx.csr, ctx.reduce = csr, reduce
+        ctx.csr, ctx.reduce, ctx.smear = csr, reduce, smear
         ctx.has_bias = (b_f is not None, b_s is not None)
         ctx.params = (w_f, b_f, w_s, b_s)
         return out
@@ -392,7 +403,8 @@ class CGConvFn(torch.autograd.Function):
         x, PQ, Wn, WeT, ea_slots = ctx.saved_tensors
         csr = ctx.csr
         N, C = x.shape
-        G = ea_slots.shape[1]
+        smear = ctx.smear
+        G = WeT.shape[0]
         g = g.contiguous()
         # mean aggregation: d(mean)/d(message) = 1/deg(dst); applied once per node here instead of
         # once per edge inside the kernel
@@ -401,12 +413,20 @@ class CGConvFn(torch.autograd.Function):
         dWeT = torch.empty_like(WeT)
         ws_bytes = lib.mdl_cgconv_workspace_bytes(N, csr.E, C, G)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        rc = lib.mdl_cgconv_bwd(_lib.ptr(gk), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
-                                _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src), _lib.ptr(csr.dst_dst),
-                                _lib.ptr(csr.src_ptr), _lib.ptr(csr.src_slot),
-                                _lib.ptr(csr.inv_deg_dst), _lib.ptr(dPQ), _lib.ptr(dWeT), N, csr.E,
-                                C, G, _lib.REDUCE[ctx.reduce], _lib.ptr(ws), ws_bytes, _lib.stream())
-        _lib.check(rc, "mdl_cgconv_bwd")
+        if smear is None:
+            rc = lib.mdl_cgconv_bwd(_lib.ptr(gk), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(WeT),
+                                    _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src), _lib.ptr(csr.dst_dst),
+                                    _lib.ptr(csr.src_ptr), _lib.ptr(csr.src_slot),
+                                    _lib.ptr(csr.inv_deg_dst), _lib.ptr(dPQ), _lib.ptr(dWeT), N, csr.E,
+                                    C, G, _lib.REDUCE[ctx.reduce], _lib.ptr(ws), ws_bytes, _lib.stream())
+            _lib.check(rc, "mdl_cgconv_bwd")
+        else:
+            rc = lib.mdl_cgconv_smear_bwd(_lib.ptr(gk), _lib.ptr(PQ), _lib.ptr(ea_slots), _lib.ptr(smear[0]),
+                                          float(smear[1]), _lib.ptr(WeT), _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src),
+                                          _lib.ptr(csr.dst_dst), _lib.ptr(csr.inv_deg_dst), _lib.ptr(dPQ),
+                                          _lib.ptr(dWeT), N, csr.E, C, G, _lib.REDUCE[ctx.reduce], _lib.ptr(ws),
+                                          ws_bytes, _lib.stream())
+            _lib.check(rc, "mdl_cgconv_smear_bwd")
         dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
         # node-level dense tail: plain library GEMMs (a hand-written split-over-nodes kernel was
         # measured slower than cuBLAS + a column sum here and was dropped)
@@ -429,7 +449,7 @@ class CGConvFn(torch.autograd.Function):
             _lib.check(rc, "mdl_copy_mapped")
             for prm in (w_f, w_s) + ((b_f,) if ctx.has_bias[0] else ()) + ((b_s,) if ctx.has_bias[1] else ()):
                 prm._mdl_written = True
-            return dx, None, None, None, None, None, None, None
+            return dx, None, None, None, None, None, None, None, None
         dWn = dPQ.t().mm(x)                                                 # [4C, C]
         db = dPQ[:, :2 * C].sum(0)
         return CGConvFn._finish(ctx, dx, dWn, db, dWeT, C)
@@ -441,11 +461,15 @@ class CGConvFn(torch.autograd.Function):
         dw_s = torch.cat([dWn[C:2 * C], dWn[3 * C:4 * C], dWe[C:2 * C]], 1)
         db_f = db[:C] if ctx.has_bias[0] else None
         db_s = db[C:] if ctx.has_bias[1] else None
-        return dx, dw_f, db_f, dw_s, db_s, None, None, None
+        return dx, dw_f, db_f, dw_s, db_s, None, None, None, None
 
 
-def cgconv(x, w_f, b_f, w_s, b_s, ea_slots, csr, reduce="mean"):
-    return CGConvFn.apply(x, w_f, b_f, w_s, b_s, ea_slots, csr, reduce)
+def cgconv(x, w_f, b_f, w_s, b_s, ea_slots, csr, reduce="mean", smear=None):
+    return CGConvFn.apply(x, w_f, b_f, w_s, b_s, ea_slots, csr, reduce, smear)
+
+
+def cgconv_smear_supported(C, G):
+    return bool(_lib.load().mdl_cgconv_smear_supported(int(C), int(G)))
 
 
 # ----------------------------------------------------------------------------

@@ -16,6 +16,7 @@ from torch import nn as tnn
 from . import functional as MF
 from . import nn as mnn
 from .csr import csr_for
+from .data import dense_edge_attr
 
 
 def _target_dim(dataset):
@@ -324,7 +325,7 @@ class MEGNet(tnn.Module):
         h = data.x
         for lin in self.pre_lin_list:
             h = act(lin(h))
-        x, e, u = h, data.edge_attr, data.u
+        x, e, u = h, dense_edge_attr(data.edge_attr), data.u
         for i, block in enumerate(self.conv_list):
             e_t = MF.apply_mlp(self.e_embed_list[i], e)     # edge-level: long batch -> tensor-core weight gradients
             x_t, u_t = MF.apply_mlp(self.x_embed_list[i], x), self.u_embed_list[i](u)

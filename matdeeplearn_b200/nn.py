@@ -20,6 +20,7 @@ from torch import nn
 
 from . import functional as MF
 from .csr import GraphCSR, csr_for
+from .data import GaussianEdgeAttr, dense_edge_attr
 
 _AGGR = {"mean": "mean", "add": "sum", "sum": "sum", "max": "max"}
 
@@ -126,6 +127,15 @@ class CGConv(nn.Module):
         _require_cuda(x, "CGConv")
         if csr is None:
             csr = csr_for(edge_index, num_nodes=x.shape[0])
+        if isinstance(edge_attr, GaussianEdgeAttr):
+            # smearing-fused form: the kernels take the normalised distance (4 B/edge) and expand the Gaussian
+            # basis themselves; edge_attr [E, G] never exists (reference process.py:580-590 inside the conv pass)
+            if (MF.cgconv_smear_supported(self.channels, edge_attr.resolution) and x.dtype == torch.float32
+                    and edge_attr.fusable()):
+                dh = edge_attr.slots(csr)
+                return MF.cgconv(x, self.lin_f.weight, self.lin_f.bias, self.lin_s.weight, self.lin_s.bias,
+                                 dh, csr, _AGGR[self.aggr], smear=(edge_attr.offset, edge_attr.coeff))
+            edge_attr = edge_attr.materialize()
         ea = csr.to_slots(edge_attr)
         return MF.cgconv(x, self.lin_f.weight, self.lin_f.bias, self.lin_s.weight, self.lin_s.bias,
                          ea, csr, _AGGR[self.aggr])
@@ -235,6 +245,7 @@ class CFConv(nn.Module):
 
     def forward(self, x, edge_index, edge_weight, edge_attr, csr: GraphCSR | None = None):
         _require_cuda(x, "CFConv")
+        edge_attr = dense_edge_attr(edge_attr)
         if csr is None:
             csr = csr_for(edge_index, num_nodes=x.shape[0])
         C = 0.5 * (torch.cos(edge_weight * math.pi / self.cutoff) + 1.0)
@@ -305,6 +316,7 @@ class NNConv(nn.Module):
 
     def forward(self, x, edge_index, edge_attr, csr: GraphCSR | None = None):
         _require_cuda(x, "NNConv")
+        edge_attr = dense_edge_attr(edge_attr)
         if csr is None:
             csr = csr_for(edge_index, num_nodes=x.shape[0])
         Ci, Co = self.in_channels, self.out_channels

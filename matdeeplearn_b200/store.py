@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .csr import GraphCSR
-from .data import Batch
+from .data import Batch, GaussianEdgeAttr
 
 
 def _box_lengths(structures):
@@ -234,15 +234,20 @@ class GraphStore:
         np.cumsum(self.n_edges[idx], out=m[2, 1:])
         return meta, B, int(m[1, B]), int(m[2, B])
 
-    def _alloc(self, B, N, E, layout, slots, d_hat):
-        """Output tensors for a batch of capacity (N nodes, E edges) + the ctypes descriptor."""
+    def _alloc(self, B, N, E, layout, slots, d_hat, lazy=False):
+        """Output tensors for a batch of capacity (N nodes, E edges) + the ctypes descriptor.
+        lazy: edge_attr stays in its 4 B/edge form (data.GaussianEdgeAttr over the batch's d_hat; the fused
+        CGConv kernels expand it on the fly) -- no [E, G] tensor is assembled at all."""
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         i64 = dict(dtype=torch.int64, device=dev)
+        if lazy and (self.d_hat is None or self.smear is None):
+            raise ValueError("lazy edge_attr needs a store that holds d_hat and the smearing parameters")
+        d_hat = d_hat or lazy
         out = Batch(
             x=torch.empty((N, self.F), **f32), edge_index=torch.empty((2, E), **i64),
-            edge_attr=torch.empty((E, self.G), **f32), edge_weight=torch.empty(E, **f32),
+            edge_attr=None if lazy else torch.empty((E, self.G), **f32), edge_weight=torch.empty(E, **f32),
             batch=torch.empty(N, **i64), u=torch.empty((B, self.U), **f32),
             y=torch.empty((B,) + self.y_shape, **f32))
         out.num_graphs = B
@@ -250,6 +255,9 @@ class GraphStore:
             if self.d_hat is None:
                 raise ValueError("store holds no d_hat")
             out.d_hat = torch.empty(E, **f32)
+        if lazy:
+            out.edge_attr = GaussianEdgeAttr(out.d_hat, **self.smear)
+            slots = False
         csr = ea_slots = None
         if layout:
             csr = object.__new__(GraphCSR)
@@ -275,7 +283,8 @@ class GraphStore:
         P = _lib.ptr
         desc = _lib.BatchOutC(
             B, N, E, meta_d[0].data_ptr(), meta_d[1].data_ptr(), meta_d[2].data_ptr(),
-            P(out.x), P(out.edge_index), P(getattr(out, "d_hat", None)), P(out.edge_weight), P(out.edge_attr),
+            P(out.x), P(out.edge_index), P(getattr(out, "d_hat", None)), P(out.edge_weight),
+            P(out.edge_attr if torch.is_tensor(out.edge_attr) else None),
             P(ea_slots), P(out.batch), P(out.u), P(out.y),
             *([P(csr.dst_ptr), P(csr.dst_src), P(csr.dst_dst), P(csr.dst_eid), P(csr.src_ptr), P(csr.src_slot),
                P(csr.inv_deg_dst), P(csr.inv_deg_src), P(csr.graph_ptr)] if csr is not None else [None] * 9),
@@ -283,13 +292,13 @@ class GraphStore:
         rc = _lib.load().mdl_assemble_batch(C.byref(self._c), C.byref(desc), _lib.stream())
         _lib.check(rc, "mdl_assemble_batch")
 
-    def batch(self, idx, layout=True, slots=True, d_hat=False):
+    def batch(self, idx, layout=True, slots=True, d_hat=False, lazy=False):
         """Assemble graphs `idx` (host sequence / numpy / CPU tensor, in that order) into a Batch on
         the store's device.  With layout=True the returned batch already carries its GraphCSR (found
         by csr_for()) and, with slots=True, the slot-ordered edge_attr (found by GraphCSR.to_slots)."""
         meta, B, N, E = self._meta(idx)
         meta_d = meta.to(self.device, non_blocking=True)   # ids + both prefix sums in one small copy
-        out, csr, ea_slots = self._alloc(B, N, E, layout, slots, d_hat)
+        out, csr, ea_slots = self._alloc(B, N, E, layout, slots, d_hat, lazy)
         self._launch(out, csr, ea_slots, meta_d, B, N, E)
         return out
 
@@ -305,14 +314,14 @@ class GraphStore:
             caps.append((cap + align - 1) // align * align + 1)   # +1: at least one padding row
         return tuple(caps)
 
-    def static_batch(self, B, N_cap=None, E_cap=None, d_hat=False):
+    def static_batch(self, B, N_cap=None, E_cap=None, d_hat=False, lazy=False):
         """Persistent padded batch buffers of fixed shape.  `load(static, idx)` stages the ids of the
         next batch; `assemble(static)` (capturable in a CUDA graph: it reads ids and sizes from device
         memory) fills the buffers.  Rows past the real batch are inert padding (include/mdl_b200.h),
         and `static._n_valid` is the device-side real node count for masked statistics."""
         if N_cap is None or E_cap is None:
             N_cap, E_cap = self.capacities(B)
-        out, csr, ea_slots = self._alloc(B, int(N_cap), int(E_cap), True, True, d_hat)
+        out, csr, ea_slots = self._alloc(B, int(N_cap), int(E_cap), True, True, d_hat, lazy)
         out._meta_d = torch.zeros((3, B + 1), dtype=torch.int64, device=self.device)
         out._n_valid = csr.graph_ptr[B:B + 1]
         out._parts = (csr, ea_slots)
@@ -335,4 +344,6 @@ class GraphStore:
     def assemble(self, static):
         csr, ea_slots = static._parts
         self._launch(static, csr, ea_slots, static._meta_d, csr.B, csr.N, csr.E)
+        if isinstance(static.edge_attr, GaussianEdgeAttr):
+            static.edge_attr.forget()   # d_hat was rewritten in place: slot-order / dense copies are recomputed
         return static
