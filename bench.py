@@ -83,6 +83,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak_tf32():
+    """Dense TF32 tensor-core peak in TFLOP/s: half the bf16 figure (measured cuBLAS bf16 burst in MEASURED_PEAKS.json,
+    else the nominal 2250)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["bf16_tflops"]) / 2.0, "measured bf16_tflops / 2 (MEASURED_PEAKS.json)"
+    return 1125.0, "nominal bf16 2250 / 2 (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -386,19 +395,41 @@ def aux_roofline(args, dev, flush_buf, peak):
         fn = lambda: MF.nnconv_message(hid, XT, XB, csr)                  # noqa: E731
         nbytes, kernel = 4 * E * K + 4 * E * O + 4 * N * (K * O + O) + 4 * E, "k_nnconv_msg (NNConv re-associated message)"
         form = "4*E*K (hidden) + 4*E*O (messages) + 4*N*(K*O+O) (per-node products) + 4*E (edge ids), K=O=64"
-    with torch.no_grad():
-        for _ in range(3):
-            fn()
-        ts = []
-        for _ in range(10):
-            flush_l2(flush_buf)
-            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); e.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(e))
-    ms = float(np.mean(ts))
-    return {"kernel": kernel, "workload": f"{base * reps} {c['kind']} graphs (N={N}, E={E}), cold L2", "ms": ms,
-            "algorithmic_bytes": nbytes, "form": form, "achieved_gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    def time_it(f):
+        with torch.no_grad():
+            for _ in range(3):
+                f()
+            ts = []
+            for _ in range(10):
+                flush_l2(flush_buf)
+                a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); f(); e.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(e))
+        return float(np.mean(ts))
+
+    ms = time_it(fn)
+    res = {"kernel": kernel, "workload": f"{base * reps} {c['kind']} graphs (N={N}, E={E}), cold L2", "ms": ms,
+           "algorithmic_bytes": nbytes, "form": form, "achieved_gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    if args.config == 2:
+        # the filter network + cutoff of the interaction (k_edge_mlp2_fwd, tcgen05 3xTF32): tensor-bound
+        G = b.edge_attr.shape[1]
+        ea = b.edge_attr.repeat(reps, 1).contiguous()
+        w1, b1 = torch.randn(Fw, G, device=dev) * 0.1, torch.randn(Fw, device=dev) * 0.1
+        w2, b2 = torch.randn(Fw, Fw, device=dev) * 0.1, torch.randn(Fw, device=dev) * 0.1
+        rs = torch.rand(E, device=dev)
+        ms2 = time_it(lambda: MF.edge_mlp2(ea, w1, b1, w2, b2, rs, "ssp"))
+        flops = 2.0 * E * (G * Fw + Fw * Fw)
+        tpeak, tsrc = tensor_peak_tf32()
+        res["filter_mlp"] = {"kernel": "k_edge_mlp2_fwd (SchNet filter network + cosine cutoff, two chained 3xTF32 tcgen05 "
+                                       "contractions per 128-edge round)", "ms": ms2, "algorithmic_flops": flops,
+                             "achieved_tflops": flops / ms2 / 1e9, "peak_tflops_tf32": tpeak, "peak_source": tsrc,
+                             "frac": flops / ms2 / 1e9 / tpeak,
+                             "note": "3xTF32 issues 3 tensor-core products per algorithmic one; fraction of the tf32 "
+                                     "pipe actually busy is 3x this",
+                             "algorithmic_bytes": 4 * E * G + 4 * E + 4 * E * Fw,
+                             "achieved_gbs": (4 * E * G + 4 * E + 4 * E * Fw) / ms2 / 1e6}
+    return res
 
 
 def run_engine(args, rank, world, local_rank):
@@ -505,7 +536,7 @@ def run_engine(args, rank, world, local_rank):
             "workload": workload_string(args.config, args.scaling, world),
             "graphs_per_step": graphs_total, "nodes_per_gpu": head["nodes_per_gpu"], "edges_per_gpu": head["edges_per_gpu"],
             "parallelism": f"dp{world}", "step": "zero_grad+fwd+l1_loss+bwd" +
-            ("+flat grad allreduce(NCCL, eager)+AdamW, two CUDA graph replays around the collective"
+            ("+flat grad allreduce (NCCL, captured inside the step's CUDA graph)+AdamW, one CUDA graph replay"
              if world > 1 else "+AdamW, one CUDA graph replay") +
             " (the metric text says fwd+bwd; the optimizer step is included, as in the reference's train() body)",
             "l2": "flushed between timed steps (512 MiB read-modify-write)",
@@ -561,6 +592,8 @@ def run_engine(args, rank, world, local_rank):
                 line["roofline"] = {"bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s",
                                     "frac": r["frac"], "traffic": None, "kernel": r["kernel"], "form": r["form"],
                                     "peak_source": peak_src, "workload": r["workload"], "ms": r["ms"]}
+                if "filter_mlp" in r:
+                    line["roofline"]["filter_mlp"] = r["filter_mlp"]
         if not args.no_cpu_baseline and world == 1:
             threads, table = best_cpu_threads(args, 1)
             ts, graphs, _ = cpu_step_times(args, 1, args.cpu_steps, 1, threads=threads)

@@ -48,6 +48,7 @@ constexpr int kC = 64, kNP = 2 * kC;
 constexpr int kVW = 2 * kC + 4;                   // row stride of the node-row tiles (bank spread)
 constexpr int kVP = kC + 4;                       // row stride of the message tile
 constexpr int kTmemColsW = 512;
+constexpr int kIdxRing = 4;                     // index / window-record buffers (staged one live round ahead of the node rows)
 
 unsigned long long* g_ws_phase_buf = nullptr;
 
@@ -64,7 +65,7 @@ bool ws_plan(int C, int G, bool smear, WsPlan* pl) {
   if (2 * kNP + 4 * KP > kTmemColsW) return false;  // two accumulators + two hi/lo A-operand buffers
   const uint32_t b = (uint32_t)kNP * KP * 4;
   const uint32_t ea = smear ? 0u : ((((uint32_t)kRowsW * G * 4 + 32) + 15u) & ~15u);
-  const uint32_t v = (uint32_t)kRowsW * kVP * 4, idx = 2 * 2 * kRowsW * 4, win = 64, info = kInfoCapW * 16;
+  const uint32_t v = (uint32_t)kRowsW * kVP * 4, idx = kIdxRing * 2 * kRowsW * 4, win = kIdxRing * 16, info = kInfoCapW * 16;
   const uint32_t fixed = 2 * b + ea + v + idx + win + info;
   if (fixed + 2 * 32 * kVW * 4 > (uint32_t)kMaxDynSmem) return false;
   int WR = (int)(((uint32_t)kMaxDynSmem - fixed) / (2 * kVW * 4)) & ~7;
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   uint8_t* sBlo = smem + pl.offBlo;
   float* sEA = reinterpret_cast<float*>(smem + pl.offEA);   // landing zone of a round's edge rows
   float* sV = reinterpret_cast<float*>(smem + pl.offV);     // [128][VP] per-slot messages
-  int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);     // [2 buffers][src | dst][128]
-  int4* sWin = reinterpret_cast<int4*>(smem + pl.offWin);   // [2 buffers] {window?, src min, dst min, nq}
+  int* sIdx = reinterpret_cast<int*>(smem + pl.offIdx);     // [kIdxRing][src | dst][128]
+  int4* sWin = reinterpret_cast<int4*>(smem + pl.offWin);   // [kIdxRing] {window?, src min, dst min, nq}
   TileInfo* sInfo = reinterpret_cast<TileInfo*>(smem + pl.offInfo);
   auto sWbuf = [&](int b) { return reinterpret_cast<float*>(smem + pl.offW + (uint32_t)b * pl.wbytes); };
 
@@ -221,53 +222,72 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       }
       __syncwarp();
     } else {
-      // ---------------- loaders: indices, window decision, node rows of a round
+      // ---------------- loaders: indices, window decision, node rows of a round.  Live rounds (cnt > 0) are counted
+      // by j on both sides: node rows in buffer j & 1, indices + window record in ring slot j & 3.  The indices and
+      // the window decision of live round j + 1 are staged while round j's rows are in flight, so what follows the
+      // consumers' release of a row buffer is only the bulk copies themselves.
       const int lt = tid - kLoadWarp0 * 32, lw = warp - kLoadWarp0;
       auto sync_loaders = [] { asm volatile("bar.sync 3, %0;" ::"n"(kLoaders) : "memory"); };
-      uint32_t ph_rf = 0, used = 0;
-      RoundW R = make_round(0, 0);
-      for (uint32_t it = 0; valid(R); ++it) {
-        const int b = it & 1;
-        if (R.cnt > 0) {
-          if ((used >> b) & 1) {  // consumers have finished with this buffer (two rounds ago)
-            WAIT(&bar_rows_free[b], (ph_rf >> b) & 1);
-            ph_rf ^= 1u << b;
-          }
-          int* bS = sIdx + b * 2 * kRowsW;
-          int s_lo = 0x7fffffff, s_hi = -1;
-          for (int i = lt; i < 2 * kRowsW; i += kLoaders) {
-            const int e = i & (kRowsW - 1);
-            int v = 0;
-            if (e < R.cnt) {
-              v = __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e);
-              if (i < kRowsW) { s_lo = min(s_lo, v); s_hi = max(s_hi, v); }
-            }
-            bS[i] = v;
-          }
-          s_lo = __reduce_min_sync(0xffffffffu, s_lo);
-          s_hi = __reduce_max_sync(0xffffffffu, s_hi);
-          if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
-          sync_loaders();  // indices and per-warp ranges visible to all loaders
-          s_lo = min(sRed[0][0], min(sRed[1][0], sRed[2][0]));
-          s_hi = max(sRed[0][1], max(sRed[1][1], sRed[2][1]));
-          const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
-          const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
-          const bool win = pl.window && nq + np_ <= WR;
-          const int nrows = win ? nq + np_ : 0;
-          if (lt == 0) {
-            sWin[b] = make_int4(win ? 1 : 0, s_lo, d_lo, nq);
-            if (nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)nrows * (uint32_t)(2 * kC * 4));
-            else mbar_arrive(&bar_rows_full[b]);
-          }
-          float* W = sWbuf(b);
-          for (int r = lt; r < nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
-            const float* g = (r < nq) ? p.PQ + (size_t)(s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(d_lo + r - nq) * (4 * kC);
-            umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
-          }
-          used |= 1u << b;
-          sync_loaders();  // sRed is rewritten next round
+      struct Dec { int win, s_lo, d_lo, nq, nrows; };
+      auto next_live = [&](RoundW R) { while (valid(R) && R.cnt == 0) R = next_round(R); return R; };
+      auto load_idx = [&](const RoundW& R, int (&v)[3]) {  // this thread's (up to) three indices: global loads in flight
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = lt + kLoaders * k, e = i & (kRowsW - 1);
+          v[k] = (i < 2 * kRowsW && e < R.cnt) ? __ldg((i < kRowsW ? p.dst_src : p.dst_dst) + R.r_lo + e) : 0;
         }
-        R = next_round(R);
+      };
+      auto finish_idx = [&](const RoundW& R, int slot, const int (&v)[3]) -> Dec {
+        int* bS = sIdx + slot * 2 * kRowsW;
+        int s_lo = 0x7fffffff, s_hi = -1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = lt + kLoaders * k, e = i & (kRowsW - 1);
+          if (i < 2 * kRowsW) {
+            if (i < kRowsW && e < R.cnt) { s_lo = min(s_lo, v[k]); s_hi = max(s_hi, v[k]); }
+            bS[i] = v[k];
+          }
+        }
+        s_lo = __reduce_min_sync(0xffffffffu, s_lo);
+        s_hi = __reduce_max_sync(0xffffffffu, s_hi);
+        if (lane == 0) { sRed[lw][0] = s_lo; sRed[lw][1] = s_hi; }
+        sync_loaders();  // indices and per-warp ranges visible to all loaders
+        s_lo = min(sRed[0][0], min(sRed[1][0], sRed[2][0]));
+        s_hi = max(sRed[0][1], max(sRed[1][1], sRed[2][1]));
+        const int d_lo = bS[kRowsW], d_hi = bS[kRowsW + R.cnt - 1];  // slots are sorted by destination
+        const int nq = s_hi - s_lo + 1, np_ = d_hi - d_lo + 1;
+        const bool win = pl.window && nq + np_ <= WR;
+        if (lt == 0) sWin[slot] = make_int4(win ? 1 : 0, s_lo, d_lo, nq);
+        sync_loaders();  // sRed is rewritten by the next call
+        return Dec{win ? 1 : 0, s_lo, d_lo, nq, win ? nq + np_ : 0};
+      };
+      uint32_t ph_rf = 0;
+      RoundW R = next_live(make_round(0, 0));
+      Dec D{0, 0, 0, 0, 0};
+      int v[3];
+      if (valid(R)) {
+        load_idx(R, v);
+        D = finish_idx(R, 0, v);
+      }
+      for (uint32_t j = 0; valid(R); ++j) {
+        const int b = j & 1;
+        const RoundW Rn = next_live(next_round(R));
+        if (valid(Rn)) load_idx(Rn, v);
+        if (j >= 2) {  // consumers have finished with this row buffer (live round j - 2)
+          WAIT(&bar_rows_free[b], (ph_rf >> b) & 1);
+          ph_rf ^= 1u << b;
+        }
+        if (lt == 0) {
+          if (D.nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)D.nrows * (uint32_t)(2 * kC * 4));
+          else mbar_arrive(&bar_rows_full[b]);
+        }
+        float* W = sWbuf(b);
+        for (int r = lt; r < D.nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
+          const float* g = (r < D.nq) ? p.PQ + (size_t)(D.s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(D.d_lo + r - D.nq) * (4 * kC);
+          umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
+        }
+        if (valid(Rn)) D = finish_idx(Rn, (int)((j + 1) & (kIdxRing - 1)), v);
+        R = Rn;
       }
     }
     __syncthreads();  // teardown barrier of the CTA
@@ -357,12 +377,14 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   const int q = warp & 3, part = warp >> 2;  // TMEM lane quadrant, channel quarter (16 channels)
   const int c_begin = part * 16;
   uint32_t ph_r = 0, ph_m = 0;
+  uint32_t live = 0;  // live rounds (cnt > 0) so far: node rows in buffer live & 1, indices / window record in ring slot live & 3
   RoundW cur = make_round(0, 0);
   for (uint32_t it = 0; valid(cur); ++it) {
-    const int b = it & 1;
+    const int b = it & 1;                                        // accumulator / A-operand buffer (issuer, splitters)
+    const int jb = live & 1, js = live & (kIdxRing - 1);         // node-row buffer, index ring slot (loaders)
     const int cnt = cur.cnt, r_lo = cur.r_lo, r_hi = cur.r_lo + cur.cnt;
     const int n_lo = sInfo[cur.k].n_lo, n_hi = sInfo[cur.k].n_hi;
-    const int* bSrc = sIdx + b * 2 * kRowsW;
+    const int* bSrc = sIdx + js * 2 * kRowsW;
     const int* bDst = bSrc + kRowsW;
     mark(0);
     // ---- reduce-stage node data of this warp's first segment (global loads in flight across the epilogue)
@@ -377,13 +399,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
     }
     if (cnt > 0) {
-      WAIT(&bar_rows_full[b], (ph_r >> b) & 1);  // indices, window record, node rows of this round
-      ph_r ^= 1u << b;
+      WAIT(&bar_rows_full[jb], (ph_r >> jb) & 1);  // indices, window record, node rows of this round
+      ph_r ^= 1u << jb;
       mark(1);
-      const int4 wr = sWin[b];
+      const int4 wr = sWin[js];
       const bool win = wr.x != 0;
       const int w_smin = wr.y, w_dmin = wr.z, w_nq = wr.w;
-      const float* sW = sWbuf(b);
+      const float* sW = sWbuf(jb);
       WAIT(&bar_mma[b], (ph_m >> b) & 1);         // this round's contraction
       ph_m ^= 1u << b;
       umma::fence_after_sync();
@@ -401,15 +423,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       const int e_ep = 32 * q + lane;
       if (e_ep < cnt) {
         const int sd = bDst[e_ep], ss = bSrc[e_ep];
-        const float* r0 = win ? sW + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
-        const float* r1 = win ? sW + (ss - w_smin) * kVW + c_begin : p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
         float* rowv = sV + e_ep * kVP + c_begin;
         const f2_t cf = pk2(-kLog2e, -kLog2e), cs = pk2(kLog2e, kLog2e);
-        auto run = [&](auto ld) {  // ld: how the node rows are read (shared or global memory)
+        auto run = [&](auto ldP, auto ldQ) {  // how the P[dst] / Q[src] rows are read (shared or global memory), by float offset
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 pf = ld(r0 + j4), ps = ld(r0 + kC + j4);
-            const float4 qf = ld(r1 + j4), qs = ld(r1 + kC + j4);
+            const float4 pf = ldP(j4), ps = ldP(kC + j4);
+            const float4 qf = ldQ(j4), qs = ldQ(kC + j4);
             // y = accumulator (already in base-2 units: W_e is pre-scaled) + c (P + Q)
             float yf0, yf1, yf2, yf3, ys0, ys1, ys2, ys3;
             upk2(fma2(cf, add2(pk2(pf.x, pf.y), pk2(qf.x, qf.y)), pk2(f[j4], f[j4 + 1])), yf0, yf1);
@@ -422,11 +442,20 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
             *reinterpret_cast<float4*>(rowv + j4) = make_float4(m0, m1, m2, m3);
           }
         };
-        if (win) run([](const float* a) { return *reinterpret_cast<const float4*>(a); });
-        else run([](const float* a) { return __ldg(reinterpret_cast<const float4*>(a)); });
+        if (win) {  // explicit shared-space loads (a pointer that may be either space compiles to generic LD.E)
+          const uint32_t a0 = umma::smem_u32(sW + (w_nq + sd - w_dmin) * kVW + c_begin);
+          const uint32_t a1 = umma::smem_u32(sW + (ss - w_smin) * kVW + c_begin);
+          run([&](int o) { return umma::lds128(a0 + 4u * (uint32_t)o); }, [&](int o) { return umma::lds128(a1 + 4u * (uint32_t)o); });
+        } else {
+          const float* r0 = p.PQ + (size_t)sd * (4 * kC) + c_begin;
+          const float* r1 = p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
+          run([&](int o) { return __ldg(reinterpret_cast<const float4*>(r0 + o)); },
+              [&](int o) { return __ldg(reinterpret_cast<const float4*>(r1 + o)); });
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_rows_free[b]);  // indices / node rows of this buffer are no longer needed
+      if (lane == 0) mbar_arrive(&bar_rows_free[jb]);  // indices / node rows of this buffer are no longer needed
+      ++live;
     }
     mark(4);
     sync_consumers();  // [S3] message tile complete

@@ -122,6 +122,13 @@ __device__ __forceinline__ void ldg256(const float* p, float* v) {  // p 32-byte
                : "l"(p));
 }
 
+// 16 bytes from a shared-memory address (explicit state space: LDS, not a generic load)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // ---- TMEM -----------------------------------------------------------------------
 // whole warp; ncols power of two >= 32; result lands in *dst_smem
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

@@ -9,6 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+import os
 from collections import OrderedDict
 
 from . import _lib, dist as mdist
@@ -36,6 +37,10 @@ class TrainStep:
         self._host_graphs = OrderedDict()   # LRU: one static batch + graph pool per (N, E, B) shape
         self.max_host_graphs = 8
         self._store_graphs = {}
+        # multi-GPU: the flat gradient all-reduce is captured INSIDE the step's CUDA graph when the backend is NCCL
+        # (one replay per step; MDL_GRAPH_ALLREDUCE=0 keeps it as an eager call between two graphs)
+        self.graph_allreduce = (mdist.is_distributed() and torch.distributed.get_backend() == "nccl"
+                                and os.environ.get("MDL_GRAPH_ALLREDUCE", "1") != "0")
         if mdist.is_distributed():
             # what DDP's constructor does (reference training.py:262-266): every replica starts from rank 0's
             # parameters and buffers, whatever seed the caller built the model with
@@ -77,6 +82,39 @@ class TrainStep:
         self._finish()
         return loss
 
+    def _capture(self, batch, pre=None):
+        """Capture one step on `batch` (after `pre()`, e.g. batch assembly or the layout build, inside the graph).
+        Single GPU: one graph.  Multi-GPU: one graph with the NCCL all-reduce of the flat gradient buffer captured
+        between backward and AdamW (`graph_allreduce`), else backward | eager all-reduce | AdamW as two graphs.
+        Returns (replay, loss tensor, kernels launched by libmdl_b200.so per step [+1 for the collective])."""
+        distributed = mdist.is_distributed()
+        fused = distributed and self.graph_allreduce
+        g1 = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g1):
+            if pre is not None:
+                pre()
+            loss = self._fwd_bwd(batch)
+            if fused:
+                self._reduce()
+            if fused or not distributed:
+                self._opt_step()
+        g2 = None
+        if distributed and not fused:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._opt_step()
+        kernels = _lib.launch_count() - n0 + (1 if distributed else 0)
+
+        def replay():
+            g1.replay()
+            if g2 is not None:
+                self._reduce()
+                g2.replay()
+            return loss
+
+        return replay, loss, kernels
+
     # -- device-resident, graph-replayed ---------------------------------------
     def resident(self, batch: Batch, warmup=3):
         assert batch.x.is_cuda
@@ -91,29 +129,8 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._restore(snap)
-        distributed = mdist.is_distributed()
-        g1 = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        with torch.cuda.graph(g1):
-            loss = self._fwd_bwd(batch)
-            if not distributed:
-                self._opt_step()
-        self.kernels_per_step = _lib.launch_count() - n0
-        g2 = None
-        if distributed:
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self._opt_step()
-            self.kernels_per_step += 2
-
-        def replay():
-            g1.replay()
-            if g2 is not None:
-                self._reduce()
-                g2.replay()
-            return loss
-
-        self._graphs[id(batch)] = (g1, g2, loss, batch)
+        replay, loss, self.kernels_per_step = self._capture(batch)
+        self._graphs[id(batch)] = (replay, loss, batch)
         return replay
 
     # -- from pinned host memory (the call a user of the reference makes) -------
@@ -198,7 +215,6 @@ class TrainStep:
         static = store.static_batch(B, lazy=store.d_hat is not None and store.smear is not None)
         if not store.load(static, idx):
             raise RuntimeError("first batch exceeds the padded capacity; pass a typical batch first")
-        distributed = mdist.is_distributed()
         snap = self._snapshot()      # the warm-up steps below must not count as training
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -209,26 +225,7 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._restore(snap)
-        g1 = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        with torch.cuda.graph(g1):
-            store.assemble(static)
-            loss = self._fwd_bwd(static)
-            if not distributed:
-                self._opt_step()
-        self.store_kernels_per_step = _lib.launch_count() - n0 + (1 if distributed else 0)
-        g2 = None
-        if distributed:
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self._opt_step()
-
-        def replay():
-            g1.replay()
-            if g2 is not None:
-                self._reduce()
-                g2.replay()
-
+        replay, loss, self.store_kernels_per_step = self._capture(static, pre=lambda: store.assemble(static))
         return static, replay, loss
 
     def _layout_inside_graph(self, static, B):
@@ -245,43 +242,20 @@ class TrainStep:
         static = host_batch.to(self.device)
         static.num_graphs = B
         names = list(Batch._TENSOR_KEYS)
-        expand = None
         if smear is not None:
             # edge_attr stays in its 4 B/edge form: CGConv expands the basis inside its fused kernels, any other
             # consumer materialises it (inside the graph: _layout_inside_graph drops the memoised copies)
             names = [n for n in names if n != "edge_attr"] + ["d_hat"]
             static.edge_attr = GaussianEdgeAttr(static.d_hat, **smear)
-        distributed = mdist.is_distributed()
         snap = self._snapshot()      # the warm-up steps below must not count as training
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                if expand is not None:
-                    expand()
                 self._layout_inside_graph(static, B)
                 self.eager(static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._restore(snap)
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            if expand is not None:
-                expand()
-            self._layout_inside_graph(static, B)
-            loss = self._fwd_bwd(static)
-            if not distributed:
-                self._opt_step()
-        g2 = None
-        if distributed:
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self._opt_step()
-
-        def replay():
-            g1.replay()
-            if g2 is not None:
-                self._reduce()
-                g2.replay()
-
+        replay, loss, _ = self._capture(static, pre=lambda: self._layout_inside_graph(static, B))
         return static, replay, loss, names

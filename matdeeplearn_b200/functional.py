@@ -265,6 +265,34 @@ def segment_reduce(src, ptr, perm=None, reduce="mean"):
     return SegmentReduceFn.apply(src, ptr, perm, reduce, ptr.shape[0] - 1)
 
 
+class ExpandBySegmentFn(torch.autograd.Function):
+    """out[r] = src[s] for every row r of segment s (u[batch] in the reference: megnet.py:55, 99); the backward is
+    the segmented sum kernel over the same segments instead of torch's sort-based index_put."""
+
+    @staticmethod
+    def forward(ctx, src, index32, ptr):
+        from .csr import gather_rows
+        ctx.save_for_backward(ptr)
+        return gather_rows(src, index32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ptr,) = ctx.saved_tensors
+        return segment_reduce(g.contiguous(), ptr, None, "sum"), None, None
+
+
+def expand_by_segment(src, index, ptr):
+    """src[index] for a sorted `index` whose segments `ptr` (int32 [S+1]) describes (S = src.shape[0])."""
+    i32 = getattr(index, "_mdl_i32", None)
+    if i32 is None or i32[0] != index._version:
+        i32 = (index._version, index.to(torch.int32))
+        try:
+            index._mdl_i32 = i32
+        except Exception:
+            pass
+    return ExpandBySegmentFn.apply(src.contiguous(), i32[1], ptr)
+
+
 # ----------------------------------------------------------------------------
 # BatchNorm1d (training mode) with a device-side row count
 # ----------------------------------------------------------------------------
@@ -580,13 +608,14 @@ class EdgeGatherAddFn(torch.autograd.Function):
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
         csr = ctx.csr
-        dpre = (g * (out > 0)) if ctx.relu else g
+        dpre = torch.ops.aten.threshold_backward(g.contiguous(), out, 0.0) if ctx.relu else g   # g * [out > 0], one pass
         dpre = dpre.contiguous()
         dA = segment_reduce(dpre, csr.src_ptr, csr.source_order_eid(), "sum")   # edges leaving each node
         dB = segment_reduce(dpre, csr.dst_ptr, csr.dst_eid, "sum")              # edges entering each node
-        dU = segment_reduce(dA, csr.graph_ptr, None, "sum") if ctx.has[0] else None
-        dbias = dpre.sum(0) if ctx.has[1] else None
-        return dpre, dA, dB, dU, dbias, None, None, None, None
+        dU = segment_reduce(dA, csr.graph_ptr, None, "sum") if (ctx.has[0] or ctx.has[1]) else None
+        # column sums over E rows = column sums of the per-graph sums (B rows): no pass over the edge tensor
+        dbias = (dU.sum(0) if dU is not None else dpre.sum(0)) if ctx.has[1] else None
+        return dpre, dA, dB, (dU if ctx.has[0] else None), dbias, None, None, None, None
 
 
 def edge_gather_add(base, A, B, U, bias, edge_index, batch, csr, relu):

@@ -263,8 +263,8 @@ class Megnet_NodeModel(_MegnetStack):
         super().__init__(dim * 3, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers, "node_mlp")
 
     def forward(self, x, edge_index, edge_attr, u, batch):
-        v_e = mnn.scatter_mean(edge_attr, edge_index[0, :], dim=0)     # by SOURCE node (megnet.py:86)
-        return self._run(torch.cat([x, v_e, u[batch]], dim=1))
+        v_e = _edge_mean_by_source(edge_attr, edge_index)               # by SOURCE node (megnet.py:86)
+        return self._run(torch.cat([x, v_e, _expand_graph_rows(u, batch, x.shape[0])], dim=1))
 
 
 class Megnet_GlobalModel(_MegnetStack):
@@ -272,10 +272,34 @@ class Megnet_GlobalModel(_MegnetStack):
         super().__init__(dim * 3, dim, act, batch_norm, batch_track_stats, dropout_rate, fc_layers, "global_mlp")
 
     def forward(self, x, edge_index, edge_attr, u, batch):
-        u_e = mnn.scatter_mean(edge_attr, edge_index[0, :], dim=0)
+        u_e = _edge_mean_by_source(edge_attr, edge_index)               # megnet.py:130 (the same tensor as :86)
         u_e = mnn.scatter_mean(u_e, batch, dim=0)
         u_v = mnn.scatter_mean(x, batch, dim=0)
         return self._run(torch.cat([u_e, u_v, u], dim=1))
+
+
+def _edge_mean_by_source(edge_attr, edge_index):
+    """scatter_mean(edge_attr, edge_index[0]): the reference computes it in the node model (megnet.py:86) and again
+    in the global model (megnet.py:130) on the same tensors; here the second call reuses the first result (memoised
+    on the tensor object, valid for its current version)."""
+    hit = getattr(edge_attr, "_mdl_src_mean", None)
+    if hit is not None and hit[0] == edge_attr._version and hit[1] is edge_index:
+        return hit[2]
+    out = mnn.scatter_mean(edge_attr, edge_index[0, :], dim=0)
+    try:
+        edge_attr._mdl_src_mean = (edge_attr._version, edge_index, out)
+    except Exception:
+        pass
+    return out
+
+
+def _expand_graph_rows(u, batch, n):
+    """u[batch] (megnet.py:99); on CUDA through the gather kernel with the segmented sum as its backward."""
+    seg = getattr(batch, "_mdl_seg", None)
+    if u.is_cuda and u.dtype == torch.float32 and seg is not None and seg[0] == batch._version and seg[2] is None \
+            and seg[1].shape[0] - 1 == u.shape[0]:
+        return MF.expand_by_segment(u, batch, seg[1])
+    return u[batch]
 
 
 def MF_edge_gather_add(*args):
