@@ -504,8 +504,9 @@ def run_engine(args, rank, world, local_rank):
         e2e_ms, _ = timed_steps(lambda: call(), e2e_steps, flush_buf, world)
         h2d = getattr(step, "last_h2d_bytes", 0)
         head.update(e2e_steps=e2e_steps, e2e_full_ms=e2e_full_ms, e2e_ms=e2e_ms, h2d_full=h2d_full, h2d=h2d, graph_ok=graph_ok)
-        # (iii) dataset resident in HBM (store.GraphStore), padded replay: CGCNN only
-        if c["model"] == "CGCNN":
+        # (iii) dataset resident in HBM (store.GraphStore), batch assembled on the GPU into capacity-padded buffers,
+        # one graph replay per step (every model family)
+        try:
             from matdeeplearn_b200.store import GraphStore
             store = GraphStore.from_dataset(ds, dev)
             perm_rng = np.random.default_rng(1234 + rank)
@@ -515,6 +516,10 @@ def run_engine(args, rank, world, local_rank):
             it = iter(perms[3:])
             store_ms, _ = timed_steps(lambda: step.from_store(store, next(it)), e2e_steps, flush_buf, world)
             head["store_ms"] = store_ms
+            del store
+        except Exception as exc:
+            head["store_error"] = repr(exc)[:200]
+            torch.cuda.synchronize()
         head["clocks"] = sampler.stop() if rank == 0 else None
         del model, step, replay
         torch.cuda.empty_cache()
@@ -564,6 +569,8 @@ def run_engine(args, rank, world, local_rank):
                               "path": "TrainStep.from_store(GraphStore, idx): dataset resident in HBM, batch = index "
                                       "list -> one assembly kernel into capacity-padded buffers + the step, one CUDA "
                                       "graph replay; loss.item() each step"}
+    if "store_error" in head:
+        line["store_step"] = {"error": head["store_error"]}
     if len(sweep) > 1:
         line["edge_length_sweep"] = sweep_out
         line["epoch_100k_graphs_s"] = {g: 100000.0 / r["graphs_per_s"] for g, r in sweep_out.items()}

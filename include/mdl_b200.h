@@ -120,6 +120,10 @@ MDL_API int mdl_cgconv_pack_weights(const float* w_f, const float* b_f, const fl
  *      elementwise op the caller fuses with its other node work) returns dPQ [N,4C] (dP = sum over in-edges of da,
  *      dQ = sum over out-edges of da), dWe [2C,G]; the caller finishes with
  *      dense node-level GEMMs (dx = grad_out + dPQ . Wn, dWn = dPQ^T x). ---- */
+/* Which of the two entry points below run on the tcgen05 kernels for layer width C and edge width G under the default
+ * dispatch: bit 0 = forward (cgconv_fwd_ws.cu), bit 1 = backward (cgconv_bwd.cu).  They serve C >= 64 (multiple of 4)
+ * in 64-channel chunks and G <= 64; other shapes take the SIMT kernels (any C % 4 == 0, any G). */
+MDL_API int mdl_cgconv_tc_supported(int32_t C, int32_t G);
 MDL_API size_t mdl_cgconv_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t C, int32_t G);
 MDL_API int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, const float* We,
                    const int32_t* dst_ptr, const int32_t* dst_src, const int32_t* dst_dst,
@@ -208,6 +212,14 @@ MDL_API int mdl_nnconv_msg_bwd(const float* hid, const float* XT, const float* d
 MDL_API int mdl_build_neighbors(const double* pos, const double* cell, const int64_t* node_ptr,
                                 int64_t num_graphs, int32_t max_nodes, double radius, int32_t neighbors,
                                 int32_t* nbr_col, float* nbr_w, int32_t* cnt, void* stream);
+/* The same with general (triclinic) cells: lattice [num_graphs, 28] f64 (NULL = none) holds, per structure, the
+ * lattice vectors (rows, 9), their inverse (9), the image-shift range per axis (3), the per-axis periodicity flags (3)
+ * and a "general cell" flag (entry 24; 0 = use the box lengths in `cell`) -- what the reference obtains from ASE's
+ * get_all_distances(mic=True) on any cell (process.py:284-287).  The minimum-image search evaluates the host
+ * builder's expressions (process._general_minimum_image) in the same order: bit-identical distances. */
+MDL_API int mdl_build_neighbors_lattice(const double* pos, const double* cell, const double* lattice,
+                                        const int64_t* node_ptr, int64_t num_graphs, int32_t max_nodes, double radius,
+                                        int32_t neighbors, int32_t* nbr_col, float* nbr_w, int32_t* cnt, void* stream);
 MDL_API int mdl_build_emit(const int32_t* nbr_col, const float* nbr_w, const int32_t* cnt,
                            const int64_t* first_edge, const int64_t* loop_pos,
                            const int64_t* node_graph_start, const int32_t* numbers, int64_t num_nodes,

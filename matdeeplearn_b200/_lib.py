@@ -63,6 +63,7 @@ SIGNATURES = {
     "mdl_cgconv_pack_weights": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "mdl_cgconv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "mdl_cgconv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p]),
+    "mdl_cgconv_tc_supported": (C.c_int, [_i32, _i32]),
     "mdl_cgconv_smear_supported": (C.c_int, [_i32, _i32]),
     "mdl_cgconv_smear_fwd": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "mdl_cgconv_smear_bwd": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p,
@@ -73,6 +74,7 @@ SIGNATURES = {
     "mdl_nnconv_msg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "mdl_nnconv_msg_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "mdl_build_neighbors": (C.c_int, [_p, _p, _p, _i64, _i32, C.c_double, _i32, _p, _p, _p, _p]),
+    "mdl_build_neighbors_lattice": (C.c_int, [_p, _p, _p, _p, _i64, _i32, C.c_double, _i32, _p, _p, _p, _p]),
     "mdl_build_emit": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
     "mdl_assemble_batch": (C.c_int, [C.POINTER(GraphStoreC), C.POINTER(BatchOutC), _p]),
     "mdl_batchnorm_workspace_bytes": (_sz, [_i64, _i32]),

@@ -29,6 +29,43 @@ __device__ __forceinline__ double mic_delta(double a, double b, double L) {
   return d;
 }
 
+// General (triclinic) cell: the shortest lattice translate of the difference vector d.  `lat` = 28 doubles per
+// structure written by the host (process.lattice_record): cell rows [0..8], inverse [9..17], image-shift range per
+// axis [18..20], periodicity flags [21..23], "general cell" flag [24].  The expressions -- fractional coordinates,
+// wrap, Cartesian vector, image search in (i, j, k) order with a strict `<` -- are the host builder's
+// (process._general_minimum_image), evaluated with explicit round-to-nearest operations in the same order.
+__device__ __forceinline__ double mic_general_dist(double d0, double d1, double d2, const double* __restrict__ lat) {
+  const double* cell = lat;
+  const double* inv = lat + 9;
+  double frac[3], w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    frac[k] = __dadd_rn(__dadd_rn(__dmul_rn(d0, inv[k]), __dmul_rn(d1, inv[3 + k])), __dmul_rn(d2, inv[6 + k]));
+    if (lat[21 + k] != 0.0) frac[k] = __dsub_rn(frac[k], rint(frac[k]));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    w[c] = __dadd_rn(__dadd_rn(__dmul_rn(frac[0], cell[c]), __dmul_rn(frac[1], cell[3 + c])), __dmul_rn(frac[2], cell[6 + c]));
+  double b0 = w[0], b1 = w[1], b2 = w[2];
+  double best = __dadd_rn(__dadd_rn(__dmul_rn(b0, b0), __dmul_rn(b1, b1)), __dmul_rn(b2, b2));
+  const int n0 = (int)lat[18], n1 = (int)lat[19], n2 = (int)lat[20];
+  for (int i = -n0; i <= n0; ++i)
+    for (int j = -n1; j <= n1; ++j)
+      for (int k = -n2; k <= n2; ++k) {
+        if (i == 0 && j == 0 && k == 0) continue;
+        double c[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double shift = __dadd_rn(__dadd_rn(__dmul_rn((double)i, cell[a]), __dmul_rn((double)j, cell[3 + a])),
+                                         __dmul_rn((double)k, cell[6 + a]));
+          c[a] = __dadd_rn(w[a], shift);
+        }
+        const double d2v = __dadd_rn(__dadd_rn(__dmul_rn(c[0], c[0]), __dmul_rn(c[1], c[1])), __dmul_rn(c[2], c[2]));
+        if (d2v < best) { best = d2v; b0 = c[0]; b1 = c[1]; b2 = c[2]; }
+      }
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(b0, b0), __dmul_rn(b1, b1)), __dmul_rn(b2, b2)));
+}
+
 // (d, j) lexicographic minimum across the warp
 __device__ __forceinline__ void warp_argmin(double& d, int& j) {
 #pragma unroll
@@ -40,10 +77,11 @@ __device__ __forceinline__ void warp_argmin(double& d, int& j) {
 }
 
 __global__ void __launch_bounds__(kBuildThreads)
-k_build_neighbors(const double* __restrict__ pos, const double* __restrict__ cell,
+k_build_neighbors(const double* __restrict__ pos, const double* __restrict__ cell, const double* __restrict__ lattice,
                   const int64_t* __restrict__ node_ptr, double radius, int K, int max_n,
                   int32_t* __restrict__ nbr_col, float* __restrict__ nbr_w, int32_t* __restrict__ cnt) {
   extern __shared__ __align__(16) double bsm[];
+  __shared__ double sLat[28];
   double* sPos = bsm;                       // [max_n][3]
   double* sRow = bsm + 3 * (size_t)max_n;   // [warps][max_n]
   const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -53,12 +91,18 @@ k_build_neighbors(const double* __restrict__ pos, const double* __restrict__ cel
   const double Ly = cell ? __ldg(cell + 3 * (size_t)g + 1) : 0.0;
   const double Lz = cell ? __ldg(cell + 3 * (size_t)g + 2) : 0.0;
   for (int i = threadIdx.x; i < 3 * n; i += kBuildThreads) sPos[i] = __ldg(pos + 3 * n0 + i);
+  if (threadIdx.x < 28) sLat[threadIdx.x] = lattice ? __ldg(lattice + 28 * (size_t)g + threadIdx.x) : 0.0;
   __syncthreads();
+  const bool general = sLat[24] != 0.0;
   double* row = sRow + (size_t)warp * max_n;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   for (int i = warp; i < n; i += kBuildWarps) {
     const double xi = sPos[3 * i], yi = sPos[3 * i + 1], zi = sPos[3 * i + 2];
     for (int j = lane; j < n; j += 32) {
+      if (general) {
+        row[j] = mic_general_dist(__dsub_rn(xi, sPos[3 * j]), __dsub_rn(yi, sPos[3 * j + 1]), __dsub_rn(zi, sPos[3 * j + 2]), sLat);
+        continue;
+      }
       const double dx = mic_delta(xi, sPos[3 * j], Lx);
       const double dy = mic_delta(yi, sPos[3 * j + 1], Ly);
       const double dz = mic_delta(zi, sPos[3 * j + 2], Lz);
@@ -137,6 +181,14 @@ using namespace mdl;
 extern "C" int mdl_build_neighbors(const double* pos, const double* cell, const int64_t* node_ptr,
                                    int64_t num_graphs, int32_t max_nodes, double radius, int32_t neighbors,
                                    int32_t* nbr_col, float* nbr_w, int32_t* cnt, void* stream) {
+  return mdl_build_neighbors_lattice(pos, cell, nullptr, node_ptr, num_graphs, max_nodes, radius, neighbors, nbr_col,
+                                     nbr_w, cnt, stream);
+}
+
+extern "C" int mdl_build_neighbors_lattice(const double* pos, const double* cell, const double* lattice,
+                                           const int64_t* node_ptr, int64_t num_graphs, int32_t max_nodes,
+                                           double radius, int32_t neighbors, int32_t* nbr_col, float* nbr_w,
+                                           int32_t* cnt, void* stream) {
   MDL_REQUIRE(num_graphs >= 0 && max_nodes >= 0 && neighbors >= 0, "build_neighbors: bad shape");
   if (num_graphs == 0) return MDL_OK;
   MDL_REQUIRE(pos && node_ptr && nbr_col && nbr_w && cnt, "build_neighbors: null pointer");
@@ -152,7 +204,7 @@ extern "C" int mdl_build_neighbors(const double* pos, const double* cell, const 
     attr_set = true;
   }
   k_build_neighbors<<<(unsigned)num_graphs, kBuildThreads, smem, as_stream(stream)>>>(
-      pos, cell, node_ptr, radius, K, max_nodes, nbr_col, nbr_w, cnt);
+      pos, cell, lattice, node_ptr, radius, K, max_nodes, nbr_col, nbr_w, cnt);
   MDL_LAUNCHED();
   return MDL_OK;
 }

@@ -270,6 +270,13 @@ __global__ void k_cg_reduce_dw(const float* __restrict__ part, int nparts, int G
   dWeT[(size_t)k * (2 * C) + col] = acc;
 }
 
+int reduce_dw_partials(const float* part, int nparts, int G, int C, int c_off, int CC, float* dWeT, cudaStream_t st) {
+  const int tot = G * 2 * CC;
+  k_cg_reduce_dw<<<ceil_div(tot, 256), 256, 0, st>>>(part, nparts, G, C, c_off, CC, dWeT);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
 struct CgPlan {
   int CC, cap, te, nitem;
   size_t smem;
@@ -391,15 +398,18 @@ extern "C" int mdl_cgconv_fwd(const float* x, const float* PQ, const float* ea, 
   p.x = x; p.PQ = PQ; p.ea = ea; p.WeT = WeT; p.seg_ptr = dst_ptr; p.dst_src = dst_src;
   p.dst_dst = dst_dst; p.inv_deg = (reduce == MDL_REDUCE_MEAN) ? inv_deg_dst : nullptr;
   p.out = out; p.N = (int)N; p.E = (int)E; p.C = C; p.G = G;
-  if (use_tc(CG_FWD, C, G)) {
-    // default: the warp-specialised forward kernel (cgconv_fwd_ws.cu); MDL_CGCONV_IMPL=pipe selects the
-    // software-pipelined one (cgconv_fwd.cu), =tc the round-serial tensor-core kernel (A/B, and the shapes /
-    // alignments the others decline)
+  {
+    // default: the warp-specialised forward kernel (cgconv_fwd_ws.cu; any C >= 64 in 64-channel chunks);
+    // MDL_CGCONV_IMPL=pipe selects the software-pipelined one (cgconv_fwd.cu), =tc the round-serial tensor-core kernel
+    // (both C = 64 only: A/B, and the alignments the first declines), =simt the SIMT kernel below
     const char* env = getenv("MDL_CGCONV_IMPL");
     const bool want_tc = env && strcmp(env, "tc") == 0, want_pipe = env && strcmp(env, "pipe") == 0;
-    if (!want_tc && !want_pipe && cgws_supported(p)) return cgws_launch(p, as_stream(stream));
-    if (!want_tc && cgfwd_supported(p)) return cgfwd_launch(p, as_stream(stream));
-    return cgtc_launch(CG_FWD, p, as_stream(stream), nullptr);
+    const bool want_simt = env && strcmp(env, "simt") == 0;
+    if (!want_simt && !want_tc && !want_pipe && cgws_supported(p)) return cgws_launch(p, as_stream(stream));
+    if (use_tc(CG_FWD, C, G)) {
+      if (!want_tc && cgfwd_supported(p)) return cgfwd_launch(p, as_stream(stream));
+      return cgtc_launch(CG_FWD, p, as_stream(stream), nullptr);
+    }
   }
   p.cap = plan.cap; p.te = plan.te;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(E, plan.te));
@@ -439,18 +449,23 @@ extern "C" int mdl_cgconv_bwd(const float* gout, const float* PQ, const float* e
   // run to run).  MDL_CGCONV_DETERMINISTIC=1 selects the two-pass scheme (second pass over the
   // by-source view, fixed summation order, bitwise reproducible).
   const char* det_env = getenv("MDL_CGCONV_DETERMINISTIC");
-  const bool dq_atomic = use_tc(CG_BWD_DST, C, G) && !(det_env && det_env[0] == '1');
+  const char* ienv = getenv("MDL_CGCONV_IMPL");
+  const char* benv = getenv("MDL_CGCONV_BWD");
+  const bool det = det_env && det_env[0] == '1';
+  p.seg_ptr = dst_ptr;
+  // default single-pass kernel: both contractions on tcgen05 (cgconv_bwd.cu; any C >= 64 in 64-channel chunks);
+  // MDL_CGCONV_BWD=tc keeps the mma.sync one (C = 64, A/B), MDL_CGCONV_IMPL=simt the SIMT kernels
+  const bool pipe_ok = !det && !(ienv && strcmp(ienv, "simt") == 0) && !(benv && strcmp(benv, "tc") == 0) && cgbwd_supported(p);
+  const bool tc64 = use_tc(CG_BWD_DST, C, G);
+  const bool dq_atomic = pipe_ok || (tc64 && !det);
   if (dq_atomic)
     MDL_CUDA(cudaMemset2DAsync(dPQ + 2 * C, (size_t)4 * C * 4, 0, (size_t)2 * C * 4, (size_t)N, st));
   // pass A: destination order -> dP and dWe
-  if (use_tc(CG_BWD_DST, C, G)) {
-    p.seg_ptr = dst_ptr;
+  if (pipe_ok) {
+    if (int rc = cgbwd_launch(p, st, dWeT)) return rc;   // per 64-channel chunk: kernel + partial sums into dWeT
+  } else if (tc64) {
     int grid = 0;
-    // default single-pass kernel: dW_e on tcgen05 (cgconv_bwd.cu); MDL_CGCONV_BWD=tc keeps the mma.sync one (A/B)
-    const char* benv = getenv("MDL_CGCONV_BWD");
-    if (dq_atomic && !(benv && strcmp(benv, "tc") == 0) && cgbwd_supported(p)) {
-      if (int rc = cgbwd_launch(p, st, &grid)) return rc;
-    } else if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid, dq_atomic ? 1 : 0)) return rc;
+    if (int rc = cgtc_launch(CG_BWD_DST, p, st, &grid, dq_atomic ? 1 : 0)) return rc;
     const int64_t tot = (int64_t)G * 2 * C;  // partial layout [G][2C] == dWeT layout (no channel chunking)
     if (int rc = sum_partials(p.dW_part, grid, tot, tot, dWeT, tot, nullptr, st)) return rc;
   } else {
@@ -514,6 +529,14 @@ static CgParams smear_params(const float* PQ, const float* d_hat, const float* o
 }
 }  // namespace mdl
 
+extern "C" int mdl_cgconv_tc_supported(int32_t C, int32_t G) {
+  static const float dummy = 0.0f;
+  CgParams p{};
+  p.ea = nullptr; p.C = C; p.G = G; p.N = 1; p.E = 1;
+  (void)dummy;
+  return (cgws_supported(p) ? 1 : 0) | (cgbwd_supported(p) ? 2 : 0);
+}
+
 extern "C" int mdl_cgconv_smear_supported(int32_t C, int32_t G) {
   if (!smear_env_ok() || G < 2) return 0;
   static const float dummy = 0.0f;
@@ -560,10 +583,7 @@ extern "C" int mdl_cgconv_smear_bwd(const float* gout, const float* PQ, const fl
               "cgconv_smear_bwd: C=%d G=%d (or the kernel switches in the environment) not supported by the fused form", C, G);
   // dQ[src] is accumulated with vector atomics inside the single pass: zero the Q half first (as mdl_cgconv_bwd)
   MDL_CUDA(cudaMemset2DAsync(dPQ + 2 * C, (size_t)4 * C * 4, 0, (size_t)2 * C * 4, (size_t)N, st));
-  int grid = 0;
-  if (int rc = cgbwd_launch(p, st, &grid)) return rc;
-  const int64_t tot = (int64_t)G * 2 * C;
-  return sum_partials(p.dW_part, grid, tot, tot, dWeT, tot, nullptr, st);
+  return cgbwd_launch(p, st, dWeT);
 }
 
 namespace mdl {

@@ -29,6 +29,7 @@ struct CgParams {
   float* dW_part;         // BWD_DST: [gridDim.x][G][2*CC] partials
   int N, E, C, G;
   int c_off, CC;          // channel chunk handled by this launch
+  int c_skip;             // tensor-core backward: leading chunk channels whose dQ the previous chunk's launch added
   int cap, te, n_tiles;
 };
 
@@ -72,7 +73,9 @@ void cgws_set_phase_buffer(unsigned long long* dev_ptr);
 void lin_set_phase_buffer(unsigned long long* dev_ptr);  // linear_tc.cu (development aid)
 // single-pass backward with dW_e on tcgen05 (cgconv_bwd.cu)
 bool cgbwd_supported(const CgParams& p);
-int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out);
+int cgbwd_launch(CgParams p, cudaStream_t st, float* dWeT);
+// dWeT[k][chunk columns] = sum over the nparts per-CTA partials ([nparts][G][2 CC], f then s), fixed order (cgconv.cu)
+int reduce_dw_partials(const float* part, int nparts, int G, int C, int c_off, int CC, float* dWeT, cudaStream_t st);
 void cgbwd_set_phase_buffer(unsigned long long* dev_ptr);
 // out0[i] (i < len0) / out1[i - len0] = sum over nparts partial vectors, fixed order (cgconv.cu)
 int sum_partials(const float* part, int nparts, int64_t stride, int64_t len, float* out0, int64_t len0,

@@ -41,7 +41,7 @@ struct Plan {
 };
 
 inline bool plan(int C, int G, bool smear, Plan* pl) {
-  if (C != kC || G < 1 || G > kKT) return false;
+  if (C < kC || (C & 3) || G < 1 || G > kKT) return false;  // a launch serves 64 channels [c_off, c_off + 64) of a C-wide layer
   const int KP = (G + 7) & ~7;
   const uint32_t b = (uint32_t)kNP * KP * 4, t = (uint32_t)(kRows / 4) * kTChunk;
   // smearing-fused form: the edge rows are expanded from d_hat inside the split, no landing zone
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   __shared__ float sMu[64];    // smearing-fused form: the basis centres (GaussianSmearing.offset)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP;
+  const int C = p.C, c_off = p.c_off;  // layer width (row strides) and this launch's 64-channel chunk
   uint8_t* sBhi = smem + pl.offBhi;
   uint8_t* sBlo = smem + pl.offBlo;
   uint8_t* sThi = smem + pl.offThi;  // ea^T hi: element (k, slot) at (slot/4)*kTChunk + (k/8)*128 + (k%8)*16 + (slot%4)*4
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
   for (int i = tid; i < kNP * KP; i += kLaunch) {
     const int n = i % kNP, k = i / kNP;
     // exponents in base 2: the f-gate columns carry -log2(e), the s-gate columns +log2(e) (as cgconv_fwd_ws.cu)
-    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) * (n < kC ? -kLog2e : kLog2e) : 0.0f;
+    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * (2 * C) + (n < kC ? c_off + n : C + c_off + n - kC)) * (n < kC ? -kLog2e : kLog2e) : 0.0f;
     const float hi = umma::tf32_hi(w);
     const int off = umma::tile_offset_bytes(n, k, kNP);
     *reinterpret_cast<float*>(sBhi + off) = hi;
@@ -268,17 +269,19 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
       w_smin = s_lo; w_dmin = d_lo; w_nq = nq;
       nrows = win ? nq + np_ : cnt;
     }
-    auto row_src = [&](int r) -> const float4* {
+    // float4 `col` (0..31) of staged row r: the chunk's f piece (16 float4) then its s piece, C floats further on
+    // in a PQ row [P_f | P_s | Q_f | Q_s]
+    auto row_src = [&](int r, int col) -> const float4* {
       const float* g;
-      if (win) g = (r < w_nq) ? p.PQ + (size_t)(w_smin + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(w_dmin + r - w_nq) * (4 * kC);
-      else g = p.PQ + (size_t)bSrc[r] * (4 * kC) + 2 * kC;
-      return reinterpret_cast<const float4*>(g);
+      if (win) g = (r < w_nq) ? p.PQ + (size_t)(w_smin + r) * (4 * C) + 2 * C : p.PQ + (size_t)(w_dmin + r - w_nq) * (4 * C);
+      else g = p.PQ + (size_t)bSrc[r] * (4 * C) + 2 * C;
+      return reinterpret_cast<const float4*>(g + c_off + (col < 16 ? 0 : C - kC)) + col;
     };
     float4 rr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = tid + kThreads * i, r = c >> 5, col = c & 31;
-      if (r < nrows) rr[i] = __ldg(row_src(r) + col);
+      if (r < nrows) rr[i] = __ldg(row_src(r, col));
     }
     const int n0 = n_lo + warp;
     int seg_a = 0, seg_b = 0;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
       if (r < nrows) *(reinterpret_cast<float4*>(sV + r * kVW) + col) = rr[i];
     }
     for (int c = tid + kThreads * 4; c < nrows * 32; c += kThreads)
-      *(reinterpret_cast<float4*>(sV + (c >> 5) * kVW) + (c & 31)) = __ldg(row_src(c >> 5) + (c & 31));
+      *(reinterpret_cast<float4*>(sV + (c >> 5) * kVW) + (c & 31)) = __ldg(row_src(c >> 5, c & 31));
     if (valid(nxt) && tid < 2 * kRows) sIdx[(buf ^ 1) * 2 * kRows + tid] = nidx;
     if (tid == 0) post(0, cnt, nxt.r_lo, valid(nxt) ? nxt.cnt : -1);
     umma::fence_proxy_async_smem();
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
     for (int j = 0; j < 4; ++j) gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
       sd = bDst[e_ep];
-      const float4* gp = reinterpret_cast<const float4*>(p.gout + (size_t)sd * kC + c_begin);
+      const float4* gp = reinterpret_cast<const float4*>(p.gout + (size_t)sd * C + c_off + c_begin);
 #pragma unroll
       for (int j = 0; j < 4; ++j) gq[j] = __ldg(gp + j);
     }
@@ -400,14 +403,14 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
       umma::tmem_ld_wait();
       if (live) {
         const int ss = bSrc[e_ep];
-        const float* r0 = win ? sV + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * kC) + c_begin;
+        const float* r0 = win ? sV + (w_nq + sd - w_dmin) * kVW + c_begin : p.PQ + (size_t)sd * (4 * C) + c_off + c_begin;
         const float* r1 = win ? sV + (ss - w_smin) * kVW + c_begin : sV + e_ep * kVW + c_begin;
         const f2_t cf = pk2(-kLog2e, -kLog2e), cs = pk2(kLog2e, kLog2e);
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
           const float4 pf = win ? *reinterpret_cast<const float4*>(r0 + j4) : __ldg(reinterpret_cast<const float4*>(r0 + j4));
           const float4 ps = win ? *reinterpret_cast<const float4*>(r0 + kC + j4)
-                                : __ldg(reinterpret_cast<const float4*>(r0 + kC + j4));
+                                : __ldg(reinterpret_cast<const float4*>(r0 + C + j4));
           const float4 qf = *reinterpret_cast<const float4*>(r1 + j4);
           const float4 qs = *reinterpret_cast<const float4*>(r1 + kC + j4);
           // y = accumulator (base-2 units: W_e is pre-scaled) + c (P + Q), one packed fma per pair
@@ -476,9 +479,13 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
         const int e = row0 + i;
         if (e < cnt) {
           const float4 v = *(reinterpret_cast<const float4*>(sV + e * kVW) + lane);
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + (size_t)bSrc[e] * (4 * kC) + 2 * kC + 4 * lane),
-                       "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                       : "memory");
+          // lanes 0-15: dQ_f piece, 16-31: dQ_s piece; channels below c_skip belong to the previous chunk's launch
+          const int ch = 4 * (lane & 15);
+          if (ch >= p.c_skip)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + (size_t)bSrc[e] * (4 * C) + 2 * C +
+                                                                                 (lane < 16 ? 0 : C) + c_off + ch),
+                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
         }
       }
     }
@@ -492,16 +499,18 @@ __global__ void __launch_bounds__(kLaunch, 1) k_cgconv_bwd_pipe(const CgParams p
       const bool empty_seg = (a == b);
       if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
       const bool first = empty_seg || (a >= r_lo);
-      float* o = p.out + (size_t)n * (4 * kC);
+      // value-tile column 32 u + lane: u = 0, 1 -> dP_f channels, u = 2, 3 -> dP_s channels of the chunk
+      float* o = p.out + (size_t)n * (4 * C) + c_off + lane;
+      const int ooff[4] = {0, 32, C, C + 32};
       float acc[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = first ? 0.0f : o[32 * u + lane];
+      for (int u = 0; u < 4; ++u) acc[u] = first ? 0.0f : o[ooff[u]];
       for (int s = lo; s < hi; ++s) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc[u] += sV[(s - r_lo) * kVW + 32 * u + lane];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) o[32 * u + lane] = acc[u];
+      for (int u = 0; u < 4; ++u) o[ooff[u]] = acc[u];
     }
     mark(15);
     if (PROFILE && pl.prof && tid == 0) atomicAdd(pl.prof + 31, 1ull);
@@ -550,7 +559,8 @@ int bwd_launch_t(const CgParams& p, const Plan& pl, int grid, cudaStream_t st) {
 
 void cgbwd_set_phase_buffer(unsigned long long* dev_ptr) { g_bwd_phase_buf = dev_ptr; }
 
-// C = 64, G <= 64, 16-byte aligned ea / PQ / gout / dPQ (bulk copy, vector loads, vector atomics)
+// C >= 64 (multiple of 4; 64 channels per launch), G <= 64, 16-byte aligned ea / PQ / gout / dPQ (bulk copy, vector
+// loads, vector atomics)
 bool cgbwd_supported(const CgParams& p) {
   Plan pl;
   return plan(p.C, p.G, p.dhat != nullptr, &pl) && (reinterpret_cast<uintptr_t>(p.ea) & 15) == 0 &&
@@ -558,18 +568,25 @@ bool cgbwd_supported(const CgParams& p) {
          (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (int64_t)p.N * 4 * p.C < (int64_t)1 << 31;
 }
 
-// dP (by destination, deterministic) + dQ (vector atomics: the caller zeroes the dQ half first) + per-CTA dW_e^T
-// partials in p.dW_part ([grid][G][2C]); *grid_out = number of partials
-int cgbwd_launch(CgParams p, cudaStream_t st, int* grid_out) {
+// dP (by destination, deterministic) + dQ (vector atomics: the caller zeroes the dQ half first) + dW_e^T: per-CTA
+// partials in p.dW_part ([grid][G][128]) summed in CTA order into dWeT [G][2C].  One launch per 64-channel chunk;
+// the last chunk of a width that is not a multiple of 64 starts at C - 64 and recomputes the channels it shares with
+// the one before (identical values; plain stores for dP / dW_e, its dQ atomics skip them: c_skip).
+int cgbwd_launch(CgParams p, cudaStream_t st, float* dWeT) {
   Plan pl;
   MDL_REQUIRE(plan(p.C, p.G, p.dhat != nullptr, &pl), "cgconv_bwd: unsupported shape C=%d G=%d", p.C, p.G);
   const char* wenv = getenv("MDL_CGCONV_WINDOW");
   pl.window = !(wenv && wenv[0] == '0');
-  p.c_off = 0; p.CC = p.C; p.cap = kRows; p.te = kTile;
+  p.CC = kC; p.cap = kRows; p.te = kTile;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTile));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
-  if (grid_out) *grid_out = grid;
-  return pl.prof ? bwd_launch_t<1>(p, pl, grid, st) : bwd_launch_t<0>(p, pl, grid, st);
+  for (int c0 = 0; c0 < p.C; c0 += kC) {
+    p.c_off = std::min(c0, p.C - kC);
+    p.c_skip = c0 - p.c_off;
+    if (int rc = pl.prof ? bwd_launch_t<1>(p, pl, grid, st) : bwd_launch_t<0>(p, pl, grid, st)) return rc;
+    if (int rc = reduce_dw_partials(p.dW_part, grid, p.G, p.C, p.c_off, kC, dWeT, st)) return rc;
+  }
+  return MDL_OK;
 }
 
 }  // namespace mdl

@@ -60,7 +60,7 @@ struct WsPlan {
 
 // smear: the edge rows are expanded in the kernel from d_hat (no landing zone; its space goes to the node-row windows)
 bool ws_plan(int C, int G, bool smear, WsPlan* pl) {
-  if (C != kC || G < 1) return false;
+  if (C < kC || (C & 3) || G < 1) return false;  // a launch serves 64 channels [c_off, c_off + 64) of a C-wide layer
   const int KP = (G + 7) & ~7;
   if (2 * kNP + 4 * KP > kTmemColsW) return false;  // two accumulators + two hi/lo A-operand buffers
   const uint32_t b = (uint32_t)kNP * KP * 4;
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   __shared__ float sMu[64];   // smearing-fused form: the basis centres (GaussianSmearing.offset), KP <= 64
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, KP = pl.KP, WR = pl.WR;
+  const int C = p.C, c_off = p.c_off;  // layer width (row strides of x / out / PQ / WeT) and this launch's channel chunk
   const uint32_t sleep_ns = (uint32_t)pl.sleep_ns;
 #define WAIT(bar, parity) umma::mbar_wait_sleep(bar, parity, sleep_ns)
 
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
   }
   for (int i = tid; i < kNP * KP; i += kLaunchW) {
     const int n = i % kNP, k = i / kNP;
-    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * kNP + n) * (n < kC ? -kLog2e : kLog2e) : 0.0f;
+    const float w = (k < G) ? __ldg(p.WeT + (size_t)k * (2 * C) + (n < kC ? c_off + n : C + c_off + n - kC)) * (n < kC ? -kLog2e : kLog2e) : 0.0f;
     const float hi = umma::tf32_hi(w);
     const int off = umma::tile_offset_bytes(n, k, kNP);
     *reinterpret_cast<float*>(sBhi + off) = hi;
@@ -283,8 +284,15 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         }
         float* W = sWbuf(b);
         for (int r = lt; r < D.nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
-          const float* g = (r < D.nq) ? p.PQ + (size_t)(D.s_lo + r) * (4 * kC) + 2 * kC : p.PQ + (size_t)(D.d_lo + r - D.nq) * (4 * kC);
-          umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
+          // a PQ row is [P_f | P_s | Q_f | Q_s], C floats each: the chunk's f and s pieces are adjacent only when C = 64
+          const float* g = (r < D.nq) ? p.PQ + (size_t)(D.s_lo + r) * (4 * C) + 2 * C + c_off
+                                      : p.PQ + (size_t)(D.d_lo + r - D.nq) * (4 * C) + c_off;
+          if (C == kC) {
+            umma::bulk_g2s(W + r * kVW, g, (uint32_t)(2 * kC * 4), &bar_rows_full[b]);
+          } else {
+            umma::bulk_g2s(W + r * kVW, g, (uint32_t)(kC * 4), &bar_rows_full[b]);
+            umma::bulk_g2s(W + r * kVW + kC, g + C, (uint32_t)(kC * 4), &bar_rows_full[b]);
+          }
         }
         if (valid(Rn)) D = finish_idx(Rn, (int)((j + 1) & (kIdxRing - 1)), v);
         R = Rn;
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       seg_a = __ldg(p.seg_ptr + n0);
       seg_b = __ldg(p.seg_ptr + n0 + 1);
       if (p.inv_deg) seg_sc = kLn2 * __ldg(p.inv_deg + n0);
-      seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * kC) + lane);
+      seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * C + c_off) + lane);
     }
     if (cnt > 0) {
       WAIT(&bar_rows_full[jb], (ph_r >> jb) & 1);  // indices, window record, node rows of this round
@@ -428,8 +436,8 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         auto run = [&](auto ldP, auto ldQ) {  // how the P[dst] / Q[src] rows are read (shared or global memory), by float offset
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 pf = ldP(j4), ps = ldP(kC + j4);
-            const float4 qf = ldQ(j4), qs = ldQ(kC + j4);
+            const float4 pf = ldP(0, j4), ps = ldP(1, j4);   // (gate f / s, channel offset)
+            const float4 qf = ldQ(0, j4), qs = ldQ(1, j4);
             // y = accumulator (already in base-2 units: W_e is pre-scaled) + c (P + Q)
             float yf0, yf1, yf2, yf3, ys0, ys1, ys2, ys3;
             upk2(fma2(cf, add2(pk2(pf.x, pf.y), pk2(qf.x, qf.y)), pk2(f[j4], f[j4 + 1])), yf0, yf1);
@@ -445,12 +453,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
         if (win) {  // explicit shared-space loads (a pointer that may be either space compiles to generic LD.E)
           const uint32_t a0 = umma::smem_u32(sW + (w_nq + sd - w_dmin) * kVW + c_begin);
           const uint32_t a1 = umma::smem_u32(sW + (ss - w_smin) * kVW + c_begin);
-          run([&](int o) { return umma::lds128(a0 + 4u * (uint32_t)o); }, [&](int o) { return umma::lds128(a1 + 4u * (uint32_t)o); });
+          run([&](int gate, int o) { return umma::lds128(a0 + 4u * (uint32_t)(gate * kC + o)); },
+              [&](int gate, int o) { return umma::lds128(a1 + 4u * (uint32_t)(gate * kC + o)); });
         } else {
-          const float* r0 = p.PQ + (size_t)sd * (4 * kC) + c_begin;
-          const float* r1 = p.PQ + (size_t)ss * (4 * kC) + 2 * kC + c_begin;
-          run([&](int o) { return __ldg(reinterpret_cast<const float4*>(r0 + o)); },
-              [&](int o) { return __ldg(reinterpret_cast<const float4*>(r1 + o)); });
+          const float* r0 = p.PQ + (size_t)sd * (4 * C) + c_off + c_begin;
+          const float* r1 = p.PQ + (size_t)ss * (4 * C) + 2 * C + c_off + c_begin;
+          run([&](int gate, int o) { return __ldg(reinterpret_cast<const float4*>(r0 + gate * C + o)); },
+              [&](int gate, int o) { return __ldg(reinterpret_cast<const float4*>(r1 + gate * C + o)); });
         }
       }
       __syncwarp();
@@ -470,12 +479,12 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       if (empty_seg ? (cur.rd != 0) : (lo >= hi)) continue;
       const bool first = empty_seg || (a >= r_lo);
       const bool lastp = empty_seg || (bq <= r_hi);
-      float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * kC) + lane;
+      float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * C + c_off) + lane;
       float sc = seg_sc;
       float2 x = seg_x;
       if (n != n0) {
         sc = p.inv_deg ? kLn2 * __ldg(p.inv_deg + n) : kLn2;
-        x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * kC) + lane);
+        x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n * C + c_off) + lane);
       }
       float2 acc = first ? make_float2(0.0f, 0.0f) : *o;
       const float2* vp = reinterpret_cast<const float2*>(sV + (lo - r_lo) * kVP) + lane;
@@ -522,7 +531,8 @@ int ws_launch_t(const CgParams& p, const WsPlan& pl, int grid, cudaStream_t st) 
 
 void cgws_set_phase_buffer(unsigned long long* dev_ptr) { g_ws_phase_buf = dev_ptr; }
 
-// C = 64, G <= 64, a tile table that fits (<= 512 tiles per CTA), 16-byte aligned ea / PQ (bulk copies)
+// C >= 64 (multiple of 4; 64 channels per launch), G <= 64, a tile table that fits (<= 512 tiles per CTA), 16-byte
+// aligned ea / PQ (bulk copies)
 bool cgws_supported(const CgParams& p) {
   WsPlan pl;
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTileW));
@@ -540,10 +550,16 @@ int cgws_launch(CgParams p, cudaStream_t st) {
   pl.window = !(wenv && wenv[0] == '0');
   const char* senv = getenv("MDL_WS_SLEEP");  // ns slept between mbarrier polls (A/B switch)
   pl.sleep_ns = senv ? atoi(senv) : 0;
-  p.c_off = 0; p.CC = p.C; p.cap = kRowsW; p.te = kTileW;
+  p.CC = kC; p.cap = kRowsW; p.te = kTileW;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTileW));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
-  return pl.prof ? ws_launch_t<1>(p, pl, grid, st) : ws_launch_t<0>(p, pl, grid, st);
+  // one launch per 64-channel chunk; the last chunk of a width that is not a multiple of 64 starts at C - 64 and
+  // recomputes the channels it shares with the one before (identical values, plain stores)
+  for (int c0 = 0; c0 < p.C; c0 += kC) {
+    p.c_off = std::min(c0, p.C - kC);
+    if (int rc = pl.prof ? ws_launch_t<1>(p, pl, grid, st) : ws_launch_t<0>(p, pl, grid, st)) return rc;
+  }
+  return MDL_OK;
 }
 
 }  // namespace mdl

@@ -569,7 +569,7 @@ class NNConvMsgFn(torch.autograd.Function):
         csr = ctx.csr
         N, K, O = ctx.dims
         dm = dm.contiguous()
-        dhid = torch.empty_like(hid)
+        dhid = torch.zeros_like(hid)     # rows no segment refers to (capacity padding) must carry a zero gradient
         dXT = torch.empty_like(XT)
         dXB = torch.empty((N, O), dtype=hid.dtype, device=hid.device)
         rc = lib.mdl_nnconv_msg_bwd(_lib.ptr(hid), _lib.ptr(XT), _lib.ptr(dm), _lib.ptr(csr.src_ptr),
@@ -602,6 +602,7 @@ class EdgeGatherAddFn(torch.autograd.Function):
         ctx.save_for_backward(out if relu else None)
         ctx.csr, ctx.relu = csr, relu
         ctx.has = (U is not None, bias is not None)
+        ctx.u_rows = U.shape[0] if U is not None else 0
         return out
 
     @staticmethod
@@ -615,7 +616,11 @@ class EdgeGatherAddFn(torch.autograd.Function):
         dU = segment_reduce(dA, csr.graph_ptr, None, "sum") if (ctx.has[0] or ctx.has[1]) else None
         # column sums over E rows = column sums of the per-graph sums (B rows): no pass over the edge tensor
         dbias = (dU.sum(0) if dU is not None else dpre.sum(0)) if ctx.has[1] else None
-        return dpre, dA, dB, (dU if ctx.has[0] else None), dbias, None, None, None, None
+        if ctx.has[0] and dU.shape[0] < ctx.u_rows:   # capacity-padded batch: U carries a zero row for the padded edges
+            dU_full = torch.cat([dU, dU.new_zeros(ctx.u_rows - dU.shape[0], dU.shape[1])], 0)
+        else:
+            dU_full = dU
+        return dpre, dA, dB, (dU_full if ctx.has[0] else None), dbias, None, None, None, None
 
 
 def edge_gather_add(base, A, B, U, bias, edge_index, batch, csr, relu):

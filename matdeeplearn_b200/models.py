@@ -220,13 +220,15 @@ class _MegnetStack(tnn.Module):
             tnn.BatchNorm1d(dim, track_running_stats=track) for _ in range(fc_layers + 1)
         ) if batch_norm == "True" else tnn.ModuleList()
 
-    def _run(self, h, first_done=False):
+    def _run(self, h, first_done=False, n_valid=None):
+        """n_valid: device-side count of real rows of a capacity-padded batch (statistics over those rows only, the
+        rest written as zero); None = every row is real and the torch module runs."""
         layers = getattr(self, self._name)
         for i, lin in enumerate(layers):
             if not (i == 0 and first_done):
                 h = getattr(F, self.act)(MF.linear(h, lin.weight, lin.bias))
             if self.batch_norm == "True":
-                h = self.bn_list[i](h)
+                h = MF.masked_batch_norm(self.bn_list[i], h, n_valid) if n_valid is not None else self.bn_list[i](h)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)
         return h
 
@@ -250,12 +252,16 @@ class Megnet_EdgeModel(_MegnetStack):
         B = x @ W[:, D:2 * D].t()
         base = MF.linear(edge_attr, W[:, 2 * D:3 * D].contiguous())     # the edge-level GEMM of the block
         U = u @ W[:, 3 * D:].t()
+        e_valid = getattr(edge_index, "_mdl_e_valid", None)
+        if e_valid is not None:
+            # capacity-padded batch: padded edges point at a padding node whose graph id is B -- give them a zero row
+            U = torch.cat([U, U.new_zeros(1, U.shape[1])], 0)
         csr = csr_for(edge_index, batch, num_nodes=x.shape[0], num_graphs=u.shape[0])
         relu = self.act == "relu"
         h = MF_edge_gather_add(base, A, B, U, lin.bias, edge_index, batch, csr, relu)
         if not relu:
             h = getattr(F, self.act)(h)
-        return self._run(h, first_done=True)
+        return self._run(h, first_done=True, n_valid=e_valid)
 
 
 class Megnet_NodeModel(_MegnetStack):
@@ -264,7 +270,8 @@ class Megnet_NodeModel(_MegnetStack):
 
     def forward(self, x, edge_index, edge_attr, u, batch):
         v_e = _edge_mean_by_source(edge_attr, edge_index)               # by SOURCE node (megnet.py:86)
-        return self._run(torch.cat([x, v_e, _expand_graph_rows(u, batch, x.shape[0])], dim=1))
+        return self._run(torch.cat([x, v_e, _expand_graph_rows(u, batch, x.shape[0])], dim=1),
+                         n_valid=getattr(batch, "_mdl_n_valid", None))
 
 
 class Megnet_GlobalModel(_MegnetStack):
@@ -296,6 +303,10 @@ def _edge_mean_by_source(edge_attr, edge_index):
 def _expand_graph_rows(u, batch, n):
     """u[batch] (megnet.py:99); on CUDA through the gather kernel with the segmented sum as its backward."""
     seg = getattr(batch, "_mdl_seg", None)
+    if getattr(batch, "_mdl_n_valid", None) is not None:
+        # capacity-padded batch: padding nodes carry graph id B; they read a zero row (and are outside every segment)
+        u = torch.cat([u, u.new_zeros(1, u.shape[1])], 0)
+        return u.index_select(0, batch)
     if u.is_cuda and u.dtype == torch.float32 and seg is not None and seg[0] == batch._version and seg[2] is None \
             and seg[1].shape[0] - 1 == u.shape[0]:
         return MF.expand_by_segment(u, batch, seg[1])

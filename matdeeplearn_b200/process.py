@@ -94,18 +94,14 @@ def orthorhombic_lengths(cell, pbc=None):
     return c
 
 
-def _general_minimum_image(d, cell, pbc=None):
-    """Minimum-image vectors for a general (triclinic) cell, rows of `cell` = lattice vectors.
-    What the reference gets from ASE (`get_all_distances(mic=True)`, process.py:284-287): the shortest
-    of all lattice translates of each difference vector.  Wrap the fractional coordinates into
-    [-0.5, 0.5), then search every integer shift that can still shorten a wrapped vector: the wrapped
-    vector is no longer than R0 = (|a1|+|a2|+|a3|)/2, so a better image needs a lattice vector shorter
-    than 2 R0, i.e. |shift_i| <= ceil(2 R0 / h_i) with h_i the cell's height along axis i."""
+def lattice_record(cell, pbc=None):
+    """What the minimum-image search of a general cell needs, computed once per structure on the host (and handed to
+    the GPU builder as 28 doubles): the lattice vectors (rows), their inverse, the image-shift range per axis, the
+    periodicity flags.  The wrapped vector is no longer than R0 = (|a1|+|a2|+|a3|)/2, so a better image needs a
+    lattice vector shorter than 2 R0, i.e. |shift_i| <= ceil(2 R0 / h_i) with h_i the cell's height along axis i."""
+    cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
     per = np.ones(3, dtype=bool) if pbc is None else np.asarray(pbc, dtype=bool)
     inv = np.linalg.inv(cell)
-    frac = d @ inv
-    frac[..., per] -= np.round(frac[..., per])   # free axes (slabs, wires) keep their coordinate
-    w = frac @ cell
     vol = abs(np.linalg.det(cell))
     r0 = 0.5 * np.linalg.norm(cell, axis=1).sum()
     heights = np.array([vol / np.linalg.norm(np.cross(cell[(i + 1) % 3], cell[(i + 2) % 3])) for i in range(3)])
@@ -113,15 +109,32 @@ def _general_minimum_image(d, cell, pbc=None):
     n[~per] = 0
     if n.max() > 8:   # (2n+1)^3 image shifts: a needle-shaped / badly reduced cell; refuse rather than truncate the search
         raise ValueError(f"minimum image: cell too skewed (needs image shifts up to {n.tolist()}); reduce the cell first")
+    return cell, inv, n, per
+
+
+def _general_minimum_image(d, cell, pbc=None):
+    """Minimum-image vectors for a general (triclinic) cell, rows of `cell` = lattice vectors.
+    What the reference gets from ASE (`get_all_distances(mic=True)`, process.py:284-287): the shortest
+    of all lattice translates of each difference vector.  Wrap the fractional coordinates into
+    [-0.5, 0.5], then search every integer shift that can still shorten a wrapped vector (lattice_record).
+    Every product and sum is written out elementwise in a fixed order (no BLAS, no FMA): the GPU builder
+    (csrc/builder.cu) evaluates the same expressions and reproduces the result bit for bit."""
+    cell, inv, n, per = lattice_record(cell, pbc)
+    frac = [(d[..., 0] * inv[0, k] + d[..., 1] * inv[1, k]) + d[..., 2] * inv[2, k] for k in range(3)]
+    for k in range(3):
+        if per[k]:   # free axes (slabs, wires) keep their coordinate
+            frac[k] = frac[k] - np.round(frac[k])
+    w = np.stack([(frac[0] * cell[0, c] + frac[1] * cell[1, c]) + frac[2] * cell[2, c] for c in range(3)], -1)
     best = w.copy()
-    best_d2 = (w * w).sum(-1)
+    best_d2 = (w[..., 0] * w[..., 0] + w[..., 1] * w[..., 1]) + w[..., 2] * w[..., 2]
     for i in range(-n[0], n[0] + 1):
         for j in range(-n[1], n[1] + 1):
             for k in range(-n[2], n[2] + 1):
                 if i == j == k == 0:
                     continue
-                c = w + (i * cell[0] + j * cell[1] + k * cell[2])
-                d2 = (c * c).sum(-1)
+                shift = (float(i) * cell[0] + float(j) * cell[1]) + float(k) * cell[2]
+                c = w + shift
+                d2 = (c[..., 0] * c[..., 0] + c[..., 1] * c[..., 1]) + c[..., 2] * c[..., 2]
                 m = d2 < best_d2
                 best[m] = c[m]
                 best_d2[m] = d2[m]

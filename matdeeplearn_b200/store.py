@@ -23,20 +23,30 @@ from .data import Batch, GaussianEdgeAttr
 
 
 def _box_lengths(structures):
-    """[num_structures, 3] float64 box lengths for the GPU builder (zeros = not periodic).  It handles
-    orthorhombic cells only; general cells go through process.assemble_dataset + GraphStore.from_dataset."""
-    from .process import orthorhombic_lengths
-    rows = []
+    """([num_structures, 3] float64 box lengths (zeros = not periodic), [num_structures, 28] lattice records or None)
+    for the GPU builder: orthorhombic cells are described by their lengths, general (triclinic) ones by
+    process.lattice_record (lattice vectors, inverse, image-shift ranges, periodicity flags)."""
+    from .process import orthorhombic_lengths, lattice_record
+    rows, lat, any_general = [], [], False
     for s in structures:
+        rec = np.zeros(28)
         if s[2] is None:
             rows.append(np.zeros(3))
+            lat.append(rec)
             continue
-        L = orthorhombic_lengths(s[2], s[3] if len(s) > 3 else None)
-        if L is None:
-            raise NotImplementedError("GraphStore.from_structures: the GPU builder handles orthorhombic cells; "
-                                      "build general cells with process.assemble_dataset + from_dataset")
+        pbc = s[3] if len(s) > 3 else None
+        L = orthorhombic_lengths(s[2], pbc)
+        if L is None and (pbc is None or np.any(pbc)):
+            cell, inv, n, per = lattice_record(s[2], pbc)
+            rec[0:9], rec[9:18], rec[18:21], rec[21:24], rec[24] = cell.reshape(-1), inv.reshape(-1), n, per, 1.0
+            any_general = True
+            L = np.zeros(3)
+        elif L is None:          # a general cell with no periodic axis: plain Euclidean distances
+            L = np.zeros(3)
         rows.append(np.asarray(L, dtype=np.float64).reshape(3))
-    return np.stack(rows) if rows else np.zeros((0, 3))
+        lat.append(rec)
+    lengths = np.stack(rows) if rows else np.zeros((0, 3))
+    return lengths, (np.stack(lat) if any_general else None)
 
 
 class GraphStore:
@@ -123,8 +133,8 @@ class GraphStore:
         followed by the dataset-global min-max edge normalisation (process.py:626-653).  The Gaussian
         basis is never materialised: batches expand it from the normalised distance (csrc/assemble.cu).
 
-        structures: iterable of (numbers, positions [n,3], cell_lengths [3] or None), the same input
-        process.assemble_dataset takes; the result is tensor-for-tensor the store that
+        structures: iterable of (numbers, positions [n,3], cell [3] lengths / 3x3 lattice vectors (rows; any
+        triclinic cell) / None [, pbc flags]), the same input process.assemble_dataset takes; the result is tensor-for-tensor the store that
         GraphStore.from_dataset(process.assemble_dataset(...)) would hold (tested bit-exact)."""
         lib = _lib.load()
         device = torch.device(device)
@@ -139,7 +149,7 @@ class GraphStore:
         self.num_nodes = int(node_ptr[-1])
         pos = np.concatenate([np.asarray(s[1], dtype=np.float64).reshape(-1, 3) for s in structures], 0)
         numbers = np.concatenate([np.asarray(s[0], dtype=np.int32).reshape(-1) for s in structures])
-        cell = _box_lengths(structures)
+        cell, lattice = _box_lengths(structures)
         K = neighbors + 1
         self.F, self.G = z_width + neighbors + 2, edge_length
         f32 = dict(dtype=torch.float32, device=device)
@@ -147,14 +157,15 @@ class GraphStore:
         pos_d = torch.from_numpy(pos).to(device)
         num_d = torch.from_numpy(numbers).to(device)
         cell_d = torch.from_numpy(cell).to(device)
+        lat_d = torch.from_numpy(lattice).to(device) if lattice is not None else None
         self.node_ptr = torch.from_numpy(node_ptr).to(device)
         nbr_col = torch.empty((self.num_nodes, K), **i32)
         nbr_w = torch.empty((self.num_nodes, K), **f32)
         cnt = torch.empty(self.num_nodes, **i32)
-        rc = lib.mdl_build_neighbors(_lib.ptr(pos_d), _lib.ptr(cell_d), _lib.ptr(self.node_ptr), self.num_graphs,
-                                     int(self.n_nodes.max()), float(radius), neighbors, _lib.ptr(nbr_col),
-                                     _lib.ptr(nbr_w), _lib.ptr(cnt), _lib.stream())
-        _lib.check(rc, "mdl_build_neighbors")
+        rc = lib.mdl_build_neighbors_lattice(_lib.ptr(pos_d), _lib.ptr(cell_d), _lib.ptr(lat_d), _lib.ptr(self.node_ptr),
+                                             self.num_graphs, int(self.n_nodes.max()), float(radius), neighbors,
+                                             _lib.ptr(nbr_col), _lib.ptr(nbr_w), _lib.ptr(cnt), _lib.stream())
+        _lib.check(rc, "mdl_build_neighbors_lattice")
         # edge offsets: a structure's edges in row-major order, then its loops
         cnt64 = cnt.long()
         csum = torch.cat([cnt64.new_zeros(1), torch.cumsum(cnt64, 0)])          # [num_nodes+1]
@@ -324,6 +335,11 @@ class GraphStore:
         out, csr, ea_slots = self._alloc(B, int(N_cap), int(E_cap), True, True, d_hat, lazy)
         out._meta_d = torch.zeros((3, B + 1), dtype=torch.int64, device=self.device)
         out._n_valid = csr.graph_ptr[B:B + 1]
+        # device-side counts of real rows, found by the models through the tensors they are handed (MetaLayer's
+        # sub-models only see x / edge_index / edge_attr / u / batch): real nodes, real edges (every padded node's
+        # dst_ptr entry is the real edge count)
+        out.batch._mdl_n_valid = out._n_valid
+        out.edge_index._mdl_e_valid = csr.dst_ptr[int(N_cap):int(N_cap) + 1]
         out._parts = (csr, ea_slots)
         out._valid = (0, 0)
         return out
@@ -344,6 +360,13 @@ class GraphStore:
     def assemble(self, static):
         csr, ea_slots = static._parts
         self._launch(static, csr, ea_slots, static._meta_d, csr.B, csr.N, csr.E)
+        # the buffers were rewritten in place (raw pointers: no version bump): everything memoised from their previous
+        # contents is recomputed -- inside the graph when this runs under capture
         if isinstance(static.edge_attr, GaussianEdgeAttr):
-            static.edge_attr.forget()   # d_hat was rewritten in place: slot-order / dense copies are recomputed
+            static.edge_attr.forget()
+        csr.src_eid = csr.src_nbr = None
+        for t in (static.batch, static.edge_index):
+            for memo in ("_mdl_i32",):
+                if hasattr(t, memo):
+                    delattr(t, memo)
         return static

@@ -70,3 +70,26 @@ def test_builder_rejects_oversized_structures_and_cpu():
         GraphStore.from_structures(big, [0.0], DEV)
     with pytest.raises(RuntimeError):
         GraphStore.from_structures(big, [0.0], "cpu")
+
+
+def test_builder_triclinic_cells_match_host_builder():
+    """general (triclinic) cells, what the reference gets from ASE's get_all_distances(mic=True) (process.py:284-287):
+    the GPU builder evaluates the host builder's minimum-image search expression for expression -- same edges, same
+    order, bit-identical float32 weights -- incl. a skewed cell that needs image shifts beyond +-1, a slab (free z
+    axis), mixed with orthorhombic and non-periodic structures in one call."""
+    rng = np.random.default_rng(21)
+    cells = [np.array([[6.0, 0, 0], [2.5, 5.0, 0], [0.5, 0.8, 7.0]]),          # generic triclinic
+             np.array([[4.0, 0, 0], [3.6, 1.9, 0], [0.3, 0.2, 9.0]]),          # strongly skewed: shifts up to +-2 or more
+             np.array([[5.0, 0, 0], [-2.5, 4.33, 0], [0, 0, 6.0]]),            # hexagonal
+             np.array([[7.0, 0.5, 0.2], [0.1, 6.5, 0.4], [0.3, 0.2, 8.0]])]    # nearly orthogonal, fully dense matrix
+    structs = []
+    for c in cells:
+        n = int(rng.integers(12, 40))
+        structs.append((rng.integers(1, 90, size=n), rng.uniform(0, 1, (n, 3)) @ c, c))
+    c = cells[0]
+    structs.append((rng.integers(1, 90, size=20), rng.uniform(0, 1, (20, 3)) @ c, c, (True, True, False)))   # slab
+    structs.append((rng.integers(1, 90, size=25), rng.uniform(0, 6.0, size=(25, 3)), np.array([6.0, 6.0, 6.0])))
+    structs.append((np.array([8, 1, 1]), np.array([[0.0, 0, 0], [0.96, 0, 0], [-0.24, 0.93, 0]]), None))
+    ys = list(rng.normal(size=len(structs)))
+    _compare(structs, ys)
+    _compare(structs, ys, radius=5.0, neighbors=6)

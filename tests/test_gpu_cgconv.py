@@ -151,6 +151,29 @@ def test_cgconv_shapes(dev, impl, C, G):
     _cgconv_case(dev, n=300, e=3000, C=C, G=G, aggr="mean", tag=impl)
 
 
+def test_wide_layers_dispatch_to_the_tensor_core_kernels():
+    """configs[0]'s default width (dim1 = 100, reference config.yml:121-123) and SchNet-style C = 128 CGCNNs run on the
+    tcgen05 kernels (64-channel chunks), forward and backward (G = 64: forward only, the backward's ea^T tiles do not fit);
+    widths below 64 and edge widths above 64 do not"""
+    from matdeeplearn_b200 import _lib
+    lib = _lib.load()
+    for C, G, want in [(64, 50, 3), (100, 50, 3), (128, 50, 3), (128, 64, 1), (256, 37, 3), (32, 50, 0), (64, 100, 0), (100, 200, 0)]:
+        assert lib.mdl_cgconv_tc_supported(C, G) == want, (C, G)
+
+
+@pytest.mark.parametrize("C,G", [(100, 50), (128, 50), (68, 37), (192, 64), (128, 51)])
+@pytest.mark.parametrize("graph", ["random", "crystal", "hub"])
+def test_cgconv_wide_layers(dev, impl, C, G, graph):
+    """C > 64 on every implementation (tensor-core kernels: 64-channel chunks, overlapping last chunk when C % 64 != 0)"""
+    if graph == "crystal":
+        ei = block_diagonal_graph([30, 7, 52, 18] * 6, 12, seed=C)
+        _cgconv_case(dev, n=int(ei.max()) + 1, e=0, C=C, G=G, aggr="mean", seed=C, tag=impl + " wide", ei=ei)
+    elif graph == "hub":
+        _cgconv_case(dev, n=500, e=3000, C=C, G=G, aggr="add", hub=(5, 300), iso=4, seed=C, tag=impl + " wide")
+    else:
+        _cgconv_case(dev, n=300, e=3000, C=C, G=G, aggr="mean", seed=C, tag=impl + " wide")
+
+
 def test_cgconv_odd_edge_width(dev, impl):
     _cgconv_case(dev, n=150, e=1200, C=32, G=37, aggr="mean", tag=impl)
 

@@ -102,17 +102,24 @@ def test_smear_fused_narrow_basis(dev):
     _case(dev, random_graph(300, 3000, 5), 300, 64, 50, "mean", seed=5, width=0.1)
 
 
+@pytest.mark.parametrize("C", [100, 128, 192])
+def test_smear_fused_wide_layers(dev, C):
+    """layer widths above 64 run as 64-channel chunks of the same kernels (the last chunk of C = 100 overlaps)"""
+    _case(dev, random_graph(300, 3000, 7), 300, C, 50, "mean", seed=C)
+    _case(dev, block_diagonal_graph([30] * 20, 12, seed=2), 600, C, 50, "add", seed=C + 1)
+
+
 def test_smear_unsupported_shapes_materialise(dev):
-    """C != 64 is not served by the fused form: CGConv expands the basis and takes the general kernels"""
+    """C < 64 is not served by the fused form: CGConv expands the basis and takes the general kernels"""
     import matdeeplearn_b200.nn as mnn
     from matdeeplearn_b200 import functional as MF
     from matdeeplearn_b200.data import GaussianEdgeAttr
-    assert MF.cgconv_smear_supported(64, 50) and not MF.cgconv_smear_supported(100, 50)
+    assert MF.cgconv_smear_supported(64, 50) and MF.cgconv_smear_supported(100, 50) and not MF.cgconv_smear_supported(32, 50)
     torch.manual_seed(0)
     ei = random_graph(100, 800, 6).to(dev)
     lazy = GaussianEdgeAttr(torch.rand(ei.shape[1], device=dev), resolution=50)
-    conv = mnn.CGConv(100, 50, aggr="mean").to(dev)
-    x = torch.randn(100, 100, device=dev)
+    conv = mnn.CGConv(32, 50, aggr="mean").to(dev)
+    x = torch.randn(100, 32, device=dev)
     a = conv(x, ei, lazy)
     b = conv(x, ei, lazy.materialize())
     assert lazy._dense is not None and torch.equal(a, b)

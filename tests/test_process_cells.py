@@ -78,12 +78,17 @@ def test_gpu_builder_cell_argument():
     s_ortho = (np.array([1, 2]), np.zeros((2, 3)), np.array([5.0, 6.0, 7.0]))
     s_diag = (np.array([1, 2]), np.zeros((2, 3)), np.diag([5.0, 6.0, 7.0]))
     s_free = (np.array([1, 2]), np.zeros((2, 3)), None)
-    got = _box_lengths([s_ortho, s_diag, s_free])
-    assert got.dtype == np.float64 and got.flags["C_CONTIGUOUS"]
+    got, lat = _box_lengths([s_ortho, s_diag, s_free])
+    assert got.dtype == np.float64 and got.flags["C_CONTIGUOUS"] and lat is None
     assert np.array_equal(got, np.array([[5.0, 6.0, 7.0], [5.0, 6.0, 7.0], [0, 0, 0]]))
-    s_tri = (np.array([1, 2]), np.zeros((2, 3)), np.array([[5.0, 0, 0], [1.0, 6.0, 0], [0, 0, 7.0]]))
-    with pytest.raises(NotImplementedError):
-        _box_lengths([s_tri])
+    # a general (triclinic) cell travels as a 28-double lattice record: vectors, inverse, shift ranges, pbc, flag
+    tri = np.array([[5.0, 0, 0], [1.0, 6.0, 0], [0, 0, 7.0]])
+    s_tri = (np.array([1, 2]), np.zeros((2, 3)), tri)
+    got, lat = _box_lengths([s_ortho, s_tri])
+    assert np.array_equal(got, np.array([[5.0, 6.0, 7.0], [0, 0, 0]])) and lat.shape == (2, 28)
+    assert lat[0, 24] == 0.0 and lat[1, 24] == 1.0
+    assert np.array_equal(lat[1, :9].reshape(3, 3), tri) and np.allclose(lat[1, 9:18].reshape(3, 3) @ tri, np.eye(3))
+    assert np.array_equal(lat[1, 21:24], np.ones(3)) and (lat[1, 18:21] >= 1).all()
 
 
 def test_slab_periodicity_is_per_axis():
@@ -96,8 +101,8 @@ def test_slab_periodicity_is_per_axis():
     assert slab[0, 1] == pytest.approx(np.sqrt(0.7 ** 2 + 9.0 ** 2))
     assert np.array_equal(pr.pairwise_distances(pos, np.array([5.0, 5.0, 0.0])), slab)   # length 0 = free axis
     assert np.array_equal(pr.pairwise_distances(pos, L, pbc=(False, False, False)), pr.pairwise_distances(pos))
-    got = _box_lengths([(np.array([1, 2]), pos, L, (True, True, False))])
-    assert np.array_equal(got, np.array([[5.0, 5.0, 0.0]]))
+    got, lat = _box_lengths([(np.array([1, 2]), pos, L, (True, True, False))])
+    assert np.array_equal(got, np.array([[5.0, 5.0, 0.0]])) and lat is None
 
 
 def test_triclinic_slab_matches_restricted_brute_force():
