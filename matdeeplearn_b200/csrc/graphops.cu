@@ -191,6 +191,132 @@ k_nnconv_msg(const float* __restrict__ hid, const float* __restrict__ XT, const 
   }
 }
 
+// ---- NNConv message, register-tiled: one WARP per source node j, lane = output pair (2l, 2l+1), the node's
+// out-edges in chunks of 16 whose hidden rows sit transposed in shared memory (sHT[k][16]: one broadcast LDS.128 feeds
+// four edges), XT[j] streamed once per chunk with coalesced 8-byte loads: 4 LDS + 1 LDG per 32 FMAs instead of the
+// 2 LDS per FMA of k_nnconv_msg above.  K, O <= 64, O even (MPNN: K = dim3, O = gc_dim; reference mpnn.py:83-88).
+//   fwd: m[e, o] = XB[j, o] + sum_k hid[e, k] XT[j, k, o]
+//   bwd: dXT[j, k, o] = sum_e hid[e, k] dm[e, o];  dXB[j, o] = sum_e dm[e, o];  dhid[e, k] = sum_o XT[j, k, o] dm[e, o]
+//        (dhid: lane = k and k + 32, XT[j] staged per warp with a padded stride, dm rows broadcast from shared memory)
+constexpr int kNw = 8;          // warps (= nodes in flight) per CTA
+constexpr int kNwChunk = 16;    // out-edges per pass
+constexpr int kHS = 20;         // row stride of the transposed hidden tile (16 + 4: 16-byte aligned rows, 4-way instead of
+                                // 16-way bank conflicts when lanes = k write it)
+
+template <bool BWD>
+__global__ void __launch_bounds__(kNw * 32)
+k_nnconv_msg_w(const float* __restrict__ hid, const float* __restrict__ XT, const float* __restrict__ XB,
+               const float* __restrict__ dm, const int32_t* __restrict__ ptr, const int32_t* __restrict__ eid,
+               float* __restrict__ m, float* __restrict__ dhid, float* __restrict__ dXT, float* __restrict__ dXB,
+               int64_t N, int K, int O) {
+  extern __shared__ __align__(16) float smw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OS = O + 1;
+  const int per_warp = kHS * 64 + (BWD ? kNwChunk * 64 + 64 * 65 : 0);
+  float* sHT = smw + (size_t)warp * per_warp;   // [K][kHS] hidden rows of the chunk, transposed
+  float* sD = sHT + kHS * 64;                   // [16][O]  dm rows of the chunk (bwd)
+  float* sXT = sD + kNwChunk * 64;              // [K][O+1] XT[j] (bwd, for dhid)
+  const int KO = K * O;
+  const bool own = 2 * lane < O;                // this lane owns outputs 2 lane, 2 lane + 1
+  for (int64_t j = (int64_t)blockIdx.x * kNw + warp; j < N; j += (int64_t)gridDim.x * kNw) {
+    const int lo = __ldg(ptr + j), hi = __ldg(ptr + j + 1);
+    const float* xt = XT + (size_t)j * KO;
+    if (BWD) {
+      __syncwarp();
+      for (int i = lane; i < KO; i += 32) {       // coalesced read, padded rows: column reads are conflict-free
+        const int k = i / O, o = i - k * O;
+        sXT[k * OS + o] = __ldg(xt + i);
+      }
+    }
+    float2 bsum = make_float2(0.0f, 0.0f);
+    for (int c0 = lo; c0 < hi || (BWD && c0 == lo); c0 += kNwChunk) {   // bwd: a node without out-edges still writes zeros
+      const int nc = max(0, min(kNwChunk, hi - c0));
+      __syncwarp();
+      // ---- stage the chunk: hidden rows transposed (zero rows beyond nc), dm rows (bwd)
+      for (int r = 0; r < kNwChunk; ++r) {
+        const size_t e = r < nc ? (size_t)__ldg(eid + c0 + r) : 0;
+        for (int k = lane; k < K; k += 32) sHT[k * kHS + r] = r < nc ? __ldg(hid + e * K + k) : 0.0f;
+        if (BWD)
+          for (int o = lane; o < O; o += 32) sD[r * O + o] = r < nc ? __ldg(dm + e * O + o) : 0.0f;
+      }
+      __syncwarp();
+      if (!BWD) {
+        float2 acc[kNwChunk];
+        const float2 b = own ? __ldg(reinterpret_cast<const float2*>(XB + (size_t)j * O) + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kNwChunk; ++r) acc[r] = b;
+        for (int k = 0; k < K; ++k) {
+          const float2 x = own ? __ldg(reinterpret_cast<const float2*>(xt + (size_t)k * O) + lane) : make_float2(0.f, 0.f);
+          const float4* hp = reinterpret_cast<const float4*>(sHT + k * kHS);
+#pragma unroll
+          for (int q = 0; q < kNwChunk / 4; ++q) {
+            const float4 h = hp[q];
+            acc[4 * q + 0].x = fmaf(h.x, x.x, acc[4 * q + 0].x); acc[4 * q + 0].y = fmaf(h.x, x.y, acc[4 * q + 0].y);
+            acc[4 * q + 1].x = fmaf(h.y, x.x, acc[4 * q + 1].x); acc[4 * q + 1].y = fmaf(h.y, x.y, acc[4 * q + 1].y);
+            acc[4 * q + 2].x = fmaf(h.z, x.x, acc[4 * q + 2].x); acc[4 * q + 2].y = fmaf(h.z, x.y, acc[4 * q + 2].y);
+            acc[4 * q + 3].x = fmaf(h.w, x.x, acc[4 * q + 3].x); acc[4 * q + 3].y = fmaf(h.w, x.y, acc[4 * q + 3].y);
+          }
+        }
+        if (own) {
+#pragma unroll
+          for (int r = 0; r < kNwChunk; ++r)
+            if (r < nc) reinterpret_cast<float2*>(m + (size_t)__ldg(eid + c0 + r) * O)[lane] = acc[r];
+        }
+      } else {
+        // ---- dXT[j, k, 2l..] (+)= sum_r hid[r, k] dm[r, 2l..];  dXB
+        float2 d[kNwChunk];
+#pragma unroll
+        for (int r = 0; r < kNwChunk; ++r) {
+          d[r] = own ? *(reinterpret_cast<const float2*>(sD + r * O) + lane) : make_float2(0.f, 0.f);
+          bsum.x += d[r].x; bsum.y += d[r].y;
+        }
+        const bool first = c0 == lo;
+        for (int k = 0; k < K; ++k) {
+          const float4* hp = reinterpret_cast<const float4*>(sHT + k * kHS);
+          float2* dst = reinterpret_cast<float2*>(dXT + (size_t)j * KO + (size_t)k * O) + lane;
+          float2 a = (first || !own) ? make_float2(0.f, 0.f) : *dst;
+#pragma unroll
+          for (int q = 0; q < kNwChunk / 4; ++q) {
+            const float4 h = hp[q];
+            a.x = fmaf(h.x, d[4 * q + 0].x, a.x); a.y = fmaf(h.x, d[4 * q + 0].y, a.y);
+            a.x = fmaf(h.y, d[4 * q + 1].x, a.x); a.y = fmaf(h.y, d[4 * q + 1].y, a.y);
+            a.x = fmaf(h.z, d[4 * q + 2].x, a.x); a.y = fmaf(h.z, d[4 * q + 2].y, a.y);
+            a.x = fmaf(h.w, d[4 * q + 3].x, a.x); a.y = fmaf(h.w, d[4 * q + 3].y, a.y);
+          }
+          if (own) *dst = a;
+        }
+        // ---- dhid[e_r, k] = sum_o XT[j, k, o] dm[r, o], lane = k (and k + 32)
+        float g0[kNwChunk], g1[kNwChunk];
+#pragma unroll
+        for (int r = 0; r < kNwChunk; ++r) { g0[r] = 0.0f; g1[r] = 0.0f; }
+        const int k0 = lane, k1 = lane + 32;
+        const float* x0p = sXT + (k0 < K ? k0 : 0) * OS;
+        const float* x1p = sXT + (k1 < K ? k1 : 0) * OS;
+        for (int o = 0; o < O; o += 4) {          // O % 4 == 0: one broadcast LDS.128 of dm per edge and four outputs
+          const float a0 = x0p[o], a1 = x0p[o + 1], a2 = x0p[o + 2], a3 = x0p[o + 3];
+          const float b0 = x1p[o], b1 = x1p[o + 1], b2 = x1p[o + 2], b3 = x1p[o + 3];
+#pragma unroll
+          for (int r = 0; r < kNwChunk; ++r) {
+            const float4 dv = *reinterpret_cast<const float4*>(sD + r * O + o);
+            g0[r] = fmaf(a3, dv.w, fmaf(a2, dv.z, fmaf(a1, dv.y, fmaf(a0, dv.x, g0[r]))));
+            g1[r] = fmaf(b3, dv.w, fmaf(b2, dv.z, fmaf(b1, dv.y, fmaf(b0, dv.x, g1[r]))));
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kNwChunk; ++r)
+          if (r < nc) {
+            float* row = dhid + (size_t)__ldg(eid + c0 + r) * K;
+            if (k0 < K) row[k0] = g0[r];
+            if (k1 < K) row[k1] = g1[r];
+          }
+      }
+    }
+    if (BWD && own) reinterpret_cast<float2*>(dXB + (size_t)j * O)[lane] = bsum;
+  }
+}
+
+static bool nnconv_w_ok(int K, int O) { return K >= 1 && K <= 64 && O >= 4 && O <= 64 && (O & 3) == 0; }
+
 static int warp_grid(int64_t items) {
   int64_t blocks = ceil_div<int64_t>(items, 8);
   if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
@@ -239,6 +365,21 @@ static int nnconv_launch(bool bwd, const float* hid, const float* XT, const floa
                          float* dXB, int64_t N, int32_t K, int32_t O, void* stream) {
   MDL_REQUIRE(N >= 0 && K > 0 && O > 0, "nnconv_msg: bad shape");
   if (N == 0) return MDL_OK;
+  {  // register-tiled warp-per-node kernels (K, O <= 64); MDL_NNCONV=cta keeps the CTA-per-node ones (A/B)
+    const char* env = getenv("MDL_NNCONV");
+    if (nnconv_w_ok(K, O) && !(env && strcmp(env, "cta") == 0)) {
+      const size_t smw_bytes = (size_t)kNw * (kHS * 64 + (bwd ? kNwChunk * 64 + 64 * 65 : 0)) * sizeof(float);
+      const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(N, kNw), (int64_t)kNumSMs * 4);
+      if (bwd) {
+        MDL_CUDA(cudaFuncSetAttribute(k_nnconv_msg_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw_bytes));
+        k_nnconv_msg_w<true><<<grid, kNw * 32, smw_bytes, as_stream(stream)>>>(hid, XT, XB, dm, ptr, eid, m, dhid, dXT, dXB, N, K, O);
+      } else {
+        k_nnconv_msg_w<false><<<grid, kNw * 32, smw_bytes, as_stream(stream)>>>(hid, XT, XB, dm, ptr, eid, m, dhid, dXT, dXB, N, K, O);
+      }
+      MDL_LAUNCHED();
+      return MDL_OK;
+    }
+  }
   size_t smem = ((size_t)K * (O + 1) + (size_t)kNnChunk * (K + O)) * 4;
   MDL_REQUIRE(smem <= 200 * 1024 && (int64_t)K * O <= (int64_t)kNnMaxAcc * 256 && O <= 256,
               "nnconv_msg: hidden %d x out %d outside the supported range", K, O);

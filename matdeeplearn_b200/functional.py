@@ -273,12 +273,16 @@ class ExpandBySegmentFn(torch.autograd.Function):
     def forward(ctx, src, index32, ptr):
         from .csr import gather_rows
         ctx.save_for_backward(ptr)
+        ctx.rows = src.shape[0]
         return gather_rows(src, index32)
 
     @staticmethod
     def backward(ctx, g):
         (ptr,) = ctx.saved_tensors
-        return segment_reduce(g.contiguous(), ptr, None, "sum"), None, None
+        gs = segment_reduce(g.contiguous(), ptr, None, "sum")
+        if gs.shape[0] < ctx.rows:   # capacity-padded batch: src carries extra rows that only padding rows read
+            gs = torch.cat([gs, gs.new_zeros((ctx.rows - gs.shape[0],) + tuple(gs.shape[1:]))], 0)
+        return gs, None, None
 
 
 def expand_by_segment(src, index, ptr):

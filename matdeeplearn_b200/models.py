@@ -303,12 +303,14 @@ def _edge_mean_by_source(edge_attr, edge_index):
 def _expand_graph_rows(u, batch, n):
     """u[batch] (megnet.py:99); on CUDA through the gather kernel with the segmented sum as its backward."""
     seg = getattr(batch, "_mdl_seg", None)
+    ok = (u.is_cuda and u.dtype == torch.float32 and seg is not None and seg[0] == batch._version and seg[2] is None
+          and seg[1].shape[0] - 1 == u.shape[0])
     if getattr(batch, "_mdl_n_valid", None) is not None:
-        # capacity-padded batch: padding nodes carry graph id B; they read a zero row (and are outside every segment)
+        # capacity-padded batch: padding nodes carry graph id B; they read a zero row (and are outside every segment,
+        # so the segmented-sum backward -- deterministic, unlike index_select's atomics -- never sees them)
         u = torch.cat([u, u.new_zeros(1, u.shape[1])], 0)
-        return u.index_select(0, batch)
-    if u.is_cuda and u.dtype == torch.float32 and seg is not None and seg[0] == batch._version and seg[2] is None \
-            and seg[1].shape[0] - 1 == u.shape[0]:
+        return MF.expand_by_segment(u, batch, seg[1]) if ok else u.index_select(0, batch)
+    if ok:
         return MF.expand_by_segment(u, batch, seg[1])
     return u[batch]
 

@@ -79,7 +79,7 @@ def test_builder_triclinic_cells_match_host_builder():
     axis), mixed with orthorhombic and non-periodic structures in one call."""
     rng = np.random.default_rng(21)
     cells = [np.array([[6.0, 0, 0], [2.5, 5.0, 0], [0.5, 0.8, 7.0]]),          # generic triclinic
-             np.array([[4.0, 0, 0], [3.6, 1.9, 0], [0.3, 0.2, 9.0]]),          # strongly skewed: shifts up to +-2 or more
+             np.array([[4.0, 0, 0], [2.6, 3.2, 0], [0.3, 0.2, 4.5]]),          # skewed: image shifts up to +-5
              np.array([[5.0, 0, 0], [-2.5, 4.33, 0], [0, 0, 6.0]]),            # hexagonal
              np.array([[7.0, 0.5, 0.2], [0.1, 6.5, 0.4], [0.3, 0.2, 8.0]])]    # nearly orthogonal, fully dense matrix
     structs = []

@@ -220,8 +220,13 @@ def test_from_store_over_capacity_batch_takes_the_exact_path():
 ])
 def test_from_store_padded_replay_other_model_families(name, kind, cfg):
     """SchNet / MPNN / MEGNet on capacity-padded batches through ONE captured graph (edge-level and node-level
-    BatchNorm masked by the device-side row counts, padded edges inert) == eager steps on the exactly assembled
-    batches (reference train() body, training.py:37-50, on batches of varying shape)."""
+    BatchNorm masked by the device-side row counts, padded edges inert).  Two checks:
+    (1) the replayed trajectory equals eager steps on the same padded buffers (same kernels, same arithmetic: any
+        stale memo or missing in-graph recomputation would show here);
+    (2) a step on the padded batch is the same function as a step on the exactly assembled batch (reference train()
+        body, training.py:37-50): equal loss, gradients equal in norm.  These are ReLU + BatchNorm networks: a forward
+        difference of 1e-6 (different summation order of the batch statistics) can flip a unit sitting at its kink,
+        which changes single gradient elements by their full value, so (2) is norm-wise and one step long."""
     from matdeeplearn_b200 import models as M
     from matdeeplearn_b200.engine import TrainStep
     from matdeeplearn_b200.store import GraphStore
@@ -230,23 +235,32 @@ def test_from_store_padded_replay_other_model_families(name, kind, cfg):
     store = GraphStore.from_dataset(ds, DEV)
     torch.manual_seed(0)
     model = getattr(M, name)(ds, **cfg)
-    m1, m2 = copy.deepcopy(model).to(DEV).train(), copy.deepcopy(model).to(DEV).train()
-    s1, s2 = TrainStep(m1, lr=1e-3), TrainStep(m2, lr=1e-3)
+    m1, m2, m3 = (copy.deepcopy(model).to(DEV).train() for _ in range(3))
+    s1, s2, s3 = TrainStep(m1, lr=1e-3), TrainStep(m2, lr=1e-3), TrainStep(m3, lr=1e-3)
     order = np.random.default_rng(4).permutation(n)
     chunks = [order[i:i + B] for i in range(0, n, B)]
+    assert len({store._meta(idx)[2:] for idx in chunks}) > 1
+    # (1) graph replay vs eager on the same padded buffers
     la = [s1.from_store(store, idx) for idx in chunks]
-    lb = [float(s2.eager(store.batch(idx)).item()) for idx in chunks]
-    assert len({store._meta(idx)[2:] for idx in chunks}) > 1 and len(s1._store_graphs) == 1
+    assert len(s1._store_graphs) == 1
+    static = store.static_batch(B, lazy=True)
+    lb = []
+    for idx in chunks:
+        assert store.load(static, idx)
+        store.assemble(static)
+        lb.append(float(s2.eager(static).item()))
     for a, b in zip(la, lb):
-        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (la, lb)
-    # Parameters whose gradient is mathematically zero -- a bias added right before BatchNorm (InteractionBlock.lin.bias
-    # at schnet.py:140-141, NNConv.bias at mpnn.py:148-150) -- receive pure rounding noise, which AdamW normalises into
-    # +-lr steps of arbitrary sign on BOTH paths: they are excluded from the comparison (the function is unchanged).
-    import re
-    noise = {"SchNet": r"conv_list\.\d+\.lin\.bias$", "MPNN": r"conv_list\.\d+\.bias$"}.get(name)
-    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
-        if noise and re.search(noise, n1):
-            continue
-        assert (p1 - p2).abs().max().item() < 2e-4 * max(1.0, p2.abs().max().item()), n1
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (la, lb)
+    assert (s1.flat.param - s2.flat.param).abs().max().item() <= 1e-6 * max(1.0, s2.flat.param.abs().max().item())
     for (n1, b1), (n2, b2) in zip(m1.named_buffers(), m2.named_buffers()):
-        assert (b1.float() - b2.float()).abs().max().item() < 1e-3 * max(1.0, b2.float().abs().max().item()), n1
+        assert (b1.float() - b2.float()).abs().max().item() <= 1e-5 * max(1.0, b2.float().abs().max().item()), n1
+    # (2) one step: padded batch vs exactly assembled batch
+    m4 = copy.deepcopy(model).to(DEV).train()
+    s4 = TrainStep(m4, lr=1e-3)
+    assert store.load(static, chunks[0])
+    store.assemble(static)
+    lp = s4._fwd_bwd(static)
+    le = s3._fwd_bwd(store.batch(chunks[0]))
+    assert abs(lp.item() - le.item()) <= 1e-5 * max(1.0, abs(le.item()))
+    gp, ge = s4.flat.grad.double(), s3.flat.grad.double()
+    assert (gp - ge).norm().item() <= 2e-2 * ge.norm().item(), ((gp - ge).norm().item(), ge.norm().item())
