@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--roofline-graphs", type=int, default=16384)
     ap.add_argument("--roofline-only", action="store_true", help="only the isolated-kernel leg (ncu captures)")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="config 1 only: skip the short train-step measurements of configs 2..4 added to the line")
     return ap.parse_args()
 
 
@@ -432,6 +434,33 @@ def aux_roofline(args, dev, flush_buf, peak):
     return res
 
 
+def quick_step(cfgno, rank, world, dev, flush_buf, steps=10):
+    """Short device-timed measurement of another BASELINE config's train step (same rules as the headline value:
+    graph replay on a resident batch, L2 flushed between steps, CUDA events, max over ranks)."""
+    from matdeeplearn_b200 import models as M
+    from matdeeplearn_b200.engine import TrainStep
+    c = CONFIGS[cfgno]
+    per = c["graphs"]
+    ds, hb = make_workload(rank, per, c["kind"], c.get("sweep", (50,))[0])
+    hb.num_graphs = per
+    torch.manual_seed(0)
+    model = getattr(M, c["model"])(ds, **c["cfg"]).to(dev)
+    model.train()
+    step = TrainStep(model, lr=LR * world)
+    db = hb.to(dev)
+    db.num_graphs = per
+    replay = step.resident(db, warmup=3)
+    for _ in range(3):
+        replay()
+    ms, _ = timed_steps(replay, steps, flush_buf, world)
+    out = {"workload": workload_string(cfgno, "weak", world), "steps": steps, "ms_per_step": ms / steps,
+           "value": per * world / (ms / steps / 1e3), "unit": "graphs/s", "nodes_per_gpu": int(hb.x.shape[0]),
+           "edges_per_gpu": int(hb.edge_index.shape[1]), "kernels_per_step": int(step.kernels_per_step)}
+    del model, step, replay, db
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_engine(args, rank, world, local_rank):
     from matdeeplearn_b200 import _lib, models as M
     from matdeeplearn_b200.engine import TrainStep
@@ -594,6 +623,16 @@ def run_engine(args, rank, world, local_rank):
                                       "graph replay; loss.item() each step"}
     if strong is not None:
         line["strong_scaling"] = strong
+    if args.config == 1 and world == 1 and not args.no_other_configs:
+        # the other BASELINE configs, short device-timed runs (their full lines: bench.py --config 2|3|4)
+        others = {}
+        for k in (2, 3, 4):
+            try:
+                others[f"configs[{k}]"] = quick_step(k, rank, world, dev, flush_buf)
+            except Exception as exc:
+                others[f"configs[{k}]"] = {"error": repr(exc)[:200]}
+                torch.cuda.synchronize()
+        line["other_configs"] = others
     if "store_error" in head:
         line["store_step"] = {"error": head["store_error"]}
     if len(sweep) > 1:
@@ -649,11 +688,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world,
                                 device_id=torch.device("cuda", local_rank))
-    try:
-        run_engine(args, rank, world, local_rank)
-    finally:
-        if world > 1:
-            dist.destroy_process_group()
+    run_engine(args, rank, world, local_rank)
+    if world > 1:
+        # Leave without tearing the communicator down: destroy_process_group() was observed to hang while CUDA graphs
+        # holding captured NCCL kernels are alive (2-GPU run, profiles/r2_multi_gpu_notes.txt).  Every rank has
+        # finished its work and rank 0 has printed the line.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

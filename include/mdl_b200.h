@@ -168,6 +168,13 @@ MDL_API int mdl_spmm_edge(const float* h, const float* w, const int32_t* ptr, co
                           const int32_t* eid, float* out, int64_t num_segments, int64_t width,
                           void* stream);
 /* out[eid[p],:] = a[ia[p],:] * b[ib[p],:]  -- CFConv filter gradient dW = grad_out[dst] * h[src] */
+/* The same aggregate with ONE coefficient per edge (GCNConv's normalised adjacency D^-1/2 A D^-1/2 with
+ * A_ij = edge_weight, reference matdeeplearn/models/gcn.py:80-82,141): out[i,:] = sum_p coef[eid[p]] * h[nbr[p],:];
+ * and its coefficient gradient: out[eid[p]] = < a[ia[p],:], b[ib[p],:] >. */
+MDL_API int mdl_spmm_edge_scalar(const float* h, const float* coef, const int32_t* ptr, const int32_t* nbr,
+                                 const int32_t* eid, float* out, int64_t num_segments, int64_t width, void* stream);
+MDL_API int mdl_edge_dot(const float* a, const float* b, const int32_t* ia, const int32_t* ib, const int32_t* eid,
+                         float* out, int64_t num_edges, int64_t width, void* stream);
 MDL_API int mdl_edge_mul(const float* a, const float* b, const int32_t* ia, const int32_t* ib,
                          const int32_t* eid, float* out, int64_t num_edges, int64_t width, void* stream);
 
@@ -383,29 +390,6 @@ MDL_API int mdl_adamw_step(float* param, const float* grad, float* exp_avg, floa
 /* ---- development aid: 32 x uint64 device counters that receive per-phase cycle sums
  * (thread 0 of every CTA) from the tensor-core CGConv kernels; NULL disables. ---- */
 MDL_API int mdl_debug_set_phase_buffer(void* dev_ptr);
-
-/* ---- tensor-core self-test: D[128,N] = A[128,K] . B[N,K]^T through the same
- * tcgen05/TMEM conventions (umma.cuh) the fused kernels use.  split=0: plain
- * TF32 (operands truncated by the hardware); split=1: 3xTF32 (fp32-faithful).
- * No reference counterpart: test infrastructure for the kernels above. ---- */
-MDL_API int mdl_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K,
-                              int32_t split, void* stream);
-/* descriptor-field probe used while bringing up umma.cuh: same staging layout, caller-chosen LBO/SBO */
-MDL_API int mdl_selftest_umma_ex(const float* A, const float* B, float* D, int32_t N, int32_t K,
-                                 int32_t split, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b, int32_t sbo_b,
-                                 void* stream);
-/* same product with A staged in tensor memory (tcgen05.st) and B in shared memory */
-MDL_API int mdl_selftest_umma_ts(const float* A, const float* B, float* D, int32_t N, int32_t K,
-                                 int32_t split, void* stream);
-/* microbenchmark (development aid): cycles of `nstores` tcgen05.st of `width` columns per warp, with `mma_count`
- * 128x128x8 MMAs issued concurrently; out = 18 x int64 (per-warp cycles, [16] MMA issue, [17] MMA complete) */
-MDL_API int mdl_selftest_tmem_st_bench(long long* out, int32_t nwarps, int32_t nstores, int32_t width,
-                                       int32_t mma_count, int32_t wait_each, void* stream);
-/* layout probe: raw shared-memory images of both operand tiles + descriptor fields, nmma K=8 MMAs */
-MDL_API int mdl_selftest_umma_probe(const float* rawA, int32_t a_floats, const float* rawB, int32_t b_floats,
-                                    float* D, int32_t N, int32_t lbo_a, int32_t sbo_a, int32_t lbo_b,
-                                    int32_t sbo_b, int32_t a_mn, int32_t b_mn, int32_t nmma, int32_t step_a,
-                                    int32_t step_b, int32_t layout_a, int32_t layout_b, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,8 @@ SIGNATURES = {
     "mdl_cgconv_smear_bwd": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p,
                                        _sz, _p]),
     "mdl_spmm_edge": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "mdl_spmm_edge_scalar": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "mdl_edge_dot": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "mdl_edge_mul": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "mdl_edge_gather_add": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p]),
     "mdl_nnconv_msg_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p]),
@@ -85,17 +87,23 @@ SIGNATURES = {
     "mdl_copy_mapped": (C.c_int, [_p, _i32, _i32, _i32, C.POINTER(WgradOutC), _p]),
     "mdl_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i64, _p]),
     "mdl_debug_set_phase_buffer": (C.c_int, [_p]),
-    "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
-    "mdl_selftest_umma_ts": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "mdl_linear_tc_supported": (C.c_int, [_i64, _i32, _i32]),
     "mdl_linear_tc": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "mdl_linear_wgrad_rs": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "mdl_edge_mlp2_supported": (C.c_int, [_i32, _i32, _i32]),
     "mdl_edge_mlp2_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
     "mdl_edge_mlp2_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+}
+
+# libmdl_b200_selftest.so (include/mdl_b200_selftest.h): tensor-core self-tests / probes, test infrastructure only
+SELFTEST_LIB_PATH = os.path.join(_HERE, "libmdl_b200_selftest.so")
+SELFTEST_SIGNATURES = {
+    "mdl_selftest_umma": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
+    "mdl_selftest_umma_ts": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "mdl_selftest_tmem_st_bench": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mdl_selftest_umma_probe": (C.c_int, [_p, _i32, _p, _i32, _p] + [_i32] * 12 + [_p]),
     "mdl_selftest_umma_ex": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mdl_last_error": (C.c_int, [C.c_char_p, _sz]),
 }
 
 REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2}
@@ -120,6 +128,24 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+_selftest = None
+
+
+def load_selftest():
+    """The self-test library (tests / profiles scripts only)."""
+    global _selftest
+    if _selftest is None:
+        if not os.path.exists(SELFTEST_LIB_PATH):
+            raise ImportError(f"{SELFTEST_LIB_PATH} is missing (run __graft_entry__.build())")
+        lib = C.CDLL(SELFTEST_LIB_PATH)
+        for name, (res, args) in SELFTEST_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _selftest = lib
+    return _selftest
 
 
 def last_error() -> str:

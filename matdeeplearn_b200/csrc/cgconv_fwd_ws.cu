@@ -54,7 +54,7 @@ unsigned long long* g_ws_phase_buf = nullptr;
 
 struct WsPlan {
   unsigned long long* prof;
-  int window, KP, WR, sleep_ns;
+  int window, KP, WR, sleep_ns, rows_cpasync;
   uint32_t offBhi, offBlo, offEA, offW, wbytes, offV, offIdx, offWin, offInfo, total;
 };
 
@@ -71,7 +71,7 @@ bool ws_plan(int C, int G, bool smear, WsPlan* pl) {
   int WR = (int)(((uint32_t)kMaxDynSmem - fixed) / (2 * kVW * 4)) & ~7;
   if (WR > kRowsW) WR = kRowsW;
   pl->prof = g_ws_phase_buf;
-  pl->window = 1; pl->KP = KP; pl->WR = WR;
+  pl->window = 1; pl->KP = KP; pl->WR = WR; pl->rows_cpasync = 1;
   pl->wbytes = (uint32_t)WR * kVW * 4;
   pl->offBhi = 0; pl->offBlo = b; pl->offEA = 2 * b; pl->offW = pl->offEA + ea;
   pl->offV = pl->offW + 2 * pl->wbytes; pl->offIdx = pl->offV + v; pl->offWin = pl->offIdx + idx;
@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       umma::mbar_init(&bar_a_full[b], 4);            // one arrival per splitter warp
       umma::mbar_init(&bar_mma[b], 1);               // tcgen05.commit
       umma::mbar_init(&bar_acc_free[b], kConsWarps); // one arrival per consumer warp
-      umma::mbar_init(&bar_rows_full[b], 1);         // loader thread 0 (+ the rows' bytes)
+      // node rows: 16-byte cp.async (warp instruction = one 512-byte row), every loader thread arrives when its copies
+      // have landed; or (MDL_CGCONV_ROWS=bulk) one bulk copy per row, loader thread 0 arrives + the rows' bytes
+      umma::mbar_init(&bar_rows_full[b], pl.rows_cpasync ? kLoaders : 1);
       umma::mbar_init(&bar_rows_free[b], kConsWarps);
     }
     umma::fence_mbar_init();
@@ -278,12 +280,22 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
           WAIT(&bar_rows_free[b], (ph_rf >> b) & 1);
           ph_rf ^= 1u << b;
         }
-        if (lt == 0) {
+        float* W = sWbuf(b);
+        if (pl.rows_cpasync) {
+          // warp per row, lane = 16-byte chunk: lanes 0-15 the chunk's f piece, 16-31 its s piece (C floats further on in
+          // a PQ row [P_f | P_s | Q_f | Q_s]).  ~14 LDGSTS.128 per warp and round instead of ~14 serialised bulk-copy
+          // issues (a UBLKCP occupies its thread for a few hundred cycles)
+          for (int r = lw; r < D.nrows; r += kLoaders / 32) {
+            const float* g = (r < D.nq) ? p.PQ + (size_t)(D.s_lo + r) * (4 * C) + 2 * C + c_off
+                                        : p.PQ + (size_t)(D.d_lo + r - D.nq) * (4 * C) + c_off;
+            cp_async16(W + r * kVW + 4 * lane, g + (lane < 16 ? 4 * lane : C + 4 * (lane - 16)));
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(&bar_rows_full[b])) : "memory");
+        } else if (lt == 0) {
           if (D.nrows) umma::mbar_arrive_expect_tx(&bar_rows_full[b], (uint32_t)D.nrows * (uint32_t)(2 * kC * 4));
           else mbar_arrive(&bar_rows_full[b]);
         }
-        float* W = sWbuf(b);
-        for (int r = lt; r < D.nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
+        for (int r = lt; !pl.rows_cpasync && r < D.nrows; r += kLoaders) {  // rows [0,nq) = Q[smin..smax], rows [nq,nq+np) = P[dmin..dmax]
           // a PQ row is [P_f | P_s | Q_f | Q_s], C floats each: the chunk's f and s pieces are adjacent only when C = 64
           const float* g = (r < D.nq) ? p.PQ + (size_t)(D.s_lo + r) * (4 * C) + 2 * C + c_off
                                       : p.PQ + (size_t)(D.d_lo + r - D.nq) * (4 * C) + c_off;
@@ -550,6 +562,8 @@ int cgws_launch(CgParams p, cudaStream_t st) {
   pl.window = !(wenv && wenv[0] == '0');
   const char* senv = getenv("MDL_WS_SLEEP");  // ns slept between mbarrier polls (A/B switch)
   pl.sleep_ns = senv ? atoi(senv) : 0;
+  const char* renv = getenv("MDL_CGCONV_ROWS");  // "bulk": node rows by one bulk (TMA) copy per row (A/B switch)
+  pl.rows_cpasync = !(renv && strcmp(renv, "bulk") == 0);
   p.CC = kC; p.cap = kRowsW; p.te = kTileW;
   p.n_tiles = (int)std::max<int64_t>(1, ceil_div<int64_t>(p.E, kTileW));
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;

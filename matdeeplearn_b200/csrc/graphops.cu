@@ -43,6 +43,58 @@ k_spmm_edge(const float* __restrict__ h, const float* __restrict__ w, const int3
   }
 }
 
+// ---- out[i,:] = sum_{p in [ptr[i],ptr[i+1])} c[eid[p]] * h[nbr[p],:]   (warp per segment; one coefficient per edge:
+// GCNConv's normalised adjacency, reference gcn.py:80-82,141)
+__global__ void __launch_bounds__(256)
+k_spmm_edge_scalar(const float* __restrict__ h, const float* __restrict__ c, const int32_t* __restrict__ ptr,
+                   const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid, float* __restrict__ out,
+                   int64_t S, int width) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = width >> 2;
+  for (int64_t s = warp; s < S; s += nwarps) {
+    const int lo = __ldg(ptr + s), hi = __ldg(ptr + s + 1);
+    for (int v0 = 0; v0 < nv; v0 += 32) {
+      const int v = v0 + lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < nv) {
+#pragma unroll 4
+        for (int p = lo; p < hi; ++p) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(h + (size_t)(nbr ? __ldg(nbr + p) : p) * width) + v);
+          const float w = __ldg(c + (eid ? __ldg(eid + p) : p));
+          acc.x = fmaf(a.x, w, acc.x); acc.y = fmaf(a.y, w, acc.y);
+          acc.z = fmaf(a.z, w, acc.z); acc.w = fmaf(a.w, w, acc.w);
+        }
+        *(reinterpret_cast<float4*>(out + (size_t)s * width) + v) = acc;
+      }
+    }
+  }
+}
+
+// ---- out[eid[p]] = < a[ia[p],:], b[ib[p],:] >   (warp per position, fixed-order lane sums + shuffle tree)
+__global__ void __launch_bounds__(256)
+k_edge_dot(const float* __restrict__ a, const float* __restrict__ b, const int32_t* __restrict__ ia,
+           const int32_t* __restrict__ ib, const int32_t* __restrict__ eid, float* __restrict__ out,
+           int64_t E, int width) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = width >> 2;
+  for (int64_t p = warp; p < E; p += nwarps) {
+    const float4* ra = reinterpret_cast<const float4*>(a + (size_t)__ldg(ia + p) * width);
+    const float4* rb = reinterpret_cast<const float4*>(b + (size_t)__ldg(ib + p) * width);
+    float acc = 0.0f;
+    for (int v = lane; v < nv; v += 32) {
+      const float4 x = __ldg(ra + v), y = __ldg(rb + v);
+      acc = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, acc))));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[eid ? __ldg(eid + p) : p] = acc;
+  }
+}
+
 // ---- out[eid[p],:] = a[ia[p],:] * b[ib[p],:]   (warp per position)
 __global__ void __launch_bounds__(256)
 k_edge_mul(const float* __restrict__ a, const float* __restrict__ b, const int32_t* __restrict__ ia,
@@ -245,6 +297,7 @@ k_nnconv_msg_w(const float* __restrict__ hid, const float* __restrict__ XT, cons
         const float2 b = own ? __ldg(reinterpret_cast<const float2*>(XB + (size_t)j * O) + lane) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kNwChunk; ++r) acc[r] = b;
+#pragma unroll 4   // four rows of XT[j] requested before the first is used
         for (int k = 0; k < K; ++k) {
           const float2 x = own ? __ldg(reinterpret_cast<const float2*>(xt + (size_t)k * O) + lane) : make_float2(0.f, 0.f);
           const float4* hp = reinterpret_cast<const float4*>(sHT + k * kHS);
@@ -333,6 +386,26 @@ extern "C" int mdl_spmm_edge(const float* h, const float* w, const int32_t* ptr,
   if (S == 0) return MDL_OK;
   MDL_REQUIRE(h && w && ptr && out, "spmm_edge: null pointer");
   k_spmm_edge<<<warp_grid(S), 256, 0, as_stream(stream)>>>(h, w, ptr, nbr, eid, out, S, (int)width);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+extern "C" int mdl_spmm_edge_scalar(const float* h, const float* coef, const int32_t* ptr, const int32_t* nbr,
+                                    const int32_t* eid, float* out, int64_t S, int64_t width, void* stream) {
+  MDL_REQUIRE(S >= 0 && width > 0 && width % 4 == 0, "spmm_edge_scalar: width must be a multiple of 4");
+  if (S == 0) return MDL_OK;
+  MDL_REQUIRE(h && coef && ptr && out, "spmm_edge_scalar: null pointer");
+  k_spmm_edge_scalar<<<warp_grid(S), 256, 0, as_stream(stream)>>>(h, coef, ptr, nbr, eid, out, S, (int)width);
+  MDL_LAUNCHED();
+  return MDL_OK;
+}
+
+extern "C" int mdl_edge_dot(const float* a, const float* b, const int32_t* ia, const int32_t* ib, const int32_t* eid,
+                            float* out, int64_t E, int64_t width, void* stream) {
+  MDL_REQUIRE(E >= 0 && width > 0 && width % 4 == 0, "edge_dot: width must be a multiple of 4");
+  if (E == 0) return MDL_OK;
+  MDL_REQUIRE(a && b && ia && ib && out, "edge_dot: null pointer");
+  k_edge_dot<<<warp_grid(E), 256, 0, as_stream(stream)>>>(a, b, ia, ib, eid, out, E, (int)width);
   MDL_LAUNCHED();
   return MDL_OK;
 }

@@ -110,6 +110,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// ---- bulk async reduction (TMA): global[dst .. dst+bytes) += shared[src .. src+bytes) as fp32 adds, performed by the
+// copy engine / L2 (the issuing thread does not wait).  src, dst 16-byte aligned, bytes a multiple of 16.  The shared
+// source must stay intact until bulk_wait_read(); generic-proxy writes to it need fence_proxy_async_smem() first.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction --------
 __device__ __forceinline__ void stg256(float* p, const float* v) {  // p 32-byte aligned
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),

@@ -4,6 +4,7 @@
 // fused edge kernels that build on them.
 #include "common.cuh"
 #include "umma.cuh"
+#include "../../include/mdl_b200_selftest.h"
 
 namespace mdl {
 

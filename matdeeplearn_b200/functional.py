@@ -547,6 +547,48 @@ def cfconv_aggregate(h, W, csr):
     return CFConvAggFn.apply(h, W, csr)
 
 
+class SpmmScalarFn(torch.autograd.Function):
+    """out[i] = sum_{e: dst(e)=i} coef[e] * h[src(e)]  (coef in reference edge order; mdl_spmm_edge_scalar / mdl_edge_dot)."""
+
+    @staticmethod
+    def forward(ctx, h, coef, csr: GraphCSR):
+        lib = _lib.load()
+        h, coef = h.contiguous(), coef.contiguous()
+        N, F_ = h.shape
+        out = torch.empty_like(h)
+        rc = lib.mdl_spmm_edge_scalar(_lib.ptr(h), _lib.ptr(coef), _lib.ptr(csr.dst_ptr), _lib.ptr(csr.dst_src),
+                                      _lib.ptr(csr.dst_eid), _lib.ptr(out), N, F_, _lib.stream())
+        _lib.check(rc, "mdl_spmm_edge_scalar")
+        ctx.save_for_backward(h, coef)
+        ctx.csr = csr
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        h, coef = ctx.saved_tensors
+        csr = ctx.csr
+        g = g.contiguous()
+        N, F_ = h.shape
+        dh = dc = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty_like(h)
+            rc = lib.mdl_spmm_edge_scalar(_lib.ptr(g), _lib.ptr(coef), _lib.ptr(csr.src_ptr),
+                                          _lib.ptr(csr.source_order_nbr()), _lib.ptr(csr.source_order_eid()),
+                                          _lib.ptr(dh), N, F_, _lib.stream())
+            _lib.check(rc, "mdl_spmm_edge_scalar(bwd)")
+        if ctx.needs_input_grad[1]:
+            dc = torch.empty_like(coef)
+            rc = lib.mdl_edge_dot(_lib.ptr(g), _lib.ptr(h), _lib.ptr(csr.dst_dst), _lib.ptr(csr.dst_src),
+                                  _lib.ptr(csr.dst_eid), _lib.ptr(dc), csr.E, F_, _lib.stream())
+            _lib.check(rc, "mdl_edge_dot")
+        return dh, dc, None
+
+
+def spmm_scalar(h, coef, csr):
+    return SpmmScalarFn.apply(h, coef, csr)
+
+
 # ----------------------------------------------------------------------------
 # NNConv message:  m[e] = sum_k hid[e,k] * XT[src(e),k,:] + XB[src(e),:]
 # ----------------------------------------------------------------------------

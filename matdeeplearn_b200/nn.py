@@ -185,8 +185,8 @@ class GCNConv(nn.Module):
     """PyG GCNConv in the one configuration the reference builds (gcn.py:80-82:
     improved=True, add_self_loops=False; called with the raw distances as edge_weight):
     x' = D^-1/2 A D^-1/2 (x W^T) + b.  Same parameter names as PyG 2.0.1 (`lin.weight`, `bias`).
-    The degree and the weighted neighbour sum run on the CSR kernels (segment sum, mdl_spmm_edge);
-    the per-edge coefficient is expanded to the row width for the latter (first version: [E,F])."""
+    The degree and the weighted neighbour sum run on the CSR kernels (segment sum, mdl_spmm_edge_scalar: one
+    coefficient per edge; its gradient is a per-edge row dot product, mdl_edge_dot)."""
 
     def __init__(self, in_channels, out_channels, improved=False, cached=False, add_self_loops=True,
                  normalize=True, bias=True):
@@ -212,7 +212,10 @@ class GCNConv(nn.Module):
         dinv = dinv.masked_fill(dinv == float("inf"), 0.0)
         norm = dinv.index_select(0, row) * edge_weight * dinv.index_select(0, col)
         h = self.lin(x)
-        out = MF.cfconv_aggregate(h, norm.view(-1, 1).expand(-1, h.shape[1]).contiguous(), csr)
+        if h.shape[1] % 4 == 0 and h.dtype == torch.float32:
+            out = MF.spmm_scalar(h, norm, csr)           # one coefficient per edge, never expanded to [E, F]
+        else:
+            out = MF.cfconv_aggregate(h, norm.view(-1, 1).expand(-1, h.shape[1]).contiguous(), csr)
         return out + self.bias if self.bias is not None else out
 
 

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from matdeeplearn_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_selftest()
 out = torch.zeros(18, dtype=torch.int64, device="cuda:0")
 print("warps stores width mma wait_each | cycles/warp (min..max)  per-store | mma issue / complete")
 for nwarps in (1, 4, 8, 16):

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 from matdeeplearn_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_selftest()
 dev = torch.device("cuda:0")
 NONE, SW128, SW64, SW32 = 0, 2, 4, 6
 

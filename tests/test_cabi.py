@@ -70,6 +70,16 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
             assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
 
 
+def test_selftest_code_is_not_in_the_product_library(lib):
+    """tensor-core self-tests / probes live in libmdl_b200_selftest.so (include/mdl_b200_selftest.h)"""
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "selftest" not in out
+    text = open(os.path.join(ROOT, "include", "mdl_b200_selftest.h")).read()
+    names = sorted(set(re.findall(r"MDL_API\s+[\w\s\*]+?\b(mdl_\w+)\s*\(", text)))
+    assert names and sorted(n for n in lib.SELFTEST_SIGNATURES if n != "mdl_last_error") == names
+    lib.load_selftest()
+
+
 def test_no_unexpected_dynamic_dependencies(lib):
     out = subprocess.run(["ldd", lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "libtorch" not in out and "libpython" not in out, "the C ABI must not depend on torch/python"

@@ -52,16 +52,26 @@ def _worker(rank, world, port, out, graph_allreduce):
                     "names": [n for n, _ in model.named_parameters()],
                     "numels": [p.numel() for p in model.parameters()]}, out)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    # no destroy_process_group(): it was observed to hang while CUDA graphs with captured NCCL kernels are alive
+    os._exit(0)
 
 
 def _run(tmp_path, graph_allreduce):
     import torch.multiprocessing as mp
     out = str(tmp_path / f"multi_{graph_allreduce}.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, graph_allreduce), nprocs=2, join=True)
+    ctx = mp.spawn(_worker, args=(2, _free_port(), out, graph_allreduce), nprocs=2, join=False)
+    import time
+    deadline = time.time() + 240
+    while not ctx.join(timeout=5):          # bounded: a stuck collective must fail the test, not hang the box
+        if time.time() > deadline:
+            for p in ctx.processes:
+                p.kill()
+            raise AssertionError("2-rank worker processes did not finish within 240 s")
     return torch.load(out, weights_only=False)
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_trainstep_two_ranks_matches_oracle_and_eager_collective(tmp_path):
     from matdeeplearn_b200 import dist as mdist, process as pr

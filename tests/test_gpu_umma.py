@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("split", [0, 1])
 def test_umma_selftest(N, K, split):
     from matdeeplearn_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_selftest()
     dev = torch.device("cuda:0")
     torch.manual_seed(N * 1000 + K)
     A = torch.randn(128, K)
@@ -32,7 +32,7 @@ def test_umma_selftest(N, K, split):
 @pytest.mark.parametrize("split", [0, 1])
 def test_umma_selftest_a_operand_in_tensor_memory(N, K, split):
     from matdeeplearn_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_selftest()
     dev = torch.device("cuda:0")
     torch.manual_seed(N * 1000 + K + 7)
     A = torch.randn(128, K)
@@ -62,7 +62,7 @@ def test_raw_fp32_operands_are_truncated_not_rounded():
     """kind::tf32 reads fp32 bit patterns from smem; the fused kernels rely on the hardware
     TRUNCATING the low 13 mantissa bits (so that lo = x - trunc(x) is the exact complement)."""
     from matdeeplearn_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_selftest()
     dev = torch.device("cuda:0")
     torch.manual_seed(5)
     N, K = 64, 64
