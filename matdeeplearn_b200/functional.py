@@ -30,6 +30,20 @@ def _grad_dest(p):
     return d
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One auxiliary stream per device for work that is independent of the main chain inside a backward (forked and
+    joined with stream waits, which CUDA-graph capture records as parallel branches)."""
+    key = (device.type, device.index)
+    st = _side_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[key] = st
+    return st
+
+
 def _ptr_off(t, floats=0):
     return None if t is None else t.data_ptr() + 4 * floats
 
@@ -62,11 +76,12 @@ def linear_wgrad_into(x, g, wmap):
 _WGRAD_TC_MIN_ROWS = 16384
 
 
-def _linear_tc(x, w, ldn, ldk, bias, K, N):
-    """x [R,K] . B^T (+ bias) with B[n][k] = w[n*ldn + k*ldk] on the tcgen05 kernel (mdl_linear_tc)."""
+def _linear_tc(x, w, ldn, ldk, bias, K, N, act=0):
+    """act(x [R,K] . B^T (+ bias)) with B[n][k] = w[n*ldn + k*ldk] on the tcgen05 kernel (mdl_linear_tc);
+    act 0 = none, 1 = relu (applied in the kernel's epilogue)."""
     x = x.contiguous()
     y = torch.empty((x.shape[0], N), dtype=torch.float32, device=x.device)
-    rc = _lib.load().mdl_linear_tc(_lib.ptr(x), _lib.ptr(w), ldn, ldk, _lib.ptr(bias), _lib.ptr(y), x.shape[0], K, N, 0,
+    rc = _lib.load().mdl_linear_tc(_lib.ptr(x), _lib.ptr(w), ldn, ldk, _lib.ptr(bias), _lib.ptr(y), x.shape[0], K, N, act,
                                    _lib.stream())
     _lib.check(rc, "mdl_linear_tc")
     return y
@@ -82,19 +97,26 @@ class LinearFn(torch.autograd.Function):
     a K = E contraction + a column sum on the reference's path) also without one."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+    def forward(ctx, x, weight, bias, relu=False):
         ctx.wb = (weight, bias)
+        ctx.relu = relu
         O, I = weight.shape
         if weight.is_contiguous() and _tc_ok(x.shape[0], I, O):
-            return _linear_tc(x, weight, I, 1, bias, I, O)          # long batch: tcgen05 (3xTF32)
-        return torch.nn.functional.linear(x, weight, bias)
+            y = _linear_tc(x, weight, I, 1, bias, I, O, 1 if relu else 0)   # long batch: tcgen05 (3xTF32), ReLU in the epilogue
+        else:
+            y = torch.nn.functional.linear(x, weight, bias)
+            if relu:
+                y = torch.relu_(y)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
         wparam, bparam = ctx.wb
         g = g.contiguous()
+        if ctx.relu:
+            g = torch.ops.aten.threshold_backward(g, y, 0.0)         # g * [y > 0]
         O_, I_ = weight.shape
         dx = None
         if ctx.needs_input_grad[0]:
@@ -110,22 +132,24 @@ class LinearFn(torch.autograd.Function):
             wparam._mdl_written = True
             if bparam is not None:
                 bparam._mdl_written = True
-            return dx, None, None
+            return dx, None, None, None
         if x.shape[0] >= 2048 and I <= 256 and I >= 8 and O >= 8:
             dW = torch.empty_like(weight)
             db = torch.empty(O, dtype=weight.dtype, device=weight.device) if bparam is not None else None
             linear_wgrad_into(x, g, _wgrad_map(O, I, [_ptr_off(dW)], [_ptr_off(db)]))
-            return dx, dW, db
-        return dx, g.t().mm(x), (g.sum(0) if bparam is not None else None)
+            return dx, dW, db, None
+        return dx, g.t().mm(x), (g.sum(0) if bparam is not None else None), None
 
 
-def linear(x, weight, bias=None):
-    """torch.nn.functional.linear; routed through LinearFn when the engine delivers gradients directly or the
-    batch is long enough for the tensor-core weight-gradient kernel."""
+def linear(x, weight, bias=None, relu=False):
+    """torch.nn.functional.linear (followed by ReLU if `relu`); routed through LinearFn when the engine delivers
+    gradients directly or the batch is long enough for the tensor-core kernels (the ReLU then runs in the dense
+    kernel's epilogue and its mask is folded into the backward's first pass)."""
     if (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and weight.requires_grad
             and (getattr(weight, "_mdl_grad_dest", None) is not None or x.shape[0] >= _WGRAD_TC_MIN_ROWS)):
-        return LinearFn.apply(x, weight, bias)
-    return torch.nn.functional.linear(x, weight, bias)
+        return LinearFn.apply(x, weight, bias, relu)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return torch.relu(y) if relu else y
 
 
 def linear_wgrad_rs_into(x, g, rowscale, wmap):
@@ -218,8 +242,16 @@ def apply_mlp(seq, x):
     """Run an nn.Sequential (or a single module) with every nn.Linear going through `linear` above; other
     layers (activations, BatchNorm) are called as they are."""
     mods = list(seq) if isinstance(seq, torch.nn.Sequential) else [seq]
-    for m in mods:
-        x = linear(x, m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m(x)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, torch.nn.Linear):
+            fuse = i + 1 < len(mods) and type(mods[i + 1]) is torch.nn.ReLU    # Linear -> ReLU: one kernel
+            x = linear(x, m.weight, m.bias, relu=fuse)
+            i += 2 if fuse else 1
+        else:
+            x = m(x)
+            i += 1
     return x
 
 
@@ -459,9 +491,6 @@ class CGConvFn(torch.autograd.Function):
                                           _lib.ptr(dWeT), N, csr.E, C, G, _lib.REDUCE[ctx.reduce], _lib.ptr(ws),
                                           ws_bytes, _lib.stream())
             _lib.check(rc, "mdl_cgconv_smear_bwd")
-        dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
-        # node-level dense tail: plain library GEMMs (a hand-written split-over-nodes kernel was
-        # measured slower than cuBLAS + a column sum here and was dropped)
         w_f, b_f, w_s, b_s = ctx.params
         dwf, dws = _grad_dest(w_f), _grad_dest(w_s)
         dbf = _grad_dest(b_f) if ctx.has_bias[0] else None
@@ -469,19 +498,32 @@ class CGConvFn(torch.autograd.Function):
         if (dwf is not None and dws is not None and (not ctx.has_bias[0] or dbf is not None)
                 and (not ctx.has_bias[1] or dbs is not None)):
             # direct delivery: [P_f | P_s | Q_f | Q_s] column blocks of dPQ^T x, the bias sums and the
-            # transposed edge block go straight into lin_f / lin_s .weight / .bias gradient storage
+            # transposed edge block go straight into lin_f / lin_s .weight / .bias gradient storage.  They depend only
+            # on dPQ / dWeT, not on dx: they run on a side stream next to the dx GEMM (small kernels that do not fill
+            # the GPU one by one; MDL_BWD_OVERLAP=0 keeps everything on one stream)
             import ctypes
+            import os
             G = dWeT.shape[0]
             ld = 2 * C + G
-            linear_wgrad_into(x, dPQ, _wgrad_map(
-                C, ld, [_ptr_off(dwf), _ptr_off(dws), _ptr_off(dwf, C), _ptr_off(dws, C)],
-                [_ptr_off(dbf), _ptr_off(dbs), None, None]))
-            m2 = _wgrad_map(C, ld, [_ptr_off(dwf, 2 * C), _ptr_off(dws, 2 * C)], [None, None])
-            rc = _lib.load().mdl_copy_mapped(_lib.ptr(dWeT), G, 2 * C, 1, ctypes.byref(m2), _lib.stream())
-            _lib.check(rc, "mdl_copy_mapped")
+            overlap = os.environ.get("MDL_BWD_OVERLAP", "1") != "0" and ctx.needs_input_grad[0]
+            cur = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device) if overlap else cur
+            if overlap:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                linear_wgrad_into(x, dPQ, _wgrad_map(
+                    C, ld, [_ptr_off(dwf), _ptr_off(dws), _ptr_off(dwf, C), _ptr_off(dws, C)],
+                    [_ptr_off(dbf), _ptr_off(dbs), None, None]))
+                m2 = _wgrad_map(C, ld, [_ptr_off(dwf, 2 * C), _ptr_off(dws, 2 * C)], [None, None])
+                rc = _lib.load().mdl_copy_mapped(_lib.ptr(dWeT), G, 2 * C, 1, ctypes.byref(m2), _lib.stream())
+                _lib.check(rc, "mdl_copy_mapped")
+            dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
+            if overlap:
+                cur.wait_stream(side)
             for prm in (w_f, w_s) + ((b_f,) if ctx.has_bias[0] else ()) + ((b_s,) if ctx.has_bias[1] else ()):
                 prm._mdl_written = True
             return dx, None, None, None, None, None, None, None, None
+        dx = torch.addmm(g, dPQ, Wn) if ctx.needs_input_grad[0] else None  # residual + projections
         dWn = dPQ.t().mm(x)                                                 # [4C, C]
         db = dPQ[:, :2 * C].sum(0)
         return CGConvFn._finish(ctx, dx, dWn, db, dWeT, C)

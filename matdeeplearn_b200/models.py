@@ -226,7 +226,10 @@ class _MegnetStack(tnn.Module):
         layers = getattr(self, self._name)
         for i, lin in enumerate(layers):
             if not (i == 0 and first_done):
-                h = getattr(F, self.act)(MF.linear(h, lin.weight, lin.bias))
+                if self.act == "relu":
+                    h = MF.linear(h, lin.weight, lin.bias, relu=True)
+                else:
+                    h = getattr(F, self.act)(MF.linear(h, lin.weight, lin.bias))
             if self.batch_norm == "True":
                 h = MF.masked_batch_norm(self.bn_list[i], h, n_valid) if n_valid is not None else self.bn_list[i](h)
             h = F.dropout(h, p=self.dropout_rate, training=self.training)

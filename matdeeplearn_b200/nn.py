@@ -326,9 +326,7 @@ class NNConv(nn.Module):
         last = self.nn[-1] if isinstance(self.nn, nn.Sequential) and isinstance(self.nn[-1], nn.Linear) else None
         if last is None:
             raise NotImplementedError("NNConv: edge network must end in a Linear (as the reference's does)")
-        hid = edge_attr
-        for layer in list(self.nn)[:-1]:
-            hid = MF.apply_mlp(layer, hid)                     # [E, K] dense edge-level GEMM + act
+        hid = MF.apply_mlp(self.nn[:-1], edge_attr)            # [E, K] dense edge-level GEMM + act (fused when ReLU)
         K = hid.shape[1]
         # last.weight [Ci*Co, K]: Theta_e[i,o] = sum_k W[i*Co+o, k] hid[k] + b[i*Co+o]
         Tm = last.weight.view(Ci, Co, K).permute(0, 2, 1).reshape(Ci, K * Co)   # x . Tm -> [N, K*Co]
