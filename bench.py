@@ -507,7 +507,7 @@ def run_engine(args, rank, world, local_rank):
             del model, step, replay
             torch.cuda.empty_cache()
             continue
-        head = dict(rec, wall=wall)
+        head = dict(rec, wall=wall, graph_allreduce=bool(getattr(step, "graph_allreduce", False)))
         # ---- end to end from pinned host buffers through the public API (e2e)
         pinned = host_batch.pin_memory()
         pinned.num_graphs = per
@@ -593,7 +593,9 @@ def run_engine(args, rank, world, local_rank):
             "workload": workload_string(args.config, args.scaling, world),
             "graphs_per_step": graphs_total, "nodes_per_gpu": head["nodes_per_gpu"], "edges_per_gpu": head["edges_per_gpu"],
             "parallelism": f"dp{world}", "step": "zero_grad+fwd+l1_loss+bwd" +
-            ("+flat grad allreduce (NCCL, captured inside the step's CUDA graph)+AdamW, one CUDA graph replay"
+            (("+flat grad allreduce (NCCL, captured inside the step's CUDA graph)+AdamW, one CUDA graph replay"
+              if head["graph_allreduce"] else
+              "+flat grad allreduce (NCCL, eager)+AdamW, two CUDA graph replays around the collective")
              if world > 1 else "+AdamW, one CUDA graph replay") +
             " (the metric text says fwd+bwd; the optimizer step is included, as in the reference's train() body)",
             "l2": "flushed between timed steps (512 MiB read-modify-write)",

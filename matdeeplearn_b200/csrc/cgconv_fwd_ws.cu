@@ -410,12 +410,13 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
     // ---- reduce-stage node data of this warp's first segment (global loads in flight across the epilogue)
     const int n0 = n_lo + warp;
     int seg_a = 0, seg_b = 0;
-    float seg_sc = kLn2;                     // the softplus' ln 2 rides in the per-node scale
+    float seg_inv = 1.0f;                    // 1/deg, multiplied by the softplus' ln 2 only where it is used (in the
+                                             // reduce stage): a multiply here would wait for the load on the spot
     float2 seg_x = make_float2(0.0f, 0.0f);  // lane l owns channels 2l, 2l+1
     if (n0 < n_hi) {
       seg_a = __ldg(p.seg_ptr + n0);
       seg_b = __ldg(p.seg_ptr + n0 + 1);
-      if (p.inv_deg) seg_sc = kLn2 * __ldg(p.inv_deg + n0);
+      if (p.inv_deg) seg_inv = __ldg(p.inv_deg + n0);
       seg_x = __ldg(reinterpret_cast<const float2*>(p.x + (size_t)n0 * C + c_off) + lane);
     }
     if (cnt > 0) {
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(kLaunchW, 1) k_cgconv_fwd_ws(const CgParams p,
       const bool first = empty_seg || (a >= r_lo);
       const bool lastp = empty_seg || (bq <= r_hi);
       float2* o = reinterpret_cast<float2*>(p.out + (size_t)n * C + c_off) + lane;
-      float sc = seg_sc;
+      float sc = kLn2 * seg_inv;
       float2 x = seg_x;
       if (n != n0) {
         sc = p.inv_deg ? kLn2 * __ldg(p.inv_deg + n) : kLn2;

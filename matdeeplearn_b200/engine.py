@@ -89,16 +89,32 @@ class TrainStep:
         Returns (replay, loss tensor, kernels launched by libmdl_b200.so per step [+1 for the collective])."""
         distributed = mdist.is_distributed()
         fused = distributed and self.graph_allreduce
-        g1 = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(g1):
-            if pre is not None:
-                pre()
-            loss = self._fwd_bwd(batch)
-            if fused:
-                self._reduce()
-            if fused or not distributed:
-                self._opt_step()
+
+        def capture_first(with_collective):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if pre is not None:
+                    pre()
+                loss_ = self._fwd_bwd(batch)
+                if with_collective:
+                    self._reduce()
+                if with_collective or not distributed:
+                    self._opt_step()
+            return g, loss_
+
+        if fused:
+            try:
+                g1, loss = capture_first(True)
+            except Exception as exc:   # a communicator that cannot be captured: eager collective between two graphs
+                import warnings
+                warnings.warn(f"all-reduce could not be captured inside the step graph ({exc!r}); "
+                              "falling back to an eager collective between two graphs")
+                torch.cuda.synchronize()
+                self.graph_allreduce = fused = False
+                n0 = _lib.launch_count()
+        if not fused:
+            g1, loss = capture_first(False)
         g2 = None
         if distributed and not fused:
             g2 = torch.cuda.CUDAGraph()
