@@ -144,7 +144,7 @@ MDL_API int mdl_cgconv_bwd(const float* grad_out, const float* PQ, const float* 
  * (slot order, i.e. permuted by dst_eid like `ea` above) plus the module's `offset` buffer [G] (device; uniform
  * spacing, G >= 2) and `coeff`, and expand the basis inside the fused edge kernels: 4 B instead of 4 G B per edge.
  * Same operator, outputs and gradients as mdl_cgconv_fwd / _bwd on ea = GaussianSmearing(d_hat) (basis within
- * 2e-6 of torch.exp's).  mdl_cgconv_smear_supported: 1 if (C, G) is served by the tensor-core kernels that
+ * 2.5e-6 of torch.exp's at the reference's parameters, 6e-6 for coarse or narrow bases).  mdl_cgconv_smear_supported: 1 if (C, G) is served by the tensor-core kernels that
  * implement this form (C = 64, G <= 64, no MDL_CGCONV_* kernel switch in the environment); otherwise the caller
  * materialises ea (mdl_gaussian_smear) and uses the entry points above. ---- */
 MDL_API int mdl_cgconv_smear_supported(int32_t C, int32_t G);

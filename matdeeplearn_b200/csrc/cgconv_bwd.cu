@@ -1,4 +1,5 @@
-// cgconv_bwd.cu -- single-pass CGConv backward (dP, dQ, dW_e) with BOTH contractions on tcgen05.
+// cgconv_bwd.cu -- single-pass CGConv backward (dP, dQ, dW_e) with BOTH contractions on tcgen05; 64 channels
+// [c_off, c_off + 64) of a C-wide layer per launch (any C >= 64), edge data = edge_attr rows or d_hat (smearing-fused form).
 //
 // Reference: autograd through PyG's CGConv (matdeeplearn/models/cgcnn.py:80-82,136-145); SURVEY.md Appendix E.1.
 // Same tile ownership, staging, gate recompute and deterministic per-destination sums as k_cgconv_tc<BWD_DST>

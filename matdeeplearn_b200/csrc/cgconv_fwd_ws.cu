@@ -1,4 +1,6 @@
-// cgconv_fwd_ws.cu -- warp-specialised forward kernel of the fused CGConv edge op (C = 64, G <= 64).
+// cgconv_fwd_ws.cu -- warp-specialised forward kernel of the fused CGConv edge op: 64 channels [c_off, c_off + 64) of a
+// C-wide layer per launch (any C >= 64, C % 4 == 0), G <= 64; edge data = materialised edge_attr rows or, in the
+// smearing-fused form, the normalised distance d_hat expanded to the Gaussian basis by the splitter warps.
 //
 // Reference: PyG CGConv.forward as the reference calls it (matdeeplearn/models/cgcnn.py:80-82,136-145):
 //   out_i = x_i + mean_{j->i} sigmoid(W_f z + b_f) * softplus(W_s z + b_s),  z = [x_i | x_j | e_ij].
@@ -10,7 +12,7 @@
 //
 //   warp 20 (one lane)   issuer: bulk (TMA) copy of a round's edge rows; the 21 tcgen05.mma of a round
 //   warps 16-19          splitters: thread = slot = TMEM lane; landing zone -> hi / lo -> tcgen05.st (A operand)
-//   warps 21-23          loaders: the round's indices, its node-row window decision, one bulk copy per P / Q row
+//   warps 21-23          loaders: indices + node-row window decision one live round ahead, one bulk copy per P / Q row
 //   warps 0-15           consumers: tcgen05.ld -> + P[dst] + Q[src] -> gates -> message tile -> per-segment sums
 //
 //   edge rows   issuer --bar_ea_full--> splitters --bar_a_full[b]--> issuer (MMA) --bar_mma[b]--> consumers

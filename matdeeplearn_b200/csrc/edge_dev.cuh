@@ -73,7 +73,9 @@ __device__ __forceinline__ void softplus_sigmoid_mufu(float x, float& sp, float&
 // Eight consecutive basis values t_k .. t_{k+7} of one edge from two exponentials: with uniform spacing dmu,
 //   t_{k+1} = t_k rho_k,  rho_k = 2^(c2 dmu (dmu - 2 (d - mu_k))),  rho_{k+1} = rho_k q2,  q2 = 2^(2 c2 dmu^2)
 // (c2 = coeff log2 e).  The chunk restarts from the module's own mu_k0 (table `mu`), so position errors do not
-// accumulate beyond seven steps; measured against torch.exp(coeff * (d - mu)^2): <= 2e-6 of the basis' scale (1).
+// accumulate beyond seven steps; against torch.exp(coeff * (d - mu)^2) in fp64, in a float32 restatement with exact
+// exponentials (tests/test_data_lazy_cpu.py): 2.2e-6 of the basis' scale (1) at the reference's parameters (G = 50),
+// up to 3.8e-6 for a coarse basis (G = 8).
 struct SmearConst { float c2, dmu, q2; };
 __device__ __forceinline__ SmearConst smear_const(const float* mu, int G, float coeff) {
   SmearConst s;
