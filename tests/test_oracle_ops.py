@@ -182,3 +182,88 @@ def test_segment_softmax_and_set2set_hand_worked():
         rows.append(q_star)
     assert got.shape == (2, 2 * C)
     assert torch.allclose(got, torch.cat(rows, 0), rtol=1e-10, atol=1e-12)
+
+
+def test_metalayer_call_convention_hand_worked():
+    """PyG MetaLayer as the reference composes it (megnet.py:235-239, 310-333): the edge model is called with
+    (x[row], x[col], edge_attr, u, batch[row]) -- row = edge_index[0] the SOURCE --, then the node model with the NEW
+    edge_attr, then the global model with the NEW x and edge_attr."""
+    seen = {}
+
+    class Edge(torch.nn.Module):
+        def forward(self, src, dest, e, u, b):
+            seen["edge"] = (src.clone(), dest.clone(), e.clone(), u.clone(), b.clone())
+            return e + src.sum(1, keepdim=True) - dest.sum(1, keepdim=True) + u[b]
+
+    class Node(torch.nn.Module):
+        def forward(self, x, ei, e, u, b):
+            seen["node_e"] = e.clone()
+            return x + O.scatter_mean(e, ei[0], dim=0, dim_size=x.shape[0])
+
+    class Glob(torch.nn.Module):
+        def forward(self, x, ei, e, u, b):
+            seen["glob_x"] = x.clone()
+            return u + O.scatter_mean(x, b, dim=0)
+
+    x = torch.tensor([[1.0], [10.0], [100.0]])
+    ei = torch.tensor([[0, 1, 2, 2], [1, 0, 0, 2]])            # 0->1, 1->0, 2->0, loop 2->2
+    e = torch.tensor([[0.5], [0.25], [0.125], [0.0]])
+    u = torch.tensor([[1000.0], [2000.0]])
+    batch = torch.tensor([0, 0, 1])
+    x2, e2, u2 = O.MetaLayer(Edge(), Node(), Glob())(x, ei, e, u, batch)
+    src, dest, e_in, u_in, b_in = seen["edge"]
+    assert src.view(-1).tolist() == [1.0, 10.0, 100.0, 100.0] and dest.view(-1).tolist() == [10.0, 1.0, 1.0, 100.0]
+    assert b_in.tolist() == [0, 0, 1, 1]                       # graph of the SOURCE node
+    want_e = torch.tensor([[0.5 + 1 - 10 + 1000], [0.25 + 10 - 1 + 1000], [0.125 + 100 - 1 + 2000], [0.0 + 2000]])
+    torch.testing.assert_close(e2, want_e)
+    torch.testing.assert_close(seen["node_e"], want_e)         # node model sees the updated edges
+    want_x = x + torch.stack([want_e[0], want_e[1], (want_e[2] + want_e[3]) / 2])   # mean over edges LEAVING each node
+    torch.testing.assert_close(x2, want_x)
+    torch.testing.assert_close(seen["glob_x"], want_x)         # global model sees the updated nodes
+    torch.testing.assert_close(u2, u + torch.stack([(want_x[0] + want_x[1]) / 2, want_x[2]]))
+
+
+def test_megnet_node_and_global_models_aggregate_edges_at_their_source():
+    """megnet.py:86 and :130: scatter_mean(edge_attr, edge_index[0]) -- edges are averaged at their SOURCE node (unlike
+    the convs, which aggregate at edge_index[1]); the global model then averages nodes and node-averaged edges per graph
+    (megnet.py:131-132)."""
+    from oracle import models as OM
+    D = 2
+    node = OM.Megnet_NodeModel(D, "relu", "False", "True", 0.0, fc_layers=0).double()
+    glob = OM.Megnet_GlobalModel(D, "relu", "False", "True", 0.0, fc_layers=0).double()
+    for m in (node, glob):                                     # identity-like first layer: output = relu(sum of the 3 blocks)
+        lin = getattr(m, m._list_name)[0]
+        with torch.no_grad():
+            lin.weight.copy_(torch.cat([torch.eye(D)] * 3, 1).double())
+            lin.bias.zero_()
+    x = torch.tensor([[1.0, 0.0], [0.0, 1.0], [2.0, 2.0]], dtype=torch.float64)
+    ei = torch.tensor([[0, 0, 1, 2], [1, 2, 0, 2]])
+    e = torch.tensor([[1.0, 0.0], [3.0, 0.0], [0.0, 5.0], [7.0, 7.0]], dtype=torch.float64)
+    u = torch.tensor([[10.0, 10.0], [20.0, 20.0]], dtype=torch.float64)
+    batch = torch.tensor([0, 0, 1])
+    v_e = torch.tensor([[2.0, 0.0], [0.0, 5.0], [7.0, 7.0]], dtype=torch.float64)      # by source: node 0 <- edges 0,1
+    torch.testing.assert_close(node(x, ei, e, u, batch), x + v_e + u[batch])
+    u_e = torch.stack([(v_e[0] + v_e[1]) / 2, v_e[2]])
+    u_v = torch.stack([(x[0] + x[1]) / 2, x[2]])
+    torch.testing.assert_close(glob(x, ei, e, u, batch), u_e + u_v + u)
+
+
+def test_cfconv_equals_explicit_edge_loop():
+    """PyG CFConv (schnet.py:81 -> InteractionBlock.conv): out_i = lin2( sum_{j->i} lin1(x)_j * (mlp(e_ij) * C(d_ij)) ),
+    C(d) = (cos(pi d / cutoff) + 1) / 2, aggregated at edge_index[1]."""
+    torch.manual_seed(3)
+    n, E, Cc, G, Fw, cutoff = 5, 9, 3, 4, 6, 8.0
+    mlp = torch.nn.Sequential(torch.nn.Linear(G, Fw), O.ShiftedSoftplus(), torch.nn.Linear(Fw, Fw)).double()
+    conv = O.CFConv(Cc, Cc, Fw, mlp, cutoff).double()
+    x = torch.randn(n, Cc, dtype=torch.float64)
+    ei = torch.randint(0, n, (2, E))
+    d = torch.rand(E, dtype=torch.float64) * cutoff
+    ea = torch.rand(E, G, dtype=torch.float64)
+    got = conv(x, ei, d, ea)
+    h = x @ conv.lin1.weight.t()
+    agg = torch.zeros(n, Fw, dtype=torch.float64)
+    for k in range(E):
+        j, i = int(ei[0, k]), int(ei[1, k])
+        w = mlp(ea[k]) * 0.5 * (math.cos(math.pi * float(d[k]) / cutoff) + 1.0)
+        agg[i] += h[j] * w
+    torch.testing.assert_close(got, agg @ conv.lin2.weight.t() + conv.lin2.bias, rtol=1e-12, atol=1e-12)
